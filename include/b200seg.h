@@ -1,0 +1,217 @@
+/* b200seg.h — C ABI of libb200seg.so: the sm_100a kernels behind the drop-in U-Net-family modules.
+ *
+ * The reference (bababyVN/medical-image-segmentation-and-classification) is pure Python and has NO FFI /
+ * plugin layer: its boundary for this path is the nn.Module surface, and every entry point below replaces the
+ * ATen/cuDNN op that a reference module line dispatches to.  Each declaration cites that call site
+ * (file:line relative to the reference root).  INTEGRATION.md shows the ctypes / torch.library binding.
+ *
+ * Conventions
+ *   - plain pointers + sizes; all pointers are DEVICE pointers owned by the caller (PyTorch allocates them);
+ *   - activations are NHWC bf16; `ld*` is the channel stride in ELEMENTS of the underlying buffer, so a channel
+ *     slice of a wider buffer can be passed without a copy;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates, never syncs;
+ *   - return 0 on success or a negative B2_ERR_* code; b2_last_error() gives the thread-local message;
+ *   - no CPU fallback, no cuDNN/cuBLAS: on a non-sm_100 device every compute entry returns B2_ERR_ARCH.
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+
+enum {
+  B2_OK = 0,
+  B2_ERR_SHAPE = -1,     /* unsupported / inconsistent dimensions */
+  B2_ERR_ALIGN = -2,     /* pointer or stride alignment (16 B) violated */
+  B2_ERR_ARCH = -3,      /* device is not sm_100 (B200) */
+  B2_ERR_CUDA = -4,      /* CUDA runtime / driver error */
+  B2_ERR_NCCL = -5,      /* reserved for the collective path */
+  B2_ERR_WORKSPACE = -6  /* caller-provided workspace too small */
+};
+
+typedef void* b2_stream_t; /* cudaStream_t */
+
+const char* b2_last_error(void);
+int b2_abi_version(void);
+int b2_arch_check(void);   /* 0 iff the current device is sm_100; B2_ERR_ARCH otherwise */
+int b2_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Convolution, stride 1, 'same' padding, ksize in {1,3}: implicit GEMM on tcgen05 (TMA -> 128B-swizzled smem ->
+ * tcgen05.mma, fp32 accumulators in TMEM).  Replaces nn.Conv2d forward at
+ *   models/segmentation_models/AttentionUNet.py:6,9,20,33,37,41   R2U_Net.py:10,27,43   R2AttU_Net.py:35,52,65-74
+ *   ResnetUnet.py:7,10,54
+ * and, run on dgrad-packed weights (b2_pack_weights), the input-gradient half of aten::convolution_backward
+ * (autograd of utils/helpers.py:329).
+ * The K dimension may come from two tensors (x0 | x1): this is the elided torch.cat of AttentionUNet.py:101,106,
+ * 111,116 / R2U_Net.py:94.. .  Epilogue: +bias, +addend (bf16 residual), optional ReLU, bf16 store, and
+ * per-channel sum / sum-of-squares of the ROUNDED output accumulated into `stats` (BatchNorm batch statistics,
+ * AttentionUNet.py:7,10,21).
+ * Requirements: c0,c1 multiples of 8 (c0 multiple of 64 when c1 > 0); cout multiple of 32; W a power of two >= 8
+ * or a multiple of 128, H*W..: see DESIGN.md "tile geometry".
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b2_conv_args {
+  int32_t n, h, w;        /* output == input spatial extent */
+  int32_t ksize;          /* 1 or 3 */
+  const void* x0;         /* NHWC bf16 */
+  int32_t c0, ldx0;
+  const void* x1;         /* optional second K source (NULL if unused) */
+  int32_t c1, ldx1;
+  const void* wpk;        /* packed bf16 [ksize*ksize][rows][ktot], rows >= cout */
+  int32_t ktot;           /* row length of wpk in elements (>= c0 + c1) */
+  int64_t w_tap_stride;   /* elements between taps in wpk */
+  int32_t cout;
+  void* y;                /* NHWC bf16 */
+  int32_t ldy;
+  const float* bias;      /* [cout] or NULL */
+  const void* addend;     /* optional NHWC bf16 [.., cout] added before rounding (NULL if unused) */
+  int32_t ldadd;
+  double* stats;          /* optional [2][cout] (sum, sumsq), ACCUMULATED into (caller zeroes) */
+  int32_t relu;
+} b2_conv_args;
+
+int b2_conv_fprop(const b2_conv_args* a, b2_stream_t stream);
+/* same kernel; `wpk` must be the dgrad packing, x0 is dY, y is dX */
+int b2_conv_dgrad(const b2_conv_args* a, b2_stream_t stream);
+
+/* Weight gradient: dW[co][tap][ci] = sum_p dY[p][co] * X[p (+) tap][ci]  (the weight half of
+ * aten::convolution_backward).  tcgen05 with MN-major operands, split-K over pixels, deterministic two-stage
+ * reduction through `workspace`.  dw is fp32 laid out [cout][ksize*ksize][c0+c1] (== channels_last weight). */
+typedef struct b2_wgrad_args {
+  int32_t n, h, w;
+  int32_t ksize;
+  const void* dy;         /* NHWC bf16 */
+  int32_t cout, lddy;
+  const void* x0;
+  int32_t c0, ldx0;
+  const void* x1;
+  int32_t c1, ldx1;
+  float* dw;
+  int32_t accumulate;     /* 1: dw += result (shared weights of R2U_Net.py:15-20), 0: overwrite */
+  void* workspace;
+  int64_t workspace_bytes;
+} b2_wgrad_args;
+
+int64_t b2_conv_wgrad_workspace(const b2_wgrad_args* a);
+int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream);
+
+/* fp32 [cout][cin][k][k] parameter with arbitrary element strides -> bf16 fprop packing [k*k][cout][cin] and
+ * (optional) dgrad packing [k*k][cin][cout] with the taps flipped. */
+int b2_pack_weights(const float* w, int32_t cout, int32_t cin, int32_t ksize, int64_t s_co, int64_t s_ci,
+                    int64_t s_kh, int64_t s_kw, void* w_fprop, void* w_dgrad, b2_stream_t stream);
+
+/* Small-Cin direct convolution (image stem: AttentionUNet.py:6 with cin=3, R2U_Net.py:43 RRCNN1.conv_1x1).
+ * x is NHWC bf16 padded to 4 channels; w is fp32 [cout][ksize*ksize][4]. */
+int b2_conv_smallc_fprop(const void* x4, int32_t n, int32_t h, int32_t w, int32_t ksize, const float* wk,
+                         const float* bias, int32_t cout, void* y, int32_t ldy, int32_t relu, b2_stream_t stream);
+int b2_conv_smallc_wgrad(const void* dy, int32_t lddy, const void* x4, int32_t n, int32_t h, int32_t w,
+                         int32_t ksize, int32_t cout, float* dw /* [cout][k*k][4], accumulated into */,
+                         b2_stream_t stream);
+
+/* Cout<=8 1x1 heads (AttentionUNet.py:84, R2U_Net.py:76, ResnetUnet.py:58): memory-bound dot products.
+ * y is fp32 NCHW [n][cout][hw]; x NHWC bf16. */
+int b2_head_fwd(const void* x, int32_t ldx, int64_t npix, int32_t hw, int32_t cin, const float* w /*[cout][cin]*/,
+                const float* bias, int32_t cout, float* y, b2_stream_t stream);
+int b2_head_bwd(const float* dy, const void* x, int32_t ldx, int64_t npix, int32_t hw, int32_t cin,
+                const float* w, int32_t cout, void* dx, int32_t lddx, float* dw /*accumulated*/,
+                float* db /*accumulated*/, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BatchNorm2d (AttentionUNet.py:7,10,21,34,38,42; R2U_Net.py:11,28; ResnetUnet.py:8,11,55), eps/momentum as args.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2_channel_stats(const void* z, int32_t ldz, int64_t npix, int32_t c, double* stats, b2_stream_t stream);
+int b2_bn_finalize(const double* stats, int32_t c, int64_t count, const float* gamma, const float* beta,
+                   float eps, float momentum, float* running_mean, float* running_var,
+                   int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+                   b2_stream_t stream);
+int b2_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                      const float* running_var, float eps, int32_t c, float* mean, float* invstd, float* scale,
+                      float* shift, b2_stream_t stream);
+/* y = act(z*scale+shift) ; optionally ysum = y + addend (Recurrent_block's x + x1, R2U_Net.py:19) */
+int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, const float* scale, const float* shift,
+                int32_t relu, void* y, int32_t ldy, const void* addend, int32_t ldadd, void* ysum,
+                int32_t ldysum, b2_stream_t stream);
+/* sums[0][c] = sum dy*mask ; sums[1][c] = sum dy*mask*xhat   (caller zeroes) */
+int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int32_t ldz, int64_t npix, int32_t c,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     int32_t relu, double* sums, b2_stream_t stream);
+/* dz = gamma*invstd*(dy*mask - [training](sums0/m + xhat*sums1/m)); also writes dgamma/dbeta (fp32) */
+int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int32_t ldz, int64_t npix, int32_t c,
+                    const float* scale, const float* shift, const float* mean, const float* invstd,
+                    const float* gamma, int32_t relu, int32_t training, const double* sums, void* dz,
+                    int32_t lddz, float* dgamma, float* dbeta, b2_stream_t stream);
+/* db[c] = sum_p dy[p][c] (bias gradient of a conv; overwrite) */
+int b2_channel_sum(const void* dy, int32_t lddy, int64_t npix, int32_t c, float* db, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pooling / upsampling / elementwise (AttentionUNet.py:61,18; R2U_Net.py:54,25,19,48)
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2_maxpool2x2_fwd(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w, int32_t c, void* y,
+                      int32_t ldy, b2_stream_t stream);
+int b2_maxpool2x2_bwd(const void* dy, int32_t lddy, const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w,
+                      int32_t c, void* dx, int32_t lddx, b2_stream_t stream);
+int b2_upsample2x_fwd(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w, int32_t c, void* y,
+                      int32_t ldy, b2_stream_t stream);
+int b2_upsample2x_bwd(const void* dy, int32_t lddy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx,
+                      int32_t lddx, b2_stream_t stream);
+int b2_add(const void* a, int32_t lda, const void* b, int32_t ldb, int64_t npix, int32_t c, void* out,
+           int32_t ldo, b2_stream_t stream);
+int b2_nchw_f32_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* y, int32_t ldy,
+                             b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention gate (AttentionUNet.py:48-54, R2AttU_Net.py:80-86) — the 1x1 GEMMs go through b2_conv_fprop.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* a = relu(bf16(bn_g(g1p)) + bf16(bn_x(x1p))); q = a . wpsi + bpsi (bf16) ; qstats += (sum q, sum q^2) */
+int b2_gate_psi_fwd(const void* g1p, const void* x1p, int32_t ld, int64_t npix, int32_t fint,
+                    const float* scale_g, const float* shift_g, const float* scale_x, const float* shift_x,
+                    const float* wpsi, const float* bpsi, void* q, double* qstats, b2_stream_t stream);
+/* psi = sigmoid(bn1(q)) ; out = x * psi */
+int b2_gate_apply_fwd(const void* x, int32_t ldx, const void* q, int64_t npix, int32_t c, const float* scale1,
+                      const float* shift1, void* psi, void* out, int32_t ldo, b2_stream_t stream);
+/* dx = dout*psi ; dsig[p] = (sum_c dout*x) * psi*(1-psi) ; sums1 += (sum dsig, sum dsig*qhat) */
+int b2_gate_apply_bwd(const void* dout, int32_t lddout, const void* x, int32_t ldx, const void* psi,
+                      const void* q, int64_t npix, int32_t c, const float* mean1, const float* invstd1,
+                      void* dx, int32_t lddx, float* dsig, double* sums1, b2_stream_t stream);
+/* per-channel coefficient pointers of the three BatchNorms inside a gate + the psi weight (all device fp32) */
+typedef struct b2_gate_coef {
+  const float *scale_g, *shift_g, *mean_g, *invstd_g, *gamma_g;   /* W_g.1 : [fint] */
+  const float *scale_x, *shift_x, *mean_x, *invstd_x, *gamma_x;   /* W_x.1 : [fint] */
+  const float *gamma1, *mean1, *invstd1;                          /* psi.1 : [1]    */
+  const float* wpsi;                                              /* psi.0.weight : [fint] */
+} b2_gate_coef;
+/* dq from dsig (BN1 backward), da = dq*wpsi*(a>0); reductions for both inner BNs and the psi conv:
+ * sums[0..3][fint] = dbeta_g, dgamma_g, dbeta_x, dgamma_x (fp64, caller zeroes);
+ * dwpsi[fint], dbpsi[1] fp32, accumulated into (caller zeroes) */
+int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const void* g1p, const void* x1p, int32_t ld,
+                           int64_t npix, int32_t fint, const b2_gate_coef* coef, const double* sums1,
+                           int32_t training, double* sums, float* dwpsi, float* dbpsi, b2_stream_t stream);
+/* dg1p, dx1p (bf16 [npix][fint]); dgamma_beta fp32 [4][fint] = dgamma_g, dbeta_g, dgamma_x, dbeta_x;
+ * dbn1 fp32 [2] = dgamma1, dbeta1 */
+int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const void* g1p, const void* x1p, int32_t ld,
+                          int64_t npix, int32_t fint, const b2_gate_coef* coef, const double* sums1,
+                          int32_t training, const double* sums, void* dg1p, void* dx1p, float* dgamma_beta,
+                          float* dbn1, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Loss: BCEWithLogits (utils/helpers.py:245,327) and 0.5*BCE + 0.5*Dice (utils/clip_seg_finetuner.py:40-74)
+ * sums[6] = sum bce_i, sum sigmoid(z)*t, sum sigmoid(z), sum t, #(pred&t), #(pred|t) with pred = z>0 (caller zeroes;
+ * the last two are the IoU counts of utils/helpers.py:223-227 at threshold 0.5)
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2_loss_fwd(const float* z, const float* t, int64_t count, double* sums, b2_stream_t stream);
+/* loss = w_bce * sums[0]/count + w_dice * (1 - (2*sums[1]+smooth)/(sums[2]+sums[3]+smooth)) */
+int b2_loss_finalize(const double* sums, int64_t count, float w_bce, float w_dice, float smooth, float* loss,
+                     b2_stream_t stream);
+/* dz = grad_out * d loss / d z */
+int b2_loss_bwd(const float* z, const float* t, int64_t count, const double* sums, float w_bce, float w_dice,
+                float smooth, const float* grad_out, float* dz, b2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

@@ -1,0 +1,127 @@
+"""ctypes binding of libb200seg.so (the C ABI declared in include/b200seg.h).
+
+The library is the product: there is no Python/ATen fallback.  If the shared object is missing or a call fails,
+this module raises — loudly — instead of computing the result some other way.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("B200SEG_LIB", _PKG_DIR.parent / "lib" / "libb200seg.so"))
+
+B2_OK = 0
+ERR_NAMES = {-1: "B2_ERR_SHAPE", -2: "B2_ERR_ALIGN", -3: "B2_ERR_ARCH", -4: "B2_ERR_CUDA", -5: "B2_ERR_NCCL",
+             -6: "B2_ERR_WORKSPACE"}
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+
+class ConvArgs(C.Structure):
+    """struct b2_conv_args"""
+    _fields_ = [("n", _i32), ("h", _i32), ("w", _i32), ("ksize", _i32),
+                ("x0", _vp), ("c0", _i32), ("ldx0", _i32),
+                ("x1", _vp), ("c1", _i32), ("ldx1", _i32),
+                ("wpk", _vp), ("ktot", _i32), ("w_tap_stride", _i64),
+                ("cout", _i32), ("y", _vp), ("ldy", _i32),
+                ("bias", _vp), ("addend", _vp), ("ldadd", _i32),
+                ("stats", _vp), ("relu", _i32)]
+
+
+class WgradArgs(C.Structure):
+    """struct b2_wgrad_args"""
+    _fields_ = [("n", _i32), ("h", _i32), ("w", _i32), ("ksize", _i32),
+                ("dy", _vp), ("cout", _i32), ("lddy", _i32),
+                ("x0", _vp), ("c0", _i32), ("ldx0", _i32),
+                ("x1", _vp), ("c1", _i32), ("ldx1", _i32),
+                ("dw", _vp), ("accumulate", _i32),
+                ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
+class GateCoef(C.Structure):
+    """struct b2_gate_coef"""
+    _fields_ = [(k, _vp) for k in (
+        "scale_g", "shift_g", "mean_g", "invstd_g", "gamma_g",
+        "scale_x", "shift_x", "mean_x", "invstd_x", "gamma_x",
+        "gamma1", "mean1", "invstd1", "wpsi")]
+
+
+# name -> (restype, argtypes); every symbol include/b200seg.h declares
+SIGNATURES = {
+    "b2_last_error": (C.c_char_p, []),
+    "b2_abi_version": (C.c_int, []),
+    "b2_arch_check": (C.c_int, []),
+    "b2_num_sms": (C.c_int, []),
+    "b2_conv_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),
+    "b2_conv_dgrad": (C.c_int, [C.POINTER(ConvArgs), _vp]),
+    "b2_conv_wgrad_workspace": (_i64, [C.POINTER(WgradArgs)]),
+    "b2_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
+    "b2_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "b2_conv_smallc_fprop": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
+    "b2_conv_smallc_wgrad": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b2_head_fwd": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "b2_head_bwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "b2_channel_stats": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
+    "b2_bn_finalize": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_bn_eval_coeffs": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "b2_bn_apply": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "b2_bn_bwd_reduce": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "b2_bn_bwd_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
+                                  _vp, _i32, _vp, _vp, _vp]),
+    "b2_channel_sum": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
+    "b2_maxpool2x2_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b2_maxpool2x2_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b2_upsample2x_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b2_upsample2x_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b2_add": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _vp]),
+    "b2_nchw_f32_to_nhwc_bf16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b2_gate_psi_fwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_gate_apply_fwd": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "b2_gate_apply_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp,
+                                    _vp]),
+    "b2_gate_psi_bwd_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, C.POINTER(GateCoef), _vp, _i32,
+                                         _vp, _vp, _vp, _vp]),
+    "b2_gate_psi_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, C.POINTER(GateCoef), _vp, _i32,
+                                        _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_loss_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "b2_loss_finalize": (C.c_int, [_vp, _i64, _f32, _f32, _f32, _vp, _vp]),
+    "b2_loss_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libb200seg.so and bind every declared symbol.  Raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B2Error(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      f"or `make -C {_PKG_DIR.parent / 'csrc'}` — there is no fallback path")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != B2_OK:
+        msg = load().b2_last_error()
+        raise B2Error(f"{what or 'libb200seg'} failed with {ERR_NAMES.get(rc, rc)}: "
+                      f"{msg.decode() if msg else ''}")
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise on a non-zero code."""
+    rc = getattr(load(), name)(*args)
+    check(rc, name)

@@ -1,0 +1,360 @@
+"""Tensor-level wrappers over the C ABI: take torch CUDA tensors, pass raw pointers + dims + the current stream.
+
+Activations are NHWC bf16 tensors of shape [N, H, W, C]; the channel stride of the underlying buffer may exceed C
+(channel-slice views are passed without a copy).  Every function here launches kernels of libb200seg.so and
+nothing else — torch is used only to allocate outputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, GateCoef, WgradArgs, call
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _nhwc(t):
+    """(N, H, W, C, ld) of an NHWC bf16 activation; rows must be dense apart from the channel stride."""
+    assert t.dtype == BF16 and t.dim() == 4 and t.is_cuda, (t.dtype, t.shape, t.device)
+    n, h, w, c = t.shape
+    ld = t.stride(2)
+    assert t.stride(3) == 1 and t.stride(1) == w * ld and t.stride(0) == h * w * ld, (t.shape, t.stride())
+    return n, h, w, c, ld
+
+
+def new_act(n, h, w, c, device):
+    return torch.empty((n, h, w, c), dtype=BF16, device=device)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# weights
+# ----------------------------------------------------------------------------------------------------------
+def pack_weights(weight, want_dgrad=True):
+    """fp32 [Cout, Cin, k, k] parameter (any strides) -> (bf16 [k*k, Cout, Cin], bf16 [k*k, Cin, Cout] flipped)."""
+    cout, cin, kh, kw = weight.shape
+    assert kh == kw and weight.dtype == torch.float32
+    taps = kh * kw
+    wf = torch.empty((taps, cout, cin), dtype=BF16, device=weight.device)
+    wd = torch.empty((taps, cin, cout), dtype=BF16, device=weight.device) if want_dgrad else None
+    s = weight.stride()
+    call("b2_pack_weights", _p(weight), cout, cin, kh, s[0], s[1], s[2], s[3], _p(wf), _p(wd), _stream())
+    return wf, wd
+
+
+# ----------------------------------------------------------------------------------------------------------
+# tcgen05 convolutions
+# ----------------------------------------------------------------------------------------------------------
+def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None, relu=False, out=None,
+               row_offset=0, dgrad=False):
+    """y = conv(x0 | x1; wpk) (+bias) (+addend) (relu); wpk is [taps, rows, ktot] bf16, rows [row_offset,
+    row_offset+cout) are used.  `stats` (fp64 [2, cout]) accumulates sum / sumsq of the rounded output."""
+    n, h, w, c0, ld0 = _nhwc(x0)
+    c1, ld1 = 0, 0
+    if x1 is not None:
+        n1, h1, w1, c1, ld1 = _nhwc(x1)
+        assert (n1, h1, w1) == (n, h, w)
+    taps, rows, ktot = wpk.shape
+    assert taps == ksize * ksize and wpk.dtype == BF16 and wpk.is_contiguous()
+    assert ktot >= c0 + c1 and row_offset + cout <= rows
+    y = out if out is not None else new_act(n, h, w, cout, x0.device)
+    _, _, _, cy, ldy = _nhwc(y)
+    assert cy == cout
+    a = ConvArgs()
+    a.n, a.h, a.w, a.ksize = n, h, w, ksize
+    a.x0, a.c0, a.ldx0 = x0.data_ptr(), c0, ld0
+    a.x1, a.c1, a.ldx1 = (x1.data_ptr() if x1 is not None else None), c1, ld1
+    a.wpk = wpk.data_ptr() + row_offset * ktot * 2
+    a.ktot = ktot
+    a.w_tap_stride = rows * ktot
+    a.cout = cout
+    a.y, a.ldy = y.data_ptr(), ldy
+    a.bias = bias.data_ptr() if bias is not None else None
+    if addend is not None:
+        _, _, _, ca, lda = _nhwc(addend)
+        assert ca == cout
+        a.addend, a.ldadd = addend.data_ptr(), lda
+    if stats is not None:
+        assert stats.dtype == torch.float64 and stats.numel() == 2 * cout
+        a.stats = stats.data_ptr()
+    a.relu = int(relu)
+    call("b2_conv_dgrad" if dgrad else "b2_conv_fprop", C.byref(a), _stream())
+    return y
+
+
+def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False):
+    """dW fp32 [Cout, k*k, C0+C1] = sum_p dY[p] (x) X[p+tap]."""
+    n, h, w, cout, lddy = _nhwc(dy)
+    _, _, _, c0, ld0 = _nhwc(x0)
+    c1, ld1 = 0, 0
+    if x1 is not None:
+        _, _, _, c1, ld1 = _nhwc(x1)
+    taps = ksize * ksize
+    dw = out if out is not None else torch.empty((cout, taps, c0 + c1), dtype=torch.float32, device=dy.device)
+    assert dw.is_contiguous() and dw.numel() == cout * taps * (c0 + c1)
+    a = WgradArgs()
+    a.n, a.h, a.w, a.ksize = n, h, w, ksize
+    a.dy, a.cout, a.lddy = dy.data_ptr(), cout, lddy
+    a.x0, a.c0, a.ldx0 = x0.data_ptr(), c0, ld0
+    a.x1, a.c1, a.ldx1 = (x1.data_ptr() if x1 is not None else None), c1, ld1
+    a.dw = dw.data_ptr()
+    a.accumulate = int(accumulate)
+    need = _lib.load().b2_conv_wgrad_workspace(C.byref(a))
+    if need < 0:
+        _lib.check(int(need), "b2_conv_wgrad_workspace")
+    ws = torch.empty(int(need), dtype=torch.uint8, device=dy.device)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), int(need)
+    call("b2_conv_wgrad", C.byref(a), _stream())
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------------------
+# small-channel convolutions
+# ----------------------------------------------------------------------------------------------------------
+def image_to_nhwc4(x):
+    """NCHW fp32 image [N, C<=4, H, W] -> NHWC bf16 [N, H, W, 4] (zero padded channels)."""
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.shape[1] <= 4
+    n, c, h, w = x.shape
+    y = torch.empty((n, h, w, 4), dtype=BF16, device=x.device)
+    call("b2_nchw_f32_to_nhwc_bf16", _p(x), n, c, h, w, _p(y), 4, _stream())
+    return y
+
+
+def pack_small_weight(weight):
+    """fp32 [Cout, Cin<=4, k, k] -> fp32 [Cout, k*k, 4] (tiny; done with torch indexing on the host stream)."""
+    cout, cin, kh, kw = weight.shape
+    wk = torch.zeros((cout, kh * kw, 4), dtype=torch.float32, device=weight.device)
+    wk[:, :, :cin] = weight.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    return wk
+
+
+def conv_smallc_fprop(x4, wk, bias, ksize, relu=False):
+    n, h, w, c4 = x4.shape
+    assert c4 == 4 and x4.is_contiguous()
+    cout = wk.shape[0]
+    y = new_act(n, h, w, cout, x4.device)
+    call("b2_conv_smallc_fprop", _p(x4), n, h, w, ksize, _p(wk), _p(bias), cout, _p(y), cout, int(relu), _stream())
+    return y
+
+
+def conv_smallc_wgrad(dy, x4, ksize):
+    n, h, w, cout, lddy = _nhwc(dy)
+    dw = torch.zeros((cout, ksize * ksize, 4), dtype=torch.float32, device=dy.device)
+    call("b2_conv_smallc_wgrad", _p(dy), lddy, _p(x4), n, h, w, ksize, cout, _p(dw), _stream())
+    return dw
+
+
+def head_fwd(x, weight2d, bias):
+    """x NHWC bf16 -> logits fp32 NCHW [N, Cout, H, W]; weight2d fp32 [Cout, Cin]."""
+    n, h, w, cin, ld = _nhwc(x)
+    cout = weight2d.shape[0]
+    y = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
+    call("b2_head_fwd", _p(x), ld, n * h * w, h * w, cin, _p(weight2d), _p(bias), cout, _p(y), _stream())
+    return y
+
+
+def head_bwd(dy, x, weight2d, need_dx=True):
+    n, h, w, cin, ld = _nhwc(x)
+    cout = weight2d.shape[0]
+    assert dy.dtype == torch.float32 and dy.is_contiguous()
+    dx = new_act(n, h, w, cin, x.device) if need_dx else None
+    dw = torch.zeros((cout, cin), dtype=torch.float32, device=x.device)
+    db = torch.zeros((cout,), dtype=torch.float32, device=x.device)
+    call("b2_head_bwd", _p(dy), _p(x), ld, n * h * w, h * w, cin, _p(weight2d), cout, _p(dx), cin, _p(dw), _p(db),
+         _stream())
+    return dx, dw, db
+
+
+# ----------------------------------------------------------------------------------------------------------
+# batch norm
+# ----------------------------------------------------------------------------------------------------------
+def channel_stats(z, stats):
+    n, h, w, c, ld = _nhwc(z)
+    call("b2_channel_stats", _p(z), ld, n * h * w, c, _p(stats), _stream())
+
+
+def channel_sum(dy):
+    n, h, w, c, ld = _nhwc(dy)
+    db = torch.empty((c,), dtype=torch.float32, device=dy.device)
+    call("b2_channel_sum", _p(dy), ld, n * h * w, c, _p(db), _stream())
+    return db
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, nbt):
+    """-> coef fp32 [4, C] = (mean, invstd, scale, shift); updates running stats in place."""
+    c = stats.numel() // 2
+    coef = torch.empty((4, c), dtype=torch.float32, device=stats.device)
+    call("b2_bn_finalize", _p(stats), c, int(count), _p(gamma), _p(beta), float(eps), float(momentum),
+         _p(running_mean), _p(running_var), _p(nbt), _p(coef[0]), _p(coef[1]), _p(coef[2]), _p(coef[3]), _stream())
+    return coef
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps):
+    c = running_mean.numel()
+    coef = torch.empty((4, c), dtype=torch.float32, device=running_mean.device)
+    call("b2_bn_eval_coeffs", _p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), c, _p(coef[0]),
+         _p(coef[1]), _p(coef[2]), _p(coef[3]), _stream())
+    return coef
+
+
+def bn_apply(z, coef, relu=True, addend=None, want_sum=False):
+    n, h, w, c, ld = _nhwc(z)
+    y = new_act(n, h, w, c, z.device)
+    ysum = new_act(n, h, w, c, z.device) if want_sum else None
+    lda = _nhwc(addend)[4] if addend is not None else 0
+    call("b2_bn_apply", _p(z), ld, n * h * w, c, _p(coef[2]), _p(coef[3]), int(relu), _p(y), c, _p(addend), lda,
+         _p(ysum), c, _stream())
+    return (y, ysum) if want_sum else y
+
+
+def bn_bwd(dy, z, coef, gamma, relu=True, training=True):
+    """-> (dz bf16, dgamma fp32, dbeta fp32)"""
+    n, h, w, c, lddy = _nhwc(dy)
+    ldz = _nhwc(z)[4]
+    npix = n * h * w
+    sums = torch.zeros((2, c), dtype=torch.float64, device=z.device)
+    call("b2_bn_bwd_reduce", _p(dy), lddy, _p(z), ldz, npix, c, _p(coef[2]), _p(coef[3]), _p(coef[0]), _p(coef[1]),
+         int(relu), _p(sums), _stream())
+    dz = new_act(n, h, w, c, z.device)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=z.device)
+    call("b2_bn_bwd_apply", _p(dy), lddy, _p(z), ldz, npix, c, _p(coef[2]), _p(coef[3]), _p(coef[0]), _p(coef[1]),
+         _p(gamma), int(relu), int(training), _p(sums), _p(dz), c, _p(dgb[0]), _p(dgb[1]), _stream())
+    return dz, dgb[0], dgb[1]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# pooling / upsampling / add
+# ----------------------------------------------------------------------------------------------------------
+def maxpool_fwd(x):
+    n, h, w, c, ld = _nhwc(x)
+    y = new_act(n, h // 2, w // 2, c, x.device)
+    call("b2_maxpool2x2_fwd", _p(x), ld, n, h, w, c, _p(y), c, _stream())
+    return y
+
+
+def maxpool_bwd(dy, x):
+    n, h, w, c, ld = _nhwc(x)
+    lddy = _nhwc(dy)[4]
+    dx = new_act(n, h, w, c, x.device)
+    call("b2_maxpool2x2_bwd", _p(dy), lddy, _p(x), ld, n, h, w, c, _p(dx), c, _stream())
+    return dx
+
+
+def upsample_fwd(x):
+    n, h, w, c, ld = _nhwc(x)
+    y = new_act(n, 2 * h, 2 * w, c, x.device)
+    call("b2_upsample2x_fwd", _p(x), ld, n, h, w, c, _p(y), c, _stream())
+    return y
+
+
+def upsample_bwd(dy):
+    n, h2, w2, c, lddy = _nhwc(dy)
+    dx = new_act(n, h2 // 2, w2 // 2, c, dy.device)
+    call("b2_upsample2x_bwd", _p(dy), lddy, n, h2 // 2, w2 // 2, c, _p(dx), c, _stream())
+    return dx
+
+
+def add(a, b):
+    n, h, w, c, lda = _nhwc(a)
+    ldb = _nhwc(b)[4]
+    out = new_act(n, h, w, c, a.device)
+    call("b2_add", _p(a), lda, _p(b), ldb, n * h * w, c, _p(out), c, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# attention gate (memory-bound part)
+# ----------------------------------------------------------------------------------------------------------
+def gate_psi_fwd(g1p, x1p, coef_g, coef_x, wpsi, bpsi):
+    n, h, w, fint, ld = _nhwc(g1p)
+    assert _nhwc(x1p)[4] == ld
+    q = torch.empty((n, h, w), dtype=BF16, device=g1p.device)
+    qstats = torch.zeros((2,), dtype=torch.float64, device=g1p.device)
+    call("b2_gate_psi_fwd", _p(g1p), _p(x1p), ld, n * h * w, fint, _p(coef_g[2]), _p(coef_g[3]), _p(coef_x[2]),
+         _p(coef_x[3]), _p(wpsi), _p(bpsi), _p(q), _p(qstats), _stream())
+    return q, qstats
+
+
+def gate_apply_fwd(x, q, coef1):
+    n, h, w, c, ld = _nhwc(x)
+    psi = torch.empty((n, h, w), dtype=BF16, device=x.device)
+    out = new_act(n, h, w, c, x.device)
+    call("b2_gate_apply_fwd", _p(x), ld, _p(q), n * h * w, c, _p(coef1[2]), _p(coef1[3]), _p(psi), _p(out), c,
+         _stream())
+    return out, psi
+
+
+def gate_apply_bwd(dout, x, psi, q, coef1):
+    n, h, w, c, ldx = _nhwc(x)
+    lddo = _nhwc(dout)[4]
+    dx = new_act(n, h, w, c, x.device)
+    dsig = torch.empty((n, h, w), dtype=torch.float32, device=x.device)
+    sums1 = torch.zeros((2,), dtype=torch.float64, device=x.device)
+    call("b2_gate_apply_bwd", _p(dout), lddo, _p(x), ldx, _p(psi), _p(q), n * h * w, c, _p(coef1[0]),
+         _p(coef1[1]), _p(dx), c, _p(dsig), _p(sums1), _stream())
+    return dx, dsig, sums1
+
+
+def _gate_coef(coef_g, gamma_g, coef_x, gamma_x, coef1, gamma1, wpsi):
+    k = GateCoef()
+    k.scale_g, k.shift_g, k.mean_g, k.invstd_g = (coef_g[2].data_ptr(), coef_g[3].data_ptr(), coef_g[0].data_ptr(),
+                                                  coef_g[1].data_ptr())
+    k.gamma_g = gamma_g.data_ptr()
+    k.scale_x, k.shift_x, k.mean_x, k.invstd_x = (coef_x[2].data_ptr(), coef_x[3].data_ptr(), coef_x[0].data_ptr(),
+                                                  coef_x[1].data_ptr())
+    k.gamma_x = gamma_x.data_ptr()
+    k.gamma1, k.mean1, k.invstd1 = gamma1.data_ptr(), coef1[0].data_ptr(), coef1[1].data_ptr()
+    k.wpsi = wpsi.data_ptr()
+    return k
+
+
+def gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coef1, gamma1, wpsi, training=True):
+    """-> dg1p, dx1p (bf16), dgb fp32 [4, fint] (dgamma_g, dbeta_g, dgamma_x, dbeta_x), dbn1 fp32 [2],
+    dwpsi fp32 [fint], dbpsi fp32 [1]"""
+    n, h, w, fint, ld = _nhwc(g1p)
+    npix = n * h * w
+    dev = g1p.device
+    k = _gate_coef(coef_g, gamma_g, coef_x, gamma_x, coef1, gamma1, wpsi)
+    sums = torch.zeros((4, fint), dtype=torch.float64, device=dev)
+    dwpsi = torch.zeros((fint,), dtype=torch.float32, device=dev)
+    dbpsi = torch.zeros((1,), dtype=torch.float32, device=dev)
+    call("b2_gate_psi_bwd_reduce", _p(dsig), _p(q), _p(g1p), _p(x1p), ld, npix, fint, C.byref(k), _p(sums1),
+         int(training), _p(sums), _p(dwpsi), _p(dbpsi), _stream())
+    dg1p = new_act(n, h, w, fint, dev)
+    dx1p = new_act(n, h, w, fint, dev)
+    dgb = torch.empty((4, fint), dtype=torch.float32, device=dev)
+    dbn1 = torch.empty((2,), dtype=torch.float32, device=dev)
+    assert ld == fint
+    call("b2_gate_psi_bwd_apply", _p(dsig), _p(q), _p(g1p), _p(x1p), ld, npix, fint, C.byref(k), _p(sums1),
+         int(training), _p(sums), _p(dg1p), _p(dx1p), _p(dgb), _p(dbn1), _stream())
+    return dg1p, dx1p, dgb, dbn1, dwpsi, dbpsi
+
+
+# ----------------------------------------------------------------------------------------------------------
+# loss
+# ----------------------------------------------------------------------------------------------------------
+def loss_fwd(z, t, w_bce=1.0, w_dice=0.0, smooth=1.0):
+    assert z.dtype == torch.float32 and t.dtype == torch.float32 and z.is_contiguous() and t.is_contiguous()
+    assert z.numel() == t.numel()
+    sums = torch.zeros((6,), dtype=torch.float64, device=z.device)
+    loss = torch.empty((), dtype=torch.float32, device=z.device)
+    call("b2_loss_fwd", _p(z), _p(t), z.numel(), _p(sums), _stream())
+    call("b2_loss_finalize", _p(sums), z.numel(), float(w_bce), float(w_dice), float(smooth), _p(loss), _stream())
+    return loss, sums
+
+
+def loss_bwd(z, t, sums, grad_out, w_bce=1.0, w_dice=0.0, smooth=1.0):
+    dz = torch.empty_like(z)
+    call("b2_loss_bwd", _p(z), _p(t), z.numel(), _p(sums), float(w_bce), float(w_dice), float(smooth),
+         _p(grad_out), _p(dz), _stream())
+    return dz

@@ -1,0 +1,403 @@
+// b200seg — BatchNorm2d kernels (memory-bound; 16-byte vector accesses, warp/block reductions, fp64 accumulators).
+// Reference call sites: nn.BatchNorm2d at models/segmentation_models/AttentionUNet.py:7,10,21,34,38,42,
+// R2U_Net.py:11,28, ResnetUnet.py:8,11,55 (eps 1e-5, momentum 0.1, biased variance for normalisation, unbiased for
+// running_var); backward = native_batch_norm_backward + threshold_backward fused.
+//
+// Thread mapping shared by every kernel here: a thread owns ONE group of 8 consecutive channels (one uint4 of
+// bf16) and walks over pixels, so per-channel coefficients live in registers and a warp reads consecutive 16-byte
+// chunks of consecutive pixels (fully coalesced for ld == C).
+#include "common.cuh"
+
+namespace b2 {
+
+static constexpr int kBlock = 256;
+
+struct ChanMap {
+  int tpp;    // threads per pixel == number of 8-channel groups
+  int rows;   // pixels per block iteration
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ void load8f(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// Sum acc[0..7] over the `rows` threads that own the same channel group; result valid in threads with r == 0.
+__device__ __forceinline__ void rows_reduce8(float* acc, int tpp, int rows, int g, int r, bool active, float* red) {
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[(r * tpp + g) * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  if (active && r == 0) {
+    for (int rr = 1; rr < rows; ++rr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += red[(rr * tpp + g) * 8 + j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-channel sum / sum of squares of a bf16 tensor (used where the conv epilogue could not produce them)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) channel_stats_kernel(const __nv_bfloat16* __restrict__ z, int ldz,
+                                                               long long npix, int C, ChanMap m,
+                                                               double* __restrict__ stats, int want_sq) {
+  __shared__ float red[kBlock * 8];
+  const int t = threadIdx.x;
+  const int g = t % m.tpp, r = t / m.tpp;
+  const bool active = r < m.rows;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (active) {
+    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] += f[j] * f[j];
+      }
+    }
+  }
+  rows_reduce8(s, m.tpp, m.rows, g, r, active, red);
+  if (active && r == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&stats[g * 8 + j], (double)s[j]);
+  }
+  if (want_sq) {
+    rows_reduce8(q, m.tpp, m.rows, g, r, active, red);
+    if (active && r == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&stats[C + g * 8 + j], (double)q[j]);
+    }
+  }
+}
+
+// db[c] = sum_p dy[p][c]  (two-stage: fp64 scratch is avoided by a single-block-per-channel-slab final pass)
+__global__ void __launch_bounds__(kBlock) channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
+                                                             long long npix, int C, ChanMap m,
+                                                             float* __restrict__ db) {
+  __shared__ float red[kBlock * 8];
+  const int t = threadIdx.x;
+  const int g = t % m.tpp, r = t / m.tpp;
+  const bool active = r < m.rows;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  if (active) {
+    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
+  }
+  rows_reduce8(s, m.tpp, m.rows, g, r, active, red);
+  if (active && r == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&db[g * 8 + j], s[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// finalize: batch mean / invstd, affine coefficients, running statistics (momentum update, unbiased variance)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, long long count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var,
+                                   long long* num_batches_tracked, float* mean, float* invstd, float* scale,
+                                   float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
+  if (c >= C) return;
+  const double m = stats[c] / (double)count;
+  double var = stats[C + c] / (double)count - m * m;
+  if (var < 0.0) var = 0.0;
+  const float fm = (float)m;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = fm;
+  invstd[c] = is;
+  const float sc = (gamma ? gamma[c] : 1.f) * is;
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - fm * sc;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * fm;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps, int C,
+                                      float* mean, float* invstd, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float is = rsqrtf(rv[c] + eps);
+  const float isx = (float)(1.0 / sqrt((double)rv[c] + (double)eps));
+  (void)is;
+  mean[c] = rm[c];
+  invstd[c] = isx;
+  const float sc = (gamma ? gamma[c] : 1.f) * isx;
+  scale[c] = sc;
+  shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// apply: y = act(z*scale + shift)   [+ ysum = y + addend]
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int ldz,
+                                                          long long npix, ChanMap m,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, int relu,
+                                                          __nv_bfloat16* __restrict__ y, int ldy,
+                                                          const __nv_bfloat16* __restrict__ addend, int ldadd,
+                                                          __nv_bfloat16* __restrict__ ysum, int ldysum) {
+  const int t = threadIdx.x;
+  const int g = t % m.tpp, r = t / m.tpp;
+  if (r >= m.rows) return;
+  float sc[8], sh[8];
+  load8f(scale + g * 8, sc);
+  load8f(shift + g * 8, sh);
+  for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (relu) f[j] = fmaxf(f[j], 0.f);
+    }
+    const uint4 o = pack8(f);
+    *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = o;
+    if (ysum != nullptr) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + p * ldadd + g * 8));
+      float fa[8], fo[8];
+      unpack8(a, fa);
+      unpack8(o, fo);   // the sum is taken on the ROUNDED activation, as torch does (x + x1 on bf16 tensors)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) fo[j] += fa[j];
+      *reinterpret_cast<uint4*>(ysum + p * ldysum + g * 8) = pack8(fo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward pass 1: sums[0][c] = sum dy*mask, sums[1][c] = sum dy*mask*xhat
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
+    int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums) {
+  __shared__ float red[kBlock * 8];
+  const int t = threadIdx.x;
+  const int g = t % m.tpp, r = t / m.tpp;
+  const bool active = r < m.rows;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  if (active) {
+    float sc[8], sh[8], mu[8], is[8];
+    load8f(scale + g * 8, sc);
+    load8f(shift + g * 8, sh);
+    load8f(mean + g * 8, mu);
+    load8f(invstd + g * 8, is);
+    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
+      const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+      float d[8], f[8];
+      unpack8(ud, d);
+      unpack8(uz, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool on = !relu || fmaf(f[j], sc[j], sh[j]) > 0.f;
+        const float dd = on ? d[j] : 0.f;
+        s0[j] += dd;
+        s1[j] += dd * ((f[j] - mu[j]) * is[j]);
+      }
+    }
+  }
+  rows_reduce8(s0, m.tpp, m.rows, g, r, active, red);
+  if (active && r == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sums[g * 8 + j], (double)s0[j]);
+  }
+  rows_reduce8(s1, m.tpp, m.rows, g, r, active, red);
+  if (active && r == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sums[C + g * 8 + j], (double)s1[j]);
+  }
+}
+
+// backward pass 2: dz = gamma*invstd*(dy*mask - [training](s0/m + xhat*s1/m))
+__global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
+    int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
+    int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
+    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int t = threadIdx.x;
+  const int g = t % m.tpp, r = t / m.tpp;
+  if (r >= m.rows) return;
+  float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], gi[8];
+  load8f(scale + g * 8, sc);
+  load8f(shift + g * 8, sh);
+  load8f(mean + g * 8, mu);
+  load8f(invstd + g * 8, is);
+  const double inv_m = 1.0 / (double)npix;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    const float ga = gamma ? __ldg(gamma + c) : 1.f;
+    gi[j] = ga * is[j];
+    const double a0 = sums[c], a1 = sums[C + c];
+    k0[j] = training ? (float)(a0 * inv_m) : 0.f;
+    k1[j] = training ? (float)(a1 * inv_m) : 0.f;
+    if (blockIdx.x == 0 && r == 0) {
+      if (dgamma) dgamma[c] = (float)a1;
+      if (dbeta) dbeta[c] = (float)a0;
+    }
+  }
+  for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
+    const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+    float d[8], f[8];
+    unpack8(ud, d);
+    unpack8(uz, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool on = !relu || fmaf(f[j], sc[j], sh[j]) > 0.f;
+      const float dd = on ? d[j] : 0.f;
+      const float xh = (f[j] - mu[j]) * is[j];
+      f[j] = gi[j] * (dd - k0[j] - xh * k1[j]);
+    }
+    *reinterpret_cast<uint4*>(dz + p * lddz + g * 8) = pack8(f);
+  }
+}
+
+static int make_map(int C, ChanMap* m) {
+  B2_REQUIRE(C > 0 && C % 8 == 0, B2_ERR_SHAPE, "channel count %d must be a positive multiple of 8", C);
+  const int cg = C / 8;
+  B2_REQUIRE(cg <= kBlock, B2_ERR_SHAPE, "channel count %d > %d unsupported", C, kBlock * 8);
+  m->tpp = cg;
+  m->rows = kBlock / cg;
+  return B2_OK;
+}
+static int chan_grid(long long npix, const ChanMap& m, int waves) {
+  long long need = (npix + m.rows - 1) / m.rows;
+  long long cap = (long long)num_sms() * waves;
+  if (need > cap) need = cap;
+  if (need < 1) need = 1;
+  return (int)need;
+}
+static bool aligned16(const void* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 8 == 0; }
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_channel_stats(const void* z, int32_t ldz, int64_t npix, int32_t c, double* stats,
+                                b2_stream_t stream) {
+  ChanMap m;
+  int rc = make_map(c, &m);
+  if (rc) return rc;
+  B2_REQUIRE(aligned16(z, ldz), B2_ERR_ALIGN, "z misaligned");
+  channel_stats_kernel<<<chan_grid(npix, m, 8), kBlock, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)z, ldz, npix, c, m, stats, 1);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_channel_sum(const void* dy, int32_t lddy, int64_t npix, int32_t c, float* db,
+                              b2_stream_t stream) {
+  ChanMap m;
+  int rc = make_map(c, &m);
+  if (rc) return rc;
+  B2_REQUIRE(aligned16(dy, lddy), B2_ERR_ALIGN, "dy misaligned");
+  B2_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, (cudaStream_t)stream));
+  channel_sum_kernel<<<chan_grid(npix, m, 8), kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
+                                                                                 npix, c, m, db);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_bn_finalize(const double* stats, int32_t c, int64_t count, const float* gamma,
+                              const float* beta, float eps, float momentum, float* running_mean,
+                              float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
+                              float* scale, float* shift, b2_stream_t stream) {
+  B2_REQUIRE(c > 0 && count > 0, B2_ERR_SHAPE, "bad bn_finalize extent");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      stats, c, count, gamma, beta, eps, momentum, running_mean, running_var,
+      reinterpret_cast<long long*>(num_batches_tracked), mean, invstd, scale, shift);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                                 const float* running_var, float eps, int32_t c, float* mean, float* invstd,
+                                 float* scale, float* shift, b2_stream_t stream) {
+  B2_REQUIRE(c > 0, B2_ERR_SHAPE, "bad channel count");
+  bn_eval_coeffs_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var,
+                                                                          eps, c, mean, invstd, scale, shift);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, const float* scale,
+                           const float* shift, int32_t relu, void* y, int32_t ldy, const void* addend,
+                           int32_t ldadd, void* ysum, int32_t ldysum, b2_stream_t stream) {
+  ChanMap m;
+  int rc = make_map(c, &m);
+  if (rc) return rc;
+  B2_REQUIRE(aligned16(z, ldz) && aligned16(y, ldy), B2_ERR_ALIGN, "bn_apply operands misaligned");
+  B2_REQUIRE(ysum == nullptr || (addend != nullptr && aligned16(addend, ldadd) && aligned16(ysum, ldysum)),
+             B2_ERR_ALIGN, "bn_apply addend/ysum misaligned or missing");
+  bn_apply_kernel<<<chan_grid(npix, m, 16), kBlock, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)z, ldz, npix, m, scale, shift, relu, (__nv_bfloat16*)y, ldy,
+      (const __nv_bfloat16*)addend, ldadd, (__nv_bfloat16*)ysum, ldysum);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int32_t ldz, int64_t npix,
+                                int32_t c, const float* scale, const float* shift, const float* mean,
+                                const float* invstd, int32_t relu, double* sums, b2_stream_t stream) {
+  ChanMap m;
+  int rc = make_map(c, &m);
+  if (rc) return rc;
+  B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz), B2_ERR_ALIGN, "bn_bwd_reduce operands misaligned");
+  bn_bwd_reduce_kernel<<<chan_grid(npix, m, 8), kBlock, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, relu,
+      sums);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int32_t ldz, int64_t npix, int32_t c,
+                               const float* scale, const float* shift, const float* mean, const float* invstd,
+                               const float* gamma, int32_t relu, int32_t training, const double* sums, void* dz,
+                               int32_t lddz, float* dgamma, float* dbeta, b2_stream_t stream) {
+  ChanMap m;
+  int rc = make_map(c, &m);
+  if (rc) return rc;
+  B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz) && aligned16(dz, lddz), B2_ERR_ALIGN,
+             "bn_bwd_apply operands misaligned");
+  bn_bwd_apply_kernel<<<chan_grid(npix, m, 16), kBlock, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
+      relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

@@ -1,0 +1,303 @@
+// b200seg — CUDA-core convolutions for the two shapes that are memory-bound by construction:
+//   * image stem, Cin <= 4 (AttentionUNet.py:6 basic_block(3,64) first conv; R2U_Net.py:43 RRCNN1.conv_1x1 3->64):
+//     K = 27 (or 3) is far below one MMA K step, the layer is 0.17 % of the step FLOPs and bound by the 64-channel
+//     output write;
+//   * Cout <= 8 1x1 heads (AttentionUNet.py:84 `out`, R2U_Net.py:76 `conv_1x1`, ResnetUnet.py:58 `out`): a dot
+//     product per pixel.
+// Weights are rounded to bf16 on load, matching what autocast feeds the reference convolution.
+#include "common.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------------------
+// stem forward: x4 NHWC bf16 (4 channels, zero padded), wk fp32 [cout][taps][4]
+// ------------------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(128) smallc_fprop_kernel(const uint2* __restrict__ x4, int n, int h, int w,
+                                                           const float* __restrict__ wk,
+                                                           const float* __restrict__ bias, int cout,
+                                                           __nv_bfloat16* __restrict__ y, int ldy, int relu) {
+  constexpr int TAPS = KS * KS;
+  extern __shared__ float sm[];
+  float* sw = sm;                       // [cout][TAPS][4]
+  float* sb = sm + cout * TAPS * 4;     // [cout]
+  for (int i = threadIdx.x; i < cout * TAPS * 4; i += blockDim.x) sw[i] = bf16_round(wk[i]);
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long total = (long long)n * h * w;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(p % w);
+    const int yy = (int)((p / w) % h);
+    float in[TAPS][4];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+      const int dy = (KS == 3) ? t / 3 - 1 : 0, dx = (KS == 3) ? t % 3 - 1 : 0;
+      const int y2 = yy + dy, x2 = xx + dx;
+      uint2 u = make_uint2(0u, 0u);
+      if (y2 >= 0 && y2 < h && x2 >= 0 && x2 < w) u = __ldg(x4 + p + (long long)dy * w + dx);
+      in[t][0] = bf16lo(u.x); in[t][1] = bf16hi(u.x); in[t][2] = bf16lo(u.y); in[t][3] = bf16hi(u.y);
+    }
+    __nv_bfloat16* yp = y + p * ldy;
+    for (int co = 0; co < cout; co += 8) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = sb[co + j];
+        const float4* wp = reinterpret_cast<const float4*>(sw + (size_t)(co + j) * TAPS * 4);
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+          const float4 wv = wp[t];
+          a = fmaf(in[t][0], wv.x, a);
+          a = fmaf(in[t][1], wv.y, a);
+          a = fmaf(in[t][2], wv.z, a);
+          a = fmaf(in[t][3], wv.w, a);
+        }
+        acc[j] = relu ? fmaxf(a, 0.f) : a;
+      }
+      *reinterpret_cast<uint4*>(yp + co) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                      pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+    }
+  }
+}
+
+// stem weight gradient: dw[co][tap][c] += sum_p dy[p][co] * x4[p (+) tap][c]
+template <int KS>
+__global__ void __launch_bounds__(256) smallc_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
+                                                           const uint2* __restrict__ x4, int n, int h, int w,
+                                                           int cout, float* __restrict__ dw) {
+  constexpr int TAPS = KS * KS;
+  const int co = threadIdx.x % cout;
+  const int q = threadIdx.x / cout;
+  const int ngrp = blockDim.x / cout;
+  float acc[TAPS][4];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  const long long total = (long long)n * h * w;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * per;
+  long long p1 = p0 + per;
+  if (p1 > total) p1 = total;
+  if (q < ngrp) {
+    for (long long p = p0; p < p1; ++p) {
+      const float d = __bfloat162float(dy[p * lddy + co]);
+      const int xx = (int)(p % w);
+      const int yy = (int)((p / w) % h);
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) {
+        if (t % ngrp != q) continue;   // taps are dealt round-robin to the thread groups
+        const int ddy = (KS == 3) ? t / 3 - 1 : 0, ddx = (KS == 3) ? t % 3 - 1 : 0;
+        const int y2 = yy + ddy, x2 = xx + ddx;
+        if (y2 >= 0 && y2 < h && x2 >= 0 && x2 < w) {
+          const uint2 u = __ldg(x4 + p + (long long)ddy * w + ddx);
+          acc[t][0] = fmaf(d, bf16lo(u.x), acc[t][0]);
+          acc[t][1] = fmaf(d, bf16hi(u.x), acc[t][1]);
+          acc[t][2] = fmaf(d, bf16lo(u.y), acc[t][2]);
+          acc[t][3] = fmaf(d, bf16hi(u.y), acc[t][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+      if (t % ngrp != q) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) atomicAdd(&dw[((size_t)co * TAPS + t) * 4 + c], acc[t][c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// heads: y[b][co][hw] = sum_c x[p][c] * w[co][c] + bias[co]      (fp32 out, NCHW)
+// L lanes cooperate on one pixel, each lane owns 8 channels (requires cin/8 <= L <= 32).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                       long long npix, int hw, int cin,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       int cout, int L, float* __restrict__ y) {
+  const int lig = threadIdx.x % L;           // lane in group
+  const int grp = threadIdx.x / L;
+  const int gpb = blockDim.x / L;
+  const bool has = lig * 8 < cin;
+  float wr[8][8];
+#pragma unroll
+  for (int co = 0; co < 8; ++co)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[co][j] = (has && co < cout) ? bf16_round(w[co * cin + lig * 8 + j]) : 0.f;
+  // block-uniform trip count so the full-mask shuffles below are always executed by every lane
+  for (long long base = (long long)blockIdx.x * gpb; base < npix; base += (long long)gridDim.x * gpb) {
+    const long long p = base + grp;
+    const bool live = p < npix;
+    float f[8];
+    if (has && live) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * ldx + lig * 8));
+      f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+      f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+    const long long b = p / hw, r = p % hw;
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      if (co < cout) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(f[j], wr[co][j], s);
+        for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lig == 0 && live) y[(b * cout + co) * hw + r] = s + (bias ? bias[co] : 0.f);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dy,
+                                                       const __nv_bfloat16* __restrict__ x, int ldx,
+                                                       long long npix, int hw, int cin,
+                                                       const float* __restrict__ w, int cout, int L,
+                                                       __nv_bfloat16* __restrict__ dx, int lddx,
+                                                       float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float sacc[];   // [cout][cin] + [cout]
+  for (int i = threadIdx.x; i < cout * cin + cout; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lig = threadIdx.x % L;
+  const int grp = threadIdx.x / L;
+  const int gpb = blockDim.x / L;
+  const bool has = lig * 8 < cin;
+  float wr[8][8], aw[8][8], ab[8];
+#pragma unroll
+  for (int co = 0; co < 8; ++co) {
+    ab[co] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wr[co][j] = (has && co < cout) ? bf16_round(w[co * cin + lig * 8 + j]) : 0.f;
+      aw[co][j] = 0.f;
+    }
+  }
+  for (long long p = (long long)blockIdx.x * gpb + grp; p < npix; p += (long long)gridDim.x * gpb) {
+    const long long b = p / hw, r = p % hw;
+    float f[8], g[8];
+    if (has) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * ldx + lig * 8));
+      f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+      f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      if (co < cout) {
+        const float d = __ldg(dy + (b * cout + co) * hw + r);
+        if (lig == 0) ab[co] += d;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          g[j] = fmaf(d, wr[co][j], g[j]);
+          aw[co][j] = fmaf(d, f[j], aw[co][j]);
+        }
+      }
+    }
+    if (has && dx != nullptr) {
+      *reinterpret_cast<uint4*>(dx + p * lddx + lig * 8) =
+          make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                     pack_bf16x2(g[6], g[7]));
+    }
+  }
+  if (has) {
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      if (co < cout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sacc[co * cin + lig * 8 + j], aw[co][j]);
+        if (lig == 0) atomicAdd(&sacc[cout * cin + co], ab[co]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) atomicAdd(&dw[i], sacc[i]);
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) atomicAdd(&db[i], sacc[cout * cin + i]);
+}
+
+static int pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_conv_smallc_fprop(const void* x4, int32_t n, int32_t h, int32_t w, int32_t ksize,
+                                    const float* wk, const float* bias, int32_t cout, void* y, int32_t ldy,
+                                    int32_t relu, b2_stream_t stream) {
+  B2_REQUIRE(ksize == 1 || ksize == 3, B2_ERR_SHAPE, "ksize %d unsupported", ksize);
+  B2_REQUIRE(cout % 8 == 0 && cout <= 512, B2_ERR_SHAPE, "cout=%d must be a multiple of 8, <= 512", cout);
+  B2_REQUIRE(ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, B2_ERR_ALIGN, "y misaligned");
+  const long long total = (long long)n * h * w;
+  long long grid = (total + 127) / 128;
+  const long long cap = (long long)num_sms() * 16;
+  if (grid > cap) grid = cap;
+  const int taps = ksize * ksize;
+  const size_t smem = (size_t)cout * taps * 4 * sizeof(float) + cout * sizeof(float);
+  if (ksize == 3)
+    smallc_fprop_kernel<3><<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(
+        (const uint2*)x4, n, h, w, wk, bias, cout, (__nv_bfloat16*)y, ldy, relu);
+  else
+    smallc_fprop_kernel<1><<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>(
+        (const uint2*)x4, n, h, w, wk, bias, cout, (__nv_bfloat16*)y, ldy, relu);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_conv_smallc_wgrad(const void* dy, int32_t lddy, const void* x4, int32_t n, int32_t h, int32_t w,
+                                    int32_t ksize, int32_t cout, float* dw, b2_stream_t stream) {
+  B2_REQUIRE(ksize == 1 || ksize == 3, B2_ERR_SHAPE, "ksize %d unsupported", ksize);
+  B2_REQUIRE(cout >= 32 && cout <= 256 && 256 % cout == 0, B2_ERR_SHAPE, "cout=%d must divide 256 (>=32)", cout);
+  const int grid = num_sms() * 4;
+  if (ksize == 3)
+    smallc_wgrad_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
+                                                                   (const uint2*)x4, n, h, w, cout, dw);
+  else
+    smallc_wgrad_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
+                                                                   (const uint2*)x4, n, h, w, cout, dw);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_head_fwd(const void* x, int32_t ldx, int64_t npix, int32_t hw, int32_t cin, const float* w,
+                           const float* bias, int32_t cout, float* y, b2_stream_t stream) {
+  B2_REQUIRE(cin % 8 == 0 && cin <= 256, B2_ERR_SHAPE, "head cin=%d must be a multiple of 8, <= 256", cin);
+  B2_REQUIRE(cout >= 1 && cout <= 8, B2_ERR_SHAPE, "head cout=%d must be in 1..8", cout);
+  B2_REQUIRE(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, B2_ERR_ALIGN, "x misaligned");
+  const int L = pow2ceil(cin / 8);
+  const int gpb = 256 / L;
+  long long grid = (npix + gpb - 1) / gpb;
+  const long long cap = (long long)num_sms() * 8;
+  if (grid > cap) grid = cap;
+  head_fwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, npix, hw, cin, w,
+                                                                   bias, cout, L, y);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_head_bwd(const float* dy, const void* x, int32_t ldx, int64_t npix, int32_t hw, int32_t cin,
+                           const float* w, int32_t cout, void* dx, int32_t lddx, float* dw, float* db,
+                           b2_stream_t stream) {
+  B2_REQUIRE(cin % 8 == 0 && cin <= 256, B2_ERR_SHAPE, "head cin=%d must be a multiple of 8, <= 256", cin);
+  B2_REQUIRE(cout >= 1 && cout <= 8, B2_ERR_SHAPE, "head cout=%d must be in 1..8", cout);
+  B2_REQUIRE(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, B2_ERR_ALIGN, "x misaligned");
+  B2_REQUIRE(dx == nullptr || (lddx % 8 == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0), B2_ERR_ALIGN,
+             "dx misaligned");
+  const int L = pow2ceil(cin / 8);
+  const int gpb = 256 / L;
+  long long grid = (npix + gpb - 1) / gpb;
+  const long long cap = (long long)num_sms() * 4;
+  if (grid > cap) grid = cap;
+  const size_t smem = (size_t)(cout * cin + cout) * sizeof(float);
+  head_bwd_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
+      dy, (const __nv_bfloat16*)x, ldx, npix, hw, cin, w, cout, L, (__nv_bfloat16*)dx, lddx, dw, db);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

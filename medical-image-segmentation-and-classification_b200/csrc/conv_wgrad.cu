@@ -1,0 +1,319 @@
+// b200seg — convolution weight gradient on tcgen05 (the dW half of aten::convolution_backward).
+//
+//   dW[co][tap][ci] = sum over pixels p   dY[p][co] * X[p (+) tap][ci]
+//
+// GEMM view: M = 128 output channels, N = up to 4 column blocks of 64 (3x3: the three taps of one filter row for one
+// 64-channel block of X; 1x1: up to four 64-channel blocks), K = pixels.  Both operands are pixel-major in NHWC
+// memory, i.e. MN-major for the MMA: a TMA box of (64 ch, Wb, Hb, Nb) lands as 64 rows (pixels) of 128 B (channels)
+// with the 128B swizzle, which is exactly the canonical MN-major SW128 atom stack (8 K-rows per 1024 B, 64-element
+// MN blocks LBO apart).  X boxes are shifted by the tap offset; TMA zero fill supplies the padding halo.
+// The dY tile is loaded once per K chunk and reused by every column block.
+// Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
+// order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
+#include "common.cuh"
+
+namespace b2 {
+
+int conv_tile_geometry(int n, int h, int w, int tile_pix, int* Wb, int* Hb, int* Nb, int* tw, int* th, int* tn);
+int encode_act_tmap(CUtensorMap* tm, const void* base, int c, int ld, int n, int h, int w, int Wb, int Hb, int Nb);
+
+static constexpr int kChunkPix = 64;            // K per pipeline stage
+static constexpr int kBoxBytes = kChunkPix * 128;  // 8 KB: 64 pixels x 64 channels bf16
+static constexpr int kWgThreads = 192;
+
+struct WgradParams {
+  int Wb, Hb, Nb, tw, th;
+  int num_chunks, chunks_per_split;
+  int taps;          // 1 or 9
+  int ncolb;         // column blocks per CTA (3x3: 3 taps; 1x1: up to 4 channel blocks)
+  int cb0, cb1;      // 64-channel blocks per X source
+  int cout, ctot;    // ctot = c0 + c1 (row length of dW)
+  int a_boxes;       // 1 if cout <= 64 else 2
+  int stages;
+  float* ws;         // [splits][cout][taps][ctot]
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
+                  const __grid_constant__ CUtensorMap tmX1, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = 2 * kBoxBytes + p.ncolb * kBoxBytes;
+  uint8_t* tail = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int split = blockIdx.x;
+  const int rg = blockIdx.y;                          // filter row (3x3) or 0
+  const int co_tiles = (p.cout + 127) / 128;
+  const int co_tile = blockIdx.z % co_tiles;
+  const int cgrp = blockIdx.z / co_tiles;             // channel-block group
+  const int cib_base = (p.taps == 9) ? cgrp : cgrp * p.ncolb;
+  const int cbt = p.cb0 + p.cb1;
+
+  const int chunk_begin = split * p.chunks_per_split;
+  int chunk_end = chunk_begin + p.chunks_per_split;
+  if (chunk_end > p.num_chunks) chunk_end = p.num_chunks;
+  const int nchunks = chunk_end - chunk_begin;        // may be <= 0 for trailing splits
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX0);
+  }
+  const uint32_t tmem_cols = 256;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // number of live column blocks for this CTA (1x1 groups may run past the last channel block)
+  int ncol_live = p.ncolb;
+  if (p.taps != 9 && cib_base + ncol_live > cbt) ncol_live = cbt - cib_base;
+
+  if (warp == 0) {
+    if (lane == 0 && nchunks > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)((p.a_boxes + ncol_live) * kBoxBytes);
+      for (int ck = chunk_begin; ck < chunk_end; ++ck) {
+        int t = ck;
+        const int tw_i = t % p.tw; t /= p.tw;
+        const int th_i = t % p.th;
+        const int tn_i = t / p.th;
+        const int w0 = tw_i * p.Wb, h0 = th_i * p.Hb, n0 = tn_i * p.Nb;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * stage_bytes;
+        uint8_t* sb = sa + 2 * kBoxBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], tx);
+        for (int b = 0; b < p.a_boxes; ++b)
+          tma_load_4d(sa + b * kBoxBytes, &tmDY, &full_bar[stage], co_tile * 128 + b * 64, w0, h0, n0);
+        for (int j = 0; j < ncol_live; ++j) {
+          int cib, dr = 0, ds = 0;
+          if (p.taps == 9) {
+            cib = cib_base;
+            dr = rg - 1;
+            ds = j - 1;
+          } else {
+            cib = cib_base + j;
+          }
+          if (cib < p.cb0)
+            tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, w0 + ds, h0 + dr, n0);
+          else
+            tma_load_4d(sb + j * kBoxBytes, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, w0 + ds, h0 + dr, n0);
+        }
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (nchunks > 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, ncol_live * 64, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < nchunks; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + 2 * kBoxBytes;
+#pragma unroll
+          for (int k = 0; k < kChunkPix / 16; ++k) {
+            // 16 pixels (K) = two 8-row groups, 1024 B apart (SBO); 64-channel MN blocks 8 KB apart (LBO)
+            const uint64_t da = umma_desc_sw128(a_addr + k * 2048, kBoxBytes, 1024);
+            const uint64_t db = umma_desc_sw128(b_addr + k * 2048, kBoxBytes, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (lane == 0) umma_commit(tmem_full_bar);
+      __syncwarp();
+    }
+  } else {
+    // epilogue: row = output channel within the tile; columns = (column block, channel)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int co = co_tile * 128 + row;
+    const bool valid = co < p.cout;
+    float* out = p.ws + ((size_t)split * p.cout + (valid ? co : 0)) * ((size_t)p.taps * p.ctot);
+    if (nchunks > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int j = 0; j < ncol_live; ++j) {
+      int tap, cib;
+      if (p.taps == 9) {
+        tap = rg * 3 + j;
+        cib = cib_base;
+      } else {
+        tap = 0;
+        cib = cib_base + j;
+      }
+      float* dst = out + (size_t)tap * p.ctot + cib * 64;
+      const int cvalid = p.ctot - cib * 64;   // channels left in this block (>= 64 except for a ragged tail)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        if (nchunks > 0) {
+          tmem_ld32(taddr + j * 64 + half * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        if (valid) {
+          if (cvalid >= 64) {
+            float4* d4 = reinterpret_cast<float4*>(dst + half * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (half * 32 + i < cvalid) dst[half * 32 + i] = v[i];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// dw[i] = (accumulate ? dw[i] : 0) + sum_s ws[s][i]   (fixed summation order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long count,
+                                    int splits, int accumulate) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= count) return;
+  float4 acc = accumulate ? *reinterpret_cast<const float4*>(dw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * count + i));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dw + i) = acc;
+}
+
+struct WgradPlan {
+  WgradParams p;
+  int splits, gy, gz, tn;
+  long long count;
+  int smem_bytes;
+};
+
+static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
+  B2_REQUIRE(a != nullptr, B2_ERR_SHAPE, "null args");
+  B2_REQUIRE(a->ksize == 1 || a->ksize == 3, B2_ERR_SHAPE, "ksize %d unsupported", a->ksize);
+  B2_REQUIRE(a->cout % 8 == 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0, B2_ERR_SHAPE, "channels must be multiples of 8");
+  B2_REQUIRE(a->c1 == 0 || a->c0 % 64 == 0, B2_ERR_SHAPE, "c0=%d must be a multiple of 64 when c1>0", a->c0);
+  B2_REQUIRE((a->c0 + a->c1) % 4 == 0, B2_ERR_SHAPE, "cin must be a multiple of 4");
+  WgradParams& p = pl->p;
+  memset(&p, 0, sizeof(p));
+  int rc = conv_tile_geometry(a->n, a->h, a->w, kChunkPix, &p.Wb, &p.Hb, &p.Nb, &p.tw, &p.th, &pl->tn);
+  if (rc) return rc;
+  p.num_chunks = p.tw * p.th * pl->tn;
+  p.taps = a->ksize * a->ksize;
+  p.cb0 = (a->c0 + 63) / 64;
+  p.cb1 = (a->c1 + 63) / 64;
+  p.cout = a->cout;
+  p.ctot = a->c0 + a->c1;
+  p.a_boxes = a->cout <= 64 ? 1 : 2;
+  const int cbt = p.cb0 + p.cb1;
+  if (p.taps == 9) {
+    p.ncolb = 3;
+    pl->gy = 3;
+    pl->gz = ((a->cout + 127) / 128) * cbt;
+  } else {
+    p.ncolb = cbt < 4 ? cbt : 4;
+    pl->gy = 1;
+    pl->gz = ((a->cout + 127) / 128) * ((cbt + p.ncolb - 1) / p.ncolb);
+  }
+  const int base = pl->gy * pl->gz;
+  int splits = (2 * num_sms() + base - 1) / base;
+  const int max_splits = (p.num_chunks + 7) / 8;   // at least 8 chunks (512 pixels) per split
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.chunks_per_split = (p.num_chunks + splits - 1) / splits;
+  splits = (p.num_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  pl->splits = splits;
+  pl->count = (long long)a->cout * p.taps * p.ctot;
+  const int stage_bytes = 2 * kBoxBytes + p.ncolb * kBoxBytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  pl->smem_bytes = stages * stage_bytes + 256 + 1024;
+  return B2_OK;
+}
+
+}  // namespace b2
+
+extern "C" int64_t b2_conv_wgrad_workspace(const b2_wgrad_args* a) {
+  b2::WgradPlan pl;
+  int rc = b2::wgrad_plan(a, &pl);
+  if (rc) return rc;
+  return (int64_t)pl.splits * pl.count * 4;
+}
+
+extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
+  using namespace b2;
+  int rc = b2_arch_check();
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  WgradPlan pl;
+  rc = wgrad_plan(a, &pl);
+  if (rc) return rc;
+  const int64_t need = (int64_t)pl.splits * pl.count * 4;
+  B2_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= need, B2_ERR_WORKSPACE,
+             "wgrad workspace too small: need %lld B, have %lld B", (long long)need, (long long)a->workspace_bytes);
+  B2_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->dw) & 15) == 0,
+             B2_ERR_ALIGN, "workspace / dw must be 16B aligned");
+  pl.p.ws = static_cast<float*>(a->workspace);
+
+  CUtensorMap tmDY, tmX0, tmX1;
+  rc = encode_act_tmap(&tmDY, a->dy, a->cout, a->lddy, a->n, a->h, a->w, pl.p.Wb, pl.p.Hb, pl.p.Nb);
+  if (rc) return rc;
+  rc = encode_act_tmap(&tmX0, a->x0, a->c0, a->ldx0, a->n, a->h, a->w, pl.p.Wb, pl.p.Hb, pl.p.Nb);
+  if (rc) return rc;
+  if (a->c1 > 0) {
+    rc = encode_act_tmap(&tmX1, a->x1, a->c1, a->ldx1, a->n, a->h, a->w, pl.p.Wb, pl.p.Hb, pl.p.Nb);
+    if (rc) return rc;
+  } else {
+    tmX1 = tmX0;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(pl.splits, pl.gy, pl.gz);
+  conv_wgrad_kernel<<<grid, kWgThreads, pl.smem_bytes, stream>>>(tmDY, tmX0, tmX1, pl.p);
+  B2_LAUNCH_CHECK();
+  const long long n4 = (pl.count + 3) / 4;
+  wgrad_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(pl.p.ws, a->dw, pl.count, pl.splits,
+                                                                       a->accumulate);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

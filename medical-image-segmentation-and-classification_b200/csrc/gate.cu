@@ -1,0 +1,399 @@
+// b200seg — attention gate (AttentionUNet.py:29-54, R2AttU_Net.py:61-86):
+//     out = x * sigmoid(BN1(psi . relu(BN_g(W_g g) + BN_x(W_x x))))
+// The two 1x1 GEMMs (W_g, W_x) run on tcgen05 through b2_conv_fprop with the BN-statistics epilogue; everything
+// after them is memory-bound and lives here.  Train-mode BatchNorm puts two grid-wide reductions inside the gate
+// (statistics of the psi pre-activation, and of its gradient), hence forward = {psi_fwd, apply_fwd} and
+// backward = {apply_bwd, psi_bwd_reduce, psi_bwd_apply}; `a = relu(..)` is recomputed, never stored.
+// Rounding points mirror autocast: every BN output, the g1+x1 sum, the psi conv output and sigmoid are bf16.
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ void g_unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 g_pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ void g_load8(const float* p, bool has, float* f) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = has ? __ldg(p + j) : 0.f;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// block-wide sum of two floats held by arbitrary threads -> fp64 atomics
+__device__ __forceinline__ void block_sum2_atomic(float a, float b, double* out0, double* out1) {
+  __shared__ float sh[2][8];
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh[0][warp] = a;
+    sh[1][warp] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ta = 0.f, tb = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      ta += sh[0][i];
+      tb += sh[1][i];
+    }
+    atomicAdd(out0, (double)ta);
+    atomicAdd(out1, (double)tb);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward phase B: q = psi_conv(relu(bn_g(g1p) + bn_x(x1p)))  + statistics of q
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
+    const __nv_bfloat16* __restrict__ g1p, const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint,
+    int L, const float* __restrict__ scale_g, const float* __restrict__ shift_g, const float* __restrict__ scale_x,
+    const float* __restrict__ shift_x, const float* __restrict__ wpsi, const float* __restrict__ bpsi,
+    __nv_bfloat16* __restrict__ q, double* __restrict__ qstats) {
+  const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
+  const bool has = lig * 8 < fint;
+  float sg[8], hg[8], sx[8], hx[8], wp[8];
+  g_load8(scale_g + lig * 8, has, sg);
+  g_load8(shift_g + lig * 8, has, hg);
+  g_load8(scale_x + lig * 8, has, sx);
+  g_load8(shift_x + lig * 8, has, hx);
+  g_load8(wpsi + lig * 8, has, wp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wp[j] = bf16_round(wp[j]);
+  const float bp = bpsi ? __ldg(bpsi) : 0.f;
+  float lsum = 0.f, lsq = 0.f;
+  for (long long base = (long long)blockIdx.x * gpb; base < npix; base += (long long)gridDim.x * gpb) {
+    const long long p = base + grp;
+    const bool live = p < npix;
+    float s = 0.f;
+    if (has && live) {
+      float g[8], x[8];
+      g_unpack8(__ldg(reinterpret_cast<const uint4*>(g1p + p * ld + lig * 8)), g);
+      g_unpack8(__ldg(reinterpret_cast<const uint4*>(x1p + p * ld + lig * 8)), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
+        const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
+        const float a = fmaxf(bf16_round(gb + xb), 0.f);
+        s = fmaf(a, wp[j], s);
+      }
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lig == 0 && live) {
+      const __nv_bfloat16 qb = __float2bfloat16_rn(s + bp);
+      q[p] = qb;
+      const float qf = __bfloat162float(qb);
+      lsum += qf;
+      lsq += qf * qf;
+    }
+  }
+  block_sum2_atomic(lsum, lsq, &qstats[0], &qstats[1]);
+}
+
+// forward phase C: psi = sigmoid(bn1(q)); out = x * psi      (thread owns an 8-channel group, walks pixels)
+__global__ void __launch_bounds__(256) gate_apply_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
+                                                             const __nv_bfloat16* __restrict__ q, long long npix,
+                                                             int tpp, int rows, const float* __restrict__ scale1,
+                                                             const float* __restrict__ shift1,
+                                                             __nv_bfloat16* __restrict__ psi,
+                                                             __nv_bfloat16* __restrict__ out, int ldo) {
+  const int g = threadIdx.x % tpp, r = threadIdx.x / tpp;
+  if (r >= rows) return;
+  const float s1 = __ldg(scale1), h1 = __ldg(shift1);
+  for (long long p = (long long)blockIdx.x * rows + r; p < npix; p += (long long)gridDim.x * rows) {
+    const float qv = __bfloat162float(q[p]);
+    const float ps = bf16_round(sigmoidf_(bf16_round(fmaf(qv, s1, h1))));
+    float f[8];
+    g_unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * ldx + g * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= ps;
+    *reinterpret_cast<uint4*>(out + p * ldo + g * 8) = g_pack8(f);
+    if (g == 0) psi[p] = __float2bfloat16_rn(ps);
+  }
+}
+
+// backward phase 1: dx = dout*psi ; dsig = (sum_c dout*x) * psi (1-psi) ; sums1 += (dsig, dsig*qhat)
+__global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dout, int lddout, const __nv_bfloat16* __restrict__ x, int ldx,
+    const __nv_bfloat16* __restrict__ psi, const __nv_bfloat16* __restrict__ q, long long npix, int cg, int L,
+    const float* __restrict__ mean1, const float* __restrict__ invstd1, __nv_bfloat16* __restrict__ dx, int lddx,
+    float* __restrict__ dsig, double* __restrict__ sums1) {
+  const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
+  const float mu1 = __ldg(mean1), is1 = __ldg(invstd1);
+  float l0 = 0.f, l1 = 0.f;
+  for (long long base = (long long)blockIdx.x * gpb; base < npix; base += (long long)gridDim.x * gpb) {
+    const long long p = base + grp;
+    const bool live = p < npix;
+    float s = 0.f;
+    float ps = 0.f;
+    if (live) {
+      ps = __bfloat162float(psi[p]);
+      for (int k = lig; k < cg; k += L) {
+        float d[8], f[8];
+        g_unpack8(__ldg(reinterpret_cast<const uint4*>(dout + p * lddout + k * 8)), d);
+        g_unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * ldx + k * 8)), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s = fmaf(d[j], f[j], s);
+          d[j] *= ps;
+        }
+        *reinterpret_cast<uint4*>(dx + p * lddx + k * 8) = g_pack8(d);
+      }
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lig == 0 && live) {
+      const float ds = s * ps * (1.f - ps);
+      dsig[p] = ds;
+      const float qh = (__bfloat162float(q[p]) - mu1) * is1;
+      l0 += ds;
+      l1 += ds * qh;
+    }
+  }
+  block_sum2_atomic(l0, l1, &sums1[0], &sums1[1]);
+}
+
+struct GateBwdCoef {
+  const float *scale_g, *shift_g, *mean_g, *invstd_g, *gamma_g;
+  const float *scale_x, *shift_x, *mean_x, *invstd_x, *gamma_x;
+  const float *gamma1, *mean1, *invstd1;
+  const float* wpsi;
+};
+
+// dq for one pixel from dsig via BN1 backward
+__device__ __forceinline__ float gate_dq(float ds, float qv, float g1, float mu1, float is1, int training,
+                                         float k0, float k1) {
+  const float qh = (qv - mu1) * is1;
+  return training ? g1 * is1 * (ds - k0 - qh * k1) : g1 * is1 * ds;
+}
+
+// backward phase 2: reductions for BN_g, BN_x and the psi conv
+__global__ void __launch_bounds__(256) gate_psi_bwd_reduce_kernel(
+    const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
+    const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int L, GateBwdCoef c,
+    const double* __restrict__ sums1, int training, double* __restrict__ sums, float* __restrict__ dwpsi,
+    float* __restrict__ dbpsi) {
+  extern __shared__ float red[];   // [4][fint] + 1
+  for (int i = threadIdx.x; i < 4 * fint + 1; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
+  const bool has = lig * 8 < fint;
+  float sg[8], hg[8], mg[8], ig[8], sx[8], hx[8], mx[8], ix[8], wp[8];
+  g_load8(c.scale_g + lig * 8, has, sg);
+  g_load8(c.shift_g + lig * 8, has, hg);
+  g_load8(c.mean_g + lig * 8, has, mg);
+  g_load8(c.invstd_g + lig * 8, has, ig);
+  g_load8(c.scale_x + lig * 8, has, sx);
+  g_load8(c.shift_x + lig * 8, has, hx);
+  g_load8(c.mean_x + lig * 8, has, mx);
+  g_load8(c.invstd_x + lig * 8, has, ix);
+  g_load8(c.wpsi + lig * 8, has, wp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wp[j] = bf16_round(wp[j]);
+  const float g1 = __ldg(c.gamma1), mu1 = __ldg(c.mean1), is1 = __ldg(c.invstd1);
+  const float k0 = (float)(sums1[0] / (double)npix), k1 = (float)(sums1[1] / (double)npix);
+  float ab[8], agg[8], agx[8], aw[8], abp = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ab[j] = agg[j] = agx[j] = aw[j] = 0.f;
+  if (has) {
+    for (long long p = (long long)blockIdx.x * gpb + grp; p < npix; p += (long long)gridDim.x * gpb) {
+      const float dq = gate_dq(__ldg(dsig + p), __bfloat162float(q[p]), g1, mu1, is1, training, k0, k1);
+      float g[8], x[8];
+      g_unpack8(__ldg(reinterpret_cast<const uint4*>(g1p + p * ld + lig * 8)), g);
+      g_unpack8(__ldg(reinterpret_cast<const uint4*>(x1p + p * ld + lig * 8)), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
+        const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
+        const float a = fmaxf(bf16_round(gb + xb), 0.f);
+        const float da = a > 0.f ? dq * wp[j] : 0.f;
+        ab[j] += da;
+        agg[j] += da * ((g[j] - mg[j]) * ig[j]);
+        agx[j] += da * ((x[j] - mx[j]) * ix[j]);
+        aw[j] = fmaf(dq, a, aw[j]);
+      }
+      if (lig == 0) abp += dq;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[0 * fint + lig * 8 + j], ab[j]);
+      atomicAdd(&red[1 * fint + lig * 8 + j], agg[j]);
+      atomicAdd(&red[2 * fint + lig * 8 + j], agx[j]);
+      atomicAdd(&red[3 * fint + lig * 8 + j], aw[j]);
+    }
+    if (lig == 0) atomicAdd(&red[4 * fint], abp);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < fint; i += blockDim.x) {
+    atomicAdd(&sums[0 * fint + i], (double)red[0 * fint + i]);   // dbeta_g
+    atomicAdd(&sums[1 * fint + i], (double)red[1 * fint + i]);   // dgamma_g
+    atomicAdd(&sums[2 * fint + i], (double)red[0 * fint + i]);   // dbeta_x (same upstream gradient)
+    atomicAdd(&sums[3 * fint + i], (double)red[2 * fint + i]);   // dgamma_x
+    atomicAdd(&dwpsi[i], red[3 * fint + i]);
+  }
+  if (threadIdx.x == 0) atomicAdd(dbpsi, red[4 * fint]);
+}
+
+// backward phase 3: gradients w.r.t. the two pre-BN GEMM outputs
+__global__ void __launch_bounds__(256) gate_psi_bwd_apply_kernel(
+    const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
+    const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int tpp, int rows, GateBwdCoef c,
+    const double* __restrict__ sums1, int training, const double* __restrict__ sums,
+    __nv_bfloat16* __restrict__ dg1p, __nv_bfloat16* __restrict__ dx1p, float* __restrict__ dgamma_beta,
+    float* __restrict__ dbn1) {
+  const int gch = threadIdx.x % tpp, r = threadIdx.x / tpp;
+  if (r >= rows) return;
+  float sg[8], hg[8], mg[8], ig[8], sx[8], hx[8], mx[8], ix[8], wp[8], cg_[8], cx_[8], kbg[8], kgg[8], kgx[8];
+  g_load8(c.scale_g + gch * 8, true, sg);
+  g_load8(c.shift_g + gch * 8, true, hg);
+  g_load8(c.mean_g + gch * 8, true, mg);
+  g_load8(c.invstd_g + gch * 8, true, ig);
+  g_load8(c.scale_x + gch * 8, true, sx);
+  g_load8(c.shift_x + gch * 8, true, hx);
+  g_load8(c.mean_x + gch * 8, true, mx);
+  g_load8(c.invstd_x + gch * 8, true, ix);
+  g_load8(c.wpsi + gch * 8, true, wp);
+  const double inv_m = 1.0 / (double)npix;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = gch * 8 + j;
+    wp[j] = bf16_round(wp[j]);
+    cg_[j] = __ldg(c.gamma_g + ch) * ig[j];
+    cx_[j] = __ldg(c.gamma_x + ch) * ix[j];
+    const double dbg = sums[0 * fint + ch], dgg = sums[1 * fint + ch], dgx = sums[3 * fint + ch];
+    kbg[j] = training ? (float)(dbg * inv_m) : 0.f;
+    kgg[j] = training ? (float)(dgg * inv_m) : 0.f;
+    kgx[j] = training ? (float)(dgx * inv_m) : 0.f;
+    if (blockIdx.x == 0 && r == 0) {
+      dgamma_beta[0 * fint + ch] = (float)dgg;
+      dgamma_beta[1 * fint + ch] = (float)dbg;
+      dgamma_beta[2 * fint + ch] = (float)dgx;
+      dgamma_beta[3 * fint + ch] = (float)dbg;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    dbn1[0] = (float)sums1[1];   // dgamma1
+    dbn1[1] = (float)sums1[0];   // dbeta1
+  }
+  const float g1 = __ldg(c.gamma1), mu1 = __ldg(c.mean1), is1 = __ldg(c.invstd1);
+  const float k0 = (float)(sums1[0] * inv_m), k1 = (float)(sums1[1] * inv_m);
+  for (long long p = (long long)blockIdx.x * rows + r; p < npix; p += (long long)gridDim.x * rows) {
+    const float dq = gate_dq(__ldg(dsig + p), __bfloat162float(q[p]), g1, mu1, is1, training, k0, k1);
+    float g[8], x[8], og[8], ox[8];
+    g_unpack8(__ldg(reinterpret_cast<const uint4*>(g1p + p * ld + gch * 8)), g);
+    g_unpack8(__ldg(reinterpret_cast<const uint4*>(x1p + p * ld + gch * 8)), x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
+      const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
+      const float a = fmaxf(bf16_round(gb + xb), 0.f);
+      const float da = a > 0.f ? dq * wp[j] : 0.f;
+      og[j] = cg_[j] * (da - kbg[j] - ((g[j] - mg[j]) * ig[j]) * kgg[j]);
+      ox[j] = cx_[j] * (da - kbg[j] - ((x[j] - mx[j]) * ix[j]) * kgx[j]);
+    }
+    *reinterpret_cast<uint4*>(dg1p + p * ld + gch * 8) = g_pack8(og);
+    *reinterpret_cast<uint4*>(dx1p + p * ld + gch * 8) = g_pack8(ox);
+  }
+}
+
+static int g_pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+static int g_grid(long long units, int per_block, int waves) {
+  long long g = (units + per_block - 1) / per_block;
+  const long long cap = (long long)num_sms() * waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+static bool g_al(const void* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 8 == 0; }
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_gate_psi_fwd(const void* g1p, const void* x1p, int32_t ld, int64_t npix, int32_t fint,
+                               const float* scale_g, const float* shift_g, const float* scale_x,
+                               const float* shift_x, const float* wpsi, const float* bpsi, void* q,
+                               double* qstats, b2_stream_t stream) {
+  B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
+  B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld), B2_ERR_ALIGN, "gate operands misaligned");
+  const int L = g_pow2ceil(fint / 8);
+  gate_psi_fwd_kernel<<<g_grid(npix, 256 / L, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L, scale_g, shift_g, scale_x, shift_x,
+      wpsi, bpsi, (__nv_bfloat16*)q, qstats);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_gate_apply_fwd(const void* x, int32_t ldx, const void* q, int64_t npix, int32_t c,
+                                 const float* scale1, const float* shift1, void* psi, void* out, int32_t ldo,
+                                 b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0 && c <= 2048, B2_ERR_SHAPE, "gate C=%d must be a multiple of 8, <= 2048", c);
+  B2_REQUIRE(g_al(x, ldx) && g_al(out, ldo), B2_ERR_ALIGN, "gate operands misaligned");
+  const int tpp = c / 8, rows = 256 / tpp;
+  gate_apply_fwd_kernel<<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)q, npix, tpp, rows, scale1, shift1, (__nv_bfloat16*)psi,
+      (__nv_bfloat16*)out, ldo);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_gate_apply_bwd(const void* dout, int32_t lddout, const void* x, int32_t ldx, const void* psi,
+                                 const void* q, int64_t npix, int32_t c, const float* mean1, const float* invstd1,
+                                 void* dx, int32_t lddx, float* dsig, double* sums1, b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0, B2_ERR_SHAPE, "gate C=%d must be a multiple of 8", c);
+  B2_REQUIRE(g_al(dout, lddout) && g_al(x, ldx) && g_al(dx, lddx), B2_ERR_ALIGN, "gate operands misaligned");
+  int L = g_pow2ceil(c / 8);
+  if (L > 32) L = 32;
+  gate_apply_bwd_kernel<<<g_grid(npix, 256 / L, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dout, lddout, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)psi,
+      (const __nv_bfloat16*)q, npix, c / 8, L, mean1, invstd1, (__nv_bfloat16*)dx, lddx, dsig, sums1);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+static GateBwdCoef make_coef(const b2_gate_coef* k) {
+  GateBwdCoef c;
+  c.scale_g = k->scale_g; c.shift_g = k->shift_g; c.mean_g = k->mean_g; c.invstd_g = k->invstd_g;
+  c.gamma_g = k->gamma_g;
+  c.scale_x = k->scale_x; c.shift_x = k->shift_x; c.mean_x = k->mean_x; c.invstd_x = k->invstd_x;
+  c.gamma_x = k->gamma_x;
+  c.gamma1 = k->gamma1; c.mean1 = k->mean1; c.invstd1 = k->invstd1;
+  c.wpsi = k->wpsi;
+  return c;
+}
+
+extern "C" int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const void* g1p, const void* x1p,
+                                      int32_t ld, int64_t npix, int32_t fint, const b2_gate_coef* coef,
+                                      const double* sums1, int32_t training, double* sums, float* dwpsi,
+                                      float* dbpsi, b2_stream_t stream) {
+  B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
+  B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld), B2_ERR_ALIGN, "gate operands misaligned");
+  const int L = g_pow2ceil(fint / 8);
+  const size_t smem = (size_t)(4 * fint + 1) * sizeof(float);
+  gate_psi_bwd_reduce_kernel<<<g_grid(npix, 256 / L, 4), 256, smem, (cudaStream_t)stream>>>(
+      dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
+      make_coef(coef), sums1, training, sums, dwpsi, dbpsi);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const void* g1p, const void* x1p,
+                                     int32_t ld, int64_t npix, int32_t fint, const b2_gate_coef* coef,
+                                     const double* sums1, int32_t training, const double* sums, void* dg1p,
+                                     void* dx1p, float* dgamma_beta, float* dbn1, b2_stream_t stream) {
+  B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
+  B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld) && g_al(dg1p, ld) && g_al(dx1p, ld), B2_ERR_ALIGN,
+             "gate operands misaligned");
+  const int tpp = fint / 8, rows = 256 / tpp;
+  gate_psi_bwd_apply_kernel<<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
+      dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
+      rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

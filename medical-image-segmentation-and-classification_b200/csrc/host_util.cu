@@ -1,0 +1,108 @@
+// b200seg — host utilities: thread-local error string, arch check, TMA descriptor encoding.
+#include <stdarg.h>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace b2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return B2_ERR_CUDA;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2_REQUIRE(fn != nullptr, B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
+  B2_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, B2_ERR_ALIGN, "TMA base pointer not 16B aligned");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i];
+      B2_REQUIRE((strides_bytes[i] & 15) == 0, B2_ERR_ALIGN, "TMA stride %d = %llu B not a multiple of 16", i,
+                 (unsigned long long)strides_bytes[i]);
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r,
+              rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return B2_ERR_CUDA;
+  }
+  return B2_OK;
+}
+
+}  // namespace b2
+
+extern "C" {
+
+const char* b2_last_error(void) { return b2::g_err; }
+int b2_abi_version(void) { return B2_ABI_VERSION; }
+int b2_num_sms(void) { return b2::num_sms(); }
+
+int b2_arch_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return b2::cuda_fail(e, "cudaGetDevice");
+  int major = 0, minor = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return b2::cuda_fail(e, "cudaDeviceGetAttribute");
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10 || minor != 0) {
+    b2::set_error("libb200seg is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
+    return B2_ERR_ARCH;
+  }
+  return B2_OK;
+}
+
+}  // extern "C"

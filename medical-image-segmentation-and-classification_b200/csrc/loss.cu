@@ -1,0 +1,117 @@
+// b200seg — segmentation losses on fp32 logits.
+//   BCEWithLogits, mean reduction          : nn.BCEWithLogitsLoss(), utils/helpers.py:244-246,327
+//   0.5*BCE + 0.5*Dice (global, smooth=1)  : CombinedLoss / DiceLoss, utils/clip_seg_finetuner.py:40-74
+// One reduction kernel (warp-shuffle + fp64 atomics) yields every sum either loss needs plus the IoU counts of
+// utils/helpers.py:223-227; one elementwise kernel yields d loss / d logits.
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ float stable_sigmoid(float z) {
+  const float e = expf(-fabsf(z));
+  return z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+}
+
+__global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                       long long count, double* __restrict__ sums) {
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float zi = __ldg(z + i), ti = __ldg(t + i);
+    a[0] += fmaxf(zi, 0.f) - zi * ti + log1pf(expf(-fabsf(zi)));
+    const float s = stable_sigmoid(zi);
+    a[1] += s * ti;
+    a[2] += s;
+    a[3] += ti;
+    const bool pr = zi > 0.f, tg = ti > 0.5f;
+    a[4] += (pr && tg) ? 1.f : 0.f;
+    a[5] += (pr || tg) ? 1.f : 0.f;
+  }
+  __shared__ float sh[6][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    a[k] = warp_sum(a[k]);
+    if (lane == 0) sh[k][warp] = a[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
+    atomicAdd(&sums[threadIdx.x], (double)s);
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, long long count, float w_bce, float w_dice,
+                                     float smooth, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double l = 0.0;
+    if (w_bce != 0.f) l += (double)w_bce * sums[0] / (double)count;
+    if (w_dice != 0.f) {
+      const double dice = (2.0 * sums[1] + smooth) / (sums[2] + sums[3] + smooth);
+      l += (double)w_dice * (1.0 - dice);
+    }
+    *loss = (float)l;
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                       long long count, const double* __restrict__ sums,
+                                                       float w_bce, float w_dice, float smooth,
+                                                       const float* __restrict__ grad_out,
+                                                       float* __restrict__ dz) {
+  const float go = grad_out ? __ldg(grad_out) : 1.f;
+  const float kb = w_bce / (float)count;
+  float num = 0.f, den = 1.f;
+  if (w_dice != 0.f) {
+    num = (float)(2.0 * sums[1] + smooth);
+    den = (float)(sums[2] + sums[3] + smooth);
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float zi = __ldg(z + i), ti = __ldg(t + i);
+    const float s = stable_sigmoid(zi);
+    float g = kb * (s - ti);
+    if (w_dice != 0.f) {
+      // d/dz [1 - num/den] = -(2 t den - num) s(1-s) / den^2
+      g -= w_dice * (2.f * ti * den - num) * s * (1.f - s) / (den * den);
+    }
+    dz[i] = go * g;
+  }
+}
+
+static int l_grid(long long count) {
+  long long g = (count + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_loss_fwd(const float* z, const float* t, int64_t count, double* sums, b2_stream_t stream) {
+  B2_REQUIRE(count > 0, B2_ERR_SHAPE, "empty loss input");
+  loss_fwd_kernel<<<l_grid(count), 256, 0, (cudaStream_t)stream>>>(z, t, count, sums);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_loss_finalize(const double* sums, int64_t count, float w_bce, float w_dice, float smooth,
+                                float* loss, b2_stream_t stream) {
+  B2_REQUIRE(count > 0, B2_ERR_SHAPE, "empty loss input");
+  loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums, count, w_bce, w_dice, smooth, loss);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_loss_bwd(const float* z, const float* t, int64_t count, const double* sums, float w_bce,
+                           float w_dice, float smooth, const float* grad_out, float* dz, b2_stream_t stream) {
+  B2_REQUIRE(count > 0, B2_ERR_SHAPE, "empty loss input");
+  loss_bwd_kernel<<<l_grid(count), 256, 0, (cudaStream_t)stream>>>(z, t, count, sums, w_bce, w_dice, smooth,
+                                                                   grad_out, dz);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

@@ -1,0 +1,265 @@
+// b200seg — memory-bound helpers: weight packing, 2x2 max-pool, nearest 2x upsample, add, layout conversion.
+// Reference call sites: nn.MaxPool2d(2,2) AttentionUNet.py:61 / R2U_Net.py:54; nn.Upsample(scale_factor=2)
+// AttentionUNet.py:18 / R2U_Net.py:25; x + x1 R2U_Net.py:19,48; input .to(device) helpers.py:318.
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ void unpack8p(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8p(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+
+// fp32 [cout][cin][k][k] (any strides) -> bf16 [tap][cout][cin] and flipped/transposed [taps-1-tap][cin][cout]
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps, int ks, long long s_co,
+                                    long long s_ci, long long s_kh, long long s_kw,
+                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const long long total = (long long)taps * cout * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % cout);
+    const int tap = (int)(i / ((long long)cin * cout));
+    const int kh = tap / ks, kw = tap % ks;
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[co * s_co + ci * s_ci + kh * s_kh + kw * s_kw]);
+    if (wf) wf[i] = v;
+    if (wd) wd[((long long)(taps - 1 - tap) * cin + ci) * cout + co] = v;
+  }
+}
+
+__global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int cg,
+                                      __nv_bfloat16* __restrict__ y, int ldy) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int b = (int)(p / ho);
+    const long long base = ((long long)(b * h + 2 * yo) * w + 2 * xo);
+    float m[8], f[8];
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(x + base * ldx + g * 8)), m);
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(x + (base + 1) * ldx + g * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(x + (base + w) * ldx + g * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(x + (base + w + 1) * ldx + g * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+    *reinterpret_cast<uint4*>(y + ((long long)(b * ho + yo) * wo + xo) * ldy + g * 8) = pack8p(m);
+  }
+}
+
+// arg-max recomputed from the saved input; first maximum in window scan order wins (ATen's tie rule)
+__global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
+                                      const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int cg,
+                                      __nv_bfloat16* __restrict__ dx, int lddx) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int b = (int)(p / ho);
+    const long long base = ((long long)(b * h + 2 * yo) * w + 2 * xo);
+    const long long off[4] = {base, base + 1, base + w, base + w + 1};
+    float v[4][8], d[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack8p(__ldg(reinterpret_cast<const uint4*>(x + off[k] * ldx + g * 8)), v[k]);
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + ((long long)(b * ho + yo) * wo + xo) * lddy + g * 8)), d);
+    float o[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float bv = v[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        if (v[k][j] > bv) {
+          bv = v[k][j];
+          best = k;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][j] = (k == best) ? d[j] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dx + off[k] * lddx + g * 8) = pack8p(o[k]);
+  }
+}
+
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int cg,
+                                      __nv_bfloat16* __restrict__ y, int ldy) {
+  const long long total = (long long)n * h * w * cg;
+  const int w2 = 2 * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int xi = (int)(p % w); p /= w;
+    const int yi = (int)(p % h);
+    const int b = (int)(p / h);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((long long)(b * h + yi) * w + xi) * ldx + g * 8));
+    const long long ob = ((long long)(b * 2 * h + 2 * yi) * w2 + 2 * xi);
+    *reinterpret_cast<uint4*>(y + ob * ldy + g * 8) = u;
+    *reinterpret_cast<uint4*>(y + (ob + 1) * ldy + g * 8) = u;
+    *reinterpret_cast<uint4*>(y + (ob + w2) * ldy + g * 8) = u;
+    *reinterpret_cast<uint4*>(y + (ob + w2 + 1) * ldy + g * 8) = u;
+  }
+}
+
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy, int n, int h, int w, int cg,
+                                      __nv_bfloat16* __restrict__ dx, int lddx) {
+  const long long total = (long long)n * h * w * cg;
+  const int w2 = 2 * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long p = i / cg;
+    const int xi = (int)(p % w); p /= w;
+    const int yi = (int)(p % h);
+    const int b = (int)(p / h);
+    const long long ob = ((long long)(b * 2 * h + 2 * yi) * w2 + 2 * xi);
+    float s[8], f[8];
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + ob * lddy + g * 8)), s);
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + (ob + 1) * lddy + g * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + (ob + w2) * lddy + g * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + (ob + w2 + 1) * lddy + g * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+    *reinterpret_cast<uint4*>(dx + ((long long)(b * h + yi) * w + xi) * lddx + g * 8) = pack8p(s);
+  }
+}
+
+__global__ void add_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b,
+                           int ldb, long long npix, int cg, __nv_bfloat16* __restrict__ out, int ldo) {
+  const long long total = npix * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long p = i / cg;
+    float fa[8], fb[8];
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(a + p * lda + g * 8)), fa);
+    unpack8p(__ldg(reinterpret_cast<const uint4*>(b + p * ldb + g * 8)), fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fa[j] += fb[j];
+    *reinterpret_cast<uint4*>(out + p * ldo + g * 8) = pack8p(fa);
+  }
+}
+
+// NCHW fp32 -> NHWC bf16 with the channel dimension zero-padded to ldy (ldy in {4, 8, ...})
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, long long hw,
+                                    __nv_bfloat16* __restrict__ y, int ldy) {
+  const long long total = (long long)n * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / hw, p = i % hw;
+    for (int ch = 0; ch < ldy; ++ch) {
+      const float v = ch < c ? __ldg(x + (b * c + ch) * hw + p) : 0.f;
+      y[i * ldy + ch] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+static int ew_grid(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+static bool al16(const void* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 8 == 0; }
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int b2_pack_weights(const float* w, int32_t cout, int32_t cin, int32_t ksize, int64_t s_co,
+                               int64_t s_ci, int64_t s_kh, int64_t s_kw, void* w_fprop, void* w_dgrad,
+                               b2_stream_t stream) {
+  B2_REQUIRE(cout > 0 && cin > 0 && ksize >= 1 && ksize <= 7, B2_ERR_SHAPE, "bad weight shape");
+  const int taps = ksize * ksize;
+  const long long total = (long long)taps * cout * cin;
+  pack_weights_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, cout, cin, taps, ksize, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_maxpool2x2_fwd(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w, int32_t c, void* y,
+                                 int32_t ldy, b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, B2_ERR_SHAPE, "maxpool needs c%%8==0 and even h,w");
+  B2_REQUIRE(al16(x, ldx) && al16(y, ldy), B2_ERR_ALIGN, "maxpool operands misaligned");
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  maxpool2x2_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)y, ldy);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_maxpool2x2_bwd(const void* dy, int32_t lddy, const void* x, int32_t ldx, int32_t n, int32_t h,
+                                 int32_t w, int32_t c, void* dx, int32_t lddx, b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, B2_ERR_SHAPE, "maxpool needs c%%8==0 and even h,w");
+  B2_REQUIRE(al16(x, ldx) && al16(dy, lddy) && al16(dx, lddx), B2_ERR_ALIGN, "maxpool operands misaligned");
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  maxpool2x2_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_upsample2x_fwd(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w, int32_t c, void* y,
+                                 int32_t ldy, b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0, B2_ERR_SHAPE, "upsample needs c%%8==0");
+  B2_REQUIRE(al16(x, ldx) && al16(y, ldy), B2_ERR_ALIGN, "upsample operands misaligned");
+  const long long total = (long long)n * h * w * (c / 8);
+  upsample2x_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, n, h,
+                                                                                w, c / 8, (__nv_bfloat16*)y, ldy);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_upsample2x_bwd(const void* dy, int32_t lddy, int32_t n, int32_t h, int32_t w, int32_t c,
+                                 void* dx, int32_t lddx, b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0, B2_ERR_SHAPE, "upsample needs c%%8==0");
+  B2_REQUIRE(al16(dy, lddy) && al16(dx, lddx), B2_ERR_ALIGN, "upsample operands misaligned");
+  const long long total = (long long)n * h * w * (c / 8);
+  upsample2x_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy, n,
+                                                                                h, w, c / 8, (__nv_bfloat16*)dx,
+                                                                                lddx);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_add(const void* a, int32_t lda, const void* b, int32_t ldb, int64_t npix, int32_t c, void* out,
+                      int32_t ldo, b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0, B2_ERR_SHAPE, "add needs c%%8==0");
+  B2_REQUIRE(al16(a, lda) && al16(b, ldb) && al16(out, ldo), B2_ERR_ALIGN, "add operands misaligned");
+  add_kernel<<<ew_grid(npix * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, npix, c / 8, (__nv_bfloat16*)out, ldo);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_nchw_f32_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* y,
+                                        int32_t ldy, b2_stream_t stream) {
+  B2_REQUIRE(c > 0 && ldy >= c && ldy <= 64, B2_ERR_SHAPE, "layout conversion supports c <= ldy <= 64");
+  const long long total = (long long)n * h * w;
+  nchw_to_nhwc_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(x, n, c, (long long)h * w,
+                                                                              (__nv_bfloat16*)y, ldy);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
