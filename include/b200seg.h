@@ -163,6 +163,11 @@ int b2_add(const void* a, int32_t lda, const void* b, int32_t ldb, int64_t npix,
            int32_t ldo, b2_stream_t stream);
 int b2_nchw_f32_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* y, int32_t ldy,
                              b2_stream_t stream);
+/* module-boundary adapters for any channel count (input arrives NCHW fp32: utils/helpers.py:318) */
+int b2_layout_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* y, int32_t ldy,
+                           b2_stream_t stream);
+int b2_layout_nhwc_to_nchw(const void* x, int32_t ldx, int32_t n, int32_t c, int32_t h, int32_t w, float* y,
+                           b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Attention gate (AttentionUNet.py:48-54, R2AttU_Net.py:80-86) — the 1x1 GEMMs go through b2_conv_fprop.

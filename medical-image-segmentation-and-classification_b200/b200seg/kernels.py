@@ -226,10 +226,11 @@ def bn_bwd(dy, z, coef, gamma, relu=True, training=True):
     call("b2_bn_bwd_reduce", _p(dy), lddy, _p(z), ldz, npix, c, _p(coef[2]), _p(coef[3]), _p(coef[0]), _p(coef[1]),
          int(relu), _p(sums), _stream())
     dz = new_act(n, h, w, c, z.device)
-    dgb = torch.empty((2, c), dtype=torch.float32, device=z.device)
+    dgamma = torch.empty((c,), dtype=torch.float32, device=z.device)
+    dbeta = torch.empty((c,), dtype=torch.float32, device=z.device)
     call("b2_bn_bwd_apply", _p(dy), lddy, _p(z), ldz, npix, c, _p(coef[2]), _p(coef[3]), _p(coef[0]), _p(coef[1]),
-         _p(gamma), int(relu), int(training), _p(sums), _p(dz), c, _p(dgb[0]), _p(dgb[1]), _stream())
-    return dz, dgb[0], dgb[1]
+         _p(gamma), int(relu), int(training), _p(sums), _p(dz), c, _p(dgamma), _p(dbeta), _stream())
+    return dz, dgamma, dbeta
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -270,6 +271,23 @@ def add(a, b):
     out = new_act(n, h, w, c, a.device)
     call("b2_add", _p(a), lda, _p(b), ldb, n * h * w, c, _p(out), c, _stream())
     return out
+
+
+def to_nhwc_bf16(x):
+    """NCHW fp32 [N, C, H, W] -> NHWC bf16 [N, H, W, C]"""
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+    n, c, h, w = x.shape
+    y = new_act(n, h, w, c, x.device)
+    call("b2_layout_nchw_to_nhwc", _p(x), n, c, h, w, _p(y), c, _stream())
+    return y
+
+
+def to_nchw_f32(x):
+    """NHWC bf16 -> NCHW fp32"""
+    n, h, w, c, ld = _nhwc(x)
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    call("b2_layout_nhwc_to_nchw", _p(x), ld, n, c, h, w, _p(y), _stream())
+    return y
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -1,0 +1,65 @@
+"""Drop-in for the reference's models/segmentation_models/AttentionUNet.py (same file name, class names,
+constructor signatures, submodule names => identical state_dict keys; Appendix B of SURVEY.md).
+forward() runs the b200seg sm_100a kernels; see b200seg/blocks.py for the block implementations."""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...blocks import AttentionGate, UpConv, basic_block, check_image  # noqa: F401  (re-exported names)
+
+
+class AttentionUNet(nn.Module):
+    """Attention U-Net — reference AttentionUNet.py:56-121.  `in_channel` is stored but ignored (first block is
+    hard-wired to 3 input channels), exactly like the reference (AttentionUNet.py:57-62)."""
+
+    def __init__(self, in_channel=3, out_channel=1):
+        super().__init__()
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self.max_pool = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.conv1 = basic_block(3, 64)
+        self.conv2 = basic_block(64, 128)
+        self.conv3 = basic_block(128, 256)
+        self.conv4 = basic_block(256, 512)
+        self.conv5 = basic_block(512, 1024)
+
+        self.up5 = UpConv(1024, 512)
+        self.att5 = AttentionGate(F_g=512, F_l=512, F_int=256)
+        self.up_conv5 = basic_block(1024, 512)
+
+        self.up4 = UpConv(512, 256)
+        self.att4 = AttentionGate(F_g=256, F_l=256, F_int=128)
+        self.up_conv4 = basic_block(512, 256)
+
+        self.up3 = UpConv(256, 128)
+        self.att3 = AttentionGate(F_g=128, F_l=128, F_int=64)
+        self.up_conv3 = basic_block(256, 128)
+
+        self.up2 = UpConv(128, 64)
+        self.att2 = AttentionGate(F_g=64, F_l=64, F_int=32)
+        self.up_conv2 = basic_block(128, 64)
+
+        self.out = nn.Conv2d(64, out_channel, kernel_size=1, stride=1, padding=0)
+
+    def features(self, x: torch.Tensor):
+        """Everything up to the head, on internal NHWC bf16 activations."""
+        pool = ops.maxpool2x2
+        x1 = self.conv1._internal(x)
+        x2 = self.conv2(pool(x1))
+        x3 = self.conv3(pool(x2))
+        x4 = self.conv4(pool(x3))
+        x5 = self.conv5(pool(x4))
+
+        d5 = self.up5(x5)
+        d5 = self.up_conv5((self.att5(g=d5, x=x4), d5))      # cat((x4, d5), dim=1): skip first (ref :101)
+        d4 = self.up4(d5)
+        d4 = self.up_conv4((self.att4(g=d4, x=x3), d4))
+        d3 = self.up3(d4)
+        d3 = self.up_conv3((self.att3(g=d3, x=x2), d3))
+        d2 = self.up2(d3)
+        d2 = self.up_conv2((self.att2(g=d2, x=x1), d2))
+        return d2
+
+    def forward(self, x: torch.Tensor):
+        d2 = self.features(check_image(x))
+        return ops.head(d2, self.out.weight, self.out.bias)    # raw logits, fp32 NCHW

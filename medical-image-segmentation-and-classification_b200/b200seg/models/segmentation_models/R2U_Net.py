@@ -1,0 +1,58 @@
+"""Drop-in for the reference's models/segmentation_models/R2U_Net.py (same file / class / submodule names =>
+identical state_dict keys).  forward() runs the b200seg sm_100a kernels (see b200seg/blocks.py)."""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...blocks import Recurrent_block, RRCNN_block, UpConv, check_image  # noqa: F401  (re-exported names)
+
+
+class R2U_Net(nn.Module):
+    """Recurrent-residual U-Net — reference R2U_Net.py:50-111 (ctor default t=5, R2U_Net.py:51)."""
+
+    def __init__(self, in_channels=3, out_channels=1, t=5):
+        super().__init__()
+        self.max_pool = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.upsample = nn.Upsample(scale_factor=2)
+
+        self.RRCNN1 = RRCNN_block(in_channels=in_channels, out_channels=64, t=t)
+        self.RRCNN2 = RRCNN_block(in_channels=64, out_channels=128, t=t)
+        self.RRCNN3 = RRCNN_block(in_channels=128, out_channels=256, t=t)
+        self.RRCNN4 = RRCNN_block(in_channels=256, out_channels=512, t=t)
+        self.RRCNN5 = RRCNN_block(in_channels=512, out_channels=1024, t=t)
+
+        self.up5 = UpConv(in_channels=1024, out_channels=512)
+        self.up_RRCNN5 = RRCNN_block(in_channels=1024, out_channels=512, t=t)
+        self.up4 = UpConv(in_channels=512, out_channels=256)
+        self.up_RRCNN4 = RRCNN_block(in_channels=512, out_channels=256, t=t)
+        self.up3 = UpConv(in_channels=256, out_channels=128)
+        self.up_RRCNN3 = RRCNN_block(in_channels=256, out_channels=128, t=t)
+        self.up2 = UpConv(in_channels=128, out_channels=64)
+        self.up_RRCNN2 = RRCNN_block(in_channels=128, out_channels=64, t=t)
+
+        self.conv_1x1 = nn.Conv2d(64, out_channels, kernel_size=1, stride=1, padding=0)
+
+    def _skip(self, lvl, d, skip):
+        return skip
+
+    def features(self, x: torch.Tensor):
+        pool = ops.maxpool2x2
+        x1 = self.RRCNN1._internal(x if self.RRCNN1.conv_1x1.in_channels <= 4 else ops.to_nhwc(x))
+        x2 = self.RRCNN2(pool(x1))
+        x3 = self.RRCNN3(pool(x2))
+        x4 = self.RRCNN4(pool(x3))
+        x5 = self.RRCNN5(pool(x4))
+
+        d5 = self.up5(x5)
+        d5 = self.up_RRCNN5((self._skip(5, d5, x4), d5))     # cat((x4, d5), dim=1) — R2U_Net.py:94
+        d4 = self.up4(d5)
+        d4 = self.up_RRCNN4((self._skip(4, d4, x3), d4))
+        d3 = self.up3(d4)
+        d3 = self.up_RRCNN3((self._skip(3, d3, x2), d3))
+        d2 = self.up2(d3)
+        d2 = self.up_RRCNN2((self._skip(2, d2, x1), d2))
+        return d2
+
+    def forward(self, x):
+        d2 = self.features(check_image(x))
+        return ops.head(d2, self.conv_1x1.weight, self.conv_1x1.bias)

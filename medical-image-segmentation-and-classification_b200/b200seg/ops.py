@@ -1,0 +1,420 @@
+"""torch.library custom ops (namespace `b200seg`) with autograd, built on the C ABI wrappers in kernels.py.
+
+Internal activation format: NHWC bf16 tensors [N, H, W, C].  Parameters stay ordinary fp32 nn.Parameters in the
+reference's shapes; weights are re-packed to bf16 MMA layouts inside the ops (a few MB per step).
+
+Each op cites the reference lines whose ATen dispatch it replaces.  There is no fallback: every op launches
+kernels of libb200seg.so or raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.library import custom_op
+
+from . import kernels as K
+
+_F64 = torch.float64
+
+
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    return t if t is None or t.is_contiguous() else t.contiguous()
+
+
+def _dw_as_param_grad(dw: Tensor, weight: Tensor) -> Tensor:
+    """[Cout, taps, Cin] fp32 -> logical [Cout, Cin, k, k] (channels_last memory, zero copy)."""
+    cout, cin, k, _ = weight.shape
+    return dw.view(cout, k, k, cin).permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# layout adapters (module boundary; helpers.py:318 hands the model an NCHW fp32 batch)
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::to_nhwc", mutates_args=())
+def to_nhwc(x: Tensor) -> Tensor:
+    return K.to_nhwc_bf16(_c(x))
+
+
+@custom_op("b200seg::to_nchw", mutates_args=())
+def to_nchw(x: Tensor) -> Tensor:
+    return K.to_nchw_f32(_c(x))
+
+
+to_nhwc.register_autograd(lambda ctx, g: to_nchw(_c(g)))
+to_nchw.register_autograd(lambda ctx, g: to_nhwc(_c(g)))
+
+
+@to_nhwc.register_fake
+def _(x):
+    n, c, h, w = x.shape
+    return x.new_empty((n, h, w, c), dtype=torch.bfloat16)
+
+
+@to_nchw.register_fake
+def _(x):
+    n, h, w, c = x.shape
+    return x.new_empty((n, c, h, w), dtype=torch.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# convolution (tcgen05 implicit GEMM): nn.Conv2d 3x3 p1 / 1x1, stride 1
+#   AttentionUNet.py:6,9,20,33,37  R2U_Net.py:10,27,43  ResnetUnet.py:7,10,54 ; x1 = elided torch.cat partner
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::conv2d", mutates_args=())
+def conv2d(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor],
+           want_stats: bool) -> Tuple[Tensor, Tensor]:
+    cout, cin, k, _ = weight.shape
+    wf, _ = K.pack_weights(weight, want_dgrad=False)
+    stats = torch.zeros((2, cout), dtype=_F64, device=x0.device) if want_stats else \
+        torch.empty((0,), dtype=_F64, device=x0.device)
+    y = K.conv_igemm(_c(x0), wf, cout, k, x1=_c(x1), bias=bias, stats=stats if want_stats else None)
+    return y, stats
+
+
+@conv2d.register_fake
+def _(x0, x1, weight, bias, want_stats):
+    n, h, w, _ = x0.shape
+    cout = weight.shape[0]
+    return (x0.new_empty((n, h, w, cout)),
+            x0.new_empty((2, cout) if want_stats else (0,), dtype=_F64))
+
+
+@custom_op("b200seg::conv2d_bwd", mutates_args=())
+def conv2d_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, need_dx0: bool, need_dx1: bool,
+               need_dw: bool, need_db: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """aten::convolution_backward: dgrad (same kernel, flipped/transposed packing), wgrad, bias grad."""
+    cout, cin, k, _ = weight.shape
+    dev = dy.device
+    dy = _c(dy)
+    c0 = x0.shape[3]
+    empty_a = torch.empty((0,), dtype=torch.bfloat16, device=dev)
+    dx0, dx1 = empty_a, empty_a
+    if need_dx0 or need_dx1:
+        _, wd = K.pack_weights(weight, want_dgrad=True)
+        if need_dx0:
+            dx0 = K.conv_igemm(dy, wd, c0, k, row_offset=0, dgrad=True)
+        if need_dx1 and x1 is not None:
+            dx1 = K.conv_igemm(dy, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
+    dw = K.conv_wgrad(dy, _c(x0), k, x1=_c(x1)) if need_dw else torch.empty((0,), device=dev)
+    db = K.channel_sum(dy) if need_db else torch.empty((0,), device=dev)
+    return dx0, dx1, dw, db
+
+
+def _conv2d_setup(ctx, inputs, output):
+    x0, x1, weight, bias, _ = inputs
+    ctx.save_for_backward(x0, x1, weight)
+    ctx.has_bias = bias is not None
+
+
+def _conv2d_backward(ctx, dy, _dstats):
+    x0, x1, weight = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    dx0, dx1, dw, db = conv2d_bwd(dy, x0, x1, weight, need[0], bool(need[1]) and x1 is not None, need[2],
+                                  bool(need[3]) and ctx.has_bias)
+    return (dx0 if need[0] else None,
+            dx1 if (need[1] and x1 is not None) else None,
+            _dw_as_param_grad(dw, weight) if need[2] else None,
+            db if (need[3] and ctx.has_bias) else None,
+            None)
+
+
+conv2d.register_autograd(_conv2d_backward, setup_context=_conv2d_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# image stem: Cin <= 4 direct convolution from the NCHW fp32 batch
+#   AttentionUNet.py:6 (basic_block(3,64) first conv), R2U_Net.py:43 (RRCNN1.conv_1x1, 3 -> 64)
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::stem_conv", mutates_args=())
+def stem_conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], want_stats: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    cout, cin, k, _ = weight.shape
+    x4 = K.image_to_nhwc4(_c(x))
+    y = K.conv_smallc_fprop(x4, K.pack_small_weight(weight), bias, k)
+    if want_stats:
+        stats = torch.zeros((2, cout), dtype=_F64, device=x.device)
+        K.channel_stats(y, stats)
+    else:
+        stats = torch.empty((0,), dtype=_F64, device=x.device)
+    return y, stats, x4
+
+
+@custom_op("b200seg::stem_conv_bwd", mutates_args=())
+def stem_conv_bwd(dy: Tensor, x4: Tensor, weight: Tensor, need_db: bool) -> Tuple[Tensor, Tensor]:
+    cout, cin, k, _ = weight.shape
+    dy = _c(dy)
+    dwk = K.conv_smallc_wgrad(dy, x4, k)                       # [cout, taps, 4]
+    dw = dwk[:, :, :cin].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
+    db = K.channel_sum(dy) if need_db else torch.empty((0,), device=dy.device)
+    return dw, db
+
+
+def _stem_setup(ctx, inputs, output):
+    _, weight, bias, _ = inputs
+    ctx.save_for_backward(output[2], weight)
+    ctx.has_bias = bias is not None
+
+
+def _stem_backward(ctx, dy, _ds, _dx4):
+    x4, weight = ctx.saved_tensors
+    dw, db = stem_conv_bwd(dy, x4, weight, ctx.has_bias)
+    return None, dw, (db if ctx.has_bias else None), None
+
+
+stem_conv.register_autograd(_stem_backward, setup_context=_stem_setup)
+
+
+@stem_conv.register_fake
+def _(x, weight, bias, want_stats):
+    n, _, h, w = x.shape
+    cout = weight.shape[0]
+    return (x.new_empty((n, h, w, cout), dtype=torch.bfloat16),
+            x.new_empty((2, cout) if want_stats else (0,), dtype=_F64),
+            x.new_empty((n, h, w, 4), dtype=torch.bfloat16))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# BatchNorm2d (+ReLU): AttentionUNet.py:7-8,10-11,21-22  R2U_Net.py:11-12,28-29  ResnetUnet.py:8-9,11-12,55-56
+#   bn_finalize_ : statistics -> (mean, invstd, scale, shift); the ONLY op that mutates the running buffers
+#   bn_apply     : functional normalise(+ReLU) with the full BatchNorm backward (dz, dgamma, dbeta)
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::bn_finalize_", mutates_args=("running_mean", "running_var", "num_batches_tracked"))
+def bn_finalize_(stats: Tensor, count: int, gamma: Tensor, beta: Tensor, running_mean: Tensor, running_var: Tensor,
+                 num_batches_tracked: Tensor, training: bool, momentum: float, eps: float) -> Tensor:
+    if training:
+        return K.bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var,
+                             num_batches_tracked)
+    return K.bn_eval_coeffs(gamma, beta, running_mean, running_var, eps)
+
+
+@bn_finalize_.register_fake
+def _(stats, count, gamma, beta, rm, rv, nbt, training, momentum, eps):
+    return gamma.new_empty((4, gamma.shape[0]), dtype=torch.float32)
+
+
+@custom_op("b200seg::bn_apply", mutates_args=())
+def bn_apply(z: Tensor, coef: Tensor, gamma: Tensor, beta: Tensor, relu: bool, training: bool) -> Tensor:
+    return K.bn_apply(_c(z), coef, relu=relu)
+
+
+@bn_apply.register_fake
+def _(z, coef, gamma, beta, relu, training):
+    return torch.empty_like(z)
+
+
+@custom_op("b200seg::bn_apply_bwd", mutates_args=())
+def bn_apply_bwd(dy: Tensor, z: Tensor, coef: Tensor, gamma: Tensor, relu: bool,
+                 training: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    return K.bn_bwd(_c(dy), z, coef, gamma, relu=relu, training=training)
+
+
+def _bn_setup(ctx, inputs, output):
+    z, coef, gamma, _beta, ctx.relu, ctx.training = inputs
+    ctx.save_for_backward(_c(z), coef, gamma)
+
+
+def _bn_backward(ctx, dy):
+    z, coef, gamma = ctx.saved_tensors
+    dz, dgamma, dbeta = bn_apply_bwd(dy, z, coef, gamma, ctx.relu, ctx.training)
+    return dz, None, dgamma, dbeta, None, None
+
+
+bn_apply.register_autograd(_bn_backward, setup_context=_bn_setup)
+
+
+def batch_norm_act(z: Tensor, stats: Tensor, bn: torch.nn.BatchNorm2d, relu: bool) -> Tensor:
+    """nn.BatchNorm2d(+ReLU) on a conv output whose epilogue already produced `stats`."""
+    n, h, w, _ = z.shape
+    training = bn.training or bn.running_mean is None
+    coef = bn_finalize_(stats.detach(), n * h * w, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                        bn.num_batches_tracked, training, float(bn.momentum), float(bn.eps))
+    return bn_apply(z, coef, bn.weight, bn.bias, relu, training)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# pooling / upsampling / add
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::maxpool2x2", mutates_args=())
+def maxpool2x2(x: Tensor) -> Tensor:
+    """nn.MaxPool2d(2, 2): AttentionUNet.py:61, R2U_Net.py:54"""
+    return K.maxpool_fwd(_c(x))
+
+
+@custom_op("b200seg::maxpool2x2_bwd", mutates_args=())
+def maxpool2x2_bwd(dy: Tensor, x: Tensor) -> Tensor:
+    return K.maxpool_bwd(_c(dy), x)
+
+
+maxpool2x2.register_autograd(lambda ctx, dy: maxpool2x2_bwd(dy, ctx.saved_tensors[0]),
+                             setup_context=lambda ctx, inputs, output: ctx.save_for_backward(_c(inputs[0])))
+
+
+@maxpool2x2.register_fake
+def _(x):
+    n, h, w, c = x.shape
+    return x.new_empty((n, h // 2, w // 2, c))
+
+
+@custom_op("b200seg::upsample2x", mutates_args=())
+def upsample2x(x: Tensor) -> Tensor:
+    """nn.Upsample(scale_factor=2) (nearest): AttentionUNet.py:18, R2U_Net.py:25"""
+    return K.upsample_fwd(_c(x))
+
+
+@custom_op("b200seg::upsample2x_bwd", mutates_args=())
+def upsample2x_bwd(dy: Tensor) -> Tensor:
+    return K.upsample_bwd(_c(dy))
+
+
+upsample2x.register_autograd(lambda ctx, dy: upsample2x_bwd(dy))
+
+
+@upsample2x.register_fake
+def _(x):
+    n, h, w, c = x.shape
+    return x.new_empty((n, 2 * h, 2 * w, c))
+
+
+@custom_op("b200seg::add", mutates_args=())
+def add(a: Tensor, b: Tensor) -> Tensor:
+    """x + x1 on activations: R2U_Net.py:19,48"""
+    return K.add(_c(a), _c(b))
+
+
+add.register_autograd(lambda ctx, g: (g, g))
+
+
+@add.register_fake
+def _(a, b):
+    return torch.empty_like(a)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# attention gate, everything after the two 1x1 GEMMs: AttentionUNet.py:48-54 / R2AttU_Net.py:80-86
+# (functional: psi.1's running statistics are updated by the caller from the returned qstats)
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::gate_mid", mutates_args=())
+def gate_mid(g1p: Tensor, x1p: Tensor, x: Tensor, coef_g: Tensor, coef_x: Tensor,
+             gamma_g: Tensor, beta_g: Tensor, gamma_x: Tensor, beta_x: Tensor,
+             wpsi: Tensor, bpsi: Tensor, gamma_1: Tensor, beta_1: Tensor, rm_1: Tensor, rv_1: Tensor,
+             training: bool, eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    n, h, w, fint = g1p.shape
+    q, qstats = K.gate_psi_fwd(_c(g1p), _c(x1p), coef_g, coef_x, wpsi, bpsi)
+    if training:
+        coef_1 = K.bn_finalize(qstats, n * h * w, gamma_1, beta_1, eps, 0.0, None, None, None)
+    else:
+        coef_1 = K.bn_eval_coeffs(gamma_1, beta_1, rm_1, rv_1, eps)
+    out, psi = K.gate_apply_fwd(_c(x), q, coef_1)
+    return out, q, psi, coef_1, qstats
+
+
+@gate_mid.register_fake
+def _(g1p, x1p, x, *rest):
+    n, h, w, fint = g1p.shape
+    return (torch.empty_like(x), x.new_empty((n, h, w)), x.new_empty((n, h, w)),
+            x.new_empty((4, 1), dtype=torch.float32), x.new_empty((2,), dtype=_F64))
+
+
+@custom_op("b200seg::gate_mid_bwd", mutates_args=())
+def gate_mid_bwd(dout: Tensor, x: Tensor, psi: Tensor, q: Tensor, g1p: Tensor, x1p: Tensor, coef_g: Tensor,
+                 gamma_g: Tensor, coef_x: Tensor, gamma_x: Tensor, coef_1: Tensor, gamma_1: Tensor, wpsi: Tensor,
+                 training: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    dx, dsig, sums1 = K.gate_apply_bwd(_c(dout), x, psi, q, coef_1)
+    dg1p, dx1p, dgb, dbn1, dwpsi, dbpsi = K.gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x,
+                                                         coef_1, gamma_1, wpsi, training=training)
+    return dg1p, dx1p, dx, dgb, dbn1, dwpsi, dbpsi
+
+
+def _gate_setup(ctx, inputs, output):
+    (g1p, x1p, x, coef_g, coef_x, gamma_g, _bg, gamma_x, _bx, wpsi, _bpsi, gamma_1, _b1, _rm1, _rv1, training,
+     _eps) = inputs
+    out, q, psi, coef_1, _qstats = output
+    ctx.save_for_backward(_c(x), psi, q, _c(g1p), _c(x1p), coef_g, gamma_g, coef_x, gamma_x, coef_1, gamma_1, wpsi)
+    ctx.training = training
+
+
+def _gate_backward(ctx, dout, *_unused):
+    x, psi, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coef_1, gamma_1, wpsi = ctx.saved_tensors
+    dg1p, dx1p, dx, dgb, dbn1, dwpsi, dbpsi = gate_mid_bwd(dout, x, psi, q, g1p, x1p, coef_g, gamma_g, coef_x,
+                                                           gamma_x, coef_1, gamma_1, wpsi, ctx.training)
+    return (dg1p, dx1p, dx, None, None,
+            dgb[0], dgb[1], dgb[2], dgb[3],
+            dwpsi.view_as(wpsi), dbpsi, dbn1[0:1], dbn1[1:2], None, None,
+            None, None)
+
+
+gate_mid.register_autograd(_gate_backward, setup_context=_gate_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# 1x1 heads -> fp32 NCHW logits: AttentionUNet.py:84,119  R2U_Net.py:76,109  ResnetUnet.py:58,81
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::head", mutates_args=())
+def head(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    cout, cin = weight.shape[0], weight.shape[1]
+    return K.head_fwd(_c(x), weight.reshape(cout, cin).contiguous(), bias)
+
+
+@head.register_fake
+def _(x, weight, bias):
+    n, h, w, _ = x.shape
+    return x.new_empty((n, weight.shape[0], h, w), dtype=torch.float32)
+
+
+@custom_op("b200seg::head_bwd", mutates_args=())
+def head_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    cout, cin = weight.shape[0], weight.shape[1]
+    dx, dw, db = K.head_bwd(_c(dy), _c(x), weight.reshape(cout, cin).contiguous(), need_dx=need_dx)
+    if dx is None:
+        dx = torch.empty((0,), dtype=torch.bfloat16, device=dy.device)
+    return dx, dw.view(weight.shape), db
+
+
+def _head_setup(ctx, inputs, output):
+    x, weight, bias = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.has_bias = bias is not None
+
+
+def _head_backward(ctx, dy):
+    x, weight = ctx.saved_tensors
+    dx, dw, db = head_bwd(dy, x, weight, ctx.needs_input_grad[0])
+    return (dx if ctx.needs_input_grad[0] else None), dw, (db if ctx.has_bias else None)
+
+
+head.register_autograd(_head_backward, setup_context=_head_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# loss: BCEWithLogits (helpers.py:245,327) and w_bce*BCE + w_dice*Dice (clip_seg_finetuner.py:61-74)
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::seg_loss", mutates_args=())
+def seg_loss(logits: Tensor, target: Tensor, w_bce: float, w_dice: float, smooth: float) -> Tuple[Tensor, Tensor]:
+    """-> (scalar loss fp32, sums fp64[6]); sums[4], sums[5] are the IoU intersection / union counts."""
+    return K.loss_fwd(_c(logits.float()), _c(target.float()), w_bce, w_dice, smooth)
+
+
+@seg_loss.register_fake
+def _(logits, target, w_bce, w_dice, smooth):
+    return logits.new_empty((), dtype=torch.float32), logits.new_empty((6,), dtype=_F64)
+
+
+@custom_op("b200seg::seg_loss_bwd", mutates_args=())
+def seg_loss_bwd(grad_out: Tensor, logits: Tensor, target: Tensor, sums: Tensor, w_bce: float, w_dice: float,
+                 smooth: float) -> Tensor:
+    return K.loss_bwd(_c(logits.float()), _c(target.float()), sums, _c(grad_out.float()), w_bce, w_dice, smooth)
+
+
+def _loss_setup(ctx, inputs, output):
+    logits, target, ctx.w_bce, ctx.w_dice, ctx.smooth = inputs
+    ctx.save_for_backward(logits, target, output[1])
+
+
+def _loss_backward(ctx, g, _gs):
+    logits, target, sums = ctx.saved_tensors
+    dz = seg_loss_bwd(g, logits, target, sums, ctx.w_bce, ctx.w_dice, ctx.smooth)
+    return dz.view_as(logits), None, None, None, None
+
+
+seg_loss.register_autograd(_loss_backward, setup_context=_loss_setup)

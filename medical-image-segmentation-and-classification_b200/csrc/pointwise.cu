@@ -263,3 +263,67 @@ extern "C" int b2_nchw_f32_to_nhwc_bf16(const float* x, int32_t n, int32_t c, in
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// general layout adapters at the module boundary: NCHW fp32 <-> NHWC bf16 (32x32 smem tile transpose)
+// ------------------------------------------------------------------------------------------------------------
+namespace b2 {
+// x [n][c][hw] fp32 -> y [n][hw][ldy] bf16
+__global__ void nchw2nhwc_tile_kernel(const float* __restrict__ x, int c, long long hw, __nv_bfloat16* __restrict__ y,
+                                      int ldy) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (ch < c && p < hw) ? x[(b * c + ch) * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int ch = c0 + threadIdx.x;
+    if (p < hw && ch < c) y[(b * hw + p) * ldy + ch] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+// x [n][hw][ldx] bf16 -> y [n][c][hw] fp32
+__global__ void nhwc2nchw_tile_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int c, long long hw,
+                                      float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long p = p0 + i;
+    const int ch = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < hw && ch < c) ? __bfloat162float(x[(b * hw + p) * ldx + ch]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int ch = c0 + i;
+    const long long p = p0 + threadIdx.x;
+    if (ch < c && p < hw) y[(b * c + ch) * hw + p] = tile[threadIdx.x][i];
+  }
+}
+}  // namespace b2
+
+extern "C" int b2_layout_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* y,
+                                      int32_t ldy, b2_stream_t stream) {
+  B2_REQUIRE(n > 0 && c > 0 && ldy >= c, B2_ERR_SHAPE, "bad layout conversion extent");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  b2::nchw2nhwc_tile_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, c, hw, (__nv_bfloat16*)y, ldy);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_layout_nhwc_to_nchw(const void* x, int32_t ldx, int32_t n, int32_t c, int32_t h, int32_t w,
+                                      float* y, b2_stream_t stream) {
+  B2_REQUIRE(n > 0 && c > 0 && ldx >= c, B2_ERR_SHAPE, "bad layout conversion extent");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
+  b2::nhwc2nchw_tile_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, c, hw, y);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

@@ -1,0 +1,144 @@
+"""ORACLE pinning — run ONLY in the build container, where the reference is importable from /root/reference:
+
+    python oracle/make_golden.py
+
+Imports the UNMODIFIED reference modules (models/segmentation_models/*.py), gives them the deterministic weights of
+oracle/synthetic.py, runs forward + BCEWithLogits + backward in fp64 (train and eval mode) and stores small golden
+vectors under tests/golden/.  AST-extracts `iou` from utils/helpers.py and `DiceLoss`/`CombinedLoss` from
+utils/clip_seg_finetuner.py (those files import matplotlib / albumentations at module level and cannot be imported
+here) and stores their values on fixed inputs.  tests/test_oracle_golden.py checks oracle/unet_oracle.py against
+these files on every CPU run; the GPU box never needs /root/reference.
+"""
+import ast
+import importlib
+import os
+import sys
+from collections import OrderedDict
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = Path(os.environ.get("B200SEG_REFERENCE", "/root/reference"))
+sys.path.insert(0, str(ROOT))
+from oracle.synthetic import fill_state_dict_, noise_batch, xray_batch  # noqa: E402
+
+SEED = 7
+CASES = {
+    # name: (module, class, ctor kwargs, batch, side)
+    "AttentionUNet": ("models.segmentation_models.AttentionUNet", "AttentionUNet", {}, 2, 32),
+    "R2U_Net": ("models.segmentation_models.R2U_Net", "R2U_Net", {"t": 2}, 2, 32),
+    "R2AttU_Net": ("models.segmentation_models.R2AttU_Net", "R2AttU_Net", {"t": 2}, 2, 32),
+    "R2U_Net_t5": ("models.segmentation_models.R2U_Net", "R2U_Net", {}, 2, 32),
+    "ResNetUnet": ("models.segmentation_models.ResnetUnet", "ResNetUnet", {}, 2, 64),
+}
+
+
+def _ast_extract(path, names, glb):
+    tree = ast.parse(Path(path).read_text(encoding="utf-8"))
+    body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
+    exec(compile(ast.Module(body=body, type_ignores=[]), str(path), "exec"), glb)
+    return glb
+
+
+def build_reference(case):
+    sys.path.insert(0, str(REF))
+    mod_name, cls_name, kw, _, _ = CASES[case]
+    if cls_name == "ResNetUnet":
+        import torchvision.models as tvm
+        orig = tvm.resnet50
+        tvm.resnet50 = lambda weights=None, **k: orig(weights=None, **k)   # pretrained download fails offline
+        try:
+            mod = importlib.import_module(mod_name)
+            m = getattr(mod, cls_name)(**kw)
+        finally:
+            tvm.resnet50 = orig
+    else:
+        mod = importlib.import_module(mod_name)
+        m = getattr(mod, cls_name)(**kw)
+    return m
+
+
+def golden_for(case):
+    _, _, kw, n, side = CASES[case]
+    m = build_reference(case)
+    fill_state_dict_(m.state_dict(), SEED)
+    m = m.double()
+    x, t = xray_batch(n, side, side, seed=11)
+    x, t = x.double(), t.double()
+    out = OrderedDict()
+    sd0 = OrderedDict((k, v.detach().clone()) for k, v in m.state_dict().items())
+    out["keys"] = np.array(list(sd0.keys()))
+    out["shapes"] = np.array([",".join(map(str, v.shape)) for v in sd0.values()])
+    out["dtypes"] = np.array([str(v.dtype).replace("torch.", "") for v in sd0.values()])
+    out["requires_grad"] = np.array([int(p.requires_grad) for p in m.parameters()])
+    out["param_names"] = np.array([k for k, _ in m.named_parameters()])
+    # eval forward
+    m.eval()
+    with torch.no_grad():
+        out["eval_logits"] = m(x).numpy()
+    # train forward + BCEWithLogits + backward (utils/helpers.py:244-246, 322-329 without AMP)
+    m.load_state_dict(sd0)
+    m.train()
+    logits = m(x)
+    loss = nn.BCEWithLogitsLoss()(logits, t)
+    loss.backward()
+    out["train_logits"] = logits.detach().numpy()
+    out["train_loss"] = np.array(float(loss))
+    names, norms = [], []
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k)
+        norms.append(float(p.grad.norm()))
+        if p.grad.numel() <= 4096:
+            out["grad::" + k] = p.grad.numpy()
+        else:
+            out["gradhead::" + k] = p.grad.reshape(-1)[:256].numpy()
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms)
+    sd1 = m.state_dict()
+    bn_keys = [k for k in sd1 if k.endswith("num_batches_tracked")]
+    out["nbt_names"] = np.array(bn_keys)
+    out["nbt"] = np.array([int(sd1[k]) for k in bn_keys])
+    rm_keys = [k for k in sd1 if k.endswith(("running_mean", "running_var"))]
+    out["running_names"] = np.array(rm_keys)
+    out["running_norms"] = np.array([float(sd1[k].norm()) for k in rm_keys])
+    return out
+
+
+def golden_losses():
+    g = {"torch": torch, "nn": nn}
+    _ast_extract(REF / "utils" / "clip_seg_finetuner.py", {"DiceLoss", "CombinedLoss"}, g)
+    _ast_extract(REF / "utils" / "helpers.py", {"iou", "acc"}, g)
+    z, t = noise_batch(3, 32, 32, seed=5)
+    z = (z[:, :1] * 2.0).double()
+    t = t.double()
+    out = OrderedDict()
+    out["z"] = z.numpy()
+    out["t"] = t.numpy()
+    out["bce"] = np.array(float(nn.BCEWithLogitsLoss()(z, t)))
+    out["dice"] = np.array(float(g["DiceLoss"]()(z, t)))
+    out["combined"] = np.array(float(g["CombinedLoss"]()(z, t)))
+    zz = z.clone().requires_grad_(True)
+    g["CombinedLoss"]()(zz, t).backward()
+    out["combined_grad"] = zz.grad.numpy()
+    out["iou"] = np.array(float(g["iou"](torch.sigmoid(z), t)))
+    return out
+
+
+def main():
+    dst = ROOT / "tests" / "golden"
+    dst.mkdir(parents=True, exist_ok=True)
+    torch.manual_seed(0)
+    for case in CASES:
+        np.savez_compressed(dst / f"{case}.npz", **golden_for(case))
+        print("wrote", case, flush=True)
+    np.savez_compressed(dst / "losses.npz", **golden_losses())
+    print("wrote losses")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""GPU parity, levels (ii)-(iv) of the pyramid: the drop-in modules (CUDA path through the C ABI)
+against the oracle restatement of the reference on identical weights and inputs.
+
+Tolerances (north_star): forward logits <= 1e-2 rel-L2, weight gradients <= 2e-2, in bf16 — attainable end-to-end
+with BatchNorm in eval mode and for block forwards in train mode.  End-to-end train-mode BatchNorm at random init
+is chaotic (the reference's OWN bf16 autocast deviates 0.27+ from fp64), so there the CUDA
+path is required to be no worse than ~1.25x the reference's own bf16 deviation measured in the same run."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _models():
+    from b200seg.models.segmentation_models import AttentionUNet, R2AttU_Net, R2U_Net
+    return {"AttentionUNet": (AttentionUNet, {}), "R2U_Net": (R2U_Net, {"t": 2}), "R2AttU_Net": (R2AttU_Net, {"t": 2})}
+
+
+def _setup(name, seed=0, init="synthetic"):
+    """init='synthetic': oracle/synthetic.py fill (non-trivial BN affine + running stats, He-normal convs);
+    init='default': PyTorch default init under torch.manual_seed(seed) — the reference's own 'random init'."""
+    from oracle.synthetic import fill_state_dict_
+    cls, kw = _models()[name]
+    torch.manual_seed(seed)
+    m = cls(**kw)
+    if init == "synthetic":
+        fill_state_dict_(m.state_dict(), seed)      # state_dict tensors alias the parameters
+    return m.cuda(), kw
+
+
+def _oracle_sd(m, dtype):
+    return {k: (v.detach().to(dtype) if v.is_floating_point() else v.detach().clone()) for k, v in m.state_dict().items()}
+
+
+def _autocast_step(O, name, sd32, x, t, training, kw):
+    """reference path at its own reduced precision: bf16 autocast forward, fp32 loss (helpers.py:321-329)"""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd32.items()
+              if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    work = {**sd32, **params}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits, _ = O.FORWARDS[name](work, x, training=training, **kw)
+    loss = O.bce_with_logits(logits.float(), t)
+    grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+    return logits.detach(), loss.detach(), dict(zip(params.keys(), grads)), None
+
+
+def _is_pre_bn_bias(name):
+    # conv biases that feed a BatchNorm have an exactly-zero true gradient -> abs tolerance
+    return name.endswith(".bias") and (".0.bias" in name or ".3.bias" in name or "up.1.bias" in name
+                                       or "conv.0.bias" in name)
+
+
+@pytest.mark.parametrize("init", ["default", "synthetic"])
+@pytest.mark.parametrize("name", ["AttentionUNet", "R2U_Net", "R2AttU_Net"])
+def test_eval_mode_forward_and_grads(name, init):
+    """Level (iii): end-to-end with BatchNorm in eval mode.  With the reference's own random init the north_star
+    gates hold absolutely (logits 1e-2, global weight-grad 2e-2).  With the harsher synthetic fill (He-normal convs,
+    no re-normalisation in eval mode) the gate is relative to the reference's own bf16-autocast deviation."""
+    from oracle import unet_oracle as O
+    from oracle.synthetic import xray_batch
+    from b200seg import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, kw = _setup(name, init=init)
+    m.eval()
+    x, t = xray_batch(2, 128, 128, seed=3, device="cuda")
+    logits = m(x)
+    loss, _ = ops.seg_loss(logits, t, 1.0, 0.0, 1.0)
+    loss.backward()
+    sd = _oracle_sd(m, torch.float64)
+    ref_logits, ref_loss, ref_grads, _ = O.train_step_grads(name, sd, x.double(), t.double(), training=False, **kw)
+    e = rel(logits, ref_logits)
+    # the reference's own reduced-precision deviation on the same weights/inputs (autocast bf16, as helpers.py:321)
+    sd32 = _oracle_sd(m, torch.float32)
+    fl_logits, fl_loss, fl_grads, _ = _autocast_step(O, name, sd32, x, t, False, kw)
+    e_floor = rel(fl_logits.float(), ref_logits)
+    print(f"{name}/{init} eval logits rel: ours {e:.3e}  reference-bf16 {e_floor:.3e}  "
+          f"loss {float(loss):.6f} vs {float(ref_loss):.6f}")
+    tol_fwd = 1e-2 if init == "default" else max(1e-2, 1.25 * e_floor)
+    assert e < tol_fwd
+    assert abs(float(loss) - float(ref_loss)) < 1e-2 * abs(float(ref_loss))
+    params = dict(m.named_parameters())
+    num = den = 0.0
+    worst = (0.0, None)
+    for k, g in ref_grads.items():
+        if g is None:
+            continue
+        mine = params[k].grad
+        assert mine is not None, k
+        num += float((mine.double() - g).norm() ** 2)
+        den += float(g.norm() ** 2)
+        r = rel(mine, g)
+        if float(g.norm()) > 1e-6 and r > worst[0]:
+            worst = (r, k)
+    glob = (num / den) ** 0.5
+    fnum = sum(float((fl_grads[k].double() - g).norm() ** 2) for k, g in ref_grads.items() if g is not None)
+    gfloor = (fnum / den) ** 0.5
+    print(f"{name}/{init} eval global weight-grad rel: ours {glob:.3e}  reference-bf16 {gfloor:.3e}; "
+          f"worst tensor {worst}")
+    assert glob < (2e-2 if init == "default" else max(2e-2, 1.25 * gfloor))
+
+
+@pytest.mark.parametrize("name", ["AttentionUNet", "R2U_Net", "R2AttU_Net"])
+def test_train_mode_vs_reference_noise_floor(name):
+    from oracle import unet_oracle as O
+    from oracle.synthetic import xray_batch
+    from b200seg import ops
+    m, kw = _setup(name, seed=1)
+    m.train()
+    x, t = xray_batch(2, 128, 128, seed=4, device="cuda")
+    sd64 = _oracle_sd(m, torch.float64)
+    sd32 = _oracle_sd(m, torch.float32)
+    nbt0 = {k: int(v) for k, v in m.state_dict().items() if k.endswith("num_batches_tracked")}
+    logits = m(x)
+    loss, _ = ops.seg_loss(logits, t, 1.0, 0.0, 1.0)
+    loss.backward()
+    ref, ref_loss, ref_grads, newb = O.train_step_grads(name, sd64, x.double(), t.double(), training=True, **kw)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        floor_logits, _ = O.FORWARDS[name](sd32, x, training=True, **kw)
+    e_mine, e_floor = rel(logits, ref), rel(floor_logits.float(), ref)
+    print(f"{name} train logits: ours {e_mine:.3e}  reference-bf16-autocast {e_floor:.3e}")
+    assert e_mine < max(1.25 * e_floor, 2e-2)
+    # side effects: running statistics and call counts (t+1 updates per Recurrent_block forward)
+    msd = m.state_dict()
+    for k, v in newb.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(msd[k]) == int(v), k
+    rm_err = max(rel(msd[k], v) for k, v in newb.items() if k.endswith("running_var"))
+    print(f"{name} running_var worst rel {rm_err:.3e}")
+    assert rm_err < max(1.25 * e_floor, 2e-2)
