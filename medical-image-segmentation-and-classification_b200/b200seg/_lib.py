@@ -123,7 +123,14 @@ def check(rc: int, what: str = "") -> None:
                       f"{msg.decode() if msg else ''}")
 
 
+# kernels launched per entry point (for bench.py's `gpu_launches` claim); entries not listed launch one kernel
+LAUNCHES_PER_CALL = {"b2_conv_wgrad": 2, "b2_channel_sum": 1}
+launch_count = 0
+
+
 def call(name: str, *args):
     """Call an int-returning entry point and raise on a non-zero code."""
+    global launch_count
     rc = getattr(load(), name)(*args)
     check(rc, name)
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)

@@ -1,0 +1,101 @@
+"""Data-parallel gradient exchange: bucketed all-reduce overlapped with backward.
+
+The reference is single-device; BASELINE.json's north_star adds plain data parallelism: the batch
+is sharded across ranks, BatchNorm statistics stay local per rank (ordinary nn.BatchNorm2d semantics), weights and
+optimizer state are replicated and the only exchange step is the average of the gradients.
+
+Parameters are grouped into flat fp32 buckets in reverse registration order (the order gradients become ready:
+head first, stem last).  A post-accumulate-grad hook packs each gradient into its bucket and, when the bucket is
+complete, launches an asynchronous all-reduce (NCCL over NVLink on the GPUs, gloo in the CPU tests) that overlaps
+the rest of backward.  `finish()` waits and writes the averaged gradients back.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+class _Bucket:
+    def __init__(self, params: List[torch.nn.Parameter], device):
+        self.params = params
+        self.offsets = []
+        off = 0
+        for p in params:
+            self.offsets.append(off)
+            off += p.numel()
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.pending = len(params)
+        self.work = None
+
+    def view(self, i):
+        p = self.params[i]
+        return self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
+
+
+class GradReducer:
+    """Usage:  reducer = GradReducer(model); ...; loss.backward(); reducer.finish(); optimizer.step()"""
+
+    def __init__(self, model: torch.nn.Module, bucket_mb: float = 32.0, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("GradReducer needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.avg_native = dist.get_backend(group) == "nccl"
+        params = [p for p in model.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("model has no trainable parameters")
+        device = params[0].device
+        cap = int(bucket_mb * (1 << 20) / 4)
+        self.buckets: List[_Bucket] = []
+        cur, size = [], 0
+        for p in reversed(params):
+            cur.append(p)
+            size += p.numel()
+            if size >= cap:
+                self.buckets.append(_Bucket(cur, device))
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(_Bucket(cur, device))
+        self._where = {}
+        self._handles = []
+        for b in self.buckets:
+            for i, p in enumerate(b.params):
+                self._where[p] = (b, i)
+                self._handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def _hook(self, p):
+        b, i = self._where[p]
+        b.view(i).copy_(p.grad)
+        b.pending -= 1
+        if b.pending == 0:
+            op = dist.ReduceOp.AVG if self.avg_native else dist.ReduceOp.SUM
+            b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+
+    def finish(self):
+        """Wait for every bucket and store the averaged gradients into param.grad."""
+        for b in self.buckets:
+            if b.pending != 0:
+                # parameters that received no gradient this step (unused branch): reduce what we have
+                for i, p in enumerate(b.params):
+                    if p.grad is None:
+                        b.view(i).zero_()
+                op = dist.ReduceOp.AVG if self.avg_native else dist.ReduceOp.SUM
+                b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+        for b in self.buckets:
+            b.work.wait()
+            if not self.avg_native:
+                b.flat.div_(self.world)
+            for i, p in enumerate(b.params):
+                if p.grad is None:
+                    p.grad = b.view(i).clone()
+                else:
+                    p.grad.copy_(b.view(i))
+            b.pending = len(b.params)
+            b.work = None
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

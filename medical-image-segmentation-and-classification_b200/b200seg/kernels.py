@@ -16,6 +16,26 @@ from ._lib import ConvArgs, GateCoef, WgradArgs, call
 BF16 = torch.bfloat16
 
 
+# Optional per-launch timing hook used by bench.py's roofline pass: when set to a list, the tensor-core
+# convolution wrappers append (kind, flops, start_event, end_event) recorded on the launching stream.
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(kind, flops, start):
+    if start is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        PROFILE.append((kind, flops, start, end))
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -88,7 +108,9 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
         assert stats.dtype == torch.float64 and stats.numel() == 2 * cout
         a.stats = stats.data_ptr()
     a.relu = int(relu)
+    t0 = _prof_begin()
     call("b2_conv_dgrad" if dgrad else "b2_conv_fprop", C.byref(a), _stream())
+    _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0)
     return y
 
 
@@ -114,7 +136,9 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False):
         _lib.check(int(need), "b2_conv_wgrad_workspace")
     ws = torch.empty(int(need), dtype=torch.uint8, device=dy.device)
     a.workspace, a.workspace_bytes = ws.data_ptr(), int(need)
+    t0 = _prof_begin()
     call("b2_conv_wgrad", C.byref(a), _stream())
+    _prof_end("conv_wgrad", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0)
     return dw
 
 

@@ -1,0 +1,114 @@
+"""Mirror of the segmentation half of the reference's utils/helpers.py: get_seg_model / iou / train with the same
+names, argument meaning, prints, checkpoint names and return value, driving the b200seg modules.
+
+Differences from the reference, all forced by the B200 path and listed in DESIGN.md:
+  * compute precision is bf16 inside the kernels, so the fp16 GradScaler of helpers.py:285 is not needed (bf16 has
+    fp32's exponent range); the autocast context is not used either — the modules always run bf16;
+  * the loss is the fused b200seg::seg_loss op (BCEWithLogits, helpers.py:245), which also yields the IoU counts,
+    so validation does not launch per-sample reductions (iou() below is kept for API compatibility);
+  * only `seg=True` is supported (the classification branch, helpers.py:257-283, is outside the hot path).
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import torch
+
+from .. import ops
+
+
+def get_seg_model(name):
+    """helpers.py:195-213 — same names, default constructors (=> t=5 for the R2 models, frozen ResNet encoder)."""
+    from ..models.segmentation_models import AttentionUNet, R2AttU_Net, R2U_Net
+
+    name_lower = name.lower()
+    if name_lower == "resnetunet":
+        from ..models.segmentation_models import ResnetUnet
+        return ResnetUnet.ResNetUnet()
+    elif name_lower == "attentionunet":
+        return AttentionUNet()
+    elif name_lower == "r2unet":
+        return R2U_Net()
+    elif name_lower == "r2attunet":
+        return R2AttU_Net()
+    raise ValueError(f"Unknown segmentation model: {name}")
+
+
+def iou(pred, mask, t=0.5):
+    """helpers.py:223-227 (host-syncing, per call) — kept for drop-in use; train() uses the fused counts."""
+    p = (pred > t).float()
+    inter = (p * mask).sum()
+    union = ((p + mask) > 0).float().sum()
+    return (inter / (union + 1e-7)).item()
+
+
+def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False, cls_head_name=None,
+          reducer=None, log=print):
+    """helpers.py:231-412, segmentation branch.  Returns the best validation loss."""
+    if not seg:
+        raise NotImplementedError("b200seg.train covers the segmentation path only (seg=True)")
+    device = torch.device(device)
+    model = model.to(device, memory_format=torch.channels_last)            # helpers.py:243
+    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=5e-4,
+                                  fused=(device.type == "cuda"))           # helpers.py:251
+    log(f"Training Segmentation model (all layers unfrozen) with LR: {lr}")
+    scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=epochs)   # helpers.py:254
+    best_score = float("inf")
+    patience, patience_counter = 10, 0
+    params = [p for p in model.parameters() if p.requires_grad]
+    start_time = time.time()
+
+    for epoch in range(1, epochs + 1):
+        model.train()
+        running = torch.zeros((), dtype=torch.float64, device=device)     # no per-step .item() (helpers.py:337)
+        seen = 0
+        for x, y in train_dl:
+            x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+            optimizer.zero_grad(set_to_none=True)
+            out = model(x)
+            if out.dim() == 3:
+                out = out.unsqueeze(1)
+            loss, _ = ops.seg_loss(out, y, 1.0, 0.0, 1.0)
+            loss.backward()
+            if reducer is not None:
+                reducer.finish()
+            torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)          # helpers.py:333
+            optimizer.step()
+            running += loss.detach().double() * x.size(0)
+            seen += x.size(0)
+
+        model.eval()
+        val_loss = torch.zeros((), dtype=torch.float64, device=device)
+        val_iou = torch.zeros((), dtype=torch.float64, device=device)
+        n_val, n_batches = 0, 0
+        with torch.no_grad():
+            for x, y in val_dl:
+                x, y = x.to(device), y.to(device)
+                out = model(x)
+                if out.dim() == 3:
+                    out = out.unsqueeze(1)
+                loss, sums = ops.seg_loss(out, y, 1.0, 0.0, 1.0)
+                val_loss += loss.double() * x.size(0)
+                val_iou += sums[4] / (sums[5] + 1e-7)                     # helpers.py:223-227 per batch
+                n_val += x.size(0)
+                n_batches += 1
+        val_loss = float(val_loss) / max(n_val, 1)
+        val_iou_f = float(val_iou) / max(n_batches, 1)
+        log(f"[{name}] Ep{epoch}: TrainLoss {float(running) / max(seen, 1):.3f} | ValLoss {val_loss:.3f} | "
+            f"IoU {val_iou_f:.3f}")
+        improved = val_loss < best_score
+        scheduler.step()
+        if improved:
+            best_score = val_loss
+            patience_counter = 0
+            os.makedirs(save_dir, exist_ok=True)
+            torch.save(model.state_dict(), os.path.join(save_dir, f"{name}_best_loss.pt"))   # helpers.py:394-400
+        else:
+            patience_counter += 1
+        if patience_counter >= patience:
+            log(f"Early stopping at epoch {epoch}. Best score: {best_score:.2f}")
+            break
+
+    log(f"Training for {name} finished in {(time.time() - start_time) / 60:.2f} minutes.")
+    return best_score
