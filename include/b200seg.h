@@ -125,6 +125,7 @@ int b2_head_bwd(const float* dy, const void* x, int32_t ldx, int64_t npix, int32
  * BatchNorm2d (AttentionUNet.py:7,10,21,34,38,42; R2U_Net.py:11,28; ResnetUnet.py:8,11,55), eps/momentum as args.
  * ---------------------------------------------------------------------------------------------------------- */
 int b2_channel_stats(const void* z, int32_t ldz, int64_t npix, int32_t c, double* stats, b2_stream_t stream);
+/* mean/invstd/scale/shift may all be NULL (running-statistics update only); running_* / nbt may be NULL */
 int b2_bn_finalize(const double* stats, int32_t c, int64_t count, const float* gamma, const float* beta,
                    float eps, float momentum, float* running_mean, float* running_var,
                    int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
@@ -140,11 +141,12 @@ int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, const float
 int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int32_t ldz, int64_t npix, int32_t c,
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      int32_t relu, double* sums, b2_stream_t stream);
-/* dz = gamma*invstd*(dy*mask - [training](sums0/m + xhat*sums1/m)); also writes dgamma/dbeta (fp32) */
+/* dz = gamma*invstd*(dy*mask - [training](sums0/m + xhat*sums1/m)); also writes dgamma/dbeta (fp32) and, if
+ * dbias != NULL, accumulates dbias[c] += sum_p dz[p][c] (bias gradient of the producing conv; caller zeroes) */
 int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int32_t ldz, int64_t npix, int32_t c,
                     const float* scale, const float* shift, const float* mean, const float* invstd,
                     const float* gamma, int32_t relu, int32_t training, const double* sums, void* dz,
-                    int32_t lddz, float* dgamma, float* dbeta, b2_stream_t stream);
+                    int32_t lddz, float* dgamma, float* dbeta, float* dbias, b2_stream_t stream);
 /* db[c] = sum_p dy[p][c] (bias gradient of a conv; overwrite) */
 int b2_channel_sum(const void* dy, int32_t lddy, int64_t npix, int32_t c, float* db, b2_stream_t stream);
 

@@ -69,7 +69,7 @@ SIGNATURES = {
     "b2_bn_apply": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "b2_bn_bwd_reduce": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "b2_bn_bwd_apply": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp,
-                                  _vp, _i32, _vp, _vp, _vp]),
+                                  _vp, _i32, _vp, _vp, _vp, _vp]),
     "b2_channel_sum": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "b2_maxpool2x2_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2_maxpool2x2_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),

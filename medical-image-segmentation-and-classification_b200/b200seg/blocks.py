@@ -39,15 +39,9 @@ def to_internal(x):
 
 
 def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True):
-    """conv (3x3 p1 or 1x1) -> BatchNorm -> optional ReLU.  `x` may be an fp32 NCHW image with <= 4 channels (stem),
-    an internal activation, or a tuple of two internal activations (virtual concat)."""
-    want = bn.training or bn.running_mean is None
-    if not isinstance(x, tuple) and x.dtype != BF16:
-        z, stats, _ = ops.stem_conv(x, conv.weight, conv.bias, want)
-    else:
-        x0, x1 = x if isinstance(x, tuple) else (x, None)
-        z, stats = ops.conv2d(x0, x1, conv.weight, conv.bias, want)
-    return ops.batch_norm_act(z, stats, bn, relu)
+    """conv (3x3 p1 or 1x1) -> BatchNorm -> optional ReLU as ONE fused autograd node.  `x` may be an fp32 NCHW image
+    with <= 4 channels (stem), an internal activation, or a tuple of two internal activations (virtual concat)."""
+    return ops.conv_bn_act_module(x, conv, bn, relu)
 
 
 def conv_plain(x, conv: nn.Conv2d):

@@ -241,8 +241,16 @@ def bn_apply(z, coef, relu=True, addend=None, want_sum=False):
     return (y, ysum) if want_sum else y
 
 
-def bn_bwd(dy, z, coef, gamma, relu=True, training=True):
-    """-> (dz bf16, dgamma fp32, dbeta fp32)"""
+def bn_update_running(stats, count, momentum, running_mean, running_var, nbt):
+    """momentum update of the running statistics from epilogue-produced (sum, sumsq); no coefficient outputs"""
+    c = stats.numel() // 2
+    z = C.c_void_p(0)
+    call("b2_bn_finalize", _p(stats), c, int(count), z, z, 0.0, float(momentum), _p(running_mean), _p(running_var),
+         _p(nbt), z, z, z, z, _stream())
+
+
+def bn_bwd(dy, z, coef, gamma, relu=True, training=True, want_dbias=False):
+    """-> (dz bf16, dgamma fp32, dbeta fp32[, dbias fp32])"""
     n, h, w, c, lddy = _nhwc(dy)
     ldz = _nhwc(z)[4]
     npix = n * h * w
@@ -252,9 +260,10 @@ def bn_bwd(dy, z, coef, gamma, relu=True, training=True):
     dz = new_act(n, h, w, c, z.device)
     dgamma = torch.empty((c,), dtype=torch.float32, device=z.device)
     dbeta = torch.empty((c,), dtype=torch.float32, device=z.device)
+    dbias = torch.zeros((c,), dtype=torch.float32, device=z.device) if want_dbias else None
     call("b2_bn_bwd_apply", _p(dy), lddy, _p(z), ldz, npix, c, _p(coef[2]), _p(coef[3]), _p(coef[0]), _p(coef[1]),
-         _p(gamma), int(relu), int(training), _p(sums), _p(dz), c, _p(dgamma), _p(dbeta), _stream())
-    return dz, dgamma, dbeta
+         _p(gamma), int(relu), int(training), _p(sums), _p(dz), c, _p(dgamma), _p(dbeta), _p(dbias), _stream())
+    return (dz, dgamma, dbeta, dbias) if want_dbias else (dz, dgamma, dbeta)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -89,8 +89,8 @@ def conv2d_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, nee
     dev = dy.device
     dy = _c(dy)
     c0 = x0.shape[3]
-    empty_a = torch.empty((0,), dtype=torch.bfloat16, device=dev)
-    dx0, dx1 = empty_a, empty_a
+    dx0 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
+    dx1 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     if need_dx0 or need_dx1:
         _, wd = K.pack_weights(weight, want_dgrad=True)
         if need_dx0:
@@ -230,6 +230,120 @@ def batch_norm_act(z: Tensor, stats: Tensor, bn: torch.nn.BatchNorm2d, relu: boo
     coef = bn_finalize_(stats.detach(), n * h * w, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                         bn.num_batches_tracked, training, float(bn.momentum), float(bn.eps))
     return bn_apply(z, coef, bn.weight, bn.bias, relu, training)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fused conv -> BatchNorm -> (ReLU): one autograd node for [Conv2d, BatchNorm2d, ReLU] of basic_block / UpConv /
+# Recurrent_block (AttentionUNet.py:6-8,9-11,20-22; R2U_Net.py:10-12,27-29; ResnetUnet.py:7-12,54-56).
+# Functional: batch statistics come back as `stats`; the caller applies the running-stat momentum update with
+# bn_update_running_.  Backward = BN backward (2 passes, the second also yields the conv bias gradient) -> dgrad
+# -> wgrad.  x0 may be the fp32 NCHW image (<= 4 channels): the CUDA-core stem kernels are used then.
+# ----------------------------------------------------------------------------------------------------------
+@custom_op("b200seg::conv_bn_act", mutates_args=())
+def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], gamma: Tensor,
+                beta: Tensor, running_mean: Tensor, running_var: Tensor, training: bool, eps: float,
+                relu: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    cout, cin, k, _ = weight.shape
+    dev = x0.device
+    stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
+    if x0.dtype != torch.bfloat16:                        # image stem
+        x4 = K.image_to_nhwc4(_c(x0))
+        z = K.conv_smallc_fprop(x4, K.pack_small_weight(weight), bias, k)
+        if training:
+            K.channel_stats(z, stats)
+    else:
+        x4 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
+        wf, _ = K.pack_weights(weight, want_dgrad=False)
+        z = K.conv_igemm(_c(x0), wf, cout, k, x1=_c(x1), bias=bias, stats=stats if training else None)
+    n, h, w, _ = z.shape
+    if training:
+        coef = K.bn_finalize(stats, n * h * w, gamma, beta, eps, 0.0, None, None, None)
+    else:
+        coef = K.bn_eval_coeffs(gamma, beta, running_mean, running_var, eps)
+    return K.bn_apply(z, coef, relu=relu), z, coef, stats, x4
+
+
+@conv_bn_act.register_fake
+def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu):
+    cout = weight.shape[0]
+    if x0.dtype != torch.bfloat16:
+        n, _, h, w = x0.shape
+        x4 = x0.new_empty((n, h, w, 4), dtype=torch.bfloat16)
+    else:
+        n, h, w, _ = x0.shape
+        x4 = x0.new_empty((0,), dtype=torch.bfloat16)
+    y = x0.new_empty((n, h, w, cout), dtype=torch.bfloat16)
+    return (y, torch.empty_like(y), x0.new_empty((4, cout), dtype=torch.float32),
+            x0.new_empty((2, cout) if training else (0,), dtype=_F64), x4)
+
+
+@custom_op("b200seg::conv_bn_act_bwd", mutates_args=())
+def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, weight: Tensor, z: Tensor,
+                    coef: Tensor, gamma: Tensor, relu: bool, training: bool, need_dx0: bool, need_dx1: bool,
+                    has_bias: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    cout, cin, k, _ = weight.shape
+    dev = dy.device
+    res = K.bn_bwd(_c(dy), z, coef, gamma, relu=relu, training=training, want_dbias=has_bias)
+    dz, dgamma, dbeta = res[0], res[1], res[2]
+    db = res[3] if has_bias else torch.empty((0,), device=dev)
+    dx0 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
+    dx1 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
+    if x4.numel() > 0:                                    # stem: no input gradient
+        dwk = K.conv_smallc_wgrad(dz, x4, k)
+        dw = dwk[:, :, :cin].reshape(cout, k * k, cin).contiguous()
+    else:
+        c0 = x0.shape[3]
+        if need_dx0 or need_dx1:
+            _, wd = K.pack_weights(weight, want_dgrad=True)
+            if need_dx0:
+                dx0 = K.conv_igemm(dz, wd, c0, k, row_offset=0, dgrad=True)
+            if need_dx1 and x1 is not None:
+                dx1 = K.conv_igemm(dz, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
+        dw = K.conv_wgrad(dz, x0, k, x1=x1)
+    return dx0, dx1, dw, db, dgamma, dbeta
+
+
+def _cba_setup(ctx, inputs, output):
+    x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu = inputs
+    _y, z, coef, _stats, x4 = output
+    stem = x0.dtype != torch.bfloat16
+    ctx.save_for_backward(None if stem else _c(x0), _c(x1), x4, weight, z, coef, gamma)
+    ctx.has_bias = bias is not None
+    ctx.stem = stem
+
+
+def _cba_backward(ctx, dy, *_unused):
+    x0, x1, x4, weight, z, coef, gamma = ctx.saved_tensors
+    need = ctx.needs_input_grad
+    need0 = bool(need[0]) and not ctx.stem
+    need1 = bool(need[1]) and x1 is not None
+    dx0, dx1, dw, db, dgamma, dbeta = conv_bn_act_bwd(dy, x0 if x0 is not None else x4, x1, x4, weight, z, coef,
+                                                      gamma, ctx.relu, ctx.training, need0, need1, ctx.has_bias)
+    return (dx0 if need0 else None, dx1 if need1 else None, _dw_as_param_grad(dw, weight),
+            db if ctx.has_bias else None, dgamma, dbeta, None, None, None, None, None)
+
+
+conv_bn_act.register_autograd(_cba_backward, setup_context=_cba_setup)
+
+
+@custom_op("b200seg::bn_update_running_", mutates_args=("running_mean", "running_var", "num_batches_tracked"))
+def bn_update_running_(stats: Tensor, count: int, momentum: float, running_mean: Tensor, running_var: Tensor,
+                       num_batches_tracked: Tensor) -> None:
+    """running_mean/var momentum update (unbiased variance) + num_batches_tracked += 1, from epilogue statistics"""
+    K.bn_update_running(stats, count, momentum, running_mean, running_var, num_batches_tracked)
+
+
+def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = True) -> Tensor:
+    """[Conv2d -> BatchNorm2d -> ReLU] on module objects; x: image | activation | (activation, activation)."""
+    x0, x1 = x if isinstance(x, tuple) else (x, None)
+    training = bn.training or bn.running_mean is None
+    y, _z, _coef, stats, _x4 = conv_bn_act(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                           bn.running_var, training, float(bn.eps), relu)
+    if training:
+        n, h, w, _ = y.shape
+        bn_update_running_(stats.detach(), n * h * w, float(bn.momentum), bn.running_mean, bn.running_var,
+                           bn.num_batches_tracked)
+    return y
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -129,11 +129,13 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, long
   if (var < 0.0) var = 0.0;
   const float fm = (float)m;
   const float is = (float)(1.0 / sqrt(var + (double)eps));
-  mean[c] = fm;
-  invstd[c] = is;
-  const float sc = (gamma ? gamma[c] : 1.f) * is;
-  scale[c] = sc;
-  shift[c] = (beta ? beta[c] : 0.f) - fm * sc;
+  if (mean != nullptr) {   // (NULL outputs: running-statistics update only)
+    mean[c] = fm;
+    invstd[c] = is;
+    const float sc = (gamma ? gamma[c] : 1.f) * is;
+    scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.f) - fm * sc;
+  }
   if (running_mean != nullptr) {
     const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * fm;
@@ -242,49 +244,69 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(
   }
 }
 
-// backward pass 2: dz = gamma*invstd*(dy*mask - [training](s0/m + xhat*s1/m))
+// backward pass 2: dz = gamma*invstd*(dy*mask - [training](s0/m + xhat*s1/m)); optionally dbias[c] += sum_p dz
+// (the bias gradient of the convolution that produced z, taken on the rounded dz the conv backward consumes)
 __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
     int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
-    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
-  if (r >= m.rows) return;
-  float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], gi[8];
-  load8f(scale + g * 8, sc);
-  load8f(shift + g * 8, sh);
-  load8f(mean + g * 8, mu);
-  load8f(invstd + g * 8, is);
-  const double inv_m = 1.0 / (double)npix;
+  const bool active = r < m.rows;
+  float bsum[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = g * 8 + j;
-    const float ga = gamma ? __ldg(gamma + c) : 1.f;
-    gi[j] = ga * is[j];
-    const double a0 = sums[c], a1 = sums[C + c];
-    k0[j] = training ? (float)(a0 * inv_m) : 0.f;
-    k1[j] = training ? (float)(a1 * inv_m) : 0.f;
-    if (blockIdx.x == 0 && r == 0) {
-      if (dgamma) dgamma[c] = (float)a1;
-      if (dbeta) dbeta[c] = (float)a0;
-    }
-  }
-  for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
-    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
-    const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
-    float d[8], f[8];
-    unpack8(ud, d);
-    unpack8(uz, f);
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  if (active) {
+    float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], gi[8];
+    load8f(scale + g * 8, sc);
+    load8f(shift + g * 8, sh);
+    load8f(mean + g * 8, mu);
+    load8f(invstd + g * 8, is);
+    const double inv_m = 1.0 / (double)npix;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const bool on = !relu || fmaf(f[j], sc[j], sh[j]) > 0.f;
-      const float dd = on ? d[j] : 0.f;
-      const float xh = (f[j] - mu[j]) * is[j];
-      f[j] = gi[j] * (dd - k0[j] - xh * k1[j]);
+      const int c = g * 8 + j;
+      const float ga = gamma ? __ldg(gamma + c) : 1.f;
+      gi[j] = ga * is[j];
+      const double a0 = sums[c], a1 = sums[C + c];
+      k0[j] = training ? (float)(a0 * inv_m) : 0.f;
+      k1[j] = training ? (float)(a1 * inv_m) : 0.f;
+      if (blockIdx.x == 0 && r == 0) {
+        if (dgamma) dgamma[c] = (float)a1;
+        if (dbeta) dbeta[c] = (float)a0;
+      }
     }
-    *reinterpret_cast<uint4*>(dz + p * lddz + g * 8) = pack8(f);
+    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
+      const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+      float d[8], f[8];
+      unpack8(ud, d);
+      unpack8(uz, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool on = !relu || fmaf(f[j], sc[j], sh[j]) > 0.f;
+        const float dd = on ? d[j] : 0.f;
+        const float xh = (f[j] - mu[j]) * is[j];
+        f[j] = gi[j] * (dd - k0[j] - xh * k1[j]);
+      }
+      const uint4 o = pack8(f);
+      *reinterpret_cast<uint4*>(dz + p * lddz + g * 8) = o;
+      if (dbias != nullptr) {
+        unpack8(o, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bsum[j] += f[j];
+      }
+    }
+  }
+  if (dbias != nullptr) {
+    rows_reduce8(bsum, m.tpp, m.rows, g, r, active, red);
+    if (active && r == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&dbias[g * 8 + j], bsum[j]);
+    }
   }
 }
 
@@ -389,7 +411,7 @@ extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int
 extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int32_t ldz, int64_t npix, int32_t c,
                                const float* scale, const float* shift, const float* mean, const float* invstd,
                                const float* gamma, int32_t relu, int32_t training, const double* sums, void* dz,
-                               int32_t lddz, float* dgamma, float* dbeta, b2_stream_t stream) {
+                               int32_t lddz, float* dgamma, float* dbeta, float* dbias, b2_stream_t stream) {
   ChanMap m;
   int rc = make_map(c, &m);
   if (rc) return rc;
@@ -397,7 +419,7 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
              "bn_bwd_apply operands misaligned");
   bn_bwd_apply_kernel<<<chan_grid(npix, m, 16), kBlock, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
-      relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta);
+      relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

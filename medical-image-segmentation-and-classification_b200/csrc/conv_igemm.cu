@@ -1,25 +1,35 @@
-// b200seg — implicit-GEMM convolution (stride 1, 'same' padding, 1x1 / 3x3) on tcgen05.
+// b200seg — implicit-GEMM convolution (stride 1, 'same' padding, 1x1 / 3x3) on tcgen05: persistent, warp-specialised.
 //
 // GEMM view:  D[M = pixels, N = cout] = sum over (tap, channel block)  A_tap[pixels, 64 ch] * W_tap[cout, 64 ch]^T
 //   A tiles : one TMA box (64 ch, Wb, Hb, Nb) of the NHWC activation per (tap, channel block); the box origin is
 //             shifted by the tap offset and TMA's out-of-bounds zero fill supplies the padding halo.  The box
 //             lands in smem as 128 rows of 128 B (K-major, 128B swizzle) == the canonical UMMA A layout.
-//   B tiles : TMA box (64 ch, BLOCK_N, 1) of the packed weights [tap][cout][cin], same layout.
-//   D       : 128 x BLOCK_N fp32 accumulator in TMEM (lane = pixel row, column = output channel).
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> +bias/+addend/ReLU -> bf16 -> global; BN sum / sum^2 of the rounded output).
-// Two CTAs are co-resident per SM so one CTA's epilogue overlaps the other's main loop.
+//             "halo" mode (tiles that are a single image-row segment, W >= 128): ONE box of Wb+2 pixels per
+//             (filter row, channel block); the three horizontal taps are three MMAs whose A descriptors start
+//             0 / 128 / 256 B into that box, so the activation is fetched 3x instead of 9x.
+//   B tiles : TMA box (64 ch, BLOCK_N, 1 or 3 taps) of the packed weights [tap][cout][cin], same layout.
+//   D       : 128 x BLOCK_N fp32 accumulators in TMEM, double buffered (2 x BLOCK_N columns).
+// One CTA per SM loops over its tiles (fixed n-tile, strided m-tiles):
+//   warp 0    TMA producer (smem ring of `stages` A+B slots, full/empty mbarriers)
+//   warp 1    TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem slots and publishes
+//             a finished accumulator (tmem_full); waits on tmem_empty before overwriting a buffer
+//   warps 2-5 epilogue: tcgen05.ld -> +bias (+addend) (ReLU) -> bf16 -> swizzled smem tile -> TMA store;
+//             BatchNorm sum / sum-of-squares of the ROUNDED output are column sums of that smem tile, kept in
+//             fp64 registers across all tiles of the CTA and flushed with one fp64 atomic per channel at the end.
+// The epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Used for fprop (reference nn.Conv2d call sites, see include/b200seg.h) and for dgrad (flipped/transposed
 // weight packing).  The K dimension may span two source tensors (elided torch.cat).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2 {
 
 static constexpr int kTileM = 128;
 static constexpr int kKBlock = 64;               // channels per K step (128 B of bf16)
-static constexpr int kABytes = kTileM * 128;     // 16 KB
 static constexpr int kThreads = 192;
+static constexpr int kMaxStages = 12;
 
 struct IgemmParams {
   int H, W, N;
@@ -28,7 +38,10 @@ struct IgemmParams {
   int taps;           // 1 or 9
   int cb0, cb1;       // 64-channel blocks in source 0 / 1
   int block_n, stages, num_k_iters;
-  int cout;
+  int cout, n_tiles, m_tiles, m_stride;
+  int halo, base_off_mode;
+  int a_stage_bytes, b_stage_bytes, a_tx_bytes;
+  int tma_store;
   __nv_bfloat16* y;
   int ldy;
   const float* bias;
@@ -38,47 +51,71 @@ struct IgemmParams {
   int relu;
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t lbo, uint32_t sbo, uint32_t bo) {
+  return umma_desc_sw128(smem_addr, lbo, sbo) | ((uint64_t)(bo & 7u) << 49);
+}
+
+// byte offset of (row, channel) inside the staged output tile (swizzled so that both the row-wise 16 B stores of
+// the TMEM drain and the column-wise reads of the statistics pass are bank-conflict free; for block_n >= 64 it is
+// exactly the TMA SWIZZLE_128B layout of 64-channel panels)
+__device__ __forceinline__ uint32_t ctile_off(int block_n, int row, int ch) {
+  if (block_n >= 64) {
+    const int panel = ch >> 6, cc = ch & 63;
+    return (uint32_t)(panel * (kTileM * 128) + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + ((cc & 7) << 1));
+  }
+  return (uint32_t)(row * 64 + ((((ch >> 3) ^ ((row >> 1) & 3))) << 4) + ((ch & 7) << 1));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+                  const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024 B alignment for the 128B swizzle atoms
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = kABytes + p.block_n * 128;
-  uint8_t* tail = smem + p.stages * stage_bytes;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  uint8_t* ctile = smem + p.stages * stage_bytes;                      // 128 x block_n bf16, 1024 B aligned
+  uint8_t* tail = ctile + kTileM * p.block_n * 2;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + 8;
-  uint64_t* tmem_full_bar = empty_bar + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(tail + 256);          // [block_n]
-  float* s_sum = s_bias + 256;                                   // [block_n]
-  float* s_sq = s_sum + 256;                                     // [block_n]
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;                    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tail + 256);                // [block_n]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates: n-tile fastest so CTAs sharing an activation tile run together
-  const int n_tiles = p.cout / p.block_n;
-  const int n_tile = blockIdx.x % n_tiles;
-  int m_tile = blockIdx.x / n_tiles;
-  const int tw_i = m_tile % p.tw;
-  m_tile /= p.tw;
-  const int th_i = m_tile % p.th;
-  const int tn_i = m_tile / p.th;
-  const int w0 = tw_i * p.Wb, h0 = th_i * p.Hb, n0 = tn_i * p.Nb;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);      // one arrival per epilogue warp
+    }
     fence_barrier_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
     if (p.cb1 > 0) tma_prefetch_desc(&tmA1);
+    if (p.tma_store) tma_prefetch_desc(&tmY);
   }
-  const uint32_t tmem_cols = p.block_n < 32 ? 32u : (uint32_t)p.block_n;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.block_n) tmem_cols <<= 1;
   if (warp == 1) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
@@ -87,37 +124,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int cbt = p.cb0 + p.cb1;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      const int cbt = p.cb0 + p.cb1;
-      int stage = 0;
-      uint32_t phase = 0;
-      int tap = 0, cb = 0;
-      for (int it = 0; it < p.num_k_iters; ++it) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-        int dr = 0, ds = 0;
-        if (p.taps == 9) {
-          dr = tap / 3 - 1;
-          ds = tap % 3 - 1;
+    // ------------------------------ TMA producer (warp-uniform control flow) ------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx = (uint32_t)(p.a_tx_bytes + p.b_stage_bytes);
+    for (int m = m_first; m < p.m_tiles; m += p.m_stride) {
+      int t = m;
+      const int tw_i = t % p.tw;
+      t /= p.tw;
+      const int th_i = t % p.th;
+      const int tn_i = t / p.th;
+      const int w0 = tw_i * p.Wb, h0 = th_i * p.Hb, n0 = tn_i * p.Nb;
+      const int outer = p.halo ? 3 : p.taps;     // halo mode: one iteration per (filter row, channel block)
+      for (int o = 0; o < outer; ++o) {
+        int dr = 0, ds = 0, tap0 = o;
+        if (p.halo) {
+          dr = o - 1;
+          ds = -1;
+          tap0 = o * 3;
+        } else if (p.taps == 9) {
+          dr = o / 3 - 1;
+          ds = o % 3 - 1;
         }
-        if (cb < p.cb0) {
-          tma_load_4d(sa, &tmA0, &full_bar[stage], cb * kKBlock, w0 + ds, h0 + dr, n0);
-        } else {
-          tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, w0 + ds, h0 + dr, n0);
-        }
-        tma_load_3d(sb, &tmB, &full_bar[stage], cb * kKBlock, n_tile * p.block_n, tap);
-        if (++cb == cbt) {
-          cb = 0;
-          ++tap;
-        }
-        if (++stage == p.stages) {
-          stage = 0;
-          phase ^= 1;
+        for (int cb = 0; cb < cbt; ++cb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (lane == 0) {
+            uint8_t* sa = smem + stage * stage_bytes;
+            uint8_t* sb = sa + p.a_stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[stage], tx);
+            if (cb < p.cb0) {
+              tma_load_4d(sa, &tmA0, &full_bar[stage], cb * kKBlock, w0 + ds, h0 + dr, n0);
+            } else {
+              tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, w0 + ds, h0 + dr, n0);
+            }
+            tma_load_3d(sb, &tmB, &full_bar[stage], cb * kKBlock, n_tile * p.block_n, tap0);
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -126,37 +175,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t idesc = umma_idesc_bf16(kTileM, p.block_n, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = 0; it < p.num_k_iters; ++it) {
-      mbar_wait(&full_bar[stage], phase);
+    int ti = 0;
+    const int sub = p.halo ? 3 : 1;
+    for (int m = m_first; m < p.m_tiles; m += p.m_stride, ++ti) {
+      const int buf = ti & 1;
+      mbar_wait(&tmem_empty_bar[buf], (((uint32_t)ti >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-        const uint32_t b_addr = a_addr + kABytes;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.block_n);
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+          for (int s = 0; s < sub; ++s) {
+            const uint32_t a_s = a_addr + s * 128;            // halo mode: shift by s pixels (rows of 128 B)
+            const uint32_t b_s = b_addr + s * p.block_n * 128;
+            const uint32_t bo = p.base_off_mode ? ((a_s >> 7) & 7u) : 0u;
 #pragma unroll
-        for (int k = 0; k < kKBlock / 16; ++k) {
-          const uint64_t da = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t db = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kKBlock / 16; ++k) {
+              const uint64_t da = umma_desc_sw128_bo(a_s + k * 32, 16, 1024, bo);
+              const uint64_t db = umma_desc_sw128(b_s + k * 32, 16, 1024);
+              umma_bf16(d_tmem, da, db, idesc, (it | s | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);   // frees this smem slot when the MMAs have read it
         }
-        umma_commit(&empty_bar[stage]);   // frees this smem stage when the MMAs have read it
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (lane == 0) umma_commit(&tmem_full_bar[buf]);
       __syncwarp();
-      if (++stage == p.stages) {
-        stage = 0;
-        phase ^= 1;
-      }
     }
-    if (lane == 0) umma_commit(tmem_full_bar);
-    __syncwarp();
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int et = threadIdx.x - 64;  // 0..127
     const int ch_base = n_tile * p.block_n;
-    for (int i = et; i < p.block_n; i += 128) {
-      s_bias[i] = p.bias ? p.bias[ch_base + i] : 0.f;
-      s_sum[i] = 0.f;
-      s_sq[i] = 0.f;
-    }
+    for (int i = et; i < p.block_n; i += 128) s_bias[i] = p.bias ? p.bias[ch_base + i] : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -164,72 +222,122 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int wl = row % p.Wb;
     const int hl = (row / p.Wb) % p.Hb;
     const int nl = row / (p.Wb * p.Hb);
-    const bool valid = (n0 + nl) < p.N;
-    const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
-    __nv_bfloat16* yrow = p.y + pix * p.ldy + ch_base;
-    const __nv_bfloat16* arow = p.addend ? p.addend + pix * p.ldadd + ch_base : nullptr;
+    // statistics mapping: thread owns one column pair for a slab of rows
+    const int npairs = p.block_n >> 1;
+    const int groups = 128 / npairs > 0 ? 128 / npairs : 1;
+    const int rows_per_group = kTileM / groups;
+    const int pair = et % npairs;
+    const int grp = et / npairs;               // < groups when block_n <= 256
+    double acc_s0 = 0.0, acc_s1 = 0.0, acc_q0 = 0.0, acc_q1 = 0.0;
+    const int chunks_per_row = p.block_n >> 3;
 
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    int ti = 0;
+    for (int m = m_first; m < p.m_tiles; m += p.m_stride, ++ti) {
+      int t = m;
+      const int tw_i = t % p.tw;
+      t /= p.tw;
+      const int th_i = t % p.th;
+      const int tn_i = t / p.th;
+      const int w0 = tw_i * p.Wb, h0 = th_i * p.Hb, n0 = tn_i * p.Nb;
+      int valid_rows = (p.N - n0) * p.Wb * p.Hb;
+      if (valid_rows > kTileM) valid_rows = kTileM;
+      const int buf = ti & 1;
 
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int c = 0; c < p.block_n; c += 32) {
-      float v[32];
-      tmem_ld32(taddr + c, v);
-      tmem_ld_wait();
-      if (arow != nullptr && valid) {
-        const uint4* ap = reinterpret_cast<const uint4*>(arow + c);
+      // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
+      if (p.tma_store && et == 0) tma_store_wait_read();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)ti >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.block_n);
+      const bool valid = row < valid_rows;
+      const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
+      const __nv_bfloat16* arow = (p.addend && valid) ? p.addend + pix * p.ldadd + ch_base : nullptr;
+      for (int c = 0; c < p.block_n; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (arow != nullptr) {
+          const uint4* ap = reinterpret_cast<const uint4*>(arow + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = __ldg(ap + q);
+            v[q * 8 + 0] += bf16lo(u.x); v[q * 8 + 1] += bf16hi(u.x);
+            v[q * 8 + 2] += bf16lo(u.y); v[q * 8 + 3] += bf16hi(u.y);
+            v[q * 8 + 4] += bf16lo(u.z); v[q * 8 + 5] += bf16hi(u.z);
+            v[q * 8 + 6] += bf16lo(u.w); v[q * 8 + 7] += bf16hi(u.w);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 u = __ldg(ap + q);
-          v[q * 8 + 0] += bf16lo(u.x); v[q * 8 + 1] += bf16hi(u.x);
-          v[q * 8 + 2] += bf16lo(u.y); v[q * 8 + 3] += bf16hi(u.y);
-          v[q * 8 + 4] += bf16lo(u.z); v[q * 8 + 5] += bf16hi(u.z);
-          v[q * 8 + 6] += bf16lo(u.w); v[q * 8 + 7] += bf16hi(u.w);
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = v[q * 8 + 2 * j] + s_bias[c + q * 8 + 2 * j];
+            float b = v[q * 8 + 2 * j + 1] + s_bias[c + q * 8 + 2 * j + 1];
+            if (p.relu) {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            pk[j] = pack_bf16x2(a, b);
+          }
+          *reinterpret_cast<uint4*>(ctile + ctile_off(p.block_n, row, c + q * 8)) =
+              make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
-      uint32_t packed[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float a = v[j] + s_bias[c + j];
-        float b = v[j + 1] + s_bias[c + j + 1];
-        if (p.relu) {
-          a = fmaxf(a, 0.f);
-          b = fmaxf(b, 0.f);
-        }
-        packed[j >> 1] = pack_bf16x2(a, b);
-      }
-      if (valid) {
-        uint4* yp = reinterpret_cast<uint4*>(yrow + c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          yp[q] = make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-      }
-      if (p.stats != nullptr) {
-        // statistics of the ROUNDED output (what BatchNorm sees under autocast)
-        float sq[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = valid ? bf16lo(packed[j]) : 0.f;
-          const float b = valid ? bf16hi(packed[j]) : 0.f;
-          v[2 * j] = a;
-          v[2 * j + 1] = b;
-          sq[2 * j] = a * a;
-          sq[2 * j + 1] = b * b;
-        }
-        const float cs = warp_transpose_sum32(v, lane);
-        const float cq = warp_transpose_sum32(sq, lane);
-        atomicAdd(&s_sum[c + lane], cs);
-        atomicAdd(&s_sq[c + lane], cq);
-      }
-    }
-    if (p.stats != nullptr) {
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA store
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < p.block_n; i += 128) {
-        atomicAdd(&p.stats[ch_base + i], (double)s_sum[i]);
-        atomicAdd(&p.stats[p.cout + ch_base + i], (double)s_sq[i]);
+
+      if (p.tma_store) {
+        if (et == 0) {
+          for (int pn = 0; pn < (p.block_n >> 6); ++pn)
+            tma_store_4d(&tmY, ctile + pn * (kTileM * 128), ch_base + pn * 64, w0, h0, n0);
+          tma_store_commit();
+        }
+      } else {
+        // coalesced copy-out: consecutive threads write consecutive 16 B of consecutive pixels
+        for (int idx = et; idx < kTileM * chunks_per_row; idx += 128) {
+          const int r = idx / chunks_per_row, ck = idx % chunks_per_row;
+          if (r < valid_rows) {
+            const int rwl = r % p.Wb, rhl = (r / p.Wb) % p.Hb, rnl = r / (p.Wb * p.Hb);
+            const long long rp = ((long long)(n0 + rnl) * p.H + (h0 + rhl)) * p.W + (w0 + rwl);
+            const uint4 u = *reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, ck * 8));
+            *reinterpret_cast<uint4*>(p.y + rp * p.ldy + ch_base + ck * 8) = u;
+          }
+        }
+      }
+      if (p.stats != nullptr && grp < groups) {
+        // column sums of the ROUNDED outputs (what BatchNorm sees under autocast)
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const int r_begin = grp * rows_per_group;
+        int r_end = r_begin + rows_per_group;
+        if (r_end > valid_rows) r_end = valid_rows;
+        for (int r = r_begin; r < r_end; ++r) {
+          const uint32_t u = *reinterpret_cast<const uint32_t*>(ctile + ctile_off(p.block_n, r, pair * 2));
+          const float a = bf16lo(u), b = bf16hi(u);
+          s0 += a;
+          s1 += b;
+          q0 = fmaf(a, a, q0);
+          q1 = fmaf(b, b, q1);
+        }
+        acc_s0 += (double)s0;
+        acc_s1 += (double)s1;
+        acc_q0 += (double)q0;
+        acc_q1 += (double)q1;
       }
     }
+    if (p.stats != nullptr && grp < groups && m_first < p.m_tiles) {
+      const int ch = ch_base + pair * 2;
+      atomicAdd(&p.stats[ch], acc_s0);
+      atomicAdd(&p.stats[ch + 1], acc_s1);
+      atomicAdd(&p.stats[p.cout + ch], acc_q0);
+      atomicAdd(&p.stats[p.cout + ch + 1], acc_q1);
+    }
+    if (p.tma_store && et == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -268,7 +376,14 @@ int encode_act_tmap(CUtensorMap* tm, const void* base, int c, int ld, int n, int
   return encode_tmap_bf16(tm, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 static int pick_block_n(int cout) {
+  const int forced = env_int("B200SEG_BLOCK_N", 0);
+  if (forced > 0 && cout % forced == 0) return forced;
   if (cout % 128 == 0) return 128;
   if (cout % 64 == 0) return 64;
   if (cout % 32 == 0) return 32;
@@ -296,8 +411,10 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.taps = a->ksize * a->ksize;
   p.cb0 = (a->c0 + 63) / 64;
   p.cb1 = (a->c1 + 63) / 64;
-  p.num_k_iters = p.taps * (p.cb0 + p.cb1);
+  const int cbt = p.cb0 + p.cb1;
   p.cout = a->cout;
+  p.n_tiles = a->cout / p.block_n;
+  p.m_tiles = p.tw * p.th * tn;
   p.y = static_cast<__nv_bfloat16*>(a->y);
   p.ldy = a->ldy;
   p.bias = a->bias;
@@ -305,19 +422,38 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.ldadd = a->ldadd;
   p.stats = a->stats;
   p.relu = a->relu;
-  const int stage_bytes = kABytes + p.block_n * 128;
-  int stages = (110 * 1024) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages > p.num_k_iters) stages = p.num_k_iters;
-  if (stages < 1) stages = 1;
+  // halo mode: 3x3, tile == one row segment of 128 pixels
+  const int halo_env = env_int("B200SEG_HALO", 0);
+  p.halo = (halo_env != 0 && p.taps == 9 && p.Hb == 1 && p.Nb == 1 && p.Wb == kTileM) ? 1 : 0;
+  p.base_off_mode = (halo_env == 2) ? 1 : 0;
+  if (p.halo) {
+    p.a_tx_bytes = (kTileM + 2) * 128;
+    p.a_stage_bytes = ((p.a_tx_bytes + 1023) / 1024) * 1024;
+    p.b_stage_bytes = 3 * p.block_n * 128;
+    p.num_k_iters = 3 * cbt;
+  } else {
+    p.a_tx_bytes = kTileM * 128;
+    p.a_stage_bytes = kTileM * 128;
+    p.b_stage_bytes = p.block_n * 128;
+    p.num_k_iters = p.taps * cbt;
+  }
+  p.tma_store = (p.block_n % 64 == 0 && env_int("B200SEG_TMA_STORE", 1) != 0) ? 1 : 0;
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int ctile_bytes = kTileM * p.block_n * 2;
+  const int tail_bytes = 256 + 256 * 4 + 256;
+  const int budget = 232448 - 1024 - tail_bytes - ctile_bytes;
+  int stages = budget / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  B2_REQUIRE(stages >= 2, B2_ERR_SHAPE, "tile configuration does not fit shared memory");
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + 256 + 3 * 256 * 4 + 1024;
+  const int smem_bytes = stages * stage_bytes + ctile_bytes + tail_bytes + 1024;
 
-  CUtensorMap tmA0, tmA1, tmB;
-  rc = encode_act_tmap(&tmA0, a->x0, a->c0, a->ldx0, a->n, a->h, a->w, p.Wb, p.Hb, p.Nb);
+  CUtensorMap tmA0, tmA1, tmB, tmY;
+  const int boxw = p.halo ? p.Wb + 2 : p.Wb;
+  rc = encode_act_tmap(&tmA0, a->x0, a->c0, a->ldx0, a->n, a->h, a->w, boxw, p.Hb, p.Nb);
   if (rc) return rc;
   if (a->c1 > 0) {
-    rc = encode_act_tmap(&tmA1, a->x1, a->c1, a->ldx1, a->n, a->h, a->w, p.Wb, p.Hb, p.Nb);
+    rc = encode_act_tmap(&tmA1, a->x1, a->c1, a->ldx1, a->n, a->h, a->w, boxw, p.Hb, p.Nb);
     if (rc) return rc;
   } else {
     tmA1 = tmA0;
@@ -325,18 +461,29 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   {
     uint64_t dims[3] = {(uint64_t)(a->c0 + a->c1), (uint64_t)a->cout, (uint64_t)p.taps};
     uint64_t str[3] = {2, (uint64_t)a->ktot * 2, (uint64_t)a->w_tap_stride * 2};
-    uint32_t box[3] = {64, (uint32_t)p.block_n, 1};
+    uint32_t box[3] = {64, (uint32_t)p.block_n, p.halo ? 3u : 1u};
     rc = encode_tmap_bf16(&tmB, a->wpk, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  if (p.tma_store) {
+    rc = encode_act_tmap(&tmY, a->y, a->cout, a->ldy, a->n, a->h, a->w, p.Wb, p.Hb, p.Nb);
+    if (rc) return rc;
+  } else {
+    tmY = tmA0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 116 * 1024));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  const long long grid = (long long)p.tw * p.th * tn * (a->cout / p.block_n);
-  B2_REQUIRE(grid > 0 && grid < (1ll << 31), B2_ERR_SHAPE, "grid too large");
-  conv_igemm_kernel<<<(unsigned)grid, kThreads, smem_bytes, stream>>>(tmA0, tmA1, tmB, p);
+  // persistent grid: a multiple of n_tiles so that every CTA keeps one n-tile (its BN statistics stay in registers)
+  int ctas = num_sms();
+  const long long total = (long long)p.m_tiles * p.n_tiles;
+  if (ctas > total) ctas = (int)total;
+  ctas = (ctas / p.n_tiles) * p.n_tiles;
+  if (ctas < p.n_tiles) ctas = p.n_tiles;
+  p.m_stride = ctas / p.n_tiles;
+  conv_igemm_kernel<<<(unsigned)ctas, kThreads, smem_bytes, stream>>>(tmA0, tmA1, tmB, tmY, p);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -61,48 +61,75 @@ __global__ void __launch_bounds__(128) smallc_fprop_kernel(const uint2* __restri
   }
 }
 
-// stem weight gradient: dw[co][tap][c] += sum_p dy[p][co] * x4[p (+) tap][c]
+// stem weight gradient: dw[co][tap][c] += sum_p dy[p][co] * x4[p (+) tap][c]      (cout == 64)
+// Register-tiled CUDA-core GEMM  [64 co] x [TAPS*4 columns] over K = pixels: a block stages 128 pixels of dY (bf16)
+// and their im2col rows (fp32) in shared memory; thread (co, group) keeps CPG accumulators and reads the im2col row
+// as warp-wide broadcasts.  Partial sums go to dw with fp32 atomics (one per accumulator per block).
 template <int KS>
 __global__ void __launch_bounds__(256) smallc_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                            const uint2* __restrict__ x4, int n, int h, int w,
-                                                           int cout, float* __restrict__ dw) {
+                                                           float* __restrict__ dw) {
   constexpr int TAPS = KS * KS;
-  const int co = threadIdx.x % cout;
-  const int q = threadIdx.x / cout;
-  const int ngrp = blockDim.x / cout;
-  float acc[TAPS][4];
+  constexpr int NC = TAPS * 4;                 // im2col columns
+  constexpr int CPG = (NC + 3) / 4;            // columns per thread group (9 or 1)
+  constexpr int GST = (CPG + 3) / 4 * 4;       // padded group stride in floats (12 or 4) -> 16 B aligned rows
+  constexpr int TP = 128;                      // pixels per tile
+  __shared__ __align__(16) __nv_bfloat16 dy_s[TP][64];
+  __shared__ __align__(16) float xc_s[TP][4 * GST];
+  const int t = threadIdx.x;
+  const int co = t & 63, grp = t >> 6;
+  float acc[CPG];
 #pragma unroll
-  for (int t = 0; t < TAPS; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  for (int k = 0; k < CPG; ++k) acc[k] = 0.f;
   const long long total = (long long)n * h * w;
-  const long long per = (total + gridDim.x - 1) / gridDim.x;
-  const long long p0 = (long long)blockIdx.x * per;
-  long long p1 = p0 + per;
-  if (p1 > total) p1 = total;
-  if (q < ngrp) {
-    for (long long p = p0; p < p1; ++p) {
-      const float d = __bfloat162float(dy[p * lddy + co]);
+  const long long tiles = (total + TP - 1) / TP;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long p0 = tile * TP;
+    // dY tile: 128 px x 64 co bf16 = 1024 x 16 B
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = t + i * 256;
+      const int px = idx >> 3, c8 = idx & 7;
+      const long long p = p0 + px;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (p < total) v = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + c8 * 8));
+      *reinterpret_cast<uint4*>(&dy_s[px][c8 * 8]) = v;
+    }
+    // im2col rows: two threads per pixel, taps split between them
+    {
+      const int px = t & 127, half = t >> 7;
+      const long long p = p0 + px;
       const int xx = (int)(p % w);
       const int yy = (int)((p / w) % h);
 #pragma unroll
-      for (int t = 0; t < TAPS; ++t) {
-        if (t % ngrp != q) continue;   // taps are dealt round-robin to the thread groups
-        const int ddy = (KS == 3) ? t / 3 - 1 : 0, ddx = (KS == 3) ? t % 3 - 1 : 0;
+      for (int tp = 0; tp < TAPS; ++tp) {
+        if ((tp & 1) != half) continue;
+        const int ddy = (KS == 3) ? tp / 3 - 1 : 0, ddx = (KS == 3) ? tp % 3 - 1 : 0;
         const int y2 = yy + ddy, x2 = xx + ddx;
-        if (y2 >= 0 && y2 < h && x2 >= 0 && x2 < w) {
-          const uint2 u = __ldg(x4 + p + (long long)ddy * w + ddx);
-          acc[t][0] = fmaf(d, bf16lo(u.x), acc[t][0]);
-          acc[t][1] = fmaf(d, bf16hi(u.x), acc[t][1]);
-          acc[t][2] = fmaf(d, bf16lo(u.y), acc[t][2]);
-          acc[t][3] = fmaf(d, bf16hi(u.y), acc[t][3]);
+        uint2 u = make_uint2(0u, 0u);
+        if (p < total && y2 >= 0 && y2 < h && x2 >= 0 && x2 < w) u = __ldg(x4 + p + (long long)ddy * w + ddx);
+        const float f[4] = {bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y)};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = tp * 4 + c;
+          xc_s[px][(col / CPG) * GST + col % CPG] = f[c];
         }
       }
     }
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < TP; ++px) {
+      const float a = __bfloat162float(dy_s[px][co]);
+      const float* xr = &xc_s[px][grp * GST];
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) {
-      if (t % ngrp != q) continue;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) atomicAdd(&dw[((size_t)co * TAPS + t) * 4 + c], acc[t][c]);
+      for (int k = 0; k < CPG; ++k) acc[k] = fmaf(a, xr[k], acc[k]);
     }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < CPG; ++k) {
+    const int col = grp * CPG + k;
+    if (col < NC) atomicAdd(&dw[(size_t)co * NC + col], acc[k]);
   }
 }
 
@@ -110,6 +137,7 @@ __global__ void __launch_bounds__(256) smallc_wgrad_kernel(const __nv_bfloat16* 
 // heads: y[b][co][hw] = sum_c x[p][c] * w[co][c] + bias[co]      (fp32 out, NCHW)
 // L lanes cooperate on one pixel, each lane owns 8 channels (requires cin/8 <= L <= 32).
 // ------------------------------------------------------------------------------------------------------------
+template <int CO>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        long long npix, int hw, int cin,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
@@ -118,9 +146,9 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
   const int grp = threadIdx.x / L;
   const int gpb = blockDim.x / L;
   const bool has = lig * 8 < cin;
-  float wr[8][8];
+  float wr[CO][8];
 #pragma unroll
-  for (int co = 0; co < 8; ++co)
+  for (int co = 0; co < CO; ++co)
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[co][j] = (has && co < cout) ? bf16_round(w[co * cin + lig * 8 + j]) : 0.f;
   // block-uniform trip count so the full-mask shuffles below are always executed by every lane
@@ -138,7 +166,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
     }
     const long long b = p / hw, r = p % hw;
 #pragma unroll
-    for (int co = 0; co < 8; ++co) {
+    for (int co = 0; co < CO; ++co) {
       if (co < cout) {
         float s = 0.f;
 #pragma unroll
@@ -150,6 +178,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
   }
 }
 
+template <int CO>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dy,
                                                        const __nv_bfloat16* __restrict__ x, int ldx,
                                                        long long npix, int hw, int cin,
@@ -163,9 +192,9 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   const int grp = threadIdx.x / L;
   const int gpb = blockDim.x / L;
   const bool has = lig * 8 < cin;
-  float wr[8][8], aw[8][8], ab[8];
+  float wr[CO][8], aw[CO][8], ab[CO];
 #pragma unroll
-  for (int co = 0; co < 8; ++co) {
+  for (int co = 0; co < CO; ++co) {
     ab[co] = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.f;
 #pragma unroll
-    for (int co = 0; co < 8; ++co) {
+    for (int co = 0; co < CO; ++co) {
       if (co < cout) {
         const float d = __ldg(dy + (b * cout + co) * hw + r);
         if (lig == 0) ab[co] += d;
@@ -206,7 +235,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   }
   if (has) {
 #pragma unroll
-    for (int co = 0; co < 8; ++co) {
+    for (int co = 0; co < CO; ++co) {
       if (co < cout) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(&sacc[co * cin + lig * 8 + j], aw[co][j]);
@@ -254,14 +283,17 @@ extern "C" int b2_conv_smallc_fprop(const void* x4, int32_t n, int32_t h, int32_
 extern "C" int b2_conv_smallc_wgrad(const void* dy, int32_t lddy, const void* x4, int32_t n, int32_t h, int32_t w,
                                     int32_t ksize, int32_t cout, float* dw, b2_stream_t stream) {
   B2_REQUIRE(ksize == 1 || ksize == 3, B2_ERR_SHAPE, "ksize %d unsupported", ksize);
-  B2_REQUIRE(cout >= 32 && cout <= 256 && 256 % cout == 0, B2_ERR_SHAPE, "cout=%d must divide 256 (>=32)", cout);
-  const int grid = num_sms() * 4;
+  B2_REQUIRE(cout == 64, B2_ERR_SHAPE, "stem wgrad supports cout == 64 (got %d)", cout);
+  B2_REQUIRE(lddy % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, B2_ERR_ALIGN, "dy misaligned");
+  const long long tiles = ((long long)n * h * w + 127) / 128;
+  long long grid = (long long)num_sms() * 5;
+  if (grid > tiles) grid = tiles;
   if (ksize == 3)
-    smallc_wgrad_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
-                                                                   (const uint2*)x4, n, h, w, cout, dw);
+    smallc_wgrad_kernel<3><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
+                                                                             (const uint2*)x4, n, h, w, dw);
   else
-    smallc_wgrad_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
-                                                                   (const uint2*)x4, n, h, w, cout, dw);
+    smallc_wgrad_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
+                                                                             (const uint2*)x4, n, h, w, dw);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -276,8 +308,10 @@ extern "C" int b2_head_fwd(const void* x, int32_t ldx, int64_t npix, int32_t hw,
   long long grid = (npix + gpb - 1) / gpb;
   const long long cap = (long long)num_sms() * 8;
   if (grid > cap) grid = cap;
-  head_fwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, npix, hw, cin, w,
-                                                                   bias, cout, L, y);
+#define B2_HEAD_FWD(CO) head_fwd_kernel<CO><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>( \
+      (const __nv_bfloat16*)x, ldx, npix, hw, cin, w, bias, cout, L, y)
+  if (cout == 1) B2_HEAD_FWD(1); else if (cout == 2) B2_HEAD_FWD(2); else if (cout <= 4) B2_HEAD_FWD(4); else B2_HEAD_FWD(8);
+#undef B2_HEAD_FWD
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -293,11 +327,13 @@ extern "C" int b2_head_bwd(const float* dy, const void* x, int32_t ldx, int64_t 
   const int L = pow2ceil(cin / 8);
   const int gpb = 256 / L;
   long long grid = (npix + gpb - 1) / gpb;
-  const long long cap = (long long)num_sms() * 4;
+  const long long cap = (long long)num_sms() * 16;
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)(cout * cin + cout) * sizeof(float);
-  head_bwd_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(
-      dy, (const __nv_bfloat16*)x, ldx, npix, hw, cin, w, cout, L, (__nv_bfloat16*)dx, lddx, dw, db);
+#define B2_HEAD_BWD(CO) head_bwd_kernel<CO><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>( \
+      dy, (const __nv_bfloat16*)x, ldx, npix, hw, cin, w, cout, L, (__nv_bfloat16*)dx, lddx, dw, db)
+  if (cout == 1) B2_HEAD_BWD(1); else if (cout == 2) B2_HEAD_BWD(2); else if (cout <= 4) B2_HEAD_BWD(4); else B2_HEAD_BWD(8);
+#undef B2_HEAD_BWD
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
