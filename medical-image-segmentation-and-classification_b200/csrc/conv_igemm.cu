@@ -96,8 +96,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_first = blockIdx.x / p.n_tiles;
+  // tiles are numbered n-fastest (CTAs that run together share an activation tile); CTA b takes b, b+G, b+2G, ...
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -131,8 +131,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx = (uint32_t)(p.a_tx_bytes + p.b_stage_bytes);
-    for (int m = m_first; m < p.m_tiles; m += p.m_stride) {
-      int t = m;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int t = tile / p.n_tiles;
       const int tw_i = t % p.tw;
       t /= p.tw;
       const int th_i = t % p.th;
@@ -151,7 +152,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         for (int cb = 0; cb < cbt; ++cb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (lane == 0) {
+          if (elect_one()) {
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + p.a_stage_bytes;
             mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -177,7 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     uint32_t phase = 0;
     int ti = 0;
     const int sub = p.halo ? 3 : 1;
-    for (int m = m_first; m < p.m_tiles; m += p.m_stride, ++ti) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int buf = ti & 1;
       mbar_wait(&tmem_empty_bar[buf], (((uint32_t)ti >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -185,7 +186,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       for (int it = 0; it < p.num_k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + p.a_stage_bytes;
           for (int s = 0; s < sub; ++s) {
@@ -207,16 +208,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           phase ^= 1;
         }
       }
-      if (lane == 0) umma_commit(&tmem_full_bar[buf]);
+      if (elect_one()) umma_commit(&tmem_full_bar[buf]);
       __syncwarp();
     }
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int et = threadIdx.x - 64;  // 0..127
-    const int ch_base = n_tile * p.block_n;
-    for (int i = et; i < p.block_n; i += 128) s_bias[i] = p.bias ? p.bias[ch_base + i] : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
     const int wl = row % p.Wb;
@@ -232,8 +229,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int chunks_per_row = p.block_n >> 3;
 
     int ti = 0;
-    for (int m = m_first; m < p.m_tiles; m += p.m_stride, ++ti) {
-      int t = m;
+    int cur_n_tile = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int n_tile = tile % p.n_tiles;
+      const int ch_base = n_tile * p.block_n;
+      if (n_tile != cur_n_tile) {
+        // new output-channel slab: flush the statistics kept for the previous one, reload the bias slice
+        if (cur_n_tile >= 0 && p.stats != nullptr && grp < groups) {
+          const int ch = cur_n_tile * p.block_n + pair * 2;
+          atomicAdd(&p.stats[ch], acc_s0);
+          atomicAdd(&p.stats[ch + 1], acc_s1);
+          atomicAdd(&p.stats[p.cout + ch], acc_q0);
+          atomicAdd(&p.stats[p.cout + ch + 1], acc_q1);
+          acc_s0 = acc_s1 = acc_q0 = acc_q1 = 0.0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // everyone is done reading the old bias slice
+        for (int i = et; i < p.block_n; i += 128) s_bias[i] = p.bias ? p.bias[ch_base + i] : 0.f;
+        cur_n_tile = n_tile;
+      }
+      int t = tile / p.n_tiles;
       const int tw_i = t % p.tw;
       t /= p.tw;
       const int th_i = t % p.th;
@@ -330,8 +344,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         acc_q1 += (double)q1;
       }
     }
-    if (p.stats != nullptr && grp < groups && m_first < p.m_tiles) {
-      const int ch = ch_base + pair * 2;
+    if (p.stats != nullptr && grp < groups && cur_n_tile >= 0) {
+      const int ch = cur_n_tile * p.block_n + pair * 2;
       atomicAdd(&p.stats[ch], acc_s0);
       atomicAdd(&p.stats[ch + 1], acc_s1);
       atomicAdd(&p.stats[p.cout + ch], acc_q0);
@@ -423,7 +437,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.stats = a->stats;
   p.relu = a->relu;
   // halo mode: 3x3, tile == one row segment of 128 pixels
-  const int halo_env = env_int("B200SEG_HALO", 0);
+  const int halo_env = env_int("B200SEG_HALO", 1);
   p.halo = (halo_env != 0 && p.taps == 9 && p.Hb == 1 && p.Nb == 1 && p.Wb == kTileM) ? 1 : 0;
   p.base_off_mode = (halo_env == 2) ? 1 : 0;
   if (p.halo) {
@@ -476,13 +490,14 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  // persistent grid: a multiple of n_tiles so that every CTA keeps one n-tile (its BN statistics stay in registers)
+  // persistent grid: one CTA per SM.  When the grid is a multiple of n_tiles every CTA keeps one n-tile for its
+  // whole life and its BN statistics stay in registers; otherwise they are flushed whenever the slab changes.
   int ctas = num_sms();
   const long long total = (long long)p.m_tiles * p.n_tiles;
+  B2_REQUIRE(total < (1ll << 31), B2_ERR_SHAPE, "too many tiles");
   if (ctas > total) ctas = (int)total;
-  ctas = (ctas / p.n_tiles) * p.n_tiles;
-  if (ctas < p.n_tiles) ctas = p.n_tiles;
-  p.m_stride = ctas / p.n_tiles;
+  if (ctas > p.n_tiles && (total / ctas) >= 16) ctas = (ctas / p.n_tiles) * p.n_tiles;   // many tiles: keep slabs fixed
+  p.m_stride = 0;
   conv_igemm_kernel<<<(unsigned)ctas, kThreads, smem_bytes, stream>>>(tmA0, tmA1, tmB, tmY, p);
   B2_LAUNCH_CHECK();
   return B2_OK;

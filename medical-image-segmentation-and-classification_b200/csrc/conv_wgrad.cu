@@ -10,6 +10,8 @@
 // The dY tile is loaded once per K chunk and reused by every column block.
 // Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -30,6 +32,9 @@ struct WgradParams {
   int cout, ctot;    // ctot = c0 + c1 (row length of dW)
   int a_boxes;       // 1 if cout <= 64 else 2
   int stages;
+  int xhalo;         // 3x3: one X box of Wb+2 pixels per line serves the three horizontal taps (LBO = 1 pixel)
+  int b_stage_bytes; // smem bytes reserved per stage for the X boxes
+  int b_tx_bytes;    // bytes the X box(es) of one stage deliver
   float* ws;         // [splits][cout][taps][ctot]
 };
 
@@ -38,7 +43,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                   const __grid_constant__ CUtensorMap tmX1, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = 2 * kBoxBytes + p.ncolb * kBoxBytes;
+  const int stage_bytes = 2 * kBoxBytes + p.b_stage_bytes;
   uint8_t* tail = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + 8;
@@ -86,35 +91,51 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (p.taps != 9 && cib_base + ncol_live > cbt) ncol_live = cbt - cib_base;
 
   if (warp == 0) {
-    if (lane == 0 && nchunks > 0) {
+    // TMA producer: warp-uniform loop, one elected lane issues; chunk coordinates advance incrementally
+    if (nchunks > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)((p.a_boxes + ncol_live) * kBoxBytes);
+      const uint32_t tx = (uint32_t)(p.a_boxes * kBoxBytes + (p.xhalo ? p.b_tx_bytes : ncol_live * kBoxBytes));
+      int tw_i = chunk_begin % p.tw;
+      int th_i = (chunk_begin / p.tw) % p.th;
+      int tn_i = chunk_begin / (p.tw * p.th);
       for (int ck = chunk_begin; ck < chunk_end; ++ck) {
-        int t = ck;
-        const int tw_i = t % p.tw; t /= p.tw;
-        const int th_i = t % p.th;
-        const int tn_i = t / p.th;
         const int w0 = tw_i * p.Wb, h0 = th_i * p.Hb, n0 = tn_i * p.Nb;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * stage_bytes;
-        uint8_t* sb = sa + 2 * kBoxBytes;
-        mbar_arrive_expect_tx(&full_bar[stage], tx);
-        for (int b = 0; b < p.a_boxes; ++b)
-          tma_load_4d(sa + b * kBoxBytes, &tmDY, &full_bar[stage], co_tile * 128 + b * 64, w0, h0, n0);
-        for (int j = 0; j < ncol_live; ++j) {
-          int cib, dr = 0, ds = 0;
-          if (p.taps == 9) {
-            cib = cib_base;
-            dr = rg - 1;
-            ds = j - 1;
-          } else {
-            cib = cib_base + j;
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + 2 * kBoxBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], tx);
+          // dY: both 64-channel blocks of the 128-row M tile in one 5-D box (.., channel block)
+          tma_load_5d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0, co_tile * 2);
+          if (p.xhalo) {
+            if (cib_base < p.cb0)
+              tma_load_4d(sb, &tmX0, &full_bar[stage], cib_base * 64, w0 - 1, h0 + rg - 1, n0);
+            else
+              tma_load_4d(sb, &tmX1, &full_bar[stage], (cib_base - p.cb0) * 64, w0 - 1, h0 + rg - 1, n0);
           }
-          if (cib < p.cb0)
-            tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, w0 + ds, h0 + dr, n0);
-          else
-            tma_load_4d(sb + j * kBoxBytes, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, w0 + ds, h0 + dr, n0);
+          for (int j = 0; j < (p.xhalo ? 0 : ncol_live); ++j) {
+            int cib, dr = 0, ds = 0;
+            if (p.taps == 9) {
+              cib = cib_base;
+              dr = rg - 1;
+              ds = j - 1;
+            } else {
+              cib = cib_base + j;
+            }
+            if (cib < p.cb0)
+              tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, w0 + ds, h0 + dr, n0);
+            else
+              tma_load_4d(sb + j * kBoxBytes, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, w0 + ds, h0 + dr, n0);
+          }
+        }
+        __syncwarp();
+        if (++tw_i == p.tw) {
+          tw_i = 0;
+          if (++th_i == p.th) {
+            th_i = 0;
+            ++tn_i;
+          }
         }
         if (++stage == p.stages) {
           stage = 0;
@@ -130,14 +151,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       for (int it = 0; it < nchunks; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + 2 * kBoxBytes;
 #pragma unroll
           for (int k = 0; k < kChunkPix / 16; ++k) {
             // 16 pixels (K) = two 8-row groups, 1024 B apart (SBO); 64-channel MN blocks 8 KB apart (LBO)
             const uint64_t da = umma_desc_sw128(a_addr + k * 2048, kBoxBytes, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 2048, kBoxBytes, 1024);
+            uint64_t db;
+            if (p.xhalo) {
+              // 16 pixels of one image line inside the (Wb+2)-wide box; the three taps are N blocks 128 B apart
+              const int line = (16 * k) / p.Wb, woff = (16 * k) % p.Wb;
+              db = umma_desc_sw128(b_addr + (uint32_t)(line * (p.Wb + 2) + woff) * 128u, 128, 1024);
+            } else {
+              db = umma_desc_sw128(b_addr + k * 2048, kBoxBytes, 1024);
+            }
             umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
@@ -148,7 +176,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           phase ^= 1;
         }
       }
-      if (lane == 0) umma_commit(tmem_full_bar);
+      if (elect_one()) umma_commit(tmem_full_bar);
       __syncwarp();
     }
   } else {
@@ -252,15 +280,35 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
     pl->gz = ((a->cout + 127) / 128) * ((cbt + p.ncolb - 1) / p.ncolb);
   }
   const int base = pl->gy * pl->gz;
-  int splits = (2 * num_sms() + base - 1) / base;
+  // split-K factor: one CTA per SM is resident, so pick the split count (up to ~3 waves) whose grid fills whole
+  // waves best; ties go to fewer splits (less workspace traffic)
   const int max_splits = (p.num_chunks + 7) / 8;   // at least 8 chunks (512 pixels) per split
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  const int sms = num_sms();
+  int splits = 1;
+  double best = 0.0;
+  for (int s = 1; s <= max_splits && (long long)s * base <= 3ll * sms + base; ++s) {
+    const long long ctas = (long long)s * base;
+    const long long waves = (ctas + sms - 1) / sms;
+    const double eff = (double)ctas / (double)(waves * sms);
+    if (eff > best + 0.02) {
+      best = eff;
+      splits = s;
+    }
+  }
   p.chunks_per_split = (p.num_chunks + splits - 1) / splits;
   splits = (p.num_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   pl->splits = splits;
   pl->count = (long long)a->cout * p.taps * p.ctot;
-  const int stage_bytes = 2 * kBoxBytes + p.ncolb * kBoxBytes;
+  p.xhalo = (p.taps == 9 && p.Wb >= 16 && p.Nb == 1 && getenv("B200SEG_WG_HALO") != nullptr &&
+             atoi(getenv("B200SEG_WG_HALO")) != 0) ? 1 : 0;
+  if (p.xhalo) {
+    p.b_tx_bytes = (p.Wb + 2) * p.Hb * 128;
+    p.b_stage_bytes = ((p.b_tx_bytes + 1023) / 1024) * 1024;
+  } else {
+    p.b_tx_bytes = p.ncolb * kBoxBytes;
+    p.b_stage_bytes = p.ncolb * kBoxBytes;
+  }
+  const int stage_bytes = 2 * kBoxBytes + p.b_stage_bytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
@@ -293,12 +341,23 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
   pl.p.ws = static_cast<float*>(a->workspace);
 
   CUtensorMap tmDY, tmX0, tmX1;
-  rc = encode_act_tmap(&tmDY, a->dy, a->cout, a->lddy, a->n, a->h, a->w, pl.p.Wb, pl.p.Hb, pl.p.Nb);
-  if (rc) return rc;
-  rc = encode_act_tmap(&tmX0, a->x0, a->c0, a->ldx0, a->n, a->h, a->w, pl.p.Wb, pl.p.Hb, pl.p.Nb);
+  {
+    // dY as a 5-D tensor (64 ch, W, H, N, channel block): one box brings both 64-channel halves of the M tile,
+    // laid out [block][pixel][64 ch] in smem
+    B2_REQUIRE(a->lddy % 8 == 0 && a->cout % 8 == 0, B2_ERR_ALIGN, "dy channel count / stride must be multiples of 8");
+    const uint64_t c_in_block = a->cout < 64 ? (uint64_t)a->cout : 64ull;
+    uint64_t dims[5] = {c_in_block, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n, (uint64_t)((a->cout + 63) / 64)};
+    uint64_t str[5] = {2, (uint64_t)a->lddy * 2, (uint64_t)a->lddy * 2 * a->w, (uint64_t)a->lddy * 2 * a->w * a->h,
+                       128};
+    uint32_t box[5] = {64, (uint32_t)pl.p.Wb, (uint32_t)pl.p.Hb, (uint32_t)pl.p.Nb, (uint32_t)pl.p.a_boxes};
+    rc = encode_tmap_bf16(&tmDY, a->dy, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const int xboxw = pl.p.xhalo ? pl.p.Wb + 2 : pl.p.Wb;
+  rc = encode_act_tmap(&tmX0, a->x0, a->c0, a->ldx0, a->n, a->h, a->w, xboxw, pl.p.Hb, pl.p.Nb);
   if (rc) return rc;
   if (a->c1 > 0) {
-    rc = encode_act_tmap(&tmX1, a->x1, a->c1, a->ldx1, a->n, a->h, a->w, pl.p.Wb, pl.p.Hb, pl.p.Nb);
+    rc = encode_act_tmap(&tmX1, a->x1, a->c1, a->ldx1, a->n, a->h, a->w, xboxw, pl.p.Hb, pl.p.Nb);
     if (rc) return rc;
   } else {
     tmX1 = tmX0;
