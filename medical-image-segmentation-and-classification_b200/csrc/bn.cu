@@ -199,8 +199,10 @@ __global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* _
 
 // ------------------------------------------------------------------------------------------------------------
 // backward pass 1: sums[0][c] = sum dy*mask, sums[1][c] = sum dy*mask*xhat
+// The loop only needs the mask coefficients: sum dy*mask*xhat = invstd*(sum dy*mask*z - mean*sum dy*mask), taken in
+// fp64 at the end.  Two pixels per iteration keep four 16-byte loads in flight per thread.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(
+__global__ void __launch_bounds__(kBlock, 3) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums) {
@@ -212,12 +214,35 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
   if (active) {
-    float sc[8], sh[8], mu[8], is[8];
+    float sc[8], sh[8];
     load8f(scale + g * 8, sc);
     load8f(shift + g * 8, sh);
-    load8f(mean + g * 8, mu);
-    load8f(invstd + g * 8, is);
-    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
+    const long long step = (long long)gridDim.x * m.rows;
+    long long p = (long long)blockIdx.x * m.rows + r;
+    for (; p + step < npix; p += 2 * step) {
+      const uint4 ud0 = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
+      const uint4 uz0 = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+      const uint4 ud1 = __ldg(reinterpret_cast<const uint4*>(dy + (p + step) * lddy + g * 8));
+      const uint4 uz1 = __ldg(reinterpret_cast<const uint4*>(z + (p + step) * ldz + g * 8));
+      float d[8], f[8];
+      unpack8(ud0, d);
+      unpack8(uz0, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dd = (!relu || fmaf(f[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+        s0[j] += dd;
+        s1[j] = fmaf(dd, f[j], s1[j]);
+      }
+      unpack8(ud1, d);
+      unpack8(uz1, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dd = (!relu || fmaf(f[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+        s0[j] += dd;
+        s1[j] = fmaf(dd, f[j], s1[j]);
+      }
+    }
+    for (; p < npix; p += step) {
       const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
       const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
       float d[8], f[8];
@@ -225,28 +250,33 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(
       unpack8(uz, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const bool on = !relu || fmaf(f[j], sc[j], sh[j]) > 0.f;
-        const float dd = on ? d[j] : 0.f;
+        const float dd = (!relu || fmaf(f[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
         s0[j] += dd;
-        s1[j] += dd * ((f[j] - mu[j]) * is[j]);
+        s1[j] = fmaf(dd, f[j], s1[j]);
       }
     }
   }
   rows_reduce8(s0, m.tpp, m.rows, g, r, active, red);
-  if (active && r == 0) {
+  float keep0[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sums[g * 8 + j], (double)s0[j]);
-  }
+  for (int j = 0; j < 8; ++j) keep0[j] = s0[j];
   rows_reduce8(s1, m.tpp, m.rows, g, r, active, red);
   if (active && r == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sums[C + g * 8 + j], (double)s1[j]);
+    for (int j = 0; j < 8; ++j) {
+      const int c = g * 8 + j;
+      const double a0 = (double)keep0[j];
+      const double a1 = (double)invstd[c] * ((double)s1[j] - (double)mean[c] * a0);
+      atomicAdd(&sums[c], a0);
+      atomicAdd(&sums[C + c], a1);
+    }
   }
 }
 
-// backward pass 2: dz = gamma*invstd*(dy*mask - [training](s0/m + xhat*s1/m)); optionally dbias[c] += sum_p dz
-// (the bias gradient of the convolution that produced z, taken on the rounded dz the conv backward consumes)
-__global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(
+// backward pass 2: dz = gamma*invstd*(dy*mask - [training](s0/m + xhat*s1/m)) = A*dy*mask + B*z + Cc per channel;
+// optionally dbias[c] += sum_p dz (the bias gradient of the convolution that produced z, taken on the rounded dz
+// the conv backward consumes).  Two pixels per iteration.
+__global__ void __launch_bounds__(kBlock, 2) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
@@ -260,44 +290,65 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_apply_kernel(
 #pragma unroll
   for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
   if (active) {
-    float sc[8], sh[8], mu[8], is[8], k0[8], k1[8], gi[8];
+    float sc[8], sh[8], ka[8], kb[8], kc[8];
     load8f(scale + g * 8, sc);
     load8f(shift + g * 8, sh);
-    load8f(mean + g * 8, mu);
-    load8f(invstd + g * 8, is);
     const double inv_m = 1.0 / (double)npix;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
       const float ga = gamma ? __ldg(gamma + c) : 1.f;
-      gi[j] = ga * is[j];
+      const float is = __ldg(invstd + c), mu = __ldg(mean + c);
       const double a0 = sums[c], a1 = sums[C + c];
-      k0[j] = training ? (float)(a0 * inv_m) : 0.f;
-      k1[j] = training ? (float)(a1 * inv_m) : 0.f;
+      const float k0 = training ? (float)(a0 * inv_m) : 0.f;
+      const float k1 = training ? (float)(a1 * inv_m) : 0.f;
+      ka[j] = ga * is;
+      kb[j] = -ka[j] * k1 * is;
+      kc[j] = -ka[j] * k0 - kb[j] * mu;
       if (blockIdx.x == 0 && r == 0) {
         if (dgamma) dgamma[c] = (float)a1;
         if (dbeta) dbeta[c] = (float)a0;
       }
     }
-    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
-      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
-      const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+    const long long step = (long long)gridDim.x * m.rows;
+    long long p = (long long)blockIdx.x * m.rows + r;
+    for (; p < npix; p += 2 * step) {
+      const bool two = p + step < npix;
+      const long long p1 = two ? p + step : p;
+      const uint4 ud0 = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
+      const uint4 uz0 = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
+      const uint4 ud1 = __ldg(reinterpret_cast<const uint4*>(dy + p1 * lddy + g * 8));
+      const uint4 uz1 = __ldg(reinterpret_cast<const uint4*>(z + p1 * ldz + g * 8));
       float d[8], f[8];
-      unpack8(ud, d);
-      unpack8(uz, f);
+      unpack8(ud0, d);
+      unpack8(uz0, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const bool on = !relu || fmaf(f[j], sc[j], sh[j]) > 0.f;
-        const float dd = on ? d[j] : 0.f;
-        const float xh = (f[j] - mu[j]) * is[j];
-        f[j] = gi[j] * (dd - k0[j] - xh * k1[j]);
+        const float dd = (!relu || fmaf(f[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+        f[j] = fmaf(ka[j], dd, fmaf(kb[j], f[j], kc[j]));
       }
-      const uint4 o = pack8(f);
+      uint4 o = pack8(f);
       *reinterpret_cast<uint4*>(dz + p * lddz + g * 8) = o;
       if (dbias != nullptr) {
         unpack8(o, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) bsum[j] += f[j];
+      }
+      if (two) {
+        unpack8(ud1, d);
+        unpack8(uz1, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dd = (!relu || fmaf(f[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+          f[j] = fmaf(ka[j], dd, fmaf(kb[j], f[j], kc[j]));
+        }
+        o = pack8(f);
+        *reinterpret_cast<uint4*>(dz + p1 * lddz + g * 8) = o;
+        if (dbias != nullptr) {
+          unpack8(o, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bsum[j] += f[j];
+        }
       }
     }
   }
@@ -401,7 +452,7 @@ extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int
   int rc = make_map(c, &m);
   if (rc) return rc;
   B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz), B2_ERR_ALIGN, "bn_bwd_reduce operands misaligned");
-  bn_bwd_reduce_kernel<<<chan_grid(npix, m, 8), kBlock, 0, (cudaStream_t)stream>>>(
+  bn_bwd_reduce_kernel<<<chan_grid(npix, m, 4), kBlock, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, relu,
       sums);
   B2_LAUNCH_CHECK();
@@ -417,7 +468,7 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
   if (rc) return rc;
   B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz) && aligned16(dz, lddz), B2_ERR_ALIGN,
              "bn_bwd_apply operands misaligned");
-  bn_bwd_apply_kernel<<<chan_grid(npix, m, 16), kBlock, 0, (cudaStream_t)stream>>>(
+  bn_bwd_apply_kernel<<<chan_grid(npix, m, 4), kBlock, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
       relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias);
   B2_LAUNCH_CHECK();
