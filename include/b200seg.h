@@ -42,7 +42,8 @@ int b2_arch_check(void);   /* 0 iff the current device is sm_100; B2_ERR_ARCH ot
 int b2_num_sms(void);
 
 /* ------------------------------------------------------------------------------------------------------------
- * Convolution, stride 1, 'same' padding, ksize in {1,3}: implicit GEMM on tcgen05 (TMA -> 128B-swizzled smem ->
+ * Convolution, ksize in {1,3} with 'same' padding (stride 1 or 2) or ksize 2 / stride 2 / no padding (the input
+ * gradient of ConvTranspose2d(k=2,s=2)): implicit GEMM on tcgen05 (TMA -> 128B-swizzled smem ->
  * tcgen05.mma, fp32 accumulators in TMEM).  Replaces nn.Conv2d forward at
  *   models/segmentation_models/AttentionUNet.py:6,9,20,33,37,41   R2U_Net.py:10,27,43   R2AttU_Net.py:35,52,65-74
  *   ResnetUnet.py:7,10,54
@@ -73,6 +74,11 @@ typedef struct b2_conv_args {
   int32_t ldadd;
   double* stats;          /* optional [2][cout] (sum, sumsq), ACCUMULATED into (caller zeroes) */
   int32_t relu;
+  /* extensions (0 = default): input sampling stride (1|2; the input extent is then h*stride x w*stride) and a
+   * strided output placement y[n, h*out_mul + out_off_h, w*out_mul + out_off_w, :] inside an (h*out_mul) x
+   * (w*out_mul) image — the pixel-shuffle scatter of ConvTranspose2d(k=2,s=2) (ResnetUnet.py:21,53) */
+  int32_t stride;
+  int32_t out_mul, out_off_h, out_off_w;
 } b2_conv_args;
 
 int b2_conv_fprop(const b2_conv_args* a, b2_stream_t stream);
@@ -95,6 +101,10 @@ typedef struct b2_wgrad_args {
   int32_t accumulate;     /* 1: dw += result (shared weights of R2U_Net.py:15-20), 0: overwrite */
   void* workspace;
   int64_t workspace_bytes;
+  /* extension (0 = 1): sampling stride of the X operand; 2 with ksize 2 computes the weight gradient of
+   * ConvTranspose2d(k=2,s=2) (dy := the transposed conv's INPUT on the coarse grid, x := its output gradient on the
+   * 2x grid; result [cin_T][2*2][cout_T]) */
+  int32_t x_stride;
 } b2_wgrad_args;
 
 int64_t b2_conv_wgrad_workspace(const b2_wgrad_args* a);
@@ -133,7 +143,8 @@ int b2_bn_finalize(const double* stats, int32_t c, int64_t count, const float* g
 int b2_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                       const float* running_var, float eps, int32_t c, float* mean, float* invstd, float* scale,
                       float* shift, b2_stream_t stream);
-/* y = act(z*scale+shift) ; optionally ysum = y + addend (Recurrent_block's x + x1, R2U_Net.py:19) */
+/* y = act(z*scale+shift) ; with ysum: also ysum = y + addend (Recurrent_block's x + x1, R2U_Net.py:19);
+ * with addend but ysum == NULL: y = act(z*scale+shift + addend) (torchvision Bottleneck residual) */
 int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, const float* scale, const float* shift,
                 int32_t relu, void* y, int32_t ldy, const void* addend, int32_t ldadd, void* ysum,
                 int32_t ldysum, b2_stream_t stream);
@@ -170,6 +181,14 @@ int b2_layout_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int3
                            b2_stream_t stream);
 int b2_layout_nhwc_to_nchw(const void* x, int32_t ldx, int32_t n, int32_t c, int32_t h, int32_t w, float* y,
                            b2_stream_t stream);
+
+/* ResNet-50 encoder of ResNetUnet (ResnetUnet.py:32-43), forward only (frozen by default):
+ * 7x7/s2/p3 stem conv 3->64 without bias (x4 = NHWC bf16 padded to 4 channels, wk fp32 [64][49][4]) and
+ * MaxPool2d(3, 2, 1); h, w are INPUT extents */
+int b2_stem7x7_fprop(const void* x4, int32_t n, int32_t h, int32_t w, const float* wk, int32_t cout, void* y,
+                     int32_t ldy, b2_stream_t stream);
+int b2_maxpool3x3s2_fwd(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w, int32_t c, void* y,
+                        int32_t ldy, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Attention gate (AttentionUNet.py:48-54, R2AttU_Net.py:80-86) — the 1x1 GEMMs go through b2_conv_fprop.

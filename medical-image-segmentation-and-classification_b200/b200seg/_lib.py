@@ -27,7 +27,8 @@ class ConvArgs(C.Structure):
                 ("wpk", _vp), ("ktot", _i32), ("w_tap_stride", _i64),
                 ("cout", _i32), ("y", _vp), ("ldy", _i32),
                 ("bias", _vp), ("addend", _vp), ("ldadd", _i32),
-                ("stats", _vp), ("relu", _i32)]
+                ("stats", _vp), ("relu", _i32),
+                ("stride", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32)]
 
 
 class WgradArgs(C.Structure):
@@ -37,7 +38,7 @@ class WgradArgs(C.Structure):
                 ("x0", _vp), ("c0", _i32), ("ldx0", _i32),
                 ("x1", _vp), ("c1", _i32), ("ldx1", _i32),
                 ("dw", _vp), ("accumulate", _i32),
-                ("workspace", _vp), ("workspace_bytes", _i64)]
+                ("workspace", _vp), ("workspace_bytes", _i64), ("x_stride", _i32)]
 
 
 class GateCoef(C.Structure):
@@ -79,6 +80,8 @@ SIGNATURES = {
     "b2_nchw_f32_to_nhwc_bf16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2_layout_nchw_to_nhwc": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2_layout_nhwc_to_nchw": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b2_stem7x7_fprop": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "b2_maxpool3x3s2_fwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2_gate_psi_fwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_gate_apply_fwd": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "b2_gate_apply_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp,

@@ -76,20 +76,24 @@ def pack_weights(weight, want_dgrad=True):
 # tcgen05 convolutions
 # ----------------------------------------------------------------------------------------------------------
 def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None, relu=False, out=None,
-               row_offset=0, dgrad=False):
+               row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0)):
     """y = conv(x0 | x1; wpk) (+bias) (+addend) (relu); wpk is [taps, rows, ktot] bf16, rows [row_offset,
-    row_offset+cout) are used.  `stats` (fp64 [2, cout]) accumulates sum / sumsq of the rounded output."""
-    n, h, w, c0, ld0 = _nhwc(x0)
+    row_offset+cout) are used.  `stats` (fp64 [2, cout]) accumulates sum / sumsq of the rounded output.
+    stride=2 samples the input on a 2x finer grid (strided conv / ConvTranspose dgrad); out_mul=2 places the result
+    at pixels (2h+off_h, 2w+off_w) of `out` (ConvTranspose pixel shuffle)."""
+    n, hi, wi, c0, ld0 = _nhwc(x0)
+    assert hi % stride == 0 and wi % stride == 0
+    h, w = hi // stride, wi // stride
     c1, ld1 = 0, 0
     if x1 is not None:
         n1, h1, w1, c1, ld1 = _nhwc(x1)
-        assert (n1, h1, w1) == (n, h, w)
+        assert (n1, h1, w1) == (n, hi, wi)
     taps, rows, ktot = wpk.shape
     assert taps == ksize * ksize and wpk.dtype == BF16 and wpk.is_contiguous()
     assert ktot >= c0 + c1 and row_offset + cout <= rows
-    y = out if out is not None else new_act(n, h, w, cout, x0.device)
-    _, _, _, cy, ldy = _nhwc(y)
-    assert cy == cout
+    y = out if out is not None else new_act(n, h * out_mul, w * out_mul, cout, x0.device)
+    ny, hy, wy, cy, ldy = _nhwc(y)
+    assert cy == cout and (ny, hy, wy) == (n, h * out_mul, w * out_mul)
     a = ConvArgs()
     a.n, a.h, a.w, a.ksize = n, h, w, ksize
     a.x0, a.c0, a.ldx0 = x0.data_ptr(), c0, ld0
@@ -108,16 +112,19 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
         assert stats.dtype == torch.float64 and stats.numel() == 2 * cout
         a.stats = stats.data_ptr()
     a.relu = int(relu)
+    a.stride, a.out_mul, a.out_off_h, a.out_off_w = stride, out_mul, out_off[0], out_off[1]
     t0 = _prof_begin()
     call("b2_conv_dgrad" if dgrad else "b2_conv_fprop", C.byref(a), _stream())
     _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0)
     return y
 
 
-def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False):
-    """dW fp32 [Cout, k*k, C0+C1] = sum_p dY[p] (x) X[p+tap]."""
+def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1):
+    """dW fp32 [Cout, k*k, C0+C1] = sum_p dY[p] (x) X[p+tap].  x_stride=2 (ksize 2): X lives on the 2x finer grid
+    (weight gradient of ConvTranspose2d(k=2,s=2) with dy := its input, x := its output gradient)."""
     n, h, w, cout, lddy = _nhwc(dy)
-    _, _, _, c0, ld0 = _nhwc(x0)
+    nx, hx, wx, c0, ld0 = _nhwc(x0)
+    assert (nx, hx, wx) == (n, h * x_stride, w * x_stride)
     c1, ld1 = 0, 0
     if x1 is not None:
         _, _, _, c1, ld1 = _nhwc(x1)
@@ -131,6 +138,7 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False):
     a.x1, a.c1, a.ldx1 = (x1.data_ptr() if x1 is not None else None), c1, ld1
     a.dw = dw.data_ptr()
     a.accumulate = int(accumulate)
+    a.x_stride = x_stride
     need = _lib.load().b2_conv_wgrad_workspace(C.byref(a))
     if need < 0:
         _lib.check(int(need), "b2_conv_wgrad_workspace")
@@ -231,7 +239,25 @@ def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps):
     return coef
 
 
+def stem7x7_fprop(x4, wk):
+    """ResNet stem: 7x7/s2/p3, <=4 -> 64, no bias.  x4 NHWC bf16 [N,H,W,4]; wk fp32 [64, 49, 4]."""
+    n, h, w, c4 = x4.shape
+    assert c4 == 4 and x4.is_contiguous()
+    cout = wk.shape[0]
+    y = new_act(n, h // 2, w // 2, cout, x4.device)
+    call("b2_stem7x7_fprop", _p(x4), n, h, w, _p(wk), cout, _p(y), cout, _stream())
+    return y
+
+
+def maxpool3x3s2_fwd(x):
+    n, h, w, c, ld = _nhwc(x)
+    y = new_act(n, h // 2, w // 2, c, x.device)
+    call("b2_maxpool3x3s2_fwd", _p(x), ld, n, h, w, c, _p(y), c, _stream())
+    return y
+
+
 def bn_apply(z, coef, relu=True, addend=None, want_sum=False):
+    """want_sum: also return y + addend; addend without want_sum: y = act(bn(z) + addend) (residual)"""
     n, h, w, c, ld = _nhwc(z)
     y = new_act(n, h, w, c, z.device)
     ysum = new_act(n, h, w, c, z.device) if want_sum else None

@@ -178,10 +178,19 @@ __global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* _
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
     float f[8];
     unpack8(u, f);
+    if (addend != nullptr && ysum == nullptr) {
+      // residual mode (torchvision Bottleneck: relu(bn3(z) + identity)): add BEFORE the activation
+      float fa[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(addend + p * ldadd + g * 8)), fa);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[j] = fmaf(f[j], sc[j], sh[j]);
-      if (relu) f[j] = fmaxf(f[j], 0.f);
+      for (int j = 0; j < 8; ++j) f[j] = bf16_round(fmaf(f[j], sc[j], sh[j])) + fa[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
     }
     const uint4 o = pack8(f);
     *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = o;
@@ -436,8 +445,9 @@ extern "C" int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, 
   int rc = make_map(c, &m);
   if (rc) return rc;
   B2_REQUIRE(aligned16(z, ldz) && aligned16(y, ldy), B2_ERR_ALIGN, "bn_apply operands misaligned");
-  B2_REQUIRE(ysum == nullptr || (addend != nullptr && aligned16(addend, ldadd) && aligned16(ysum, ldysum)),
-             B2_ERR_ALIGN, "bn_apply addend/ysum misaligned or missing");
+  B2_REQUIRE(ysum == nullptr || (addend != nullptr && aligned16(ysum, ldysum)), B2_ERR_ALIGN,
+             "bn_apply ysum misaligned or addend missing");
+  B2_REQUIRE(addend == nullptr || aligned16(addend, ldadd), B2_ERR_ALIGN, "bn_apply addend misaligned");
   bn_apply_kernel<<<chan_grid(npix, m, 16), kBlock, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)z, ldz, npix, m, scale, shift, relu, (__nv_bfloat16*)y, ldy,
       (const __nv_bfloat16*)addend, ldadd, (__nv_bfloat16*)ysum, ldysum);

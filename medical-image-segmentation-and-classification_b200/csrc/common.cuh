@@ -36,7 +36,8 @@ int num_sms();
 // TMA descriptor encode (driver entry point fetched through the runtime; no libcuda link dependency).
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1; bf16 elements.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                     const uint32_t* elem_strides = nullptr);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

@@ -40,6 +40,8 @@ struct IgemmParams {
   int block_n, stages, num_k_iters;
   int cout, n_tiles, m_tiles, m_stride;
   int halo, base_off_mode;
+  int stride, ksize, pad;
+  long long y_sn, y_sh, y_sw;   // element strides of the output pixel grid (strided placement for ConvT)
   int a_stage_bytes, b_stage_bytes, a_tx_bytes;
   int tma_store;
   __nv_bfloat16* y;
@@ -146,9 +148,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           dr = o - 1;
           ds = -1;
           tap0 = o * 3;
-        } else if (p.taps == 9) {
-          dr = o / 3 - 1;
-          ds = o % 3 - 1;
+        } else {
+          dr = o / p.ksize - p.pad;
+          ds = o % p.ksize - p.pad;
         }
         for (int cb = 0; cb < cbt; ++cb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -157,9 +159,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             uint8_t* sb = sa + p.a_stage_bytes;
             mbar_arrive_expect_tx(&full_bar[stage], tx);
             if (cb < p.cb0) {
-              tma_load_4d(sa, &tmA0, &full_bar[stage], cb * kKBlock, w0 + ds, h0 + dr, n0);
+              tma_load_4d(sa, &tmA0, &full_bar[stage], cb * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
             } else {
-              tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, w0 + ds, h0 + dr, n0);
+              tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, p.stride * w0 + ds,
+                          p.stride * h0 + dr, n0);
             }
             tma_load_3d(sb, &tmB, &full_bar[stage], cb * kKBlock, n_tile * p.block_n, tap0);
           }
@@ -318,9 +321,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int r = idx / chunks_per_row, ck = idx % chunks_per_row;
           if (r < valid_rows) {
             const int rwl = r % p.Wb, rhl = (r / p.Wb) % p.Hb, rnl = r / (p.Wb * p.Hb);
-            const long long rp = ((long long)(n0 + rnl) * p.H + (h0 + rhl)) * p.W + (w0 + rwl);
+            const long long ro = (n0 + rnl) * p.y_sn + (h0 + rhl) * p.y_sh + (w0 + rwl) * p.y_sw;
             const uint4 u = *reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, ck * 8));
-            *reinterpret_cast<uint4*>(p.y + rp * p.ldy + ch_base + ck * 8) = u;
+            *reinterpret_cast<uint4*>(p.y + ro + ch_base + ck * 8) = u;
           }
         }
       }
@@ -382,12 +385,22 @@ int conv_tile_geometry(int n, int h, int w, int tile_pix, int* Wb, int* Hb, int*
   return B2_OK;
 }
 
-int encode_act_tmap(CUtensorMap* tm, const void* base, int c, int ld, int n, int h, int w, int Wb, int Hb, int Nb) {
-  B2_REQUIRE(ld % 8 == 0 && c % 8 == 0, B2_ERR_ALIGN, "channel count %d / stride %d must be multiples of 8", c, ld);
+// General NHWC view: element strides (s_w, s_h, s_n) of the pixel grid, optional traversal stride `es` in w and h
+// (box extents are given in LOADED pixels).
+int encode_act_tmap_ex(CUtensorMap* tm, const void* base, int c, int n, int h, int w, long long s_w, long long s_h,
+                       long long s_n, int Wb, int Hb, int Nb, int es) {
+  B2_REQUIRE(s_w % 8 == 0 && s_h % 8 == 0 && s_n % 8 == 0 && c % 8 == 0, B2_ERR_ALIGN,
+             "channel count %d / pixel strides must be multiples of 8 elements", c);
+  B2_REQUIRE(Wb * es <= 256 && Hb * es <= 256, B2_ERR_SHAPE, "TMA box too large for stride %d", es);
   uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-  uint64_t str[4] = {2, (uint64_t)ld * 2, (uint64_t)ld * 2 * w, (uint64_t)ld * 2 * w * h};
-  uint32_t box[4] = {64, (uint32_t)Wb, (uint32_t)Hb, (uint32_t)Nb};
-  return encode_tmap_bf16(tm, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  uint64_t str[4] = {2, (uint64_t)s_w * 2, (uint64_t)s_h * 2, (uint64_t)s_n * 2};
+  uint32_t box[4] = {64, (uint32_t)(Wb * es), (uint32_t)(Hb * es), (uint32_t)Nb};
+  uint32_t est[4] = {1, (uint32_t)es, (uint32_t)es, 1};
+  return encode_tmap_bf16(tm, base, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, est);
+}
+
+int encode_act_tmap(CUtensorMap* tm, const void* base, int c, int ld, int n, int h, int w, int Wb, int Hb, int Nb) {
+  return encode_act_tmap_ex(tm, base, c, n, h, w, ld, (long long)ld * w, (long long)ld * w * h, Wb, Hb, Nb, 1);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -406,7 +419,14 @@ static int pick_block_n(int cout) {
 
 static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   B2_REQUIRE(a != nullptr, B2_ERR_SHAPE, "null args");
-  B2_REQUIRE(a->ksize == 1 || a->ksize == 3, B2_ERR_SHAPE, "ksize %d unsupported (1 or 3)", a->ksize);
+  const int stride = a->stride == 0 ? 1 : a->stride;
+  const int out_mul = a->out_mul == 0 ? 1 : a->out_mul;
+  B2_REQUIRE(a->ksize >= 1 && a->ksize <= 3, B2_ERR_SHAPE, "ksize %d unsupported (1, 2 or 3)", a->ksize);
+  B2_REQUIRE(stride == 1 || stride == 2, B2_ERR_SHAPE, "stride %d unsupported (1 or 2)", stride);
+  B2_REQUIRE(a->ksize != 2 || stride == 2, B2_ERR_SHAPE, "ksize 2 is only supported with stride 2");
+  B2_REQUIRE(out_mul >= 1 && a->out_off_h >= 0 && a->out_off_h < out_mul && a->out_off_w >= 0 &&
+                 a->out_off_w < out_mul,
+             B2_ERR_SHAPE, "bad output placement mul=%d off=(%d,%d)", out_mul, a->out_off_h, a->out_off_w);
   B2_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0, B2_ERR_SHAPE, "bad extent n=%d h=%d w=%d", a->n, a->h, a->w);
   B2_REQUIRE(a->c0 > 0 && a->c1 >= 0, B2_ERR_SHAPE, "bad channel counts c0=%d c1=%d", a->c0, a->c1);
   B2_REQUIRE(a->c1 == 0 || a->c0 % 64 == 0, B2_ERR_SHAPE, "c0=%d must be a multiple of 64 when c1>0", a->c0);
@@ -438,7 +458,10 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.relu = a->relu;
   // halo mode: 3x3, tile == one row segment of 128 pixels
   const int halo_env = env_int("B200SEG_HALO", 1);
-  p.halo = (halo_env != 0 && p.taps == 9 && p.Hb == 1 && p.Nb == 1 && p.Wb == kTileM) ? 1 : 0;
+  p.stride = stride;
+  p.ksize = a->ksize;
+  p.pad = a->ksize == 3 ? 1 : 0;
+  p.halo = (halo_env != 0 && p.taps == 9 && stride == 1 && p.Hb == 1 && p.Nb == 1 && p.Wb == kTileM) ? 1 : 0;
   p.base_off_mode = (halo_env == 2) ? 1 : 0;
   if (p.halo) {
     p.a_tx_bytes = (kTileM + 2) * 128;
@@ -464,10 +487,13 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
 
   CUtensorMap tmA0, tmA1, tmB, tmY;
   const int boxw = p.halo ? p.Wb + 2 : p.Wb;
-  rc = encode_act_tmap(&tmA0, a->x0, a->c0, a->ldx0, a->n, a->h, a->w, boxw, p.Hb, p.Nb);
+  const int ih = a->h * stride, iw = a->w * stride;      // input extent
+  rc = encode_act_tmap_ex(&tmA0, a->x0, a->c0, a->n, ih, iw, a->ldx0, (long long)a->ldx0 * iw,
+                          (long long)a->ldx0 * iw * ih, boxw, p.Hb, p.Nb, stride);
   if (rc) return rc;
   if (a->c1 > 0) {
-    rc = encode_act_tmap(&tmA1, a->x1, a->c1, a->ldx1, a->n, a->h, a->w, boxw, p.Hb, p.Nb);
+    rc = encode_act_tmap_ex(&tmA1, a->x1, a->c1, a->n, ih, iw, a->ldx1, (long long)a->ldx1 * iw,
+                            (long long)a->ldx1 * iw * ih, boxw, p.Hb, p.Nb, stride);
     if (rc) return rc;
   } else {
     tmA1 = tmA0;
@@ -479,8 +505,14 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     rc = encode_tmap_bf16(&tmB, a->wpk, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  // output pixel grid (possibly a strided sub-lattice of a larger image: ConvTranspose pixel shuffle)
+  const long long ow = (long long)a->w * out_mul, oh = (long long)a->h * out_mul;
+  p.y_sw = (long long)out_mul * a->ldy;
+  p.y_sh = (long long)out_mul * ow * a->ldy;
+  p.y_sn = oh * ow * a->ldy;
+  p.y = static_cast<__nv_bfloat16*>(a->y) + ((long long)a->out_off_h * ow + a->out_off_w) * a->ldy;
   if (p.tma_store) {
-    rc = encode_act_tmap(&tmY, a->y, a->cout, a->ldy, a->n, a->h, a->w, p.Wb, p.Hb, p.Nb);
+    rc = encode_act_tmap_ex(&tmY, p.y, a->cout, a->n, a->h, a->w, p.y_sw, p.y_sh, p.y_sn, p.Wb, p.Hb, p.Nb, 1);
     if (rc) return rc;
   } else {
     tmY = tmA0;

@@ -18,6 +18,8 @@ namespace b2 {
 
 int conv_tile_geometry(int n, int h, int w, int tile_pix, int* Wb, int* Hb, int* Nb, int* tw, int* th, int* tn);
 int encode_act_tmap(CUtensorMap* tm, const void* base, int c, int ld, int n, int h, int w, int Wb, int Hb, int Nb);
+int encode_act_tmap_ex(CUtensorMap* tm, const void* base, int c, int n, int h, int w, long long s_w, long long s_h,
+                       long long s_n, int Wb, int Hb, int Nb, int es);
 
 static constexpr int kChunkPix = 64;            // K per pipeline stage
 static constexpr int kBoxBytes = kChunkPix * 128;  // 8 KB: 64 pixels x 64 channels bf16
@@ -26,8 +28,10 @@ static constexpr int kWgThreads = 192;
 struct WgradParams {
   int Wb, Hb, Nb, tw, th;
   int num_chunks, chunks_per_split;
-  int taps;          // 1 or 9
-  int ncolb;         // column blocks per CTA (3x3: 3 taps; 1x1: up to 4 channel blocks)
+  int taps;          // ksize^2
+  int ksize, pad, xstride;   // X-operand tap geometry: offsets (r - pad, s - pad), sampling stride
+  int cpb;           // 64-channel X blocks per CTA
+  int ncolb;         // column blocks per CTA = ksize (taps of one filter row) x cpb
   int cb0, cb1;      // 64-channel blocks per X source
   int cout, ctot;    // ctot = c0 + c1 (row length of dW)
   int a_boxes;       // 1 if cout <= 64 else 2
@@ -58,7 +62,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const int co_tiles = (p.cout + 127) / 128;
   const int co_tile = blockIdx.z % co_tiles;
   const int cgrp = blockIdx.z / co_tiles;             // channel-block group
-  const int cib_base = (p.taps == 9) ? cgrp : cgrp * p.ncolb;
+  const int cib_base = cgrp * p.cpb;
   const int cbt = p.cb0 + p.cb1;
 
   const int chunk_begin = split * p.chunks_per_split;
@@ -87,8 +91,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   // number of live column blocks for this CTA (1x1 groups may run past the last channel block)
-  int ncol_live = p.ncolb;
-  if (p.taps != 9 && cib_base + ncol_live > cbt) ncol_live = cbt - cib_base;
+  int live_cb = p.cpb;
+  if (cib_base + live_cb > cbt) live_cb = cbt - cib_base;
+  const int ncol_live = live_cb * p.ksize;
 
   if (warp == 0) {
     // TMA producer: warp-uniform loop, one elected lane issues; chunk coordinates advance incrementally
@@ -115,18 +120,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
               tma_load_4d(sb, &tmX1, &full_bar[stage], (cib_base - p.cb0) * 64, w0 - 1, h0 + rg - 1, n0);
           }
           for (int j = 0; j < (p.xhalo ? 0 : ncol_live); ++j) {
-            int cib, dr = 0, ds = 0;
-            if (p.taps == 9) {
-              cib = cib_base;
-              dr = rg - 1;
-              ds = j - 1;
-            } else {
-              cib = cib_base + j;
-            }
+            const int cib = cib_base + j / p.ksize;
+            const int xw = p.xstride * w0 + (j % p.ksize) - p.pad;
+            const int xh = p.xstride * h0 + rg - p.pad;
             if (cib < p.cb0)
-              tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, w0 + ds, h0 + dr, n0);
+              tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, xw, xh, n0);
             else
-              tma_load_4d(sb + j * kBoxBytes, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, w0 + ds, h0 + dr, n0);
+              tma_load_4d(sb + j * kBoxBytes, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, xw, xh, n0);
           }
         }
         __syncwarp();
@@ -192,14 +192,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int j = 0; j < ncol_live; ++j) {
-      int tap, cib;
-      if (p.taps == 9) {
-        tap = rg * 3 + j;
-        cib = cib_base;
-      } else {
-        tap = 0;
-        cib = cib_base + j;
-      }
+      const int tap = rg * p.ksize + (j % p.ksize);
+      const int cib = cib_base + j / p.ksize;
       float* dst = out + (size_t)tap * p.ctot + cib * 64;
       const int cvalid = p.ctot - cib * 64;   // channels left in this block (>= 64 except for a ragged tail)
 #pragma unroll
@@ -254,7 +248,10 @@ struct WgradPlan {
 
 static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   B2_REQUIRE(a != nullptr, B2_ERR_SHAPE, "null args");
-  B2_REQUIRE(a->ksize == 1 || a->ksize == 3, B2_ERR_SHAPE, "ksize %d unsupported", a->ksize);
+  const int xstride = a->x_stride == 0 ? 1 : a->x_stride;
+  B2_REQUIRE(a->ksize >= 1 && a->ksize <= 3, B2_ERR_SHAPE, "ksize %d unsupported", a->ksize);
+  B2_REQUIRE(xstride == 1 || (xstride == 2 && a->ksize == 2), B2_ERR_SHAPE,
+             "x_stride %d unsupported (2 only with ksize 2)", xstride);
   B2_REQUIRE(a->cout % 8 == 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0, B2_ERR_SHAPE, "channels must be multiples of 8");
   B2_REQUIRE(a->c1 == 0 || a->c0 % 64 == 0, B2_ERR_SHAPE, "c0=%d must be a multiple of 64 when c1>0", a->c0);
   B2_REQUIRE((a->c0 + a->c1) % 4 == 0, B2_ERR_SHAPE, "cin must be a multiple of 4");
@@ -270,15 +267,14 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   p.ctot = a->c0 + a->c1;
   p.a_boxes = a->cout <= 64 ? 1 : 2;
   const int cbt = p.cb0 + p.cb1;
-  if (p.taps == 9) {
-    p.ncolb = 3;
-    pl->gy = 3;
-    pl->gz = ((a->cout + 127) / 128) * cbt;
-  } else {
-    p.ncolb = cbt < 4 ? cbt : 4;
-    pl->gy = 1;
-    pl->gz = ((a->cout + 127) / 128) * ((cbt + p.ncolb - 1) / p.ncolb);
-  }
+  p.ksize = a->ksize;
+  p.pad = a->ksize == 3 ? 1 : 0;
+  p.xstride = xstride;
+  p.cpb = a->ksize == 3 ? 1 : (a->ksize == 2 ? 2 : 4);
+  if (p.cpb > cbt) p.cpb = cbt;
+  p.ncolb = p.ksize * p.cpb;
+  pl->gy = p.ksize;
+  pl->gz = ((a->cout + 127) / 128) * ((cbt + p.cpb - 1) / p.cpb);
   const int base = pl->gy * pl->gz;
   // split-K factor: one CTA per SM is resident, so pick the split count (up to ~3 waves) whose grid fills whole
   // waves best; ties go to fewer splits (less workspace traffic)
@@ -299,7 +295,7 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   splits = (p.num_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   pl->splits = splits;
   pl->count = (long long)a->cout * p.taps * p.ctot;
-  p.xhalo = (p.taps == 9 && p.Wb >= 16 && p.Nb == 1 && getenv("B200SEG_WG_HALO") != nullptr &&
+  p.xhalo = (p.taps == 9 && xstride == 1 && p.Wb >= 16 && p.Nb == 1 && getenv("B200SEG_WG_HALO") != nullptr &&
              atoi(getenv("B200SEG_WG_HALO")) != 0) ? 1 : 0;
   if (p.xhalo) {
     p.b_tx_bytes = (p.Wb + 2) * p.Hb * 128;
@@ -354,10 +350,13 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     if (rc) return rc;
   }
   const int xboxw = pl.p.xhalo ? pl.p.Wb + 2 : pl.p.Wb;
-  rc = encode_act_tmap(&tmX0, a->x0, a->c0, a->ldx0, a->n, a->h, a->w, xboxw, pl.p.Hb, pl.p.Nb);
+  const int xs = pl.p.xstride, xh = a->h * xs, xw = a->w * xs;     // X extent (2x the dY grid for ConvTranspose)
+  rc = encode_act_tmap_ex(&tmX0, a->x0, a->c0, a->n, xh, xw, a->ldx0, (long long)a->ldx0 * xw,
+                          (long long)a->ldx0 * xw * xh, xboxw, pl.p.Hb, pl.p.Nb, xs);
   if (rc) return rc;
   if (a->c1 > 0) {
-    rc = encode_act_tmap(&tmX1, a->x1, a->c1, a->ldx1, a->n, a->h, a->w, xboxw, pl.p.Hb, pl.p.Nb);
+    rc = encode_act_tmap_ex(&tmX1, a->x1, a->c1, a->n, xh, xw, a->ldx1, (long long)a->ldx1 * xw,
+                            (long long)a->ldx1 * xw * xh, xboxw, pl.p.Hb, pl.p.Nb, xs);
     if (rc) return rc;
   } else {
     tmX1 = tmX0;

@@ -51,7 +51,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
+                     const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   B2_REQUIRE(fn != nullptr, B2_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no driver?)");
   B2_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, B2_ERR_ALIGN, "TMA base pointer not 16B aligned");
@@ -62,7 +63,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) {
       gstr[i - 1] = strides_bytes[i];
       B2_REQUIRE((strides_bytes[i] & 15) == 0, B2_ERR_ALIGN, "TMA stride %d = %llu B not a multiple of 16", i,

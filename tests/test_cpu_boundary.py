@@ -1,0 +1,90 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/b200seg.h declares,
+the ctypes table covers the header, the modules have the reference's exact state_dict layout (from the golden
+fixtures written by the real reference), and nothing silently falls back to a CPU path."""
+import re
+import warnings
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+def _header_symbols():
+    text = (ROOT / "include" / "b200seg.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from b200seg import _lib
+    lib = _lib.load()
+    names = _header_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200seg.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in b200seg/_lib.py"
+    assert set(_lib.SIGNATURES) <= set(names), set(_lib.SIGNATURES) - set(names)
+    assert lib.b2_abi_version() == 1
+
+
+def test_no_gpu_means_error_not_fallback():
+    from b200seg import _lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    rc = lib.b2_arch_check()
+    assert rc < 0 and lib.b2_last_error()
+    from b200seg.models.segmentation_models import AttentionUNet
+    m = AttentionUNet()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("case,cls,kw", [("AttentionUNet", "AttentionUNet", {}), ("R2U_Net", "R2U_Net", {"t": 2}),
+                                         ("R2AttU_Net", "R2AttU_Net", {"t": 2}), ("R2U_Net_t5", "R2U_Net", {}),
+                                         ("ResNetUnet", "ResNetUnet", {})])
+def test_state_dict_layout_matches_reference(case, cls, kw):
+    from b200seg.models import segmentation_models as M
+    g = np.load(GOLD / f"{case}.npz")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = getattr(M, cls)(**kw)
+    sd = m.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    for (k, v), shp, dt in zip(sd.items(), g["shapes"], g["dtypes"]):
+        assert ",".join(map(str, v.shape)) == str(shp), k
+        assert str(v.dtype).replace("torch.", "") == str(dt), k
+    assert [int(p.requires_grad) for p in m.parameters()] == [int(r) for r in g["requires_grad"]]
+
+
+def test_factory_and_ops_registered():
+    from b200seg.utils import helpers
+    import b200seg.ops  # noqa: F401
+    import b200seg.ops_resnet  # noqa: F401
+    for name, cls in (("attentionunet", "AttentionUNet"), ("r2unet", "R2U_Net"), ("r2attunet", "R2AttU_Net")):
+        assert type(helpers.get_seg_model(name)).__name__ == cls
+    with pytest.raises(ValueError):
+        helpers.get_seg_model("nope")
+    for op in ("conv2d", "conv_bn_act", "bn_apply", "gate_mid", "head", "seg_loss", "maxpool2x2", "upsample2x",
+               "conv_transpose2x2", "enc_conv_bn"):
+        assert hasattr(torch.ops.b200seg, op), op
+
+
+def test_fake_kernels_give_reference_shapes():
+    """register_fake implementations (shape/dtype propagation without a GPU)"""
+    import b200seg.ops as ops
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        x = torch.empty(2, 32, 32, 64, dtype=torch.bfloat16, device="cuda")
+        w = torch.empty(128, 64, 3, 3, device="cuda")
+        g = torch.empty(128, device="cuda")
+        y, z, coef, stats, x4 = ops.conv_bn_act(x, None, w, None, g, g, g, g, True, 1e-5, True)
+        assert y.shape == (2, 32, 32, 128) and y.dtype == torch.bfloat16 and coef.shape == (4, 128)
+        assert ops.maxpool2x2(y).shape == (2, 16, 16, 128)
+        assert ops.upsample2x(y).shape == (2, 64, 64, 128)
+        hw = torch.empty(1, 128, 1, 1, device="cuda")
+        assert ops.head(y, hw, None).shape == (2, 1, 32, 32)
