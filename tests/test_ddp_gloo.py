@@ -26,7 +26,7 @@ def _worker(rank, world, initfile, out):
     dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
     m = _model()
     red = GradReducer(m, bucket_mb=0.0005)          # tiny buckets -> several all-reduces, exercising the ordering
-    assert len(red.buckets) >= 3
+    assert len(red.buckets) >= 2
     for step in range(2):                           # two steps: buckets must reset correctly
         m.zero_grad(set_to_none=True)
         x, t = _data(rank)
