@@ -33,8 +33,9 @@ for _p in (str(ROOT), str(PKG)):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-METRIC = "AttU_Net 256x256 train images/sec"
-TRAIN_GFLOP_PER_IMG = {"AttentionUNet": 398.32, "R2U_Net": 1697.66, "R2AttU_Net": 1704.13}
+METRIC = "AttU_Net 256x256 train images/sec"     # other --model values report "<model> ... train images/sec"
+TRAIN_GFLOP_PER_IMG = {"AttentionUNet": 398.32, "R2U_Net": 1697.66, "R2AttU_Net": 1704.13,
+                       "ResNetUnet": 234.43}   # SURVEY.md §8(d); R2 figures are for the ctor default t=5
 
 
 def parse():
@@ -44,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
-    ap.add_argument("--model", default="AttentionUNet", choices=["AttentionUNet", "R2U_Net", "R2AttU_Net"])
+    ap.add_argument("--model", default="AttentionUNet", choices=["AttentionUNet", "R2U_Net", "R2AttU_Net", "ResNetUnet"])
     ap.add_argument("--t", type=int, default=None, help="recurrence depth for the R2 models (reference default 5)")
     ap.add_argument("--side", type=int, default=256)
     ap.add_argument("--cpu-batch", type=int, default=4)
@@ -117,8 +118,10 @@ def cpu_reference_steps(model_name, kw, batch, side, steps, warmup, with_optimiz
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     sd = {k: v.detach().clone() for k, v in getattr(M, model_name)(**kw).state_dict().items()}
+    frozen = ("encoder",) if model_name == "ResNetUnet" else ()      # reference default freeze=True
     params = {k: v.requires_grad_(True) for k, v in sd.items()
-              if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+              if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))
+              and not k.startswith(frozen or ("\0",))}
     opt = torch.optim.AdamW(list(params.values()), lr=1e-6, weight_decay=5e-4)
     x, t = xray_batch(batch, side, side, seed=0)
     times = []
@@ -189,7 +192,8 @@ def run_b200(args):
     torch.manual_seed(0)
     model = getattr(M, args.model)(**kw).to(dev, memory_format=torch.channels_last)   # helpers.py:243
     model.train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-6, weight_decay=5e-4, fused=True)   # helpers.py:251
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-6, weight_decay=5e-4,
+                            fused=True)   # helpers.py:251
     reducer = GradReducer(model, bucket_mb=32) if world > 1 else None
     B, S = args.batch, args.side
     x_host, t_host = xray_batch(B, S, S, seed=100 + rank)
@@ -269,7 +273,8 @@ def run_b200(args):
     ach_w = fw / (tw * 1e-3) / 1e12
     step_ms = ms / args.steps
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if args.model == "AttentionUNet" else f"{args.model} {S}x{S} train images/sec",
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.model} {S}x{S} training step (fwd + BCEWithLogits + bwd + clip_grad_norm + "

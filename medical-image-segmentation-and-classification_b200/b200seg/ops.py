@@ -103,6 +103,7 @@ def conv2d_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, nee
 
 
 def _conv2d_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
     x0, x1, weight, bias, _ = inputs
     ctx.save_for_backward(x0, x1, weight)
     ctx.has_bias = bias is not None
@@ -151,6 +152,7 @@ def stem_conv_bwd(dy: Tensor, x4: Tensor, weight: Tensor, need_db: bool) -> Tupl
 
 
 def _stem_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
     _, weight, bias, _ = inputs
     ctx.save_for_backward(output[2], weight)
     ctx.has_bias = bias is not None
@@ -304,6 +306,7 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
 
 
 def _cba_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
     x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu = inputs
     _y, z, coef, _stats, x4 = output
     stem = x0.dtype != torch.bfloat16
@@ -441,6 +444,7 @@ def gate_mid_bwd(dout: Tensor, x: Tensor, psi: Tensor, q: Tensor, g1p: Tensor, x
 
 
 def _gate_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
     (g1p, x1p, x, coef_g, coef_x, gamma_g, _bg, gamma_x, _bx, wpsi, _bpsi, gamma_1, _b1, _rm1, _rv1, training,
      _eps) = inputs
     out, q, psi, coef_1, _qstats = output
@@ -521,6 +525,7 @@ def seg_loss_bwd(grad_out: Tensor, logits: Tensor, target: Tensor, sums: Tensor,
 
 
 def _loss_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
     logits, target, ctx.w_bce, ctx.w_dice, ctx.smooth = inputs
     ctx.save_for_backward(logits, target, output[1])
 
