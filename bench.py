@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--side", type=int, default=256)
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="capture the whole training step in a CUDA graph (single-GPU runs); 0 = eager launches")
     return ap.parse_args()
 
 
@@ -192,8 +194,9 @@ def run_b200(args):
     torch.manual_seed(0)
     model = getattr(M, args.model)(**kw).to(dev, memory_format=torch.channels_last)   # helpers.py:243
     model.train()
+    use_graph = bool(args.graph) and world == 1
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-6, weight_decay=5e-4,
-                            fused=True)   # helpers.py:251
+                            fused=True, capturable=use_graph)   # helpers.py:251
     reducer = GradReducer(model, bucket_mb=32) if world > 1 else None
     B, S = args.batch, args.side
     x_host, t_host = xray_batch(B, S, S, seed=100 + rank)
@@ -230,18 +233,53 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, t_dev)
+    # warm-up (eager) on a side stream, then optionally capture the whole step — forward, loss, backward, clip, AdamW —
+    # in ONE CUDA graph: every kernel of the step is replayed without any Python / launch overhead
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(args.warmup, 3)):
+            step(x_dev, t_dev)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph, static_loss, launches_per_step = None, None, None
+    if use_graph:
+        try:
+            opt.zero_grad(set_to_none=True)
+            l_before = _lib.launch_count
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step(x_dev, t_dev)
+            launches_per_step = _lib.launch_count - l_before
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:   # keep the eager path measurable if capture is refused
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
+                  file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return step(x_dev, t_dev)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count
-    ms = timed(lambda: step(x_dev, t_dev), args.steps)
-    launches = (_lib.launch_count - l0)
+    ms = timed(run_step, args.steps)
+    launches = (_lib.launch_count - l0) if graph is None else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end: pinned host batch -> device, loss -> host, every step
     def e2e_step():
+        if graph is not None:
+            x_dev.copy_(x_host, non_blocking=True)
+            t_dev.copy_(t_host, non_blocking=True)
+            graph.replay()
+            return float(static_loss)
         x = x_host.to(dev, non_blocking=True)
         t = t_host.to(dev, non_blocking=True)
         return float(step(x, t))
@@ -281,7 +319,7 @@ def run_b200(args):
                                f"AdamW), batch {B} per GPU, random init, synthetic X-ray-shaped inputs",
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2",
-                   "model_kwargs": kw},
+                   "model_kwargs": kw, "cuda_graph": graph is not None},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

@@ -79,6 +79,12 @@ typedef struct b2_conv_args {
    * (w*out_mul) image — the pixel-shuffle scatter of ConvTranspose2d(k=2,s=2) (ResnetUnet.py:21,53) */
   int32_t stride;
   int32_t out_mul, out_off_h, out_off_w;
+  /* the A operand may likewise be the sub-lattice x[n, h*in_mul + in_off_h, w*in_mul + in_off_w, :] of an
+   * (h*in_mul) x (w*in_mul) image, and the tap offsets (r - pad_h, s - pad_w) may be overridden (custom_pad != 0):
+   * the four 2x2 phase convolutions that nearest-x2 upsampling + conv3x3 decomposes into (UpConv,
+   * AttentionUNet.py:15-27) are expressed with ksize 2, custom pads and these placements */
+  int32_t in_mul, in_off_h, in_off_w;
+  int32_t custom_pad, pad_h, pad_w;
 } b2_conv_args;
 
 int b2_conv_fprop(const b2_conv_args* a, b2_stream_t stream);
@@ -105,6 +111,9 @@ typedef struct b2_wgrad_args {
    * ConvTranspose2d(k=2,s=2) (dy := the transposed conv's INPUT on the coarse grid, x := its output gradient on the
    * 2x grid; result [cin_T][2*2][cout_T]) */
   int32_t x_stride;
+  /* dY as the sub-lattice dy[n, h*dy_mul + dy_off_h, w*dy_mul + dy_off_w, :]; custom X tap offsets (see b2_conv_args) */
+  int32_t dy_mul, dy_off_h, dy_off_w;
+  int32_t custom_pad, pad_h, pad_w;
 } b2_wgrad_args;
 
 int64_t b2_conv_wgrad_workspace(const b2_wgrad_args* a);
@@ -114,6 +123,15 @@ int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream);
  * (optional) dgrad packing [k*k][cin][cout] with the taps flipped. */
 int b2_pack_weights(const float* w, int32_t cout, int32_t cin, int32_t ksize, int64_t s_co, int64_t s_ci,
                     int64_t s_kh, int64_t s_kw, void* w_fprop, void* w_dgrad, b2_stream_t stream);
+
+/* UpConv folding (AttentionUNet.py:15-27: nearest x2 upsample followed by conv3x3): phase (a,b) of the 2x output grid
+ * is a 2x2 convolution of the LOW-resolution input with weights W_ab[u][v] = sum_{r in R_a(u)} sum_{s in R_b(v)} W[r][s],
+ * R_0 = ({0},{1,2}), R_1 = ({0,1},{2})  — 2.25x fewer FLOPs, exact algebra.
+ * w_fprop: bf16 [4 phases][4 taps][cout][cin];  w_dgrad: bf16 [4 phases][4 taps flipped][cin][cout] (may be NULL) */
+int b2_pack_weights_upfold(const float* w, int32_t cout, int32_t cin, int64_t s_co, int64_t s_ci, int64_t s_kh,
+                           int64_t s_kw, void* w_fprop, void* w_dgrad, b2_stream_t stream);
+/* adjoint of the folding: dw[cout][9][cin] = scatter-sum of dweff[4 phases][cout][4 taps][cin] (fp32) */
+int b2_fold_upconv_wgrad(const float* dweff, int32_t cout, int32_t cin, float* dw, b2_stream_t stream);
 
 /* Small-Cin direct convolution (image stem: AttentionUNet.py:6 with cin=3, R2U_Net.py:43 RRCNN1.conv_1x1).
  * x is NHWC bf16 padded to 4 channels; w is fp32 [cout][ksize*ksize][4]. */

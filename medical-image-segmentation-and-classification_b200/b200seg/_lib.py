@@ -28,7 +28,9 @@ class ConvArgs(C.Structure):
                 ("cout", _i32), ("y", _vp), ("ldy", _i32),
                 ("bias", _vp), ("addend", _vp), ("ldadd", _i32),
                 ("stats", _vp), ("relu", _i32),
-                ("stride", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32)]
+                ("stride", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32),
+                ("in_mul", _i32), ("in_off_h", _i32), ("in_off_w", _i32),
+                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32)]
 
 
 class WgradArgs(C.Structure):
@@ -38,7 +40,9 @@ class WgradArgs(C.Structure):
                 ("x0", _vp), ("c0", _i32), ("ldx0", _i32),
                 ("x1", _vp), ("c1", _i32), ("ldx1", _i32),
                 ("dw", _vp), ("accumulate", _i32),
-                ("workspace", _vp), ("workspace_bytes", _i64), ("x_stride", _i32)]
+                ("workspace", _vp), ("workspace_bytes", _i64), ("x_stride", _i32),
+                ("dy_mul", _i32), ("dy_off_h", _i32), ("dy_off_w", _i32),
+                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32)]
 
 
 class GateCoef(C.Structure):
@@ -60,6 +64,8 @@ SIGNATURES = {
     "b2_conv_wgrad_workspace": (_i64, [C.POINTER(WgradArgs)]),
     "b2_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "b2_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "b2_pack_weights_upfold": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "b2_fold_upconv_wgrad": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "b2_conv_smallc_fprop": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
     "b2_conv_smallc_wgrad": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b2_head_fwd": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),

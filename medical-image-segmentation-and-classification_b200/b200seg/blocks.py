@@ -10,12 +10,15 @@ Calling convention
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
 from . import ops
 
 BF16 = torch.bfloat16
+UPFOLD = os.environ.get("B200SEG_UPFOLD", "1") != "0"
 
 
 def _is_external(x) -> bool:
@@ -103,7 +106,10 @@ class UpConv(nn.Module):
     def forward(self, x):
         ext = _is_external(x)
         x = to_internal(x)
-        y = conv_bn_act(ops.upsample2x(x), self.up[1], self.up[2])
+        if UPFOLD:     # folded: four 2x2 phase convolutions on the low-resolution input (see ops.upconv_bn_act)
+            y = ops.upconv_bn_act_module(x, self.up[1], self.up[2])
+        else:          # literal: materialise the upsampled tensor, then conv3x3
+            y = conv_bn_act(ops.upsample2x(x), self.up[1], self.up[2])
         return ops.to_nchw(y) if ext else y
 
 

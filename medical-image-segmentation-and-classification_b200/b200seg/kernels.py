@@ -72,18 +72,37 @@ def pack_weights(weight, want_dgrad=True):
     return wf, wd
 
 
+def pack_weights_upfold(weight, want_dgrad=True):
+    """UpConv folding: fp32 [Cout, Cin, 3, 3] -> bf16 [4 phases, 4 taps, Cout, Cin] (+ [4, 4 flipped, Cin, Cout])"""
+    cout, cin, kh, kw = weight.shape
+    assert kh == 3 and kw == 3 and weight.dtype == torch.float32
+    wf = torch.empty((4, 4, cout, cin), dtype=BF16, device=weight.device)
+    wd = torch.empty((4, 4, cin, cout), dtype=BF16, device=weight.device) if want_dgrad else None
+    s = weight.stride()
+    call("b2_pack_weights_upfold", _p(weight), cout, cin, s[0], s[1], s[2], s[3], _p(wf), _p(wd), _stream())
+    return wf, wd
+
+
+def fold_upconv_wgrad(dweff):
+    """fp32 [4 phases, Cout, 4 taps, Cin] -> fp32 [Cout, 9, Cin]"""
+    _, cout, _, cin = dweff.shape
+    dw = torch.empty((cout, 9, cin), dtype=torch.float32, device=dweff.device)
+    call("b2_fold_upconv_wgrad", _p(dweff), cout, cin, _p(dw), _stream())
+    return dw
+
+
 # ----------------------------------------------------------------------------------------------------------
 # tcgen05 convolutions
 # ----------------------------------------------------------------------------------------------------------
 def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None, relu=False, out=None,
-               row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0)):
+               row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0), in_mul=1, in_off=(0, 0), pad=None):
     """y = conv(x0 | x1; wpk) (+bias) (+addend) (relu); wpk is [taps, rows, ktot] bf16, rows [row_offset,
     row_offset+cout) are used.  `stats` (fp64 [2, cout]) accumulates sum / sumsq of the rounded output.
     stride=2 samples the input on a 2x finer grid (strided conv / ConvTranspose dgrad); out_mul=2 places the result
     at pixels (2h+off_h, 2w+off_w) of `out` (ConvTranspose pixel shuffle)."""
     n, hi, wi, c0, ld0 = _nhwc(x0)
-    assert hi % stride == 0 and wi % stride == 0
-    h, w = hi // stride, wi // stride
+    assert hi % (stride * in_mul) == 0 and wi % (stride * in_mul) == 0
+    h, w = hi // (stride * in_mul), wi // (stride * in_mul)     # output grid (in_mul: x0 is read as a sub-lattice)
     c1, ld1 = 0, 0
     if x1 is not None:
         n1, h1, w1, c1, ld1 = _nhwc(x1)
@@ -113,16 +132,21 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
         a.stats = stats.data_ptr()
     a.relu = int(relu)
     a.stride, a.out_mul, a.out_off_h, a.out_off_w = stride, out_mul, out_off[0], out_off[1]
+    a.in_mul, a.in_off_h, a.in_off_w = in_mul, in_off[0], in_off[1]
+    if pad is not None:
+        a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
     t0 = _prof_begin()
     call("b2_conv_dgrad" if dgrad else "b2_conv_fprop", C.byref(a), _stream())
     _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0)
     return y
 
 
-def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1):
+def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, dy_mul=1, dy_off=(0, 0), pad=None):
     """dW fp32 [Cout, k*k, C0+C1] = sum_p dY[p] (x) X[p+tap].  x_stride=2 (ksize 2): X lives on the 2x finer grid
     (weight gradient of ConvTranspose2d(k=2,s=2) with dy := its input, x := its output gradient)."""
-    n, h, w, cout, lddy = _nhwc(dy)
+    n, hd, wd_, cout, lddy = _nhwc(dy)
+    assert hd % dy_mul == 0 and wd_ % dy_mul == 0
+    h, w = hd // dy_mul, wd_ // dy_mul                          # dY is read as a sub-lattice when dy_mul > 1
     nx, hx, wx, c0, ld0 = _nhwc(x0)
     assert (nx, hx, wx) == (n, h * x_stride, w * x_stride)
     c1, ld1 = 0, 0
@@ -139,6 +163,9 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1):
     a.dw = dw.data_ptr()
     a.accumulate = int(accumulate)
     a.x_stride = x_stride
+    a.dy_mul, a.dy_off_h, a.dy_off_w = dy_mul, dy_off[0], dy_off[1]
+    if pad is not None:
+        a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
     need = _lib.load().b2_conv_wgrad_workspace(C.byref(a))
     if need < 0:
         _lib.check(int(need), "b2_conv_wgrad_workspace")

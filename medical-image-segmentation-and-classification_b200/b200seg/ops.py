@@ -350,6 +350,102 @@ def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu:
 
 
 # ----------------------------------------------------------------------------------------------------------
+# UpConv = Upsample(x2, nearest) -> Conv3x3 -> BN -> ReLU (AttentionUNet.py:15-27, R2U_Net.py:22-34), folded:
+# phase (a,b) of the 2x grid is a 2x2 convolution of the LOW-resolution input with summed weights, so the upsampled
+# tensor is never built and the three GEMMs (fprop, dgrad, wgrad) do 16/36 of the reference's FLOPs.  Exact algebra;
+# the only numerical difference is that the 3x3 taps are summed in fp32 before the bf16 rounding of the weights.
+# ----------------------------------------------------------------------------------------------------------
+_PHASES = ((0, 0), (0, 1), (1, 0), (1, 1))
+
+
+@custom_op("b200seg::upconv_bn_act", mutates_args=())
+def upconv_bn_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], gamma: Tensor, beta: Tensor,
+                  running_mean: Tensor, running_var: Tensor, training: bool, eps: float,
+                  relu: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    cout, cin, _, _ = weight.shape
+    x = _c(x)
+    n, h, w, _ = x.shape
+    dev = x.device
+    stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
+    wf, _ = K.pack_weights_upfold(weight, want_dgrad=False)
+    z = K.new_act(n, 2 * h, 2 * w, cout, dev)
+    for ph, (a, b) in enumerate(_PHASES):
+        K.conv_igemm(x, wf[ph], cout, 2, bias=bias, stats=stats if training else None, out=z, out_mul=2,
+                     out_off=(a, b), pad=(1 - a, 1 - b))
+    if training:
+        coef = K.bn_finalize(stats, n * 4 * h * w, gamma, beta, eps, 0.0, None, None, None)
+    else:
+        coef = K.bn_eval_coeffs(gamma, beta, running_mean, running_var, eps)
+    return K.bn_apply(z, coef, relu=relu), z, coef, stats
+
+
+@upconv_bn_act.register_fake
+def _(x, weight, bias, gamma, beta, rm, rv, training, eps, relu):
+    n, h, w, _ = x.shape
+    cout = weight.shape[0]
+    y = x.new_empty((n, 2 * h, 2 * w, cout))
+    return (y, torch.empty_like(y), x.new_empty((4, cout), dtype=torch.float32),
+            x.new_empty((2, cout) if training else (0,), dtype=_F64))
+
+
+@custom_op("b200seg::upconv_bn_act_bwd", mutates_args=())
+def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Tensor, gamma: Tensor, relu: bool,
+                      training: bool, need_dx: bool, has_bias: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    cout, cin, _, _ = weight.shape
+    dev = dy.device
+    res = K.bn_bwd(_c(dy), z, coef, gamma, relu=relu, training=training, want_dbias=has_bias)
+    dz, dgamma, dbeta = res[0], res[1], res[2]
+    db = res[3] if has_bias else torch.empty((0,), device=dev)
+    n, h, w, _ = x.shape
+    if need_dx:
+        _, wd = K.pack_weights_upfold(weight, want_dgrad=True)
+        dx = K.new_act(n, h, w, cin, dev)
+        for ph, (a, b) in enumerate(_PHASES):
+            # 2x2 conv of the (a,b) sub-lattice of dz with the flipped/transposed phase weights, chained through the
+            # epilogue's addend so the four phases sum into one dx
+            K.conv_igemm(dz, wd[ph], cin, 2, addend=dx if ph > 0 else None, out=dx, dgrad=True, in_mul=2,
+                         in_off=(a, b), pad=(a, b))
+    else:
+        dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)
+    dweff = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=dev)
+    for ph, (a, b) in enumerate(_PHASES):
+        K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b))
+    dw = K.fold_upconv_wgrad(dweff)
+    return dx, dw, db, dgamma, dbeta
+
+
+def _ucba_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    x, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu = inputs
+    _y, z, coef, _stats = output
+    ctx.save_for_backward(_c(x), weight, z, coef, gamma)
+    ctx.has_bias = bias is not None
+
+
+def _ucba_backward(ctx, dy, *_unused):
+    x, weight, z, coef, gamma = ctx.saved_tensors
+    need_dx = bool(ctx.needs_input_grad[0])
+    dx, dw, db, dgamma, dbeta = upconv_bn_act_bwd(dy, x, weight, z, coef, gamma, ctx.relu, ctx.training, need_dx,
+                                                  ctx.has_bias)
+    return (dx if need_dx else None, _dw_as_param_grad(dw, weight), db if ctx.has_bias else None, dgamma, dbeta,
+            None, None, None, None, None)
+
+
+upconv_bn_act.register_autograd(_ucba_backward, setup_context=_ucba_setup)
+
+
+def upconv_bn_act_module(x: Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = True) -> Tensor:
+    training = bn.training or bn.running_mean is None
+    y, _z, _coef, stats = upconv_bn_act(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                        bn.running_var, training, float(bn.eps), relu)
+    if training:
+        n, h, w, _ = y.shape
+        bn_update_running_(stats.detach(), n * h * w, float(bn.momentum), bn.running_mean, bn.running_var,
+                           bn.num_batches_tracked)
+    return y
+
+
+# ----------------------------------------------------------------------------------------------------------
 # pooling / upsampling / add
 # ----------------------------------------------------------------------------------------------------------
 @custom_op("b200seg::maxpool2x2", mutates_args=())

@@ -40,7 +40,7 @@ struct IgemmParams {
   int block_n, stages, num_k_iters;
   int cout, n_tiles, m_tiles, m_stride;
   int halo, base_off_mode;
-  int stride, ksize, pad;
+  int stride, ksize, pad_h, pad_w;
   long long y_sn, y_sh, y_sw;   // element strides of the output pixel grid (strided placement for ConvT)
   int a_stage_bytes, b_stage_bytes, a_tx_bytes;
   int tma_store;
@@ -149,8 +149,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           ds = -1;
           tap0 = o * 3;
         } else {
-          dr = o / p.ksize - p.pad;
-          ds = o % p.ksize - p.pad;
+          dr = o / p.ksize - p.pad_h;
+          ds = o % p.ksize - p.pad_w;
         }
         for (int cb = 0; cb < cbt; ++cb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -423,7 +423,12 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   const int out_mul = a->out_mul == 0 ? 1 : a->out_mul;
   B2_REQUIRE(a->ksize >= 1 && a->ksize <= 3, B2_ERR_SHAPE, "ksize %d unsupported (1, 2 or 3)", a->ksize);
   B2_REQUIRE(stride == 1 || stride == 2, B2_ERR_SHAPE, "stride %d unsupported (1 or 2)", stride);
-  B2_REQUIRE(a->ksize != 2 || stride == 2, B2_ERR_SHAPE, "ksize 2 is only supported with stride 2");
+  const int in_mul = a->in_mul == 0 ? 1 : a->in_mul;
+  B2_REQUIRE(a->ksize != 2 || stride == 2 || a->custom_pad != 0, B2_ERR_SHAPE,
+             "ksize 2 needs stride 2 or explicit tap offsets");
+  B2_REQUIRE(in_mul >= 1 && (in_mul == 1 || stride == 1) && a->in_off_h >= 0 && a->in_off_h < in_mul &&
+                 a->in_off_w >= 0 && a->in_off_w < in_mul,
+             B2_ERR_SHAPE, "bad input placement mul=%d off=(%d,%d)", in_mul, a->in_off_h, a->in_off_w);
   B2_REQUIRE(out_mul >= 1 && a->out_off_h >= 0 && a->out_off_h < out_mul && a->out_off_w >= 0 &&
                  a->out_off_w < out_mul,
              B2_ERR_SHAPE, "bad output placement mul=%d off=(%d,%d)", out_mul, a->out_off_h, a->out_off_w);
@@ -460,8 +465,10 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   const int halo_env = env_int("B200SEG_HALO", 1);
   p.stride = stride;
   p.ksize = a->ksize;
-  p.pad = a->ksize == 3 ? 1 : 0;
-  p.halo = (halo_env != 0 && p.taps == 9 && stride == 1 && p.Hb == 1 && p.Nb == 1 && p.Wb == kTileM) ? 1 : 0;
+  p.pad_h = a->custom_pad ? a->pad_h : (a->ksize == 3 ? 1 : 0);
+  p.pad_w = a->custom_pad ? a->pad_w : (a->ksize == 3 ? 1 : 0);
+  p.halo = (halo_env != 0 && p.taps == 9 && stride == 1 && !a->custom_pad && p.Hb == 1 && p.Nb == 1 &&
+            p.Wb == kTileM) ? 1 : 0;
   p.base_off_mode = (halo_env == 2) ? 1 : 0;
   if (p.halo) {
     p.a_tx_bytes = (kTileM + 2) * 128;
@@ -487,11 +494,18 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
 
   CUtensorMap tmA0, tmA1, tmB, tmY;
   const int boxw = p.halo ? p.Wb + 2 : p.Wb;
-  const int ih = a->h * stride, iw = a->w * stride;      // input extent
-  rc = encode_act_tmap_ex(&tmA0, a->x0, a->c0, a->n, ih, iw, a->ldx0, (long long)a->ldx0 * iw,
-                          (long long)a->ldx0 * iw * ih, boxw, p.Hb, p.Nb, stride);
-  if (rc) return rc;
+  const int ih = a->h * stride, iw = a->w * stride;      // extent of the sampled input grid
+  {
+    // underlying image is (ih*in_mul) x (iw*in_mul); the operand is its (in_off_h, in_off_w) sub-lattice
+    const long long fw = (long long)iw * in_mul, fh = (long long)ih * in_mul;
+    const long long off0 = ((long long)a->in_off_h * fw + a->in_off_w) * a->ldx0;
+    rc = encode_act_tmap_ex(&tmA0, static_cast<const __nv_bfloat16*>(a->x0) + off0, a->c0, a->n, ih, iw,
+                            (long long)in_mul * a->ldx0, (long long)in_mul * fw * a->ldx0, fh * fw * a->ldx0, boxw,
+                            p.Hb, p.Nb, stride);
+    if (rc) return rc;
+  }
   if (a->c1 > 0) {
+    B2_REQUIRE(in_mul == 1, B2_ERR_SHAPE, "input placement is not supported with two K sources");
     rc = encode_act_tmap_ex(&tmA1, a->x1, a->c1, a->n, ih, iw, a->ldx1, (long long)a->ldx1 * iw,
                             (long long)a->ldx1 * iw * ih, boxw, p.Hb, p.Nb, stride);
     if (rc) return rc;

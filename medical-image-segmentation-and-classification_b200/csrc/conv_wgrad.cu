@@ -29,7 +29,7 @@ struct WgradParams {
   int Wb, Hb, Nb, tw, th;
   int num_chunks, chunks_per_split;
   int taps;          // ksize^2
-  int ksize, pad, xstride;   // X-operand tap geometry: offsets (r - pad, s - pad), sampling stride
+  int ksize, pad_h, pad_w, xstride;   // X-operand tap geometry: offsets (r - pad_h, s - pad_w), sampling stride
   int cpb;           // 64-channel X blocks per CTA
   int ncolb;         // column blocks per CTA = ksize (taps of one filter row) x cpb
   int cb0, cb1;      // 64-channel blocks per X source
@@ -121,8 +121,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           }
           for (int j = 0; j < (p.xhalo ? 0 : ncol_live); ++j) {
             const int cib = cib_base + j / p.ksize;
-            const int xw = p.xstride * w0 + (j % p.ksize) - p.pad;
-            const int xh = p.xstride * h0 + rg - p.pad;
+            const int xw = p.xstride * w0 + (j % p.ksize) - p.pad_w;
+            const int xh = p.xstride * h0 + rg - p.pad_h;
             if (cib < p.cb0)
               tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, xw, xh, n0);
             else
@@ -252,6 +252,8 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   B2_REQUIRE(a->ksize >= 1 && a->ksize <= 3, B2_ERR_SHAPE, "ksize %d unsupported", a->ksize);
   B2_REQUIRE(xstride == 1 || (xstride == 2 && a->ksize == 2), B2_ERR_SHAPE,
              "x_stride %d unsupported (2 only with ksize 2)", xstride);
+  B2_REQUIRE(a->ksize != 2 || xstride == 2 || a->custom_pad != 0, B2_ERR_SHAPE,
+             "ksize 2 needs x_stride 2 or explicit tap offsets");
   B2_REQUIRE(a->cout % 8 == 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0, B2_ERR_SHAPE, "channels must be multiples of 8");
   B2_REQUIRE(a->c1 == 0 || a->c0 % 64 == 0, B2_ERR_SHAPE, "c0=%d must be a multiple of 64 when c1>0", a->c0);
   B2_REQUIRE((a->c0 + a->c1) % 4 == 0, B2_ERR_SHAPE, "cin must be a multiple of 4");
@@ -268,7 +270,8 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   p.a_boxes = a->cout <= 64 ? 1 : 2;
   const int cbt = p.cb0 + p.cb1;
   p.ksize = a->ksize;
-  p.pad = a->ksize == 3 ? 1 : 0;
+  p.pad_h = a->custom_pad ? a->pad_h : (a->ksize == 3 ? 1 : 0);
+  p.pad_w = a->custom_pad ? a->pad_w : (a->ksize == 3 ? 1 : 0);
   p.xstride = xstride;
   p.cpb = a->ksize == 3 ? 1 : (a->ksize == 2 ? 2 : 4);
   if (p.cpb > cbt) p.cpb = cbt;
@@ -295,7 +298,7 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   splits = (p.num_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   pl->splits = splits;
   pl->count = (long long)a->cout * p.taps * p.ctot;
-  p.xhalo = (p.taps == 9 && xstride == 1 && p.Wb >= 16 && p.Nb == 1 && getenv("B200SEG_WG_HALO") != nullptr &&
+  p.xhalo = (p.taps == 9 && xstride == 1 && !a->custom_pad && p.Wb >= 16 && p.Nb == 1 && getenv("B200SEG_WG_HALO") != nullptr &&
              atoi(getenv("B200SEG_WG_HALO")) != 0) ? 1 : 0;
   if (p.xhalo) {
     p.b_tx_bytes = (p.Wb + 2) * p.Hb * 128;
@@ -342,11 +345,16 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     // laid out [block][pixel][64 ch] in smem
     B2_REQUIRE(a->lddy % 8 == 0 && a->cout % 8 == 0, B2_ERR_ALIGN, "dy channel count / stride must be multiples of 8");
     const uint64_t c_in_block = a->cout < 64 ? (uint64_t)a->cout : 64ull;
+    const int dm = a->dy_mul == 0 ? 1 : a->dy_mul;
+    B2_REQUIRE(a->dy_off_h >= 0 && a->dy_off_h < dm && a->dy_off_w >= 0 && a->dy_off_w < dm, B2_ERR_SHAPE,
+               "bad dY placement mul=%d off=(%d,%d)", dm, a->dy_off_h, a->dy_off_w);
+    const uint64_t fw = (uint64_t)a->w * dm, fh = (uint64_t)a->h * dm;     // underlying dY image extent
+    const __nv_bfloat16* dyb = static_cast<const __nv_bfloat16*>(a->dy) +
+                               ((long long)a->dy_off_h * fw + a->dy_off_w) * a->lddy;
     uint64_t dims[5] = {c_in_block, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n, (uint64_t)((a->cout + 63) / 64)};
-    uint64_t str[5] = {2, (uint64_t)a->lddy * 2, (uint64_t)a->lddy * 2 * a->w, (uint64_t)a->lddy * 2 * a->w * a->h,
-                       128};
+    uint64_t str[5] = {2, (uint64_t)dm * a->lddy * 2, (uint64_t)dm * fw * a->lddy * 2, fh * fw * a->lddy * 2, 128};
     uint32_t box[5] = {64, (uint32_t)pl.p.Wb, (uint32_t)pl.p.Hb, (uint32_t)pl.p.Nb, (uint32_t)pl.p.a_boxes};
-    rc = encode_tmap_bf16(&tmDY, a->dy, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = encode_tmap_bf16(&tmDY, dyb, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   const int xboxw = pl.p.xhalo ? pl.p.Wb + 2 : pl.p.Wb;

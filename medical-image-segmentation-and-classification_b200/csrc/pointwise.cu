@@ -31,6 +31,57 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   }
 }
 
+// UpConv folding: which 3x3 taps collapse onto tap u (0/1) of phase a (0/1): a=0 -> {0},{1,2}; a=1 -> {0,1},{2}
+__device__ __forceinline__ bool upfold_member(int a, int u, int r) {
+  return a == 0 ? (u == 0 ? r == 0 : r >= 1) : (u == 0 ? r <= 1 : r == 2);
+}
+
+// fp32 [cout][cin][3][3] -> bf16 wf [phase][tap][cout][cin], wd [phase][3 - tap][cin][cout]
+__global__ void pack_weights_upfold_kernel(const float* __restrict__ w, int cout, int cin, long long s_co,
+                                           long long s_ci, long long s_kh, long long s_kw,
+                                           __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const long long total = 16ll * cout * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int co = (int)((i / cin) % cout);
+    const int pt = (int)(i / ((long long)cin * cout));   // phase * 4 + tap
+    const int phase = pt >> 2, tap = pt & 3;
+    const int a = phase >> 1, b = phase & 1, u = tap >> 1, v = tap & 1;
+    float s = 0.f;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        if (upfold_member(a, u, r) && upfold_member(b, v, c)) s += w[co * s_co + ci * s_ci + r * s_kh + c * s_kw];
+    const __nv_bfloat16 val = __float2bfloat16_rn(s);
+    if (wf) wf[i] = val;
+    if (wd) wd[(((long long)phase * 4 + (3 - tap)) * cin + ci) * cout + co] = val;
+  }
+}
+
+// dw[co][r*3+c][ci] = sum over (a,u) containing r and (b,v) containing c of dweff[a*2+b][co][u*2+v][ci]
+__global__ void fold_upconv_wgrad_kernel(const float* __restrict__ dweff, int cout, int cin,
+                                         float* __restrict__ dw) {
+  const long long total = 9ll * cout * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin);
+    const int tap = (int)((i / cin) % 9);
+    const int co = (int)(i / (9ll * cin));
+    const int r = tap / 3, c = tap % 3;
+    float s = 0.f;
+    for (int a = 0; a < 2; ++a)
+      for (int u = 0; u < 2; ++u) {
+        if (!upfold_member(a, u, r)) continue;
+        for (int b = 0; b < 2; ++b)
+          for (int v = 0; v < 2; ++v) {
+            if (!upfold_member(b, v, c)) continue;
+            s += dweff[(((long long)(a * 2 + b) * cout + co) * 4 + (u * 2 + v)) * cin + ci];
+          }
+      }
+    dw[i] = s;
+  }
+}
+
 __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int cg,
                                       __nv_bfloat16* __restrict__ y, int ldy) {
   const int ho = h / 2, wo = w / 2;
@@ -195,6 +246,23 @@ extern "C" int b2_pack_weights(const float* w, int32_t cout, int32_t cin, int32_
   const long long total = (long long)taps * cout * cin;
   pack_weights_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
       w, cout, cin, taps, ksize, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_pack_weights_upfold(const float* w, int32_t cout, int32_t cin, int64_t s_co, int64_t s_ci,
+                                      int64_t s_kh, int64_t s_kw, void* w_fprop, void* w_dgrad,
+                                      b2_stream_t stream) {
+  B2_REQUIRE(cout > 0 && cin > 0, B2_ERR_SHAPE, "bad weight shape");
+  pack_weights_upfold_kernel<<<ew_grid(16ll * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
+      w, cout, cin, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_fold_upconv_wgrad(const float* dweff, int32_t cout, int32_t cin, float* dw, b2_stream_t stream) {
+  B2_REQUIRE(cout > 0 && cin > 0, B2_ERR_SHAPE, "bad weight shape");
+  fold_upconv_wgrad_kernel<<<ew_grid(9ll * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(dweff, cout, cin, dw);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -133,3 +133,39 @@ def test_train_mode_vs_reference_noise_floor(name):
     rm_err = max(rel(msd[k], v) for k, v in newb.items() if k.endswith("running_var"))
     print(f"{name} running_var worst rel {rm_err:.3e}")
     assert rm_err < max(1.25 * e_floor, 2e-2)
+
+
+@pytest.mark.parametrize("cin,cout,h", [(128, 64, 32), (1024, 512, 16), (256, 128, 64)])
+def test_upconv_folded_matches_literal_and_oracle(cin, cout, h):
+    """UpConv with the upsample folded into four 2x2 phase convolutions vs the fp64 oracle (and vs the literal
+    upsample -> conv3x3 CUDA path): forward <= 1e-2 (block level, train mode), gradients vs the reference's own bf16."""
+    import torch.nn as nn
+    from b200seg import blocks
+    from oracle import unet_oracle as O
+    torch.manual_seed(3)
+    m = blocks.UpConv(cin, cout).cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(2, cin, h, h, device="cuda", generator=g)
+    dy = torch.randn(2, cout, 2 * h, 2 * h, device="cuda", generator=g)
+    res = {}
+    for mode in (True, False):
+        blocks.UPFOLD = mode
+        m.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        y = m(xi)
+        y.backward(dy)
+        res[mode] = (y.detach(), xi.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters()})
+    blocks.UPFOLD = True
+    sd = {("up.up." + k): v.detach().double() if v.is_floating_point() else v.detach().clone() for k, v in m.up.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    xr = x.double().requires_grad_(True)
+    yr, _ = O.up_conv({**sd, **params}, xr, "up", training=True)
+    yr.backward(dy.double())
+    for mode in (True, False):
+        y, dx, gr = res[mode]
+        e_y, e_dx = rel(y, yr), rel(dx, xr.grad)
+        e_w = rel(gr["up.1.weight"], params["up.up.1.weight"].grad)
+        print(f"UpConv {cin}->{cout} @{h} folded={mode}: y {e_y:.2e} dx {e_dx:.2e} dW {e_w:.2e}")
+        assert e_y < 1e-2
+        assert e_dx < 8e-2 and e_w < 8e-2      # reference's own bf16 block gradients deviate 3.5e-2 (SURVEY App. C)
+    assert rel(res[True][0], res[False][0]) < 1e-2
