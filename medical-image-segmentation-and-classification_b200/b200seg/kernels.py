@@ -29,11 +29,13 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(kind, flops, start):
+def _prof_end(kind, flops, start, alg_scale=1.0):
+    """flops = executed by the launch; alg_scale * flops = the reference's algorithmic count for the same work
+    (9/4 for the folded UpConv phases, which do 4 taps on the coarse grid instead of 9 on the fine one)"""
     if start is not None:
         end = torch.cuda.Event(enable_timing=True)
         end.record()
-        PROFILE.append((kind, flops, start, end))
+        PROFILE.append((kind, flops, flops * alg_scale, start, end))
 
 
 def _stream():
@@ -95,7 +97,8 @@ def fold_upconv_wgrad(dweff):
 # tcgen05 convolutions
 # ----------------------------------------------------------------------------------------------------------
 def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None, relu=False, out=None,
-               row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0), in_mul=1, in_off=(0, 0), pad=None):
+               row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0), in_mul=1, in_off=(0, 0), pad=None,
+               alg_scale=1.0):
     """y = conv(x0 | x1; wpk) (+bias) (+addend) (relu); wpk is [taps, rows, ktot] bf16, rows [row_offset,
     row_offset+cout) are used.  `stats` (fp64 [2, cout]) accumulates sum / sumsq of the rounded output.
     stride=2 samples the input on a 2x finer grid (strided conv / ConvTranspose dgrad); out_mul=2 places the result
@@ -137,11 +140,12 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
         a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
     t0 = _prof_begin()
     call("b2_conv_dgrad" if dgrad else "b2_conv_fprop", C.byref(a), _stream())
-    _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0)
+    _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale)
     return y
 
 
-def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, dy_mul=1, dy_off=(0, 0), pad=None):
+def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, dy_mul=1, dy_off=(0, 0), pad=None,
+               alg_scale=1.0):
     """dW fp32 [Cout, k*k, C0+C1] = sum_p dY[p] (x) X[p+tap].  x_stride=2 (ksize 2): X lives on the 2x finer grid
     (weight gradient of ConvTranspose2d(k=2,s=2) with dy := its input, x := its output gradient)."""
     n, hd, wd_, cout, lddy = _nhwc(dy)
@@ -173,7 +177,7 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, d
     a.workspace, a.workspace_bytes = ws.data_ptr(), int(need)
     t0 = _prof_begin()
     call("b2_conv_wgrad", C.byref(a), _stream())
-    _prof_end("conv_wgrad", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0)
+    _prof_end("conv_wgrad", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale)
     return dw
 
 

@@ -371,7 +371,7 @@ def upconv_bn_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], gamma: Tens
     z = K.new_act(n, 2 * h, 2 * w, cout, dev)
     for ph, (a, b) in enumerate(_PHASES):
         K.conv_igemm(x, wf[ph], cout, 2, bias=bias, stats=stats if training else None, out=z, out_mul=2,
-                     out_off=(a, b), pad=(1 - a, 1 - b))
+                     out_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
     if training:
         coef = K.bn_finalize(stats, n * 4 * h * w, gamma, beta, eps, 0.0, None, None, None)
     else:
@@ -404,12 +404,12 @@ def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Te
             # 2x2 conv of the (a,b) sub-lattice of dz with the flipped/transposed phase weights, chained through the
             # epilogue's addend so the four phases sum into one dx
             K.conv_igemm(dz, wd[ph], cin, 2, addend=dx if ph > 0 else None, out=dx, dgrad=True, in_mul=2,
-                         in_off=(a, b), pad=(a, b))
+                         in_off=(a, b), pad=(a, b), alg_scale=2.25)
     else:
         dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     dweff = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=dev)
     for ph, (a, b) in enumerate(_PHASES):
-        K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b))
+        K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
     dw = K.fold_upconv_wgrad(dweff)
     return dx, dw, db, dgamma, dbeta
 

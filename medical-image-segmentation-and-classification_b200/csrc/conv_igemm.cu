@@ -408,9 +408,11 @@ static int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-static int pick_block_n(int cout) {
+static int pick_block_n(int cout, bool wide_rows) {
   const int forced = env_int("B200SEG_BLOCK_N", 0);
-  if (forced > 0 && cout % forced == 0) return forced;
+  // N = 256 tiles do not leave room for >= 3 pipeline stages in halo mode (3 taps of B per stage)
+  if (forced > 0 && cout % forced == 0 && !(forced > 128 && wide_rows)) return forced;
+  if (cout % 256 == 0 && !wide_rows) return 256;   // deep layers: halves the activation re-fetch, 96 B/clk smem feed
   if (cout % 128 == 0) return 128;
   if (cout % 64 == 0) return 64;
   if (cout % 32 == 0) return 32;
@@ -438,7 +440,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   B2_REQUIRE(a->ktot >= a->c0 + a->c1 && a->ktot % 8 == 0, B2_ERR_SHAPE, "ktot=%d inconsistent", a->ktot);
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  p.block_n = pick_block_n(a->cout);
+  p.block_n = pick_block_n(a->cout, a->ksize == 3 && a->w >= kTileM);
   B2_REQUIRE(p.block_n != 0, B2_ERR_SHAPE, "cout=%d must be a multiple of 32", a->cout);
   B2_REQUIRE(a->ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(a->y) & 15) == 0, B2_ERR_ALIGN, "y misaligned");
   B2_REQUIRE(a->addend == nullptr || (a->ldadd % 8 == 0 && (reinterpret_cast<uintptr_t>(a->addend) & 15) == 0),
