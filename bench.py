@@ -194,7 +194,7 @@ def run_b200(args):
     torch.manual_seed(0)
     model = getattr(M, args.model)(**kw).to(dev, memory_format=torch.channels_last)   # helpers.py:243
     model.train()
-    use_graph = bool(args.graph) and (world == 1 or os.environ.get("B200SEG_GRAPH_DDP", "0") == "1")
+    use_graph = bool(args.graph)     # the bucketed NCCL all-reduces are captured in the graph as well
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-6, weight_decay=5e-4,
                             fused=True, capturable=use_graph)   # helpers.py:251
     reducer = GradReducer(model, bucket_mb=32) if world > 1 else None
@@ -235,12 +235,13 @@ def run_b200(args):
 
     # warm-up (eager) on a side stream, then optionally capture the whole step — forward, loss, backward, clip, AdamW —
     # in ONE CUDA graph: every kernel of the step is replayed without any Python / launch overhead
+    # Everything below runs on ONE non-default stream (the autograd AccumulateGrad nodes bind to the stream of their
+    # first use; mixing streams between warm-up and timing would add synchronisation).
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(max(args.warmup, 3)):
-            step(x_dev, t_dev)
-    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.set_stream(side)
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, t_dev)
     torch.cuda.synchronize()
     graph, static_loss, launches_per_step = None, None, None
     if use_graph:
@@ -287,6 +288,7 @@ def run_b200(args):
     ms_e2e = timed(e2e_step, args.steps)
 
     # instrumented pass for the roofline of the tensor-core kernels
+    K.invalidate_pack_cache()      # graph replays changed the parameters behind the cache's back
     K.PROFILE = []
     step(x_dev, t_dev)
     step(x_dev, t_dev)

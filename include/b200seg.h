@@ -236,11 +236,12 @@ int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const void* g1p, co
                            int64_t npix, int32_t fint, const b2_gate_coef* coef, const double* sums1,
                            int32_t training, double* sums, float* dwpsi, float* dbpsi, b2_stream_t stream);
 /* dg1p, dx1p (bf16 [npix][fint]); dgamma_beta fp32 [4][fint] = dgamma_g, dbeta_g, dgamma_x, dbeta_x;
- * dbn1 fp32 [2] = dgamma1, dbeta1 */
+ * dbn1 fp32 [2] = dgamma1, dbeta1; dbias (optional, fp32 [2][fint], accumulated, caller zeroes) = column sums of
+ * dg1p / dx1p = bias gradients of the W_g / W_x convolutions */
 int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const void* g1p, const void* x1p, int32_t ld,
                           int64_t npix, int32_t fint, const b2_gate_coef* coef, const double* sums1,
                           int32_t training, const double* sums, void* dg1p, void* dx1p, float* dgamma_beta,
-                          float* dbn1, b2_stream_t stream);
+                          float* dbn1, float* dbias, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Loss: BCEWithLogits (utils/helpers.py:245,327) and 0.5*BCE + 0.5*Dice (utils/clip_seg_finetuner.py:40-74)

@@ -95,7 +95,7 @@ SIGNATURES = {
     "b2_gate_psi_bwd_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, C.POINTER(GateCoef), _vp, _i32,
                                          _vp, _vp, _vp, _vp]),
     "b2_gate_psi_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, C.POINTER(GateCoef), _vp, _i32,
-                                        _vp, _vp, _vp, _vp, _vp, _vp]),
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_loss_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "b2_loss_finalize": (C.c_int, [_vp, _i64, _f32, _f32, _f32, _vp, _vp]),
     "b2_loss_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp, _vp, _vp]),

@@ -129,25 +129,8 @@ class AttentionGate(nn.Module):
     def forward(self, g, x):
         ext = _is_external(x)
         g, x = to_internal(g), to_internal(x)
-        bn_g, bn_x, bn_1 = self.W_g[1], self.W_x[1], self.psi[1]
-        training = bn_g.training
-        n, h, w, _ = x.shape
-        npix = n * h * w
-        g1p, stats_g = ops.conv2d(g, None, self.W_g[0].weight, self.W_g[0].bias, training)
-        x1p, stats_x = ops.conv2d(x, None, self.W_x[0].weight, self.W_x[0].bias, training)
-        coef_g = ops.bn_finalize_(stats_g.detach(), npix, bn_g.weight.detach(), bn_g.bias.detach(), bn_g.running_mean,
-                                  bn_g.running_var, bn_g.num_batches_tracked, training, float(bn_g.momentum),
-                                  float(bn_g.eps))
-        coef_x = ops.bn_finalize_(stats_x.detach(), npix, bn_x.weight.detach(), bn_x.bias.detach(), bn_x.running_mean,
-                                  bn_x.running_var, bn_x.num_batches_tracked, training, float(bn_x.momentum),
-                                  float(bn_x.eps))
-        out, _q, _psi, _coef1, qstats = ops.gate_mid(
-            g1p, x1p, x, coef_g, coef_x, bn_g.weight, bn_g.bias, bn_x.weight, bn_x.bias,
-            self.psi[0].weight, self.psi[0].bias, bn_1.weight, bn_1.bias, bn_1.running_mean, bn_1.running_var,
-            training, float(bn_1.eps))
-        if training:   # running statistics of psi.1 (momentum update only; coefficients were computed in gate_mid)
-            ops.bn_finalize_(qstats.detach(), npix, bn_1.weight.detach(), bn_1.bias.detach(), bn_1.running_mean,
-                             bn_1.running_var, bn_1.num_batches_tracked, True, float(bn_1.momentum), float(bn_1.eps))
+        from .ops_gate import attention_gate_module
+        out = attention_gate_module(self, g, x)
         return ops.to_nchw(out) if ext else out
 
 

@@ -534,7 +534,7 @@ def gate_mid_bwd(dout: Tensor, x: Tensor, psi: Tensor, q: Tensor, g1p: Tensor, x
                  gamma_g: Tensor, coef_x: Tensor, gamma_x: Tensor, coef_1: Tensor, gamma_1: Tensor, wpsi: Tensor,
                  training: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     dx, dsig, sums1 = K.gate_apply_bwd(_c(dout), x, psi, q, coef_1)
-    dg1p, dx1p, dgb, dbn1, dwpsi, dbpsi = K.gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x,
+    dg1p, dx1p, dgb, dbn1, dwpsi, dbpsi, _dbias = K.gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x,
                                                          coef_1, gamma_1, wpsi, training=training)
     return dg1p, dx1p, dx, dgb, dbn1, dwpsi, dbpsi
 

@@ -236,65 +236,105 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_reduce_kernel(
   if (threadIdx.x == 0) atomicAdd(dbpsi, red[4 * fint]);
 }
 
-// backward phase 3: gradients w.r.t. the two pre-BN GEMM outputs
+// backward phase 3: gradients w.r.t. the two pre-BN GEMM outputs.  Per channel the BatchNorm backward collapses to
+//   dg1p = Wg*dq*[a>0] + Bg*g + Cg     with Wg = gamma*invstd*wpsi, Bg = -gamma*invstd^2*dgamma/m,
+//                                           Cg = -gamma*invstd*dbeta/m - Bg*mean          (same for the x branch)
+// so only the mask coefficients and three constants per branch stay in registers.  Also accumulates the column sums
+// of the ROUNDED outputs = bias gradients of the W_g / W_x convolutions (dbias[0][c], dbias[1][c]).
 __global__ void __launch_bounds__(256) gate_psi_bwd_apply_kernel(
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int tpp, int rows, GateBwdCoef c,
     const double* __restrict__ sums1, int training, const double* __restrict__ sums,
     __nv_bfloat16* __restrict__ dg1p, __nv_bfloat16* __restrict__ dx1p, float* __restrict__ dgamma_beta,
-    float* __restrict__ dbn1) {
+    float* __restrict__ dbn1, float* __restrict__ dbias) {
+  __shared__ float red[256 * 8];
   const int gch = threadIdx.x % tpp, r = threadIdx.x / tpp;
-  if (r >= rows) return;
-  float sg[8], hg[8], mg[8], ig[8], sx[8], hx[8], mx[8], ix[8], wp[8], cg_[8], cx_[8], kbg[8], kgg[8], kgx[8];
-  g_load8(c.scale_g + gch * 8, true, sg);
-  g_load8(c.shift_g + gch * 8, true, hg);
-  g_load8(c.mean_g + gch * 8, true, mg);
-  g_load8(c.invstd_g + gch * 8, true, ig);
-  g_load8(c.scale_x + gch * 8, true, sx);
-  g_load8(c.shift_x + gch * 8, true, hx);
-  g_load8(c.mean_x + gch * 8, true, mx);
-  g_load8(c.invstd_x + gch * 8, true, ix);
-  g_load8(c.wpsi + gch * 8, true, wp);
-  const double inv_m = 1.0 / (double)npix;
+  const bool active = r < rows;
+  float bsg[8], bsx[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = gch * 8 + j;
-    wp[j] = bf16_round(wp[j]);
-    cg_[j] = __ldg(c.gamma_g + ch) * ig[j];
-    cx_[j] = __ldg(c.gamma_x + ch) * ix[j];
-    const double dbg = sums[0 * fint + ch], dgg = sums[1 * fint + ch], dgx = sums[3 * fint + ch];
-    kbg[j] = training ? (float)(dbg * inv_m) : 0.f;
-    kgg[j] = training ? (float)(dgg * inv_m) : 0.f;
-    kgx[j] = training ? (float)(dgx * inv_m) : 0.f;
-    if (blockIdx.x == 0 && r == 0) {
-      dgamma_beta[0 * fint + ch] = (float)dgg;
-      dgamma_beta[1 * fint + ch] = (float)dbg;
-      dgamma_beta[2 * fint + ch] = (float)dgx;
-      dgamma_beta[3 * fint + ch] = (float)dbg;
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    dbn1[0] = (float)sums1[1];   // dgamma1
-    dbn1[1] = (float)sums1[0];   // dbeta1
-  }
-  const float g1 = __ldg(c.gamma1), mu1 = __ldg(c.mean1), is1 = __ldg(c.invstd1);
-  const float k0 = (float)(sums1[0] * inv_m), k1 = (float)(sums1[1] * inv_m);
-  for (long long p = (long long)blockIdx.x * rows + r; p < npix; p += (long long)gridDim.x * rows) {
-    const float dq = gate_dq(__ldg(dsig + p), __bfloat162float(q[p]), g1, mu1, is1, training, k0, k1);
-    float g[8], x[8], og[8], ox[8];
-    g_unpack8(__ldg(reinterpret_cast<const uint4*>(g1p + p * ld + gch * 8)), g);
-    g_unpack8(__ldg(reinterpret_cast<const uint4*>(x1p + p * ld + gch * 8)), x);
+  for (int j = 0; j < 8; ++j) bsg[j] = bsx[j] = 0.f;
+  if (active) {
+    float sg[8], hg[8], sx[8], hx[8], wg[8], bg[8], cg[8], wx[8], bx[8], cx[8];
+    g_load8(c.scale_g + gch * 8, true, sg);
+    g_load8(c.shift_g + gch * 8, true, hg);
+    g_load8(c.scale_x + gch * 8, true, sx);
+    g_load8(c.shift_x + gch * 8, true, hx);
+    const double inv_m = 1.0 / (double)npix;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
-      const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
-      const float a = fmaxf(bf16_round(gb + xb), 0.f);
-      const float da = a > 0.f ? dq * wp[j] : 0.f;
-      og[j] = cg_[j] * (da - kbg[j] - ((g[j] - mg[j]) * ig[j]) * kgg[j]);
-      ox[j] = cx_[j] * (da - kbg[j] - ((x[j] - mx[j]) * ix[j]) * kgx[j]);
+      const int ch = gch * 8 + j;
+      const float wp = bf16_round(__ldg(c.wpsi + ch));
+      const float igv = __ldg(c.invstd_g + ch), mgv = __ldg(c.mean_g + ch);
+      const float ixv = __ldg(c.invstd_x + ch), mxv = __ldg(c.mean_x + ch);
+      const float cgv = __ldg(c.gamma_g + ch) * igv, cxv = __ldg(c.gamma_x + ch) * ixv;
+      const double dbg = sums[0 * fint + ch], dgg = sums[1 * fint + ch], dgx = sums[3 * fint + ch];
+      const float kb = training ? (float)(dbg * inv_m) : 0.f;
+      const float kgg = training ? (float)(dgg * inv_m) : 0.f;
+      const float kgx = training ? (float)(dgx * inv_m) : 0.f;
+      wg[j] = cgv * wp;
+      bg[j] = -cgv * kgg * igv;
+      cg[j] = -cgv * kb - bg[j] * mgv;
+      wx[j] = cxv * wp;
+      bx[j] = -cxv * kgx * ixv;
+      cx[j] = -cxv * kb - bx[j] * mxv;
+      if (blockIdx.x == 0 && r == 0) {
+        dgamma_beta[0 * fint + ch] = (float)dgg;
+        dgamma_beta[1 * fint + ch] = (float)dbg;
+        dgamma_beta[2 * fint + ch] = (float)dgx;
+        dgamma_beta[3 * fint + ch] = (float)dbg;
+      }
     }
-    *reinterpret_cast<uint4*>(dg1p + p * ld + gch * 8) = g_pack8(og);
-    *reinterpret_cast<uint4*>(dx1p + p * ld + gch * 8) = g_pack8(ox);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      dbn1[0] = (float)sums1[1];   // dgamma1
+      dbn1[1] = (float)sums1[0];   // dbeta1
+    }
+    const float g1 = __ldg(c.gamma1), mu1 = __ldg(c.mean1), is1 = __ldg(c.invstd1);
+    const float k0 = (float)(sums1[0] * inv_m), k1 = (float)(sums1[1] * inv_m);
+    for (long long p = (long long)blockIdx.x * rows + r; p < npix; p += (long long)gridDim.x * rows) {
+      const float dq = gate_dq(__ldg(dsig + p), __bfloat162float(q[p]), g1, mu1, is1, training, k0, k1);
+      float g[8], x[8];
+      g_unpack8(__ldg(reinterpret_cast<const uint4*>(g1p + p * ld + gch * 8)), g);
+      g_unpack8(__ldg(reinterpret_cast<const uint4*>(x1p + p * ld + gch * 8)), x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
+        const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
+        const float dqm = bf16_round(gb + xb) > 0.f ? dq : 0.f;
+        g[j] = fmaf(wg[j], dqm, fmaf(bg[j], g[j], cg[j]));
+        x[j] = fmaf(wx[j], dqm, fmaf(bx[j], x[j], cx[j]));
+      }
+      const uint4 og = g_pack8(g), ox = g_pack8(x);
+      *reinterpret_cast<uint4*>(dg1p + p * ld + gch * 8) = og;
+      *reinterpret_cast<uint4*>(dx1p + p * ld + gch * 8) = ox;
+      if (dbias != nullptr) {
+        g_unpack8(og, g);
+        g_unpack8(ox, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          bsg[j] += g[j];
+          bsx[j] += x[j];
+        }
+      }
+    }
+  }
+  if (dbias != nullptr) {
+    for (int which = 0; which < 2; ++which) {
+      float* v = which == 0 ? bsg : bsx;
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(r * tpp + gch) * 8 + j] = v[j];
+      }
+      __syncthreads();
+      if (active && r == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float s = 0.f;
+          for (int rr = 0; rr < rows; ++rr) s += red[(rr * tpp + gch) * 8 + j];
+          atomicAdd(&dbias[which * fint + gch * 8 + j], s);
+        }
+      }
+    }
   }
 }
 
@@ -386,14 +426,16 @@ extern "C" int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const vo
 extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const void* g1p, const void* x1p,
                                      int32_t ld, int64_t npix, int32_t fint, const b2_gate_coef* coef,
                                      const double* sums1, int32_t training, const double* sums, void* dg1p,
-                                     void* dx1p, float* dgamma_beta, float* dbn1, b2_stream_t stream) {
+                                     void* dx1p, float* dgamma_beta, float* dbn1, float* dbias,
+                                     b2_stream_t stream) {
   B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld) && g_al(dg1p, ld) && g_al(dx1p, ld), B2_ERR_ALIGN,
              "gate operands misaligned");
   const int tpp = fint / 8, rows = 256 / tpp;
   gate_psi_bwd_apply_kernel<<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
       dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
-      rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1);
+      rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
+      dbias);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -169,3 +169,39 @@ def test_upconv_folded_matches_literal_and_oracle(cin, cout, h):
         assert e_y < 1e-2
         assert e_dx < 8e-2 and e_w < 8e-2      # reference's own bf16 block gradients deviate 3.5e-2
     assert rel(res[True][0], res[False][0]) < 1e-2
+
+
+@pytest.mark.parametrize("c,fint,h", [(128, 64, 64), (64, 32, 128), (512, 256, 16)])
+def test_attention_gate_block(c, fint, h):
+    """Level (ii): AttentionGate in train mode on identical block inputs vs the fp64 oracle — forward <= 1e-2;
+    gradients within the reference's own bf16 block-gradient deviation (5e-2 .. 7e-2)."""
+    from b200seg import blocks
+    from oracle import unet_oracle as O
+    torch.manual_seed(4)
+    m = blocks.AttentionGate(c, c, fint).cuda().train()
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    g = torch.randn(2, c, h, h, device="cuda", generator=gen)
+    x = torch.randn(2, c, h, h, device="cuda", generator=gen)
+    dy = torch.randn(2, c, h, h, device="cuda", generator=gen)
+    gi, xi = g.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y = m(g=gi, x=xi)
+    y.backward(dy)
+    sd = {("att." + k): v.detach().double() if v.is_floating_point() else v.detach().clone()
+          for k, v in m.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    gr, xr = g.double().requires_grad_(True), x.double().requires_grad_(True)
+    yr, newb = O.attention_gate({**sd, **params}, gr, xr, "att", training=True)
+    yr.backward(dy.double())
+    e_y, e_dg, e_dx = rel(y, yr), rel(gi.grad, gr.grad), rel(xi.grad, xr.grad)
+    mine = dict(m.named_parameters())
+    worst = max((rel(mine[k[4:]].grad, p.grad), k) for k, p in params.items()
+                if float(p.grad.norm()) > 1e-9 and not k.endswith("0.bias") or k.endswith("psi.0.bias"))
+    print(f"AttentionGate C={c} F_int={fint} @{h}: y {e_y:.2e} dg {e_dg:.2e} dx {e_dx:.2e} worst param grad {worst}")
+    assert e_y < 1e-2
+    assert e_dg < 1e-1 and e_dx < 1e-1 and worst[0] < 1.5e-1
+    msd = m.state_dict()
+    for k, v in newb.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(msd[k[4:]]) == int(v)
+        elif k.endswith("running_var"):
+            assert rel(msd[k[4:]], v) < 1e-2, k
