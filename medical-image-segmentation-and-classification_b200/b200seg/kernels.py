@@ -62,52 +62,20 @@ def new_act(n, h, w, c, device):
 # ----------------------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------------------
-# Packed-weight cache: a parameter is re-packed only when its storage or its version counter changed, so the t+1
-# applications of a Recurrent_block's shared conv and the backward of every conv reuse the forward's packing.
-# (Disabled while a CUDA graph is being captured: cached tensors must not leak between capture pools.)
-_PACK_CACHE = {}
-_PACK_CACHE_MAX = 512
-
-
 def invalidate_pack_cache():
-    """Call after replaying a captured training graph (replays update parameters without bumping `_version`)."""
-    _PACK_CACHE.clear()
-
-
-def _cache_get(kind, weight, want_dgrad):
-    if torch.cuda.is_current_stream_capturing():
-        _PACK_CACHE.clear()
-        return None
-    key = (kind, weight.data_ptr(), tuple(weight.shape), tuple(weight.stride()))
-    hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == weight._version and (hit[2] is not None or not want_dgrad):
-        return hit[1], hit[2]
-    return None
-
-
-def _cache_put(kind, weight, wf, wd):
-    if torch.cuda.is_current_stream_capturing():
-        return
-    if len(_PACK_CACHE) >= _PACK_CACHE_MAX:
-        _PACK_CACHE.clear()
-    key = (kind, weight.data_ptr(), tuple(weight.shape), tuple(weight.stride()))
-    _PACK_CACHE[key] = (weight._version, wf, wd)
+    """kept for API compatibility: packed weights are never cached across calls (a cache keyed on storage address
+    and version counter is unsafe: freed parameters get their addresses reused)"""
 
 
 def pack_weights(weight, want_dgrad=True):
     """fp32 [Cout, Cin, k, k] parameter (any strides) -> (bf16 [k*k, Cout, Cin], bf16 [k*k, Cin, Cout] flipped)."""
     cout, cin, kh, kw = weight.shape
     assert kh == kw and weight.dtype == torch.float32
-    hit = _cache_get("plain", weight, want_dgrad)
-    if hit is not None:
-        return hit
     taps = kh * kw
-    want_dgrad = want_dgrad or weight.requires_grad          # the backward will ask for it: pack both now
     wf = torch.empty((taps, cout, cin), dtype=BF16, device=weight.device)
     wd = torch.empty((taps, cin, cout), dtype=BF16, device=weight.device) if want_dgrad else None
     s = weight.stride()
     call("b2_pack_weights", _p(weight), cout, cin, kh, s[0], s[1], s[2], s[3], _p(wf), _p(wd), _stream())
-    _cache_put("plain", weight, wf, wd)
     return wf, wd
 
 
@@ -115,15 +83,10 @@ def pack_weights_upfold(weight, want_dgrad=True):
     """UpConv folding: fp32 [Cout, Cin, 3, 3] -> bf16 [4 phases, 4 taps, Cout, Cin] (+ [4, 4 flipped, Cin, Cout])"""
     cout, cin, kh, kw = weight.shape
     assert kh == 3 and kw == 3 and weight.dtype == torch.float32
-    hit = _cache_get("upfold", weight, want_dgrad)
-    if hit is not None:
-        return hit
-    want_dgrad = want_dgrad or weight.requires_grad
     wf = torch.empty((4, 4, cout, cin), dtype=BF16, device=weight.device)
     wd = torch.empty((4, 4, cin, cout), dtype=BF16, device=weight.device) if want_dgrad else None
     s = weight.stride()
     call("b2_pack_weights_upfold", _p(weight), cout, cin, s[0], s[1], s[2], s[3], _p(wf), _p(wd), _stream())
-    _cache_put("upfold", weight, wf, wd)
     return wf, wd
 
 
