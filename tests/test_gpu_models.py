@@ -183,11 +183,11 @@ def test_attention_gate_block(c, fint, h):
     g = torch.randn(2, c, h, h, device="cuda", generator=gen)
     x = torch.randn(2, c, h, h, device="cuda", generator=gen)
     dy = torch.randn(2, c, h, h, device="cuda", generator=gen)
+    sd = {("att." + k): v.detach().double() if v.is_floating_point() else v.detach().clone()
+          for k, v in m.state_dict().items()}          # snapshot BEFORE the forward updates the running statistics
     gi, xi = g.clone().requires_grad_(True), x.clone().requires_grad_(True)
     y = m(g=gi, x=xi)
     y.backward(dy)
-    sd = {("att." + k): v.detach().double() if v.is_floating_point() else v.detach().clone()
-          for k, v in m.state_dict().items()}
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
     gr, xr = g.double().requires_grad_(True), x.double().requires_grad_(True)
     yr, newb = O.attention_gate({**sd, **params}, gr, xr, "att", training=True)
