@@ -171,7 +171,17 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------------------
+def _tick(msg, t0=[None]):
+    """wall-clock phase markers on stderr (B200SEG_BENCH_VERBOSE=1)"""
+    if os.environ.get("B200SEG_BENCH_VERBOSE"):
+        now = time.perf_counter()
+        if t0[0] is None:
+            t0[0] = now
+        print(f"[bench +{now - t0[0]:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def run_b200(args):
+    _tick("start")
     import torch
     import torch.distributed as dist
 
@@ -240,9 +250,11 @@ def run_b200(args):
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     torch.cuda.set_stream(side)
+    _tick("model built, warm-up begins")
     for _ in range(max(args.warmup, 3)):
         step(x_dev, t_dev)
     torch.cuda.synchronize()
+    _tick("warm-up done")
     graph, static_loss, launches_per_step = None, None, None
     if use_graph:
         try:
@@ -254,6 +266,7 @@ def run_b200(args):
             launches_per_step = _lib.launch_count - l_before
             graph.replay()
             torch.cuda.synchronize()
+            _tick("graph captured and replayed once")
         except Exception as e:   # keep the eager path measurable if capture is refused
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
                   file=sys.stderr)
@@ -273,6 +286,7 @@ def run_b200(args):
     ms = timed(run_step, args.steps)
     launches = (_lib.launch_count - l0) if graph is None else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
+    _tick("timed region done")
 
     # end-to-end: pinned host batch -> device, loss -> host, every step
     def e2e_step():
@@ -286,6 +300,7 @@ def run_b200(args):
         return float(step(x, t))
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    _tick("e2e done")
 
     # instrumented pass for the roofline of the tensor-core kernels
     K.invalidate_pack_cache()      # graph replays changed the parameters behind the cache's back
@@ -305,9 +320,19 @@ def run_b200(args):
     K.PROFILE = None
     peak_tf, peak_hbm, peak_src = measured_peaks()
 
-    if rank != 0:
+    def leave():
+        """Multi-rank exit: NCCL communicator teardown can block while a captured graph still references NCCL work, so
+        ranks rendezvous once more and leave without destroying the process group."""
         if world > 1:
-            dist.destroy_process_group()
+            _tick("leaving")
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
     imgs = B * world * args.steps
     value = imgs / (ms / 1e3)
@@ -356,8 +381,7 @@ def run_b200(args):
                       f"(fwd+BCE+bwd+clip+AdamW), best of 3 after 1 warm-up, {os.cpu_count()} threads",
             "median_s_per_step": statistics.median(times)}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():
