@@ -292,14 +292,17 @@ def maxpool3x3s2_fwd(x):
     return y
 
 
-def bn_apply(z, coef, relu=True, addend=None, want_sum=False):
-    """want_sum: also return y + addend; addend without want_sum: y = act(bn(z) + addend) (residual)"""
+def bn_apply(z, coef, relu=True, addend=None, want_sum=False, sum_only=False):
+    """want_sum: also return y + addend; sum_only: return ONLY act(bn(z)) + addend (the x + x1 re-injection of
+    Recurrent_block, R2U_Net.py:19); addend without either: y = act(bn(z) + addend) (ResNet residual)"""
     n, h, w, c, ld = _nhwc(z)
-    y = new_act(n, h, w, c, z.device)
-    ysum = new_act(n, h, w, c, z.device) if want_sum else None
+    y = None if sum_only else new_act(n, h, w, c, z.device)
+    ysum = new_act(n, h, w, c, z.device) if (want_sum or sum_only) else None
     lda = _nhwc(addend)[4] if addend is not None else 0
     call("b2_bn_apply", _p(z), ld, n * h * w, c, _p(coef[2]), _p(coef[3]), int(relu), _p(y), c, _p(addend), lda,
          _p(ysum), c, _stream())
+    if sum_only:
+        return ysum
     return (y, ysum) if want_sum else y
 
 

@@ -244,7 +244,9 @@ def batch_norm_act(z: Tensor, stats: Tensor, bn: torch.nn.BatchNorm2d, relu: boo
 @custom_op("b200seg::conv_bn_act", mutates_args=())
 def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], gamma: Tensor,
                 beta: Tensor, running_mean: Tensor, running_var: Tensor, training: bool, eps: float,
-                relu: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                relu: bool, addend: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """`addend`: the first output becomes act(bn(conv(x))) + addend (Recurrent_block's x + x1, R2U_Net.py:19); the
+    un-summed activation is then never written."""
     cout, cin, k, _ = weight.shape
     dev = x0.device
     stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
@@ -262,11 +264,13 @@ def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional
         coef = K.bn_finalize(stats, n * h * w, gamma, beta, eps, 0.0, None, None, None)
     else:
         coef = K.bn_eval_coeffs(gamma, beta, running_mean, running_var, eps)
+    if addend is not None:
+        return K.bn_apply(z, coef, relu=relu, addend=_c(addend), sum_only=True), z, coef, stats, x4
     return K.bn_apply(z, coef, relu=relu), z, coef, stats, x4
 
 
 @conv_bn_act.register_fake
-def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu):
+def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=None):
     cout = weight.shape[0]
     if x0.dtype != torch.bfloat16:
         n, _, h, w = x0.shape
@@ -307,7 +311,8 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
 
 def _cba_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
-    x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu = inputs
+    x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu, addend = inputs
+    ctx.has_addend = addend is not None
     _y, z, coef, _stats, x4 = output
     stem = x0.dtype != torch.bfloat16
     ctx.save_for_backward(None if stem else _c(x0), _c(x1), x4, weight, z, coef, gamma)
@@ -323,7 +328,8 @@ def _cba_backward(ctx, dy, *_unused):
     dx0, dx1, dw, db, dgamma, dbeta = conv_bn_act_bwd(dy, x0 if x0 is not None else x4, x1, x4, weight, z, coef,
                                                       gamma, ctx.relu, ctx.training, need0, need1, ctx.has_bias)
     return (dx0 if need0 else None, dx1 if need1 else None, _dw_as_param_grad(dw, weight),
-            db if ctx.has_bias else None, dgamma, dbeta, None, None, None, None, None)
+            db if ctx.has_bias else None, dgamma, dbeta, None, None, None, None, None,
+            dy if (ctx.has_addend and need[11]) else None)      # d(addend) = d(output): the sum is linear
 
 
 conv_bn_act.register_autograd(_cba_backward, setup_context=_cba_setup)
@@ -336,12 +342,13 @@ def bn_update_running_(stats: Tensor, count: int, momentum: float, running_mean:
     K.bn_update_running(stats, count, momentum, running_mean, running_var, num_batches_tracked)
 
 
-def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = True) -> Tensor:
-    """[Conv2d -> BatchNorm2d -> ReLU] on module objects; x: image | activation | (activation, activation)."""
+def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = True,
+                       addend: Optional[Tensor] = None) -> Tensor:
+    """[Conv2d -> BatchNorm2d -> ReLU] (+ addend) on module objects; x: image | activation | (activation, activation)."""
     x0, x1 = x if isinstance(x, tuple) else (x, None)
     training = bn.training or bn.running_mean is None
     y, _z, _coef, stats, _x4 = conv_bn_act(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
-                                           bn.running_var, training, float(bn.eps), relu)
+                                           bn.running_var, training, float(bn.eps), relu, addend)
     if training:
         n, h, w, _ = y.shape
         bn_update_running_(stats.detach(), n * h * w, float(bn.momentum), bn.running_mean, bn.running_var,

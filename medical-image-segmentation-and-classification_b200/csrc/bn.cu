@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* _
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
     }
     const uint4 o = pack8(f);
-    *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = o;
+    if (y != nullptr) *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = o;   // y may be skipped when only y+addend is needed
     if (ysum != nullptr) {
       const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + p * ldadd + g * 8));
       float fa[8], fo[8];
@@ -444,7 +444,8 @@ extern "C" int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, 
   ChanMap m;
   int rc = make_map(c, &m);
   if (rc) return rc;
-  B2_REQUIRE(aligned16(z, ldz) && aligned16(y, ldy), B2_ERR_ALIGN, "bn_apply operands misaligned");
+  B2_REQUIRE(aligned16(z, ldz) && (y == nullptr ? ysum != nullptr : aligned16(y, ldy)), B2_ERR_ALIGN,
+             "bn_apply operands misaligned (y may be NULL only when ysum is given)");
   B2_REQUIRE(ysum == nullptr || (addend != nullptr && aligned16(ysum, ldysum)), B2_ERR_ALIGN,
              "bn_apply ysum misaligned or addend missing");
   B2_REQUIRE(addend == nullptr || aligned16(addend, ldadd), B2_ERR_ALIGN, "bn_apply addend misaligned");
