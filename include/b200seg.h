@@ -85,6 +85,7 @@ typedef struct b2_conv_args {
    * AttentionUNet.py:15-27) are expressed with ksize 2, custom pads and these placements */
   int32_t in_mul, in_off_h, in_off_w;
   int32_t custom_pad, pad_h, pad_w;
+  int32_t add_after_act;  /* 1: y = act(conv + bias) + addend (Recurrent_block's x + x1 in the folded inference path) */
 } b2_conv_args;
 
 int b2_conv_fprop(const b2_conv_args* a, b2_stream_t stream);
@@ -123,6 +124,13 @@ int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream);
  * (optional) dgrad packing [k*k][cin][cout] with the taps flipped. */
 int b2_pack_weights(const float* w, int32_t cout, int32_t cin, int32_t ksize, int64_t s_co, int64_t s_ci,
                     int64_t s_kh, int64_t s_kw, void* w_fprop, void* w_dgrad, b2_stream_t stream);
+
+/* Inference (eval-mode) BatchNorm folding, Appendix D.3 of SURVEY.md: W' = W * scale[co] packed for fprop (plain, or
+ * the 16-tap UpConv folding when upfold != 0) and b' = bias * scale + shift, so that conv + BN + ReLU is ONE tcgen05
+ * launch with a bias/ReLU epilogue (pipeline.py:340-357 / tester.py:264-289 inference path). */
+int b2_pack_weights_folded(const float* w, int32_t cout, int32_t cin, int32_t ksize, int64_t s_co, int64_t s_ci,
+                           int64_t s_kh, int64_t s_kw, const float* scale, const float* shift, const float* bias,
+                           int32_t upfold, void* w_fprop, float* bias_out, b2_stream_t stream);
 
 /* UpConv folding (AttentionUNet.py:15-27: nearest x2 upsample followed by conv3x3): phase (a,b) of the 2x output grid
  * is a 2x2 convolution of the LOW-resolution input with weights W_ab[u][v] = sum_{r in R_a(u)} sum_{s in R_b(v)} W[r][s],

@@ -30,7 +30,7 @@ class ConvArgs(C.Structure):
                 ("stats", _vp), ("relu", _i32),
                 ("stride", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32),
                 ("in_mul", _i32), ("in_off_h", _i32), ("in_off_w", _i32),
-                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32)]
+                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32), ("add_after_act", _i32)]
 
 
 class WgradArgs(C.Structure):
@@ -64,6 +64,8 @@ SIGNATURES = {
     "b2_conv_wgrad_workspace": (_i64, [C.POINTER(WgradArgs)]),
     "b2_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), _vp]),
     "b2_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "b2_pack_weights_folded": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp,
+                                         _vp]),
     "b2_pack_weights_upfold": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "b2_fold_upconv_wgrad": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "b2_conv_smallc_fprop": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _i32, _i32, _vp]),
@@ -133,7 +135,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 # kernels launched per entry point (for bench.py's `gpu_launches` claim); entries not listed launch one kernel
-LAUNCHES_PER_CALL = {"b2_conv_wgrad": 2, "b2_channel_sum": 1}
+LAUNCHES_PER_CALL = {"b2_conv_wgrad": 2, "b2_channel_sum": 1, "b2_pack_weights_folded": 2}
 launch_count = 0
 
 

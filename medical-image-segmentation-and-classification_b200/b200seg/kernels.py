@@ -90,6 +90,18 @@ def pack_weights_upfold(weight, want_dgrad=True):
     return wf, wd
 
 
+def pack_weights_folded(weight, bias, coef, upfold=False):
+    """eval-mode BN folding: (bf16 packed W * scale[co], fp32 bias * scale + shift); coef = [mean, invstd, scale, shift]"""
+    cout, cin, kh, kw = weight.shape
+    shape = (4, 4, cout, cin) if upfold else (kh * kw, cout, cin)
+    wf = torch.empty(shape, dtype=BF16, device=weight.device)
+    bf = torch.empty((cout,), dtype=torch.float32, device=weight.device)
+    s = weight.stride()
+    call("b2_pack_weights_folded", _p(weight), cout, cin, kh, s[0], s[1], s[2], s[3], _p(coef[2]), _p(coef[3]),
+         _p(bias), int(upfold), _p(wf), _p(bf), _stream())
+    return wf, bf
+
+
 def fold_upconv_wgrad(dweff):
     """fp32 [4 phases, Cout, 4 taps, Cin] -> fp32 [Cout, 9, Cin]"""
     _, cout, _, cin = dweff.shape
@@ -103,7 +115,7 @@ def fold_upconv_wgrad(dweff):
 # ----------------------------------------------------------------------------------------------------------
 def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None, relu=False, out=None,
                row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0), in_mul=1, in_off=(0, 0), pad=None,
-               alg_scale=1.0):
+               alg_scale=1.0, add_after_act=False):
     """y = conv(x0 | x1; wpk) (+bias) (+addend) (relu); wpk is [taps, rows, ktot] bf16, rows [row_offset,
     row_offset+cout) are used.  `stats` (fp64 [2, cout]) accumulates sum / sumsq of the rounded output.
     stride=2 samples the input on a 2x finer grid (strided conv / ConvTranspose dgrad); out_mul=2 places the result
@@ -141,6 +153,7 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
     a.relu = int(relu)
     a.stride, a.out_mul, a.out_off_h, a.out_off_w = stride, out_mul, out_off[0], out_off[1]
     a.in_mul, a.in_off_h, a.in_off_w = in_mul, in_off[0], in_off[1]
+    a.add_after_act = int(add_after_act)
     if pad is not None:
         a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
     t0 = _prof_begin()

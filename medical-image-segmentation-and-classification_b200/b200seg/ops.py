@@ -8,6 +8,7 @@ kernels of libb200seg.so or raises.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -347,6 +348,11 @@ def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu:
     """[Conv2d -> BatchNorm2d -> ReLU] (+ addend) on module objects; x: image | activation | (activation, activation)."""
     x0, x1 = x if isinstance(x, tuple) else (x, None)
     training = bn.training or bn.running_mean is None
+    if x0.dtype == torch.bfloat16 and os.environ.get("B200SEG_FOLD_BN", "1") != "0":
+        from . import ops_infer
+        if ops_infer.inference_mode(bn):       # eval + no_grad: conv with folded BN, bias/ReLU in the epilogue
+            return ops_infer.conv_bn_act_infer(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                               bn.running_var, float(bn.eps), relu, addend)
     y, _z, _coef, stats, _x4 = conv_bn_act(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                            bn.running_var, training, float(bn.eps), relu, addend)
     if training:
@@ -443,6 +449,11 @@ upconv_bn_act.register_autograd(_ucba_backward, setup_context=_ucba_setup)
 
 def upconv_bn_act_module(x: Tensor, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = True) -> Tensor:
     training = bn.training or bn.running_mean is None
+    if os.environ.get("B200SEG_FOLD_BN", "1") != "0":
+        from . import ops_infer
+        if ops_infer.inference_mode(bn):
+            return ops_infer.upconv_bn_act_infer(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                                 bn.running_var, float(bn.eps), relu)
     y, _z, _coef, stats = upconv_bn_act(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                         bn.running_var, training, float(bn.eps), relu)
     if training:

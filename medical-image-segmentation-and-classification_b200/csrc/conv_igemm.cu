@@ -51,6 +51,7 @@ struct IgemmParams {
   int ldadd;
   double* stats;
   int relu;
+  int add_after_act;
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem, int c0, int c1, int c2, int c3) {
@@ -274,27 +275,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         float v[32];
         tmem_ld32(taddr + c, v);
         tmem_ld_wait();
-        if (arow != nullptr) {
+        float av[32];
+        const bool has_add = arow != nullptr;
+        if (has_add) {
           const uint4* ap = reinterpret_cast<const uint4*>(arow + c);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 u = __ldg(ap + q);
-            v[q * 8 + 0] += bf16lo(u.x); v[q * 8 + 1] += bf16hi(u.x);
-            v[q * 8 + 2] += bf16lo(u.y); v[q * 8 + 3] += bf16hi(u.y);
-            v[q * 8 + 4] += bf16lo(u.z); v[q * 8 + 5] += bf16hi(u.z);
-            v[q * 8 + 6] += bf16lo(u.w); v[q * 8 + 7] += bf16hi(u.w);
+            av[q * 8 + 0] = bf16lo(u.x); av[q * 8 + 1] = bf16hi(u.x);
+            av[q * 8 + 2] = bf16lo(u.y); av[q * 8 + 3] = bf16hi(u.y);
+            av[q * 8 + 4] = bf16lo(u.z); av[q * 8 + 5] = bf16hi(u.z);
+            av[q * 8 + 6] = bf16lo(u.w); av[q * 8 + 7] = bf16hi(u.w);
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) av[j] = 0.f;
         }
+        const bool add_first = has_add && !p.add_after_act;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t pk[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float a = v[q * 8 + 2 * j] + s_bias[c + q * 8 + 2 * j];
-            float b = v[q * 8 + 2 * j + 1] + s_bias[c + q * 8 + 2 * j + 1];
+            const int e = q * 8 + 2 * j;
+            float a = v[e] + s_bias[c + e] + (add_first ? av[e] : 0.f);
+            float b = v[e + 1] + s_bias[c + e + 1] + (add_first ? av[e + 1] : 0.f);
             if (p.relu) {
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
+            }
+            if (p.add_after_act) {      // x + relu(conv(.)): the addend joins after the activation (on rounded values)
+              a = bf16_round(a) + av[e];
+              b = bf16_round(b) + av[e + 1];
             }
             pk[j] = pack_bf16x2(a, b);
           }
@@ -463,6 +475,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.ldadd = a->ldadd;
   p.stats = a->stats;
   p.relu = a->relu;
+  p.add_after_act = (a->addend != nullptr && a->add_after_act) ? 1 : 0;
   // halo mode: 3x3, tile == one row segment of 128 pixels
   const int halo_env = env_int("B200SEG_HALO", 1);
   p.stride = stride;

@@ -7,7 +7,8 @@
 // memory, i.e. MN-major for the MMA: a TMA box of (64 ch, Wb, Hb, Nb) lands as 64 rows (pixels) of 128 B (channels)
 // with the 128B swizzle, which is exactly the canonical MN-major SW128 atom stack (8 K-rows per 1024 B, 64-element
 // MN blocks LBO apart).  X boxes are shifted by the tap offset; TMA zero fill supplies the padding halo.
-// The dY tile is loaded once per K chunk and reused by every column block.
+// The dY tile is loaded once per K chunk and reused by every column block (3x3: 2 X blocks x 3 taps = N 384, issued as
+// two N=192 MMAs into adjacent TMEM columns); the kernel is L2->SM bandwidth bound, so bytes per FLOP is what counts.
 // Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
 #include <stdlib.h>
@@ -36,9 +37,7 @@ struct WgradParams {
   int cout, ctot;    // ctot = c0 + c1 (row length of dW)
   int a_boxes;       // 1 if cout <= 64 else 2
   int stages;
-  int xhalo;         // 3x3: one X box of Wb+2 pixels per line serves the three horizontal taps (LBO = 1 pixel)
   int b_stage_bytes; // smem bytes reserved per stage for the X boxes
-  int b_tx_bytes;    // bytes the X box(es) of one stage deliver
   float* ws;         // [splits][cout][taps][ctot]
 };
 
@@ -80,7 +79,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX0);
   }
-  const uint32_t tmem_cols = 256;
+  const uint32_t tmem_cols = p.ncolb * 64 > 256 ? 512u : 256u;
   if (warp == 1) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
@@ -100,7 +99,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     if (nchunks > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)(p.a_boxes * kBoxBytes + (p.xhalo ? p.b_tx_bytes : ncol_live * kBoxBytes));
+      const uint32_t tx = (uint32_t)((p.a_boxes + ncol_live) * kBoxBytes);
       int tw_i = chunk_begin % p.tw;
       int th_i = (chunk_begin / p.tw) % p.th;
       int tn_i = chunk_begin / (p.tw * p.th);
@@ -113,13 +112,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           // dY: both 64-channel blocks of the 128-row M tile in one 5-D box (.., channel block)
           tma_load_5d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0, co_tile * 2);
-          if (p.xhalo) {
-            if (cib_base < p.cb0)
-              tma_load_4d(sb, &tmX0, &full_bar[stage], cib_base * 64, w0 - 1, h0 + rg - 1, n0);
-            else
-              tma_load_4d(sb, &tmX1, &full_bar[stage], (cib_base - p.cb0) * 64, w0 - 1, h0 + rg - 1, n0);
-          }
-          for (int j = 0; j < (p.xhalo ? 0 : ncol_live); ++j) {
+          for (int j = 0; j < ncol_live; ++j) {
             const int cib = cib_base + j / p.ksize;
             const int xw = p.xstride * w0 + (j % p.ksize) - p.pad_w;
             const int xh = p.xstride * h0 + rg - p.pad_h;
@@ -145,7 +138,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
   } else if (warp == 1) {
     if (nchunks > 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, ncol_live * 64, 1, 1);
+      // up to 6 column blocks (3x3: two 64-channel X blocks x three taps): N <= 256 per instruction, so the columns
+      // are issued as two MMAs that share the dY tile (A) and write adjacent TMEM column ranges
+      const int ncol0 = ncol_live > 4 ? 3 : ncol_live;
+      const int ncol1 = ncol_live - ncol0;
+      const uint32_t idesc = umma_idesc_bf16(128, ncol0 * 64, 1, 1);
+      const uint32_t idesc1 = ncol1 > 0 ? umma_idesc_bf16(128, ncol1 * 64, 1, 1) : 0u;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nchunks; ++it) {
@@ -158,15 +156,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           for (int k = 0; k < kChunkPix / 16; ++k) {
             // 16 pixels (K) = two 8-row groups, 1024 B apart (SBO); 64-channel MN blocks 8 KB apart (LBO)
             const uint64_t da = umma_desc_sw128(a_addr + k * 2048, kBoxBytes, 1024);
-            uint64_t db;
-            if (p.xhalo) {
-              // 16 pixels of one image line inside the (Wb+2)-wide box; the three taps are N blocks 128 B apart
-              const int line = (16 * k) / p.Wb, woff = (16 * k) % p.Wb;
-              db = umma_desc_sw128(b_addr + (uint32_t)(line * (p.Wb + 2) + woff) * 128u, 128, 1024);
-            } else {
-              db = umma_desc_sw128(b_addr + k * 2048, kBoxBytes, 1024);
-            }
+            const uint64_t db = umma_desc_sw128(b_addr + k * 2048, kBoxBytes, 1024);
             umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+            if (ncol1 > 0) {
+              const uint64_t db1 = umma_desc_sw128(b_addr + ncol0 * kBoxBytes + k * 2048, kBoxBytes, 1024);
+              umma_bf16(tmem_base + (uint32_t)(ncol0 * 64), da, db1, idesc1, (it | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
         }
@@ -273,7 +268,11 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   p.pad_h = a->custom_pad ? a->pad_h : (a->ksize == 3 ? 1 : 0);
   p.pad_w = a->custom_pad ? a->pad_w : (a->ksize == 3 ? 1 : 0);
   p.xstride = xstride;
-  p.cpb = a->ksize == 3 ? 1 : (a->ksize == 2 ? 2 : 4);
+  // 3x3: one X block x 3 taps (N 192, 5 pipeline stages) by default; B200SEG_WG_CPB=2 selects two X blocks x 3 taps
+  // (N 384 as two MMAs sharing the dY tile, 3 stages) — faster on the 32x32 layers, slower on the DRAM-streaming ones
+  const char* cpb_env = getenv("B200SEG_WG_CPB");
+  const int cpb3 = (cpb_env != nullptr && atoi(cpb_env) == 2) ? 2 : 1;
+  p.cpb = a->ksize == 3 ? cpb3 : (a->ksize == 2 ? 2 : 4);
   if (p.cpb > cbt) p.cpb = cbt;
   p.ncolb = p.ksize * p.cpb;
   pl->gy = p.ksize;
@@ -298,15 +297,7 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   splits = (p.num_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   pl->splits = splits;
   pl->count = (long long)a->cout * p.taps * p.ctot;
-  p.xhalo = (p.taps == 9 && xstride == 1 && !a->custom_pad && p.Wb >= 16 && p.Nb == 1 && getenv("B200SEG_WG_HALO") != nullptr &&
-             atoi(getenv("B200SEG_WG_HALO")) != 0) ? 1 : 0;
-  if (p.xhalo) {
-    p.b_tx_bytes = (p.Wb + 2) * p.Hb * 128;
-    p.b_stage_bytes = ((p.b_tx_bytes + 1023) / 1024) * 1024;
-  } else {
-    p.b_tx_bytes = p.ncolb * kBoxBytes;
-    p.b_stage_bytes = p.ncolb * kBoxBytes;
-  }
+  p.b_stage_bytes = p.ncolb * kBoxBytes;
   const int stage_bytes = 2 * kBoxBytes + p.b_stage_bytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -357,7 +348,7 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     rc = encode_tmap_bf16(&tmDY, dyb, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  const int xboxw = pl.p.xhalo ? pl.p.Wb + 2 : pl.p.Wb;
+  const int xboxw = pl.p.Wb;
   const int xs = pl.p.xstride, xh = a->h * xs, xw = a->w * xs;     // X extent (2x the dY grid for ConvTranspose)
   rc = encode_act_tmap_ex(&tmX0, a->x0, a->c0, a->n, xh, xw, a->ldx0, (long long)a->ldx0 * xw,
                           (long long)a->ldx0 * xw * xh, xboxw, pl.p.Hb, pl.p.Nb, xs);

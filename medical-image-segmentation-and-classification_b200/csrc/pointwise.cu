@@ -17,7 +17,8 @@ __device__ __forceinline__ uint4 pack8p(const float* f) {
 // fp32 [cout][cin][k][k] (any strides) -> bf16 [tap][cout][cin] and flipped/transposed [taps-1-tap][cin][cout]
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int taps, int ks, long long s_co,
                                     long long s_ci, long long s_kh, long long s_kw,
-                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
+                                    const float* __restrict__ oscale) {
   const long long total = (long long)taps * cout * cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -25,7 +26,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
     const int co = (int)((i / cin) % cout);
     const int tap = (int)(i / ((long long)cin * cout));
     const int kh = tap / ks, kw = tap % ks;
-    const __nv_bfloat16 v = __float2bfloat16_rn(w[co * s_co + ci * s_ci + kh * s_kh + kw * s_kw]);
+    // oscale: per-output-channel factor folded into the weights (eval-mode BatchNorm folding, gamma / sqrt(var+eps))
+    const __nv_bfloat16 v =
+        __float2bfloat16_rn(w[co * s_co + ci * s_ci + kh * s_kh + kw * s_kw] * (oscale ? oscale[co] : 1.f));
     if (wf) wf[i] = v;
     if (wd) wd[((long long)(taps - 1 - tap) * cin + ci) * cout + co] = v;
   }
@@ -39,7 +42,8 @@ __device__ __forceinline__ bool upfold_member(int a, int u, int r) {
 // fp32 [cout][cin][3][3] -> bf16 wf [phase][tap][cout][cin], wd [phase][3 - tap][cin][cout]
 __global__ void pack_weights_upfold_kernel(const float* __restrict__ w, int cout, int cin, long long s_co,
                                            long long s_ci, long long s_kh, long long s_kw,
-                                           __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+                                           __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd,
+                                           const float* __restrict__ oscale) {
   const long long total = 16ll * cout * cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -52,7 +56,7 @@ __global__ void pack_weights_upfold_kernel(const float* __restrict__ w, int cout
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c)
         if (upfold_member(a, u, r) && upfold_member(b, v, c)) s += w[co * s_co + ci * s_ci + r * s_kh + c * s_kw];
-    const __nv_bfloat16 val = __float2bfloat16_rn(s);
+    const __nv_bfloat16 val = __float2bfloat16_rn(s * (oscale ? oscale[co] : 1.f));
     if (wf) wf[i] = val;
     if (wd) wd[(((long long)phase * 4 + (3 - tap)) * cin + ci) * cout + co] = val;
   }
@@ -245,7 +249,35 @@ extern "C" int b2_pack_weights(const float* w, int32_t cout, int32_t cin, int32_
   const int taps = ksize * ksize;
   const long long total = (long long)taps * cout * cin;
   pack_weights_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w, cout, cin, taps, ksize, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad);
+      w, cout, cin, taps, ksize, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad, nullptr);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+// eval-mode BatchNorm folding: W' = W * scale[co] (bf16 fprop packing), b' = b * scale + shift
+__global__ void fold_bn_bias_kernel(const float* __restrict__ bias, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int c, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) out[i] = (bias ? bias[i] : 0.f) * scale[i] + shift[i];
+}
+
+extern "C" int b2_pack_weights_folded(const float* w, int32_t cout, int32_t cin, int32_t ksize, int64_t s_co,
+                                      int64_t s_ci, int64_t s_kh, int64_t s_kw, const float* scale,
+                                      const float* shift, const float* bias, int32_t upfold, void* w_fprop,
+                                      float* bias_out, b2_stream_t stream) {
+  B2_REQUIRE(cout > 0 && cin > 0 && ksize >= 1 && ksize <= 7 && scale != nullptr && shift != nullptr,
+             B2_ERR_SHAPE, "bad folded-weight request");
+  if (upfold) {
+    B2_REQUIRE(ksize == 3, B2_ERR_SHAPE, "UpConv folding needs a 3x3 kernel");
+    pack_weights_upfold_kernel<<<ew_grid(16ll * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
+        w, cout, cin, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, nullptr, scale);
+  } else {
+    const int taps = ksize * ksize;
+    pack_weights_kernel<<<ew_grid((long long)taps * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
+        w, cout, cin, taps, ksize, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, nullptr, scale);
+  }
+  B2_LAUNCH_CHECK();
+  fold_bn_bias_kernel<<<(cout + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bias, scale, shift, cout, bias_out);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -255,7 +287,7 @@ extern "C" int b2_pack_weights_upfold(const float* w, int32_t cout, int32_t cin,
                                       b2_stream_t stream) {
   B2_REQUIRE(cout > 0 && cin > 0, B2_ERR_SHAPE, "bad weight shape");
   pack_weights_upfold_kernel<<<ew_grid(16ll * cout * cin, 256), 256, 0, (cudaStream_t)stream>>>(
-      w, cout, cin, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad);
+      w, cout, cin, s_co, s_ci, s_kh, s_kw, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad, nullptr);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -49,3 +49,40 @@ def test_r2u_inference_small_batch_and_512(batch, side):
     err = float((y.double() - ref).norm() / ref.norm())
     print(f"R2U_Net inference b{batch} {side}^2: rel {err:.2e}")
     assert err < 1e-2
+
+
+@pytest.mark.parametrize("name", ["AttentionUNet", "R2U_Net", "R2AttU_Net"])
+def test_inference_bn_folding_matches_unfolded_and_oracle(name):
+    """eval + no_grad takes the BN-folded single-launch path; it must agree with the oracle (<= 1e-2) and with the
+    unfolded eval path (conv -> BN-apply) of the same module."""
+    import os
+    from b200seg.models import segmentation_models as M
+    from oracle import unet_oracle as O
+    from oracle.synthetic import xray_batch
+    torch.manual_seed(5)
+    kw = {} if name == "AttentionUNet" else {"t": 2}
+    m = getattr(M, name)(**kw).cuda()
+    x, t = xray_batch(2, 128, 128, seed=9, device="cuda")
+    m.train()
+    with torch.no_grad():
+        for _ in range(3):                        # move the running statistics away from (0, 1)
+            m(x)
+    m.eval()
+    with torch.no_grad():
+        y_fold = m(x)
+        os.environ["B200SEG_FOLD_BN"] = "0"
+        try:
+            y_plain = m(x)
+        finally:
+            os.environ["B200SEG_FOLD_BN"] = "1"
+        sd = {k: v.detach().double() if v.is_floating_point() else v for k, v in m.state_dict().items()}
+        ref, _ = O.FORWARDS[name](sd, x.double(), training=False, **kw)
+        sd32 = {k: v.detach().float() if v.is_floating_point() else v for k, v in m.state_dict().items()}
+        with torch.autocast("cuda", dtype=torch.bfloat16):      # the reference's own reduced-precision deviation
+            fl, _ = O.FORWARDS[name](sd32, x, training=False, **kw)
+    e_fold = float((y_fold.double() - ref).norm() / ref.norm())
+    e_plain = float((y_plain.double() - ref).norm() / ref.norm())
+    e_floor = float((fl.double() - ref).norm() / ref.norm())
+    print(f"{name} eval: folded {e_fold:.2e}  unfolded {e_plain:.2e}  reference-bf16 {e_floor:.2e}")
+    tol = max(1e-2, 1.25 * e_floor)
+    assert e_fold < tol and e_plain < tol

@@ -32,12 +32,12 @@ for side in map(int, a.sides.split(",")):
         x, _ = xray_batch(min(b, 8), side, side, seed=0, device=dev)
         x = x.repeat((b + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:b].contiguous()
         with torch.no_grad():
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
+            wstream = torch.cuda.Stream()
+            wstream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(wstream):
                 for _ in range(2):
                     model(x)
-            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.current_stream().wait_stream(wstream)
             torch.cuda.synchronize()
             graph = None
             if a.graph:                      # static shapes: replay the whole forward as one CUDA graph
