@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--side", type=int, default=256)
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="fused: b200seg FusedClipAdamW (clip + AdamW, 2 launches); torch: clip_grad_norm_ + AdamW(fused)")
     ap.add_argument("--graph", type=int, default=1,
                     help="capture the whole training step in a CUDA graph (single-GPU runs); 0 = eager launches")
     return ap.parse_args()
@@ -205,8 +207,12 @@ def run_b200(args):
     model = getattr(M, args.model)(**kw).to(dev, memory_format=torch.channels_last)   # helpers.py:243
     model.train()
     use_graph = bool(args.graph)     # the bucketed NCCL all-reduces are captured in the graph as well
-    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-6, weight_decay=5e-4,
-                            fused=True, capturable=use_graph)   # helpers.py:251
+    trainable = [p for p in model.parameters() if p.requires_grad]
+    if args.optimizer == "fused":     # clip_grad_norm_(1.0) + AdamW in two launches of libb200seg (helpers.py:251,333-335)
+        from b200seg.optim import FusedClipAdamW
+        opt = FusedClipAdamW(trainable, lr=1e-6, weight_decay=5e-4, max_norm=1.0)
+    else:
+        opt = torch.optim.AdamW(trainable, lr=1e-6, weight_decay=5e-4, fused=True, capturable=use_graph)
     reducer = GradReducer(model, bucket_mb=32) if world > 1 else None
     B, S = args.batch, args.side
     x_host, t_host = xray_batch(B, S, S, seed=100 + rank)
@@ -221,7 +227,8 @@ def run_b200(args):
         loss.backward()
         if reducer is not None:
             reducer.finish()
-        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        if args.optimizer != "fused":
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
         return loss
 
@@ -353,7 +360,7 @@ def run_b200(args):
                                f"AdamW), batch {B} per GPU, random init, synthetic X-ray-shaped inputs",
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2",
-                   "model_kwargs": kw, "cuda_graph": graph is not None},
+                   "model_kwargs": kw, "cuda_graph": graph is not None, "optimizer": args.optimizer},
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

@@ -264,6 +264,27 @@ int b2_loss_finalize(const double* sums, int64_t count, float w_bce, float w_dic
 int b2_loss_bwd(const float* z, const float* t, int64_t count, const double* sums, float w_bce, float w_dice,
                 float smooth, const float* grad_out, float* dz, b2_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer step (utils/helpers.py:333-335): clip_grad_norm_(max_norm) + AdamW over all parameters in two launches.
+ * `refs` is a DEVICE array of tensor references (fp32, element-wise aligned layouts); block b processes elements
+ * [block_chunk[b]*chunk_elems, ...) of tensor block_tensor[b].  `step` (device float) is incremented by
+ * b2_grad_sqnorm_multi and read by b2_adamw_multi for the bias correction; `lr` is a device float.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b2_tensor_ref {
+  float* p;        /* parameter */
+  const float* g;  /* gradient */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  int64_t n;       /* elements */
+} b2_tensor_ref;
+
+int b2_grad_sqnorm_multi(const b2_tensor_ref* refs, const int32_t* block_tensor, const int32_t* block_chunk,
+                         int32_t nblocks, int32_t chunk_elems, double* sqnorm, float* step, b2_stream_t stream);
+int b2_adamw_multi(const b2_tensor_ref* refs, const int32_t* block_tensor, const int32_t* block_chunk,
+                   int32_t nblocks, int32_t chunk_elems, const double* sqnorm, float max_norm, const float* lr,
+                   float beta1, float beta2, float eps, float weight_decay, const float* step,
+                   float* total_norm_out, b2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

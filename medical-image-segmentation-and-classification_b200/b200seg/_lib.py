@@ -98,6 +98,8 @@ SIGNATURES = {
                                          _vp, _vp, _vp, _vp]),
     "b2_gate_psi_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, C.POINTER(GateCoef), _vp, _i32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_grad_sqnorm_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "b2_adamw_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "b2_loss_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "b2_loss_finalize": (C.c_int, [_vp, _i64, _f32, _f32, _f32, _vp, _vp]),
     "b2_loss_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp, _vp, _vp]),
@@ -135,7 +137,8 @@ def check(rc: int, what: str = "") -> None:
 
 
 # kernels launched per entry point (for bench.py's `gpu_launches` claim); entries not listed launch one kernel
-LAUNCHES_PER_CALL = {"b2_conv_wgrad": 2, "b2_channel_sum": 1, "b2_pack_weights_folded": 2}
+LAUNCHES_PER_CALL = {"b2_conv_wgrad": 2, "b2_channel_sum": 1, "b2_pack_weights_folded": 2,
+                     "b2_grad_sqnorm_multi": 1}
 launch_count = 0
 
 

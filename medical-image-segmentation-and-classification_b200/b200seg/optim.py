@@ -1,0 +1,113 @@
+"""FusedClipAdamW — clip_grad_norm_(max_norm) + AdamW(lr, betas, eps, weight_decay) for all parameters in two kernel
+launches of libb200seg.so (b2_grad_sqnorm_multi, b2_adamw_multi).
+
+Drop-in for the optimizer half of the reference's hot loop (utils/helpers.py:251,333-335):
+
+    opt = FusedClipAdamW(model.parameters(), lr=lr, weight_decay=5e-4, max_norm=1.0)
+    loss.backward(); opt.step()                     # == clip_grad_norm_(params, 1.0); AdamW.step()
+
+It is a torch.optim.Optimizer (param_groups / state_dict / LR schedulers work; the learning rate is mirrored into a
+device scalar so a captured CUDA graph sees scheduler updates).  Gradients may be re-allocated every step
+(zero_grad(set_to_none=True)): the device-side pointer table is refreshed from a pinned staging buffer when any
+pointer changed; inside a CUDA-graph capture the upload is captured too, from a private snapshot of the table.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .kernels import _p, _stream
+
+_CHUNK = 1 << 16          # elements per block
+
+
+class FusedClipAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=1.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedClipAdamW supports a single parameter group (as the reference's train() uses)")
+        self.max_norm = float(max_norm)
+        self._params = [p for p in self.param_groups[0]["params"] if p.requires_grad]
+        if not self._params:
+            raise ValueError("no trainable parameters")
+        dev = self._params[0].device
+        for p in self._params:
+            if p.dtype != torch.float32 or not p.is_cuda:
+                raise ValueError("FusedClipAdamW needs fp32 CUDA parameters")
+            st = self.state[p]
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        # block -> (tensor, chunk) map
+        bt, bc = [], []
+        for i, p in enumerate(self._params):
+            for c in range((p.numel() + _CHUNK - 1) // _CHUNK):
+                bt.append(i)
+                bc.append(c)
+        self._nblocks = len(bt)
+        self._block_tensor = torch.tensor(bt, dtype=torch.int32, device=dev)
+        self._block_chunk = torch.tensor(bc, dtype=torch.int32, device=dev)
+        n = len(self._params)
+        self._refs_host = torch.zeros((n, 5), dtype=torch.int64).pin_memory()
+        self._refs_dev = torch.zeros((n, 5), dtype=torch.int64, device=dev)
+        self._grad_ptrs = [0] * n
+        self._captured_tables = []
+        self._sqnorm = torch.zeros((), dtype=torch.float64, device=dev)
+        self._step = torch.zeros((), dtype=torch.float32, device=dev)
+        self._lr = torch.full((), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = float(lr)
+        self.total_norm = torch.zeros((), dtype=torch.float32, device=dev)
+        for i, p in enumerate(self._params):
+            st = self.state[p]
+            self._refs_host[i, 0] = p.data_ptr()
+            self._refs_host[i, 2] = st["exp_avg"].data_ptr()
+            self._refs_host[i, 3] = st["exp_avg_sq"].data_ptr()
+            self._refs_host[i, 4] = p.numel()
+
+    def _grad_for(self, p):
+        g = p.grad
+        if g is None:
+            raise RuntimeError("FusedClipAdamW.step(): a trainable parameter has no gradient")
+        if g.stride() != p.stride():      # element-wise kernels need identical memory order
+            g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
+            p.grad = g
+        return g
+
+    def _refresh_refs(self):
+        changed = False
+        for i, p in enumerate(self._params):
+            ptr = self._grad_for(p).data_ptr()
+            if ptr != self._grad_ptrs[i]:
+                self._grad_ptrs[i] = ptr
+                self._refs_host[i, 1] = ptr
+                changed = True
+        if changed:
+            if torch.cuda.is_current_stream_capturing():
+                # becomes a captured H2D copy: replays re-upload the static capture-time addresses.  The source must
+                # never change afterwards, so it is a private pinned snapshot kept alive with the optimizer.
+                snap = self._refs_host.clone().pin_memory()
+                self._captured_tables.append(snap)
+                self._refs_dev.copy_(snap, non_blocking=True)
+                self._grad_ptrs = [0] * len(self._params)      # force a fresh upload on the next eager step
+            else:
+                self._refs_dev.copy_(self._refs_host, non_blocking=True)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise ValueError("closures are not supported")
+        g = self.param_groups[0]
+        if float(g["lr"]) != self._lr_host and not torch.cuda.is_current_stream_capturing():
+            self._lr_host = float(g["lr"])
+            self._lr.fill_(self._lr_host)
+        self._refresh_refs()
+        b1, b2 = g["betas"]
+        refs = C.c_void_p(self._refs_dev.data_ptr())
+        _lib.call("b2_grad_sqnorm_multi", refs, _p(self._block_tensor), _p(self._block_chunk), self._nblocks, _CHUNK,
+                  _p(self._sqnorm), _p(self._step), _stream())
+        _lib.call("b2_adamw_multi", refs, _p(self._block_tensor), _p(self._block_chunk), self._nblocks, _CHUNK,
+                  _p(self._sqnorm), self.max_norm, _p(self._lr), float(b1), float(b2), float(g["eps"]),
+                  float(g["weight_decay"]), _p(self._step), _p(self.total_norm), _stream())
+        return None

@@ -50,8 +50,8 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
         raise NotImplementedError("b200seg.train covers the segmentation path only (seg=True)")
     device = torch.device(device)
     model = model.to(device, memory_format=torch.channels_last)            # helpers.py:243
-    optimizer = torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=5e-4,
-                                  fused=(device.type == "cuda"))           # helpers.py:251
+    from ..optim import FusedClipAdamW
+    optimizer = FusedClipAdamW(model.parameters(), lr=lr, weight_decay=5e-4, max_norm=1.0)   # helpers.py:251,333
     log(f"Training Segmentation model (all layers unfrozen) with LR: {lr}")
     scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=epochs)   # helpers.py:254
     best_score = float("inf")
@@ -73,8 +73,7 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
             loss.backward()
             if reducer is not None:
                 reducer.finish()
-            torch.nn.utils.clip_grad_norm_(params, max_norm=1.0)          # helpers.py:333
-            optimizer.step()
+            optimizer.step()                                              # clip_grad_norm_(1.0) + AdamW, fused
             running += loss.detach().double() * x.size(0)
             seen += x.size(0)
 
