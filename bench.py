@@ -65,6 +65,20 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic():
+    """mean DRAM bytes per launch of the tensor-core kernels, from the committed ncu capture of one training step of
+    the default workload (tools/profile_step.py + tools/summarize_traffic.py); {} if the capture is absent"""
+    p = ROOT / "profiles" / "r01_final_traffic.json"
+    if not p.exists():
+        return {}
+    d = json.loads(p.read_text())
+    out = {}
+    for short, name in (("conv_igemm", "b2::conv_igemm_kernel"), ("conv_wgrad", "b2::conv_wgrad_kernel")):
+        if name in d and d[name]["launches"]:
+            out[short] = (d[name]["read_GB"] + d[name]["write_GB"]) * 1e9 / d[name]["launches"]
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -318,12 +332,12 @@ def run_b200(args):
     agg = {}
     if os.environ.get("B200SEG_BENCH_DUMP") and rank == 0:
         with open(os.environ["B200SEG_BENCH_DUMP"], "w") as f:
-            for kind, flops, _alg, a, b in K.PROFILE[len(K.PROFILE) // 2:]:
+            for kind, flops, _alg, _nb, a, b in K.PROFILE[len(K.PROFILE) // 2:]:
                 ms_ = a.elapsed_time(b)
                 f.write(f"{kind} {flops / 1e9:10.2f} GF {ms_:8.4f} ms {flops / ms_ / 1e9:8.1f} TF/s\n")
-    for kind, flops, alg, a, b in K.PROFILE:
-        f, fa, tms, n = agg.get(kind, (0.0, 0.0, 0.0, 0))
-        agg[kind] = (f + flops, fa + alg, tms + a.elapsed_time(b), n + 1)
+    for kind, flops, alg, nb, a, b in K.PROFILE:
+        f, fa, by, tms, n = agg.get(kind, (0.0, 0.0, 0.0, 0.0, 0))
+        agg[kind] = (f + flops, fa + alg, by + nb, tms + a.elapsed_time(b), n + 1)
     K.PROFILE = None
     peak_tf, peak_hbm, peak_src = measured_peaks()
 
@@ -344,10 +358,11 @@ def run_b200(args):
     imgs = B * world * args.steps
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
-    f, fa, tms, n = agg.get("conv_igemm", (0.0, 0.0, 1.0, 1))
+    f, fa, by_i, tms, n = agg.get("conv_igemm", (0.0, 0.0, 0.0, 1.0, 1))
     ach = f / (tms * 1e-3) / 1e12
     ach_alg = fa / (tms * 1e-3) / 1e12
-    fw, fwa, tw, nw = agg.get("conv_wgrad", (0.0, 0.0, 1.0, 1))
+    fw, fwa, by_w, tw, nw = agg.get("conv_wgrad", (0.0, 0.0, 0.0, 1.0, 1))
+    traffic = measured_traffic()
     ach_w = fw / (tw * 1e-3) / 1e12
     ach_w_alg = fwa / (tw * 1e-3) / 1e12
     step_ms = ms / args.steps
@@ -370,10 +385,14 @@ def run_b200(args):
                      "achieved_algorithmic": ach_alg,
                      "note": "achieved = FLOPs the launches executed / their CUDA-event time; achieved_algorithmic "
                              "counts the folded UpConv launches at the reference's 3x3-on-the-fine-grid FLOPs (x2.25)",
-                     "traffic": None, "peak_source": peak_src, "launches_per_step": n // 2,
+                     "traffic": traffic.get("conv_igemm"), "traffic_unit": "bytes per launch (mean over the step's "
+                     "launches; ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_final_traffic.json)",
+                     "algorithmic_bytes_per_launch": by_i / max(n, 1),
+                     "peak_source": peak_src, "launches_per_step": n // 2,
                      "ms_per_step_in_kernel": tms / 2, "share_of_step": (tms / 2) / step_ms},
         "roofline_wgrad": {"kernel": "conv_wgrad_kernel + wgrad_reduce_kernel", "bound": "tensor", "achieved": ach_w,
-                           "achieved_algorithmic": ach_w_alg,
+                           "achieved_algorithmic": ach_w_alg, "traffic": traffic.get("conv_wgrad"),
+                           "algorithmic_bytes_per_launch": by_w / max(nw, 1),
                            "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_w / peak_tf,
                            "launches_per_step": nw // 2, "ms_per_step_in_kernel": tw / 2,
                            "share_of_step": (tw / 2) / step_ms},

@@ -29,13 +29,13 @@ def _prof_begin():
     return ev
 
 
-def _prof_end(kind, flops, start, alg_scale=1.0):
+def _prof_end(kind, flops, start, alg_scale=1.0, nbytes=0.0):
     """flops = executed by the launch; alg_scale * flops = the reference's algorithmic count for the same work
     (9/4 for the folded UpConv phases, which do 4 taps on the coarse grid instead of 9 on the fine one)"""
     if start is not None:
         end = torch.cuda.Event(enable_timing=True)
         end.record()
-        PROFILE.append((kind, flops, flops * alg_scale, start, end))
+        PROFILE.append((kind, flops, flops * alg_scale, nbytes, start, end))
 
 
 def _stream():
@@ -158,7 +158,9 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
         a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
     t0 = _prof_begin()
     call("b2_conv_dgrad" if dgrad else "b2_conv_fprop", C.byref(a), _stream())
-    _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale)
+    # algorithmic DRAM bytes of the launch: every input element once, every output element once, the weights once
+    _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale,
+              2.0 * (n * hi * wi * (c0 + c1) // (in_mul * in_mul) + n * h * w * cout + taps * cout * (c0 + c1)))
     return y
 
 
@@ -195,7 +197,8 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, d
     a.workspace, a.workspace_bytes = ws.data_ptr(), int(need)
     t0 = _prof_begin()
     call("b2_conv_wgrad", C.byref(a), _stream())
-    _prof_end("conv_wgrad", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale)
+    _prof_end("conv_wgrad", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale,
+              2.0 * (n * h * w * cout + n * hx * wx * (c0 + c1)) + 4.0 * taps * cout * (c0 + c1))
     return dw
 
 
