@@ -28,7 +28,8 @@ namespace b2 {
 
 static constexpr int kTileM = 128;
 static constexpr int kKBlock = 64;               // channels per K step (128 B of bf16)
-static constexpr int kThreads = 192;
+static constexpr int kMaxEpiGroups = 2;
+static constexpr int kThreads = 64 + 128 * kMaxEpiGroups;   // producer + MMA warps, then 4 epilogue warps per group
 static constexpr int kMaxStages = 12;
 
 struct IgemmParams {
@@ -44,6 +45,10 @@ struct IgemmParams {
   long long y_sn, y_sh, y_sw;   // element strides of the output pixel grid (strided placement for ConvT)
   int a_stage_bytes, b_stage_bytes, a_tx_bytes;
   int tma_store;
+  int epi_groups;     // 1 or 2 epilogue warp groups (two staging tiles)
+  int debug_skip;     // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs, 4 = no drain
+  int cluster;        // CTAs per cluster (1, 2 or 4): they work on consecutive m-tiles of one n-tile and share the
+                      // weight tiles, each CTA fetching 1/cluster of the rows and multicasting them
   __nv_bfloat16* y;
   int ldy;
   const float* bias;
@@ -81,6 +86,7 @@ __device__ __forceinline__ uint32_t ctile_off(int block_n, int row, int ch) {
   return (uint32_t)(row * 64 + ((((ch >> 3) ^ ((row >> 1) & 3))) << 4) + ((ch & 7) << 1));
 }
 
+template <bool kHasAdd>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
@@ -88,24 +94,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  uint8_t* ctile = smem + p.stages * stage_bytes;                      // 128 x block_n bf16, 1024 B aligned
-  uint8_t* tail = ctile + kTileM * p.block_n * 2;
+  const int ctile_bytes = kTileM * p.block_n * 2;
+  uint8_t* ctile0 = smem + p.stages * stage_bytes;                     // per group: 128 x block_n bf16, 1024 B aligned
+  uint8_t* tail = ctile0 + p.epi_groups * ctile_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;                    // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;                        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(tail + 256);                // [block_n]
+  float* s_bias0 = reinterpret_cast<float*>(tail + 256);               // [group][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // tiles are numbered n-fastest (CTAs that run together share an activation tile); CTA b takes b, b+G, b+2G, ...
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // Work items ("super tiles") are numbered n-fastest: item u = (m-group u / n_tiles, n-tile u % n_tiles); the CTA of
+  // rank r in its cluster takes m-tile m-group * cluster + r, cluster q takes items q, q + #clusters, ...
+  const int C = p.cluster;
+  const uint32_t crank = C > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << C) - 1u);
+  const int cluster_id = (int)blockIdx.x / C;
+  const int num_clusters = (int)gridDim.x / C;
+  const int total_items = ((p.m_tiles + C - 1) / C) * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)C);   // every CTA of the cluster reads the shared weight slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -125,6 +138,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();       // peers' barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int cbt = p.cb0 + p.cb1;
@@ -134,9 +148,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t tx = (uint32_t)(p.a_tx_bytes + p.b_stage_bytes);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      int t = tile / p.n_tiles;
+    const int b_taps = p.halo ? 3 : 1;           // weight taps per stage
+    const int b_rows = p.block_n / C;            // weight rows this CTA fetches (and multicasts) per tap
+    for (int item = cluster_id; item < total_items; item += num_clusters) {
+      const int n_tile = item % p.n_tiles;
+      int t = (item / p.n_tiles) * C + (int)crank;
+      if (t >= p.m_tiles) t = p.m_tiles - 1;     // ragged last group: recompute the last tile (its result is dropped)
       const int tw_i = t % p.tw;
       t /= p.tw;
       const int th_i = t % p.th;
@@ -158,6 +175,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (elect_one()) {
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + p.a_stage_bytes;
+            if (p.debug_skip & 1) {
+              mbar_arrive(&full_bar[stage]);
+            } else {
             mbar_arrive_expect_tx(&full_bar[stage], tx);
             if (cb < p.cb0) {
               tma_load_4d(sa, &tmA0, &full_bar[stage], cb * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
@@ -165,7 +185,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, p.stride * w0 + ds,
                           p.stride * h0 + dr, n0);
             }
-            tma_load_3d(sb, &tmB, &full_bar[stage], cb * kKBlock, n_tile * p.block_n, tap0);
+            if (C == 1) {
+              tma_load_3d(sb, &tmB, &full_bar[stage], cb * kKBlock, n_tile * p.block_n, tap0);
+            } else {
+              for (int tp = 0; tp < b_taps; ++tp)
+                tma_load_3d_mc(sb + (tp * p.block_n + (int)crank * b_rows) * 128, &tmB, &full_bar[stage],
+                               cb * kKBlock, n_tile * p.block_n + (int)crank * b_rows, tap0 + tp, cmask);
+            }
+            }
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -182,7 +209,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     uint32_t phase = 0;
     int ti = 0;
     const int sub = p.halo ? 3 : 1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (int item = cluster_id; item < total_items; item += num_clusters, ++ti) {
       const int buf = ti & 1;
       mbar_wait(&tmem_empty_bar[buf], (((uint32_t)ti >> 1) & 1u) ^ 1u);
       tc_fence_after();
@@ -193,7 +220,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + p.a_stage_bytes;
-          for (int s = 0; s < sub; ++s) {
+          for (int s = 0; s < ((p.debug_skip & 2) ? 0 : sub); ++s) {
             const uint32_t a_s = a_addr + s * 128;            // halo mode: shift by s pixels (rows of 128 B)
             const uint32_t b_s = b_addr + s * p.block_n * 128;
             const uint32_t bo = p.base_off_mode ? ((a_s >> 7) & 7u) : 0u;
@@ -204,7 +231,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               umma_bf16(d_tmem, da, db, idesc, (it | s | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);   // frees this smem slot when the MMAs have read it
+          // frees this smem slot (in every CTA that multicasts into it) when the MMAs have read it
+          if (C == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], cmask);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -215,43 +244,81 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (elect_one()) umma_commit(&tmem_full_bar[buf]);
       __syncwarp();
     }
-  } else {
-    // ------------------------------ epilogue (warps 2..5) ------------------------------
-    const int et = threadIdx.x - 64;  // 0..127
+  } else if (((warp - 2) >> 2) < p.epi_groups) {
+    // ---------------- epilogue: group 0 = warps 2..5, group 1 = warps 6..9 (tiles alternate between groups) ----------------
+    const int g = (warp - 2) >> 2;
+    const int G = p.epi_groups;
+    const int et = (threadIdx.x - 64) & 127;   // 0..127 within the group
+    uint8_t* ctile = ctile0 + g * ctile_bytes;
+    float* s_bias = s_bias0 + g * 256;
+    const int bar_id = 1 + g;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
     const int wl = row % p.Wb;
     const int hl = (row / p.Wb) % p.Hb;
     const int nl = row / (p.Wb * p.Hb);
-    // statistics mapping: thread owns one column pair for a slab of rows
-    const int npairs = p.block_n >> 1;
-    const int groups = 128 / npairs > 0 ? 128 / npairs : 1;
-    const int rows_per_group = kTileM / groups;
-    const int pair = et % npairs;
-    const int grp = et / npairs;               // < groups when block_n <= 256
-    double acc_s0 = 0.0, acc_s1 = 0.0, acc_q0 = 0.0, acc_q1 = 0.0;
-    const int chunks_per_row = p.block_n >> 3;
+    const bool relu = p.relu != 0;
+    // statistics mapping: a thread owns one 16 B chunk (8 channels) for a slab of `nchunks` rows
+    const int nchunks = p.block_n >> 3;        // 4, 8, 16 or 32 chunks per row; 128 / nchunks slabs
+    const int schunk = lane % nchunks;         // == et % nchunks (nchunks divides 32)
+    const int sgrp = et / nchunks;
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
 
-    int ti = 0;
+    // add the group's partial sums into stats[]: lanes owning the same chunk are combined by shuffles, the four
+    // warps through the (idle) staging tile, so each channel costs one fp64 atomic per group and flush
+    auto flush_stats = [&](int n_tile_) {
+      for (int off = nchunks; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+      }
+      if (p.tma_store && et == 0) tma_store_wait_read();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");    // staging tile is free
+      double* red = reinterpret_cast<double*>(ctile);                 // [warp][sum | sumsq][block_n]
+      if (lane < nchunks) {
+        double* r0 = red + ((warp - 2) & 3) * 2 * p.block_n + schunk * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          r0[j] = acc[j];
+          r0[p.block_n + j] = acc[8 + j];
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      for (int i = et; i < 2 * p.block_n; i += 128) {
+        const int which = i / p.block_n, c = i % p.block_n;
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) v += red[(w * 2 + which) * p.block_n + c];
+        atomicAdd(&p.stats[which * p.cout + n_tile_ * p.block_n + c], v);
+      }
+      // (the staging tile is next written after another group barrier, see the tile loop)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    };
+
     int cur_n_tile = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      const int n_tile = tile % p.n_tiles;
+    for (int item = cluster_id + g * num_clusters, ti = g; item < total_items; item += G * num_clusters, ti += G) {
+      const int n_tile = item % p.n_tiles;
       const int ch_base = n_tile * p.block_n;
+      int t = (item / p.n_tiles) * C + (int)crank;
+      if (t >= p.m_tiles || (p.debug_skip & 4)) {
+        // ragged last group: this CTA only kept the pipeline protocol going; hand the accumulator straight back
+        const int dbuf = ti & 1;
+        mbar_wait(&tmem_full_bar[dbuf], ((uint32_t)ti >> 1) & 1u);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[dbuf]);
+        continue;
+      }
       if (n_tile != cur_n_tile) {
         // new output-channel slab: flush the statistics kept for the previous one, reload the bias slice
-        if (cur_n_tile >= 0 && p.stats != nullptr && grp < groups) {
-          const int ch = cur_n_tile * p.block_n + pair * 2;
-          atomicAdd(&p.stats[ch], acc_s0);
-          atomicAdd(&p.stats[ch + 1], acc_s1);
-          atomicAdd(&p.stats[p.cout + ch], acc_q0);
-          atomicAdd(&p.stats[p.cout + ch + 1], acc_q1);
-          acc_s0 = acc_s1 = acc_q0 = acc_q1 = 0.0;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // everyone is done reading the old bias slice
+        if (cur_n_tile >= 0 && p.stats != nullptr) flush_stats(cur_n_tile);
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // everyone is done reading the old bias slice
         for (int i = et; i < p.block_n; i += 128) s_bias[i] = p.bias ? p.bias[ch_base + i] : 0.f;
         cur_n_tile = n_tile;
       }
-      int t = tile / p.n_tiles;
       const int tw_i = t % p.tw;
       t /= p.tw;
       const int th_i = t % p.th;
@@ -261,56 +328,75 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (valid_rows > kTileM) valid_rows = kTileM;
       const int buf = ti & 1;
 
-      // the previous tile's TMA store must have finished READING the staging tile before it is overwritten
+      // the group's previous TMA store must have finished READING the staging tile before it is overwritten
       if (p.tma_store && et == 0) tma_store_wait_read();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)ti >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.block_n);
       const bool valid = row < valid_rows;
-      const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
-      const __nv_bfloat16* arow = (p.addend && valid) ? p.addend + pix * p.ldadd + ch_base : nullptr;
+      const uint32_t row_off = p.block_n >= 64 ? (uint32_t)row * 128u : (uint32_t)row * 64u;
+      const uint32_t row_x = p.block_n >= 64 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
+      const __nv_bfloat16* arow = nullptr;
+      if (kHasAdd) {
+        const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
+        arow = valid ? p.addend + pix * p.ldadd + ch_base : nullptr;
+      }
       for (int c = 0; c < p.block_n; c += 32) {
         float v[32];
         tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        float av[32];
-        const bool has_add = arow != nullptr;
-        if (has_add) {
-          const uint4* ap = reinterpret_cast<const uint4*>(arow + c);
+        // bias slice for these 32 columns (broadcast reads) while the TMEM load is in flight
+        float bs[32];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = __ldg(ap + q);
-            av[q * 8 + 0] = bf16lo(u.x); av[q * 8 + 1] = bf16hi(u.x);
-            av[q * 8 + 2] = bf16lo(u.y); av[q * 8 + 3] = bf16hi(u.y);
-            av[q * 8 + 4] = bf16lo(u.z); av[q * 8 + 5] = bf16hi(u.z);
-            av[q * 8 + 6] = bf16lo(u.w); av[q * 8 + 7] = bf16hi(u.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) av[j] = 0.f;
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
+          bs[q * 4 + 0] = b4.x; bs[q * 4 + 1] = b4.y; bs[q * 4 + 2] = b4.z; bs[q * 4 + 3] = b4.w;
         }
-        const bool add_first = has_add && !p.add_after_act;
+        uint4 au[4];
+        if (kHasAdd) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            au[q] = arow != nullptr ? __ldg(reinterpret_cast<const uint4*>(arow + c) + q) : make_uint4(0, 0, 0, 0);
+        }
+        tmem_ld_wait();
+        // staging address of this row's 16 B chunks: panel (64 channels) + row + swizzled chunk
+        const uint32_t cbase = (uint32_t)(c >> 6) * (uint32_t)(kTileM * 128) + row_off;
+        const uint32_t chunk0 = (uint32_t)((c & 63) >> 3);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t pk[4];
+          const uint32_t aw[4] = {kHasAdd ? au[q].x : 0u, kHasAdd ? au[q].y : 0u, kHasAdd ? au[q].z : 0u,
+                                  kHasAdd ? au[q].w : 0u};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int e = q * 8 + 2 * j;
-            float a = v[e] + s_bias[c + e] + (add_first ? av[e] : 0.f);
-            float b = v[e + 1] + s_bias[c + e + 1] + (add_first ? av[e + 1] : 0.f);
-            if (p.relu) {
+            float a = v[e] + bs[e];
+            float b = v[e + 1] + bs[e + 1];
+            if (kHasAdd) {
+              const float a0 = bf16lo(aw[j]), a1 = bf16hi(aw[j]);
+              if (p.add_after_act) {    // x + relu(conv(.)): the addend joins after the activation (on rounded values)
+                if (relu) {
+                  a = fmaxf(a, 0.f);
+                  b = fmaxf(b, 0.f);
+                }
+                a = bf16_round(a) + a0;
+                b = bf16_round(b) + a1;
+              } else {
+                a += a0;
+                b += a1;
+                if (relu) {
+                  a = fmaxf(a, 0.f);
+                  b = fmaxf(b, 0.f);
+                }
+              }
+            } else if (relu) {
               a = fmaxf(a, 0.f);
               b = fmaxf(b, 0.f);
             }
-            if (p.add_after_act) {      // x + relu(conv(.)): the addend joins after the activation (on rounded values)
-              a = bf16_round(a) + av[e];
-              b = bf16_round(b) + av[e + 1];
-            }
             pk[j] = pack_bf16x2(a, b);
           }
-          *reinterpret_cast<uint4*>(ctile + ctile_off(p.block_n, row, c + q * 8)) =
+          *reinterpret_cast<uint4*>(ctile + cbase + (((chunk0 + q) ^ row_x) << 4)) =
               make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
@@ -319,18 +405,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
       fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA store
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 
       if (p.tma_store) {
         if (et == 0) {
-          for (int pn = 0; pn < (p.block_n >> 6); ++pn)
-            tma_store_4d(&tmY, ctile + pn * (kTileM * 128), ch_base + pn * 64, w0, h0, n0);
+          if (p.block_n >= 64) {
+            for (int pn = 0; pn < (p.block_n >> 6); ++pn)
+              tma_store_4d(&tmY, ctile + pn * (kTileM * 128), ch_base + pn * 64, w0, h0, n0);
+          } else {
+            tma_store_4d(&tmY, ctile, ch_base, w0, h0, n0);     // 32-channel tile: 64 B rows, 64B-swizzle map
+          }
           tma_store_commit();
         }
       } else {
         // coalesced copy-out: consecutive threads write consecutive 16 B of consecutive pixels
-        for (int idx = et; idx < kTileM * chunks_per_row; idx += 128) {
-          const int r = idx / chunks_per_row, ck = idx % chunks_per_row;
+        for (int idx = et; idx < kTileM * nchunks; idx += 128) {
+          const int r = idx / nchunks, ck = idx % nchunks;
           if (r < valid_rows) {
             const int rwl = r % p.Wb, rhl = (r / p.Wb) % p.Hb, rnl = r / (p.Wb * p.Hb);
             const long long ro = (n0 + rnl) * p.y_sn + (h0 + rhl) * p.y_sh + (w0 + rwl) * p.y_sw;
@@ -339,38 +429,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
         }
       }
-      if (p.stats != nullptr && grp < groups) {
-        // column sums of the ROUNDED outputs (what BatchNorm sees under autocast)
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        const int r_begin = grp * rows_per_group;
-        int r_end = r_begin + rows_per_group;
+      if (p.stats != nullptr) {
+        // column sums of the ROUNDED outputs (what BatchNorm sees under autocast), 8 channels per thread
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+        const int r_begin = sgrp * nchunks;
+        int r_end = r_begin + nchunks;
         if (r_end > valid_rows) r_end = valid_rows;
         for (int r = r_begin; r < r_end; ++r) {
-          const uint32_t u = *reinterpret_cast<const uint32_t*>(ctile + ctile_off(p.block_n, r, pair * 2));
-          const float a = bf16lo(u), b = bf16hi(u);
-          s0 += a;
-          s1 += b;
-          q0 = fmaf(a, a, q0);
-          q1 = fmaf(b, b, q1);
+          const uint4 u = *reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, schunk * 8));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = bf16lo(w4[j]), b = bf16hi(w4[j]);
+            s[2 * j] += a;
+            s[2 * j + 1] += b;
+            q[2 * j] = fmaf(a, a, q[2 * j]);
+            q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
+          }
         }
-        acc_s0 += (double)s0;
-        acc_s1 += (double)s1;
-        acc_q0 += (double)q0;
-        acc_q1 += (double)q1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] += (double)s[j];
+          acc[8 + j] += (double)q[j];
+        }
       }
     }
-    if (p.stats != nullptr && grp < groups && cur_n_tile >= 0) {
-      const int ch = cur_n_tile * p.block_n + pair * 2;
-      atomicAdd(&p.stats[ch], acc_s0);
-      atomicAdd(&p.stats[ch + 1], acc_s1);
-      atomicAdd(&p.stats[p.cout + ch], acc_q0);
-      atomicAdd(&p.stats[p.cout + ch + 1], acc_q1);
-    }
+    if (p.stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
     if (p.tma_store && et == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (C > 1) cluster_sync_all();       // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -496,16 +588,45 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     p.b_stage_bytes = p.block_n * 128;
     p.num_k_iters = p.taps * cbt;
   }
-  p.tma_store = (p.block_n % 64 == 0 && env_int("B200SEG_TMA_STORE", 1) != 0) ? 1 : 0;
+  p.tma_store = env_int("B200SEG_TMA_STORE", 1) != 0 ? 1 : 0;
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int ctile_bytes = kTileM * p.block_n * 2;
-  const int tail_bytes = 256 + 256 * 4 + 256;
-  const int budget = 232448 - 1024 - tail_bytes - ctile_bytes;
+  const int tail_bytes = 256 + kMaxEpiGroups * 256 * 4 + 256;
+  // Two epilogue groups (two staging tiles) when the accumulator drain, not the MMA, paces a tile: the drain costs
+  // about 1750 + 36 * BLOCK_N clocks per tile per group (measured), the MMAs K/16 * BLOCK_N/2.  A second group is
+  // not worth giving up pipeline stages for when the main loop is the longer of the two anyway.
+  {
+    const long long mma_clk = (long long)p.num_k_iters * (p.halo ? 3 : 1) * (kKBlock / 16) * (p.block_n / 2);
+    const long long epi_clk = 1750 + 36ll * p.block_n;
+    const int forced_g = env_int("B200SEG_EPI_GROUPS", 0);
+    p.epi_groups = forced_g > 0 ? (forced_g > kMaxEpiGroups ? kMaxEpiGroups : forced_g)
+                                : (mma_clk * 5 < epi_clk * 6 ? 2 : 1);
+    const int budget2 = 232448 - 1024 - tail_bytes - 2 * ctile_bytes;
+    if (p.epi_groups == 2 && budget2 / stage_bytes < 2) p.epi_groups = 1;
+  }
+  // Clusters: per tile a CTA streams A_bytes + B_bytes / cluster from L2; at about 42 B/clk per SM (L2 -> SM fabric,
+  // 6300 B/clk chip-wide) the weight re-fetch is what bounds every layer with BLOCK_N <= 128.
+  {
+    const double a_bytes = (double)p.a_tx_bytes * p.num_k_iters, b_bytes = (double)p.b_stage_bytes * p.num_k_iters;
+    const double mma_clk = (double)p.num_k_iters * (p.halo ? 3 : 1) * (kKBlock / 16) * (p.block_n / 2);
+    // Measured on B200: no gain at cluster sizes 2 and 4 (the multicast does not relieve what bounds these tiles),
+    // so clusters are opt-in (B200SEG_CLUSTER=2|4) and the default is 1.
+    (void)a_bytes; (void)b_bytes; (void)mma_clk;
+    int c = 1;
+    p.debug_skip = env_int("B200SEG_DEBUG_SKIP", 0);
+    const int forced_c = env_int("B200SEG_CLUSTER", 0);
+    if (forced_c == 1 || forced_c == 2 || forced_c == 4) c = forced_c;
+    while (c > 1 && ((p.block_n / c) % 8 != 0 || p.m_tiles < c)) c /= 2;
+    p.cluster = c;
+  }
+  const int budget = 232448 - 1024 - tail_bytes - p.epi_groups * ctile_bytes;
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
+  if (env_int("B200SEG_MAX_STAGES", 0) >= 2 && stages > env_int("B200SEG_MAX_STAGES", 0))
+    stages = env_int("B200SEG_MAX_STAGES", 0);
   B2_REQUIRE(stages >= 2, B2_ERR_SHAPE, "tile configuration does not fit shared memory");
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + ctile_bytes + tail_bytes + 1024;
+  const int smem_bytes = stages * stage_bytes + p.epi_groups * ctile_bytes + tail_bytes + 1024;
 
   CUtensorMap tmA0, tmA1, tmB, tmY;
   const int boxw = p.halo ? p.Wb + 2 : p.Wb;
@@ -531,6 +652,10 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     uint64_t dims[3] = {(uint64_t)(a->c0 + a->c1), (uint64_t)a->cout, (uint64_t)p.taps};
     uint64_t str[3] = {2, (uint64_t)a->ktot * 2, (uint64_t)a->w_tap_stride * 2};
     uint32_t box[3] = {64, (uint32_t)p.block_n, p.halo ? 3u : 1u};
+    if (p.cluster > 1) {          // one multicast box per tap: this CTA's share of the rows
+      box[1] = (uint32_t)(p.block_n / p.cluster);
+      box[2] = 1u;
+    }
     rc = encode_tmap_bf16(&tmB, a->wpk, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -541,25 +666,71 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.y_sn = oh * ow * a->ldy;
   p.y = static_cast<__nv_bfloat16*>(a->y) + ((long long)a->out_off_h * ow + a->out_off_w) * a->ldy;
   if (p.tma_store) {
-    rc = encode_act_tmap_ex(&tmY, p.y, a->cout, a->n, a->h, a->w, p.y_sw, p.y_sh, p.y_sn, p.Wb, p.Hb, p.Nb, 1);
+    if (p.block_n >= 64) {
+      rc = encode_act_tmap_ex(&tmY, p.y, a->cout, a->n, a->h, a->w, p.y_sw, p.y_sh, p.y_sn, p.Wb, p.Hb, p.Nb, 1);
+    } else {
+      // 32-channel tiles are staged as 64 B rows with chunk ^= (row >> 1) & 3 == TMA's 64B swizzle
+      uint64_t dims[4] = {(uint64_t)a->cout, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n};
+      uint64_t str[4] = {2, (uint64_t)p.y_sw * 2, (uint64_t)p.y_sh * 2, (uint64_t)p.y_sn * 2};
+      uint32_t box[4] = {32, (uint32_t)p.Wb, (uint32_t)p.Hb, (uint32_t)p.Nb};
+      rc = encode_tmap_bf16(&tmY, p.y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    }
     if (rc) return rc;
   } else {
     tmY = tmA0;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  // persistent grid: one CTA per SM.  When the grid is a multiple of n_tiles every CTA keeps one n-tile for its
-  // whole life and its BN statistics stay in registers; otherwise they are flushed whenever the slab changes.
-  int ctas = num_sms();
-  const long long total = (long long)p.m_tiles * p.n_tiles;
+  // persistent grid: one CTA per SM.  When the number of clusters is a multiple of n_tiles every CTA keeps one n-tile
+  // for its whole life and its BN statistics stay in registers; otherwise they are flushed whenever the slab changes.
+  const int C = p.cluster;
+  int clusters = num_sms() / C;
+  if (C > 1) {
+    static int max_clusters[5] = {0, 0, 0, 0, 0};
+    if (max_clusters[C] == 0) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3((unsigned)(num_sms() / C * C));
+      qc.blockDim = dim3(kThreads);
+      qc.dynamicSmemBytes = 232448;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = (unsigned)C;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int n = 0;
+      B2_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_igemm_kernel<false>, &qc));
+      B2_REQUIRE(n > 0, B2_ERR_CUDA, "no cluster of %d CTAs can be resident", C);
+      max_clusters[C] = n;
+    }
+    if (clusters > max_clusters[C]) clusters = max_clusters[C];
+  }
+  const long long total = (long long)((p.m_tiles + C - 1) / C) * p.n_tiles;
   B2_REQUIRE(total < (1ll << 31), B2_ERR_SHAPE, "too many tiles");
-  if (ctas > total) ctas = (int)total;
-  if (ctas > p.n_tiles && (total / ctas) >= 16) ctas = (ctas / p.n_tiles) * p.n_tiles;   // many tiles: keep slabs fixed
+  if (clusters > total) clusters = (int)total;
+  if (clusters > p.n_tiles && (total / clusters) >= 16) clusters = (clusters / p.n_tiles) * p.n_tiles;
   p.m_stride = 0;
-  conv_igemm_kernel<<<(unsigned)ctas, kThreads, smem_bytes, stream>>>(tmA0, tmA1, tmB, tmY, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * C));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (p.addend != nullptr)
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmA0, tmA1, tmB, tmY, p));
+  else
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA0, tmA1, tmB, tmY, p));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -38,6 +38,7 @@ struct WgradParams {
   int a_boxes;       // 1 if cout <= 64 else 2
   int stages;
   int b_stage_bytes; // smem bytes reserved per stage for the X boxes
+  int debug_skip;    // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs
   float* ws;         // [splits][cout][taps][ctot]
 };
 
@@ -56,11 +57,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int split = blockIdx.x;
-  const int rg = blockIdx.y;                          // filter row (3x3) or 0
+  // CTAs that read the same pixels (same split; different filter row / channel group) have adjacent block indices,
+  // so they run in the same wave and the dY / X chunks they share are fetched from DRAM once
+  const int split = blockIdx.y;
+  const int rg = blockIdx.x % p.ksize;                // filter row (3x3) or 0
+  const int zz = blockIdx.x / p.ksize;
   const int co_tiles = (p.cout + 127) / 128;
-  const int co_tile = blockIdx.z % co_tiles;
-  const int cgrp = blockIdx.z / co_tiles;             // channel-block group
+  const int co_tile = zz % co_tiles;
+  const int cgrp = zz / co_tiles;                     // channel-block group
   const int cib_base = cgrp * p.cpb;
   const int cbt = p.cb0 + p.cb1;
 
@@ -109,6 +113,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         if (elect_one()) {
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + 2 * kBoxBytes;
+          if (p.debug_skip & 1) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           // dY: both 64-channel blocks of the 128-row M tile in one 5-D box (.., channel block)
           tma_load_5d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0, co_tile * 2);
@@ -120,6 +127,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
               tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, xw, xh, n0);
             else
               tma_load_4d(sb + j * kBoxBytes, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, xw, xh, n0);
+          }
           }
         }
         __syncwarp();
@@ -153,7 +161,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + 2 * kBoxBytes;
 #pragma unroll
-          for (int k = 0; k < kChunkPix / 16; ++k) {
+          for (int k = 0; k < ((p.debug_skip & 2) ? 0 : kChunkPix / 16); ++k) {
             // 16 pixels (K) = two 8-row groups, 1024 B apart (SBO); 64-channel MN blocks 8 KB apart (LBO)
             const uint64_t da = umma_desc_sw128(a_addr + k * 2048, kBoxBytes, 1024);
             const uint64_t db = umma_desc_sw128(b_addr + k * 2048, kBoxBytes, 1024);
@@ -268,10 +276,15 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   p.pad_h = a->custom_pad ? a->pad_h : (a->ksize == 3 ? 1 : 0);
   p.pad_w = a->custom_pad ? a->pad_w : (a->ksize == 3 ? 1 : 0);
   p.xstride = xstride;
-  // 3x3: one X block x 3 taps (N 192, 5 pipeline stages) by default; B200SEG_WG_CPB=2 selects two X blocks x 3 taps
-  // (N 384 as two MMAs sharing the dY tile, 3 stages) — faster on the 32x32 layers, slower on the DRAM-streaming ones
+  // 3x3: two 64-channel X blocks x 3 taps per CTA (N 384 as two MMAs that share the dY tile, 3 pipeline stages):
+  // the kernel is bound by the L2 -> SM load rate, and this moves 64 KB per 6.3 MFLOP instead of 40 KB per 3.1
+  // (B200SEG_WG_CPB=1 selects the older one-block layout, N 192 with 5 stages)
   const char* cpb_env = getenv("B200SEG_WG_CPB");
-  const int cpb3 = (cpb_env != nullptr && atoi(cpb_env) == 2) ? 2 : 1;
+  const int cpb3 = (cpb_env != nullptr && atoi(cpb_env) == 1) ? 1 : 2;
+  {
+    const char* dbg = getenv("B200SEG_DEBUG_SKIP");
+    p.debug_skip = dbg ? atoi(dbg) : 0;
+  }
   p.cpb = a->ksize == 3 ? cpb3 : (a->ksize == 2 ? 2 : 4);
   if (p.cpb > cbt) p.cpb = cbt;
   p.ncolb = p.ksize * p.cpb;
@@ -365,7 +378,7 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
-  dim3 grid(pl.splits, pl.gy, pl.gz);
+  dim3 grid(pl.gy * pl.gz, pl.splits, 1);
   conv_wgrad_kernel<<<grid, kWgThreads, pl.smem_bytes, stream>>>(tmDY, tmX0, tmX1, pl.p);
   B2_LAUNCH_CHECK();
   const long long n4 = (pl.count + 3) / 4;

@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--ncu", action="store_true")
 ap.add_argument("--out", default="gpurun_out/conv_layers.json")
+ap.add_argument("--layers", default="", help="override the layer list: cin,cout,side,k[;cin,cout,side,k...]")
 a = ap.parse_args()
 N = a.batch
 # (cin, cout, side, ksize) of every distinct AttU_Net tensor-core conv
@@ -50,6 +51,8 @@ def bench(fn, reps=5):
 
 rows = []
 layers = REPR if a.ncu else LAYERS
+if a.layers:
+    layers = [tuple(int(v) for v in item.split(",")) for item in a.layers.split(";")]
 for cin, cout, s, k in layers:
     x = torch.randn(N, s, s, cin, device=dev, generator=g).to(torch.bfloat16)
     dy = torch.randn(N, s, s, cout, device=dev, generator=g).to(torch.bfloat16)
