@@ -9,6 +9,9 @@
 // MN blocks LBO apart).  X boxes are shifted by the tap offset; TMA zero fill supplies the padding halo.
 // The dY tile is loaded once per K chunk and reused by every column block (3x3: 2 X blocks x 3 taps = N 384, issued as
 // two N=192 MMAs into adjacent TMEM columns); the kernel is L2->SM bandwidth bound, so bytes per FLOP is what counts.
+// Cout == 64 ("row pair" mode): instead of leaving half of the 128 MMA rows idle, rows 64..127 hold dY of the NEXT
+// image row, so against the same X row they produce the gradient of the filter row above; with X rows h and h+1 as
+// the two column groups one CTA yields all three filter rows from two MMAs per K step (one quarter is redundant).
 // Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
 #include <stdlib.h>
@@ -38,6 +41,8 @@ struct WgradParams {
   int a_boxes;       // 1 if cout <= 64 else 2
   int stages;
   int b_stage_bytes; // smem bytes reserved per stage for the X boxes
+  int gy;            // CTAs per (split, channel group): filter rows handled by separate CTAs (1 in row-pair mode)
+  int rowpair;       // Cout == 64, 3x3: M rows 0..63 = dY of image row h, rows 64..127 = dY of row h+1 (see kernel)
   int debug_skip;    // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs
   float* ws;         // [splits][cout][taps][ctot]
 };
@@ -60,8 +65,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   // CTAs that read the same pixels (same split; different filter row / channel group) have adjacent block indices,
   // so they run in the same wave and the dY / X chunks they share are fetched from DRAM once
   const int split = blockIdx.y;
-  const int rg = blockIdx.x % p.ksize;                // filter row (3x3) or 0
-  const int zz = blockIdx.x / p.ksize;
+  const int rg = blockIdx.x % p.gy;                   // filter row (3x3) or 0
+  const int zz = blockIdx.x / p.gy;
   const int co_tiles = (p.cout + 127) / 128;
   const int co_tile = zz % co_tiles;
   const int cgrp = zz / co_tiles;                     // channel-block group
@@ -96,7 +101,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   // number of live column blocks for this CTA (1x1 groups may run past the last channel block)
   int live_cb = p.cpb;
   if (cib_base + live_cb > cbt) live_cb = cbt - cib_base;
-  const int ncol_live = live_cb * p.ksize;
+  const int ncol_live = p.rowpair ? 6 : live_cb * p.ksize;
 
   if (warp == 0) {
     // TMA producer: warp-uniform loop, one elected lane issues; chunk coordinates advance incrementally
@@ -118,11 +123,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           // dY: both 64-channel blocks of the 128-row M tile in one 5-D box (.., channel block)
-          tma_load_5d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0, co_tile * 2);
+          if (p.rowpair) {     // dY rows h0 and h0 + 1 (zero fill below the image)
+            tma_load_4d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0);
+            tma_load_4d(sa + kBoxBytes, &tmDY, &full_bar[stage], 0, w0, h0 + 1, n0);
+          } else {
+            tma_load_5d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0, co_tile * 2);
+          }
           for (int j = 0; j < ncol_live; ++j) {
-            const int cib = cib_base + j / p.ksize;
+            const int cib = p.rowpair ? cib_base : cib_base + j / p.ksize;
             const int xw = p.xstride * w0 + (j % p.ksize) - p.pad_w;
-            const int xh = p.xstride * h0 + rg - p.pad_h;
+            const int xh = p.rowpair ? h0 + j / 3 : p.xstride * h0 + rg - p.pad_h;
             if (cib < p.cb0)
               tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, xw, xh, n0);
             else
@@ -186,7 +196,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     // epilogue: row = output channel within the tile; columns = (column block, channel)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int co = co_tile * 128 + row;
+    const int co = p.rowpair ? (row & 63) : co_tile * 128 + row;
     const bool valid = co < p.cout;
     float* out = p.ws + ((size_t)split * p.cout + (valid ? co : 0)) * ((size_t)p.taps * p.ctot);
     if (nchunks > 0) {
@@ -195,8 +205,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int j = 0; j < ncol_live; ++j) {
-      const int tap = rg * p.ksize + (j % p.ksize);
-      const int cib = cib_base + j / p.ksize;
+      int tap = rg * p.ksize + (j % p.ksize);
+      int cib = cib_base + j / p.ksize;
+      bool live = valid;
+      if (p.rowpair) {
+        // X row h (j < 3): dY row h -> filter row 1, dY row h+1 -> filter row 0; X row h+1: dY row h -> filter row 2
+        const int fr = j < 3 ? (row < 64 ? 1 : 0) : (row < 64 ? 2 : -1);
+        live = fr >= 0;
+        tap = (fr < 0 ? 0 : fr) * 3 + j % 3;
+        cib = cib_base;
+      }
       float* dst = out + (size_t)tap * p.ctot + cib * 64;
       const int cvalid = p.ctot - cib * 64;   // channels left in this block (>= 64 except for a ragged tail)
 #pragma unroll
@@ -209,7 +227,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (valid) {
+        if (live) {
           if (cvalid >= 64) {
             float4* d4 = reinterpret_cast<float4*>(dst + half * 32);
 #pragma unroll
@@ -289,6 +307,19 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   if (p.cpb > cbt) p.cpb = cbt;
   p.ncolb = p.ksize * p.cpb;
   pl->gy = p.ksize;
+  {
+    const char* rp_env = getenv("B200SEG_WG_ROWPAIR");
+    const int dm = a->dy_mul == 0 ? 1 : a->dy_mul;
+    p.rowpair = (a->cout == 64 && a->ksize == 3 && xstride == 1 && !a->custom_pad && dm == 1 && p.Hb == 1 &&
+                 p.Nb == 1 && !(rp_env != nullptr && atoi(rp_env) == 0)) ? 1 : 0;
+    if (p.rowpair) {
+      p.cpb = 1;
+      p.ncolb = 6;
+      p.a_boxes = 2;
+      pl->gy = 1;
+    }
+  }
+  p.gy = pl->gy;
   pl->gz = ((a->cout + 127) / 128) * ((cbt + p.cpb - 1) / p.cpb);
   const int base = pl->gy * pl->gz;
   // split-K factor: one CTA per SM is resident, so pick the split count (up to ~3 waves) whose grid fills whole
@@ -358,7 +389,12 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     uint64_t dims[5] = {c_in_block, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n, (uint64_t)((a->cout + 63) / 64)};
     uint64_t str[5] = {2, (uint64_t)dm * a->lddy * 2, (uint64_t)dm * fw * a->lddy * 2, fh * fw * a->lddy * 2, 128};
     uint32_t box[5] = {64, (uint32_t)pl.p.Wb, (uint32_t)pl.p.Hb, (uint32_t)pl.p.Nb, (uint32_t)pl.p.a_boxes};
-    rc = encode_tmap_bf16(&tmDY, dyb, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (pl.p.rowpair) {
+      uint32_t box4[4] = {64, (uint32_t)pl.p.Wb, 1, 1};
+      rc = encode_tmap_bf16(&tmDY, dyb, 4, dims, str, box4, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      rc = encode_tmap_bf16(&tmDY, dyb, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (rc) return rc;
   }
   const int xboxw = pl.p.Wb;

@@ -34,6 +34,8 @@ SHAPES = [
     (2, 256, 256, 64, 32, 1),
     (2, 32, 32, 32, 64, 1),
     (1, 512, 512, 64, 64, 3),
+    (2, 128, 128, 128, 64, 3),      # Cout = 64 weight gradient: row-pair mode, two channel blocks
+    (3, 64, 64, 64, 64, 3),         # ... at the narrowest width it applies to
 ]
 
 
