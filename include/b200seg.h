@@ -265,6 +265,18 @@ int b2_loss_bwd(const float* z, const float* t, int64_t count, const double* sum
                 float smooth, const float* grad_out, float* dz, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Validation / test metrics and the served mask
+ * counts[n][3] = {TP, #pred, #target} per sample with pred = z > thr_logit (== sigmoid(z) > threshold,
+ * thr_logit = log(thr / (1 - thr))) and target = t > thr_target: the integers behind calculate_iou / calculate_dice /
+ * calculate_pixel_accuracy / calculate_segmentation_metrics (utils/tester.py:92-193) and iou (utils/helpers.py:223-227).
+ * The library zeroes counts. z, t: [n][per_sample] fp32 contiguous.
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2_seg_counts(const float* z, const float* t, int32_t n, int64_t per_sample, float thr_logit, float thr_target,
+                  uint64_t* counts, b2_stream_t stream);
+/* mask[i] = (z[i] > thr_logit) ? 255 : 0 — the uint8 image of utils/pipeline.py:352-354 */
+int b2_logits_to_mask(const float* z, int64_t count, float thr_logit, uint8_t* mask, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Optimizer step (utils/helpers.py:333-335): clip_grad_norm_(max_norm) + AdamW over all parameters in two launches.
  * `refs` is a DEVICE array of tensor references (fp32, element-wise aligned layouts); block b processes elements
  * [block_chunk[b]*chunk_elems, ...) of tensor block_tensor[b].  `step` (device float) is incremented by

@@ -486,6 +486,35 @@ def loss_fwd(z, t, w_bce=1.0, w_dice=0.0, smooth=1.0):
     return loss, sums
 
 
+def _thr_logit(threshold):
+    import math
+    if threshold <= 0.0:
+        return -float("inf")
+    if threshold >= 1.0:
+        return float("inf")
+    return math.log(threshold / (1.0 - threshold))
+
+
+def seg_counts(z, t, threshold=0.5, probabilities=False):
+    """[N, ...] fp32 logits (or probabilities) / targets -> int64 [N, 3] = (TP, #pred, #target) per sample
+    (b2_seg_counts); pred = sigmoid(z) > threshold, evaluated as z > logit(threshold)."""
+    assert z.dtype == torch.float32 and t.dtype == torch.float32 and z.is_contiguous() and t.is_contiguous()
+    assert z.shape == t.shape and z.dim() >= 2
+    n = z.shape[0]
+    counts = torch.empty((n, 3), dtype=torch.int64, device=z.device)
+    thr = float(threshold) if probabilities else _thr_logit(threshold)
+    call("b2_seg_counts", _p(z), _p(t), n, z.numel() // n, thr, float(threshold), _p(counts), _stream())
+    return counts
+
+
+def logits_to_mask(z, threshold=0.5):
+    """fp32 logits -> uint8 {0, 255} mask of the same shape (b2_logits_to_mask)."""
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    mask = torch.empty(z.shape, dtype=torch.uint8, device=z.device)
+    call("b2_logits_to_mask", _p(z), z.numel(), _thr_logit(threshold), _p(mask), _stream())
+    return mask
+
+
 def loss_bwd(z, t, sums, grad_out, w_bce=1.0, w_dice=0.0, smooth=1.0):
     dz = torch.empty_like(z)
     call("b2_loss_bwd", _p(z), _p(t), z.numel(), _p(sums), float(w_bce), float(w_dice), float(smooth),

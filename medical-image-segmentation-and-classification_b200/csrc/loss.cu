@@ -80,6 +80,59 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(const float* __restrict__
   }
 }
 
+// Per-sample confusion counts for the validation / test metrics (utils/tester.py:92-193, utils/helpers.py:223-227):
+// pred = z > thr_logit  (== sigmoid(z) > threshold), target = t > thr_target; counts[n] = {TP, #pred, #target}.
+// Everything the reference derives per sample (IoU, Dice, pixel accuracy, precision, recall, F1) is a function of
+// these three integers and H*W, so one pass over the logits replaces ~10 reductions and 8 host syncs per sample.
+__global__ void __launch_bounds__(256) seg_counts_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                         long long per_sample, float thr_logit, float thr_target,
+                                                         unsigned long long* __restrict__ counts) {
+  const int n = blockIdx.y;
+  const float* zn = z + (long long)n * per_sample;
+  const float* tn = t + (long long)n * per_sample;
+  unsigned tp = 0, np = 0, nt = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample;
+       i += (long long)gridDim.x * blockDim.x) {
+    const bool pr = __ldg(zn + i) > thr_logit, tg = __ldg(tn + i) > thr_target;
+    tp += (pr && tg) ? 1u : 0u;
+    np += pr ? 1u : 0u;
+    nt += tg ? 1u : 0u;
+  }
+  tp = __reduce_add_sync(0xffffffffu, tp);
+  np = __reduce_add_sync(0xffffffffu, np);
+  nt = __reduce_add_sync(0xffffffffu, nt);
+  __shared__ unsigned sh[3][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    sh[0][warp] = tp;
+    sh[1][warp] = np;
+    sh[2][warp] = nt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    unsigned long long s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
+    if (s) atomicAdd(&counts[n * 3 + threadIdx.x], s);
+  }
+}
+
+// binary mask image of utils/pipeline.py:352-354: (sigmoid(z) > threshold) * 255 as uint8
+__global__ void __launch_bounds__(256) logits_to_mask_kernel(const float* __restrict__ z, long long count,
+                                                             float thr_logit, uint8_t* __restrict__ mask) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < count) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(z + i4));
+    uchar4 m;
+    m.x = v.x > thr_logit ? 255 : 0;
+    m.y = v.y > thr_logit ? 255 : 0;
+    m.z = v.z > thr_logit ? 255 : 0;
+    m.w = v.w > thr_logit ? 255 : 0;
+    *reinterpret_cast<uchar4*>(mask + i4) = m;
+  } else {
+    for (long long i = i4; i < count; ++i) mask[i] = __ldg(z + i) > thr_logit ? 255 : 0;
+  }
+}
+
 static int l_grid(long long count) {
   long long g = (count + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
@@ -112,6 +165,31 @@ extern "C" int b2_loss_bwd(const float* z, const float* t, int64_t count, const 
   B2_REQUIRE(count > 0, B2_ERR_SHAPE, "empty loss input");
   loss_bwd_kernel<<<l_grid(count), 256, 0, (cudaStream_t)stream>>>(z, t, count, sums, w_bce, w_dice, smooth,
                                                                    grad_out, dz);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_seg_counts(const float* z, const float* t, int32_t n, int64_t per_sample, float thr_logit,
+                             float thr_target, uint64_t* counts, b2_stream_t stream) {
+  B2_REQUIRE(n > 0 && n <= 65535 && per_sample > 0, B2_ERR_SHAPE, "bad seg_counts extent n=%d per_sample=%lld", n,
+             (long long)per_sample);
+  B2_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)n * 3 * sizeof(uint64_t), (cudaStream_t)stream));
+  long long gx = (per_sample + 256 * 8 - 1) / (256 * 8);
+  const long long cap = ((long long)num_sms() * 8 + n - 1) / n;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  seg_counts_kernel<<<dim3((unsigned)gx, (unsigned)n), 256, 0, (cudaStream_t)stream>>>(
+      z, t, per_sample, thr_logit, thr_target, reinterpret_cast<unsigned long long*>(counts));
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_logits_to_mask(const float* z, int64_t count, float thr_logit, uint8_t* mask, b2_stream_t stream) {
+  B2_REQUIRE(count > 0, B2_ERR_SHAPE, "empty mask input");
+  B2_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3) == 0, B2_ERR_ALIGN,
+             "logits must be 16 B aligned, mask 4 B aligned");
+  const long long n4 = (count + 3) / 4;
+  logits_to_mask_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, count, thr_logit, mask);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

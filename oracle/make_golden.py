@@ -129,6 +129,31 @@ def golden_losses():
     return out
 
 
+def golden_metrics():
+    """Per-sample outputs of the reference's calculate_segmentation_metrics (utils/tester.py:158-193) on seeded data,
+    including an all-background prediction and an empty target (the 1e-7 guards)."""
+    g = {"torch": torch}
+    _ast_extract(REF / "utils" / "tester.py", {"calculate_iou", "calculate_dice", "calculate_pixel_accuracy",
+                                               "calculate_segmentation_metrics"}, g)
+    z, t = noise_batch(6, 32, 32, seed=11)
+    z = (z[:, :1] * 2.0).float()
+    t = t.float()
+    z[4] = -5.0            # nothing predicted
+    t[5] = 0.0             # empty ground truth
+    out = OrderedDict()
+    out["z"] = z.numpy()
+    out["t"] = t.numpy()
+    keys = ["iou", "dice", "pixel_accuracy", "precision", "recall", "f1"]
+    for thr in (0.5, 0.3):
+        rows = []
+        for i in range(z.shape[0]):
+            m = g["calculate_segmentation_metrics"](torch.sigmoid(z[i]), t[i], thr)
+            rows.append([m[k] for k in keys])
+        out[f"metrics_thr{int(thr * 10)}"] = np.array(rows, dtype=np.float64)
+    out["keys"] = np.array(keys)
+    return out
+
+
 def main():
     dst = ROOT / "tests" / "golden"
     dst.mkdir(parents=True, exist_ok=True)
@@ -138,6 +163,8 @@ def main():
         print("wrote", case, flush=True)
     np.savez_compressed(dst / "losses.npz", **golden_losses())
     print("wrote losses")
+    np.savez_compressed(dst / "metrics.npz", **golden_metrics())
+    print("wrote metrics")
 
 
 if __name__ == "__main__":

@@ -234,6 +234,27 @@ def iou(pred, target, thresh=0.5):
     return float(inter / (union + 1e-7))
 
 
+def segmentation_metrics(pred, target, threshold=0.5):
+    """calculate_segmentation_metrics of utils/tester.py:158-193 (with calculate_iou :92-111, calculate_dice :114-134,
+    calculate_pixel_accuracy :137-155) for ONE sample: pred = probabilities after sigmoid.  Returns the same dict
+    (values in percent)."""
+    pb = (pred > threshold).double()
+    tb = (target > threshold).double()
+    inter = (pb * tb).sum()
+    union = ((pb + tb) > 0).double().sum()
+    iou_ = (inter + 1e-7) / (union + 1e-7)
+    dice = (2.0 * inter + 1e-7) / (pb.sum() + tb.sum() + 1e-7)
+    pix = (pb == tb).double().sum() / tb.numel()
+    tp = float(inter)
+    fp = float((pb * (1 - tb)).sum())
+    fn = float(((1 - pb) * tb).sum())
+    precision = (tp + 1e-7) / (tp + fp + 1e-7)
+    recall = (tp + 1e-7) / (tp + fn + 1e-7)
+    f1 = 2 * (precision * recall) / (precision + recall + 1e-7)
+    return {"iou": float(iou_) * 100, "dice": float(dice) * 100, "pixel_accuracy": float(pix) * 100,
+            "precision": precision * 100, "recall": recall * 100, "f1": f1 * 100}
+
+
 def train_step_grads(name, sd, x, target, training=True, loss="bce", **fw_kwargs):
     """forward + loss + backward w.r.t. every floating-point parameter in `sd` (helpers.py:321-329 without AMP).
     Returns (logits, loss, grads: dict name -> tensor, new_buffers)."""

@@ -178,3 +178,37 @@ def test_loss(w_bce, w_dice):
     assert rel(dz, 2 * zr.grad) < 1e-4
     pred = z > 0
     assert int(sums[4]) == int((pred & (t > 0.5)).sum()) and int(sums[5]) == int((pred | (t > 0.5)).sum())
+
+
+def test_seg_counts_and_mask_vs_golden_and_torch():
+    """b2_seg_counts / b2_logits_to_mask: integer-exact against torch, metrics against the reference's own outputs."""
+    import numpy as np
+    from pathlib import Path
+    from b200seg import kernels as K
+    from b200seg.utils import tester as T
+    g = np.load(Path(__file__).parent / "golden" / "metrics.npz")
+    z = torch.from_numpy(g["z"]).cuda()
+    t = torch.from_numpy(g["t"]).cuda()
+    for thr, name in ((0.5, "metrics_thr5"), (0.3, "metrics_thr3")):
+        counts = T.segmentation_counts(z, t, thr)
+        pred = torch.sigmoid(z) > thr
+        tgt = t > thr
+        ref = torch.stack([(pred & tgt).flatten(1).sum(1), pred.flatten(1).sum(1), tgt.flatten(1).sum(1)], 1)
+        assert torch.equal(counts, ref)
+        m = T.metrics_from_counts(counts, z[0].numel())
+        got = np.stack([m[k].cpu().numpy() for k in T.METRIC_KEYS], 1)
+        assert np.allclose(got, g[name], rtol=2e-6, atol=1e-6)
+        one = T.calculate_segmentation_metrics(torch.sigmoid(z[1]), t[1], thr)
+        assert np.allclose([one[k] for k in T.METRIC_KEYS], g[name][1], rtol=2e-6, atol=1e-6)
+    # ragged size (not a multiple of the vector width), large sample
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    zz = torch.randn(3, 1, 257, 131, device="cuda", generator=gen)
+    tt = (torch.rand(3, 1, 257, 131, device="cuda", generator=gen) > 0.6).float()
+    c = K.seg_counts(zz, tt, 0.5)
+    p = zz > 0
+    ref = torch.stack([(p & (tt > 0.5)).flatten(1).sum(1), p.flatten(1).sum(1), (tt > 0.5).flatten(1).sum(1)], 1)
+    assert torch.equal(c, ref)
+    mask = K.logits_to_mask(zz, 0.5)
+    assert mask.dtype == torch.uint8 and torch.equal(mask, (zz > 0).to(torch.uint8) * 255)
+    zr = zz.flatten()[:1001].contiguous()
+    assert torch.equal(K.logits_to_mask(zr, 0.5), (zr > 0).to(torch.uint8) * 255)

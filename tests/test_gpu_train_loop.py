@@ -86,3 +86,35 @@ def test_inference_bn_folding_matches_unfolded_and_oracle(name):
     print(f"{name} eval: folded {e_fold:.2e}  unfolded {e_plain:.2e}  reference-bf16 {e_floor:.2e}")
     tol = max(1e-2, 1.25 * e_floor)
     assert e_fold < tol and e_plain < tol
+
+
+def test_tester_mirror_matches_oracle_per_sample_metrics():
+    """test_segmentation_model (utils/tester.py:249-312 mirror) == average of the oracle's per-sample metrics on the
+    same logits; predict_mask == (sigmoid > 0.5) * 255."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle import unet_oracle as O
+    from oracle.synthetic import xray_batch
+    from b200seg.models.segmentation_models import AttentionUNet
+    from b200seg.utils import tester as T
+    torch.manual_seed(0)
+    model = AttentionUNet().cuda()
+    x, y = xray_batch(4, 64, 64, seed=3)
+    loader = [(x[:2], y[:2]), (x[2:], y[2:])]
+    lines = []
+    avg = T.test_segmentation_model(model, loader, "cuda", "AttentionUNet", log=lines.append)
+    model.eval()
+    with torch.no_grad():
+        logits = model(x.cuda()).float().cpu()
+    want = {k: 0.0 for k in T.METRIC_KEYS}
+    for i in range(4):
+        m = O.segmentation_metrics(torch.sigmoid(logits[i]), y[i], 0.5)
+        for k in want:
+            want[k] += m[k] / 4
+    for k in T.METRIC_KEYS:
+        assert abs(avg[k] - want[k]) < 1e-4 * max(1.0, abs(want[k])), (k, avg[k], want[k])
+    assert any("IoU (Jaccard)" in s for s in lines)
+    mask = T.predict_mask(model, x[:1])
+    assert mask.shape == (64, 64) and mask.dtype.name == "uint8"
+    assert (mask == ((logits[0, 0] > 0).numpy() * 255)).all()

@@ -84,3 +84,25 @@ def test_losses_match_reference():
     c.backward()
     assert rel(z.grad, g["combined_grad"]) < 1e-10
     assert abs(O.iou(torch.sigmoid(z.detach()), t) - float(g["iou"])) < 1e-9
+
+
+def test_segmentation_metrics_match_reference():
+    """oracle.segmentation_metrics and the host-side metrics_from_counts (b200seg.utils.tester) against the outputs of the
+    reference's calculate_segmentation_metrics (tests/golden/metrics.npz, made by oracle/make_golden.py)."""
+    from b200seg.utils.tester import METRIC_KEYS, metrics_from_counts
+    g = np.load(GOLD / "metrics.npz")
+    z, t = torch.from_numpy(g["z"]), torch.from_numpy(g["t"])
+    assert tuple(str(k) for k in g["keys"]) == METRIC_KEYS
+    for thr, name in ((0.5, "metrics_thr5"), (0.3, "metrics_thr3")):
+        want = g[name]
+        for i in range(z.shape[0]):
+            m = O.segmentation_metrics(torch.sigmoid(z[i]), t[i], thr)
+            got = np.array([m[k] for k in METRIC_KEYS])
+            assert np.allclose(got, want[i], rtol=2e-6, atol=1e-6), (thr, i, got, want[i])
+        # host formula on integer counts (what the CUDA kernel produces)
+        pred = torch.sigmoid(z) > thr
+        tgt = t > thr
+        counts = torch.stack([(pred & tgt).flatten(1).sum(1), pred.flatten(1).sum(1), tgt.flatten(1).sum(1)], 1)
+        m = metrics_from_counts(counts, z[0].numel())
+        got = np.stack([m[k].numpy() for k in METRIC_KEYS], 1)
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-6)
