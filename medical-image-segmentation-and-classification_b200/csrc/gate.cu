@@ -124,32 +124,73 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
   const float mu1 = __ldg(mean1), is1 = __ldg(invstd1);
   float l0 = 0.f, l1 = 0.f;
-  for (long long base = (long long)blockIdx.x * gpb; base < npix; base += (long long)gridDim.x * gpb) {
-    const long long p = base + grp;
-    const bool live = p < npix;
-    float s = 0.f;
-    float ps = 0.f;
-    if (live) {
-      ps = __bfloat162float(psi[p]);
-      for (int k = lig; k < cg; k += L) {
+  const long long stride = (long long)gridDim.x * gpb;
+  constexpr int U = 2;                        // pixels in flight per thread (cg <= L: one 8-channel group each)
+  for (long long base = (long long)blockIdx.x * gpb; base < npix; base += U * stride) {
+    float s[U], ps[U];
+    bool live[U];
+    if (cg <= L) {
+      uint4 dv[U], fv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = base + u * stride + grp;
+        live[u] = p < npix;
+        const bool ld = live[u] && lig < cg;
+        const long long pc = live[u] ? p : 0;
+        ps[u] = __bfloat162float(psi[pc]);
+        dv[u] = ld ? __ldg(reinterpret_cast<const uint4*>(dout + pc * lddout + lig * 8)) : make_uint4(0, 0, 0, 0);
+        fv[u] = ld ? __ldg(reinterpret_cast<const uint4*>(x + pc * ldx + lig * 8)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = base + u * stride + grp;
         float d[8], f[8];
-        g_unpack8(__ldg(reinterpret_cast<const uint4*>(dout + p * lddout + k * 8)), d);
-        g_unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * ldx + k * 8)), f);
+        g_unpack8(dv[u], d);
+        g_unpack8(fv[u], f);
+        float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          s = fmaf(d[j], f[j], s);
-          d[j] *= ps;
+          acc = fmaf(d[j], f[j], acc);
+          d[j] *= ps[u];
         }
-        *reinterpret_cast<uint4*>(dx + p * lddx + k * 8) = g_pack8(d);
+        s[u] = acc;
+        if (live[u] && lig < cg) *reinterpret_cast<uint4*>(dx + p * lddx + lig * 8) = g_pack8(d);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long p = base + u * stride + grp;
+        live[u] = p < npix;
+        s[u] = 0.f;
+        ps[u] = 0.f;
+        if (live[u]) {
+          ps[u] = __bfloat162float(psi[p]);
+          for (int k = lig; k < cg; k += L) {
+            float d[8], f[8];
+            g_unpack8(__ldg(reinterpret_cast<const uint4*>(dout + p * lddout + k * 8)), d);
+            g_unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * ldx + k * 8)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s[u] = fmaf(d[j], f[j], s[u]);
+              d[j] *= ps[u];
+            }
+            *reinterpret_cast<uint4*>(dx + p * lddx + k * 8) = g_pack8(d);
+          }
+        }
       }
     }
-    for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lig == 0 && live) {
-      const float ds = s * ps * (1.f - ps);
-      dsig[p] = ds;
-      const float qh = (__bfloat162float(q[p]) - mu1) * is1;
-      l0 += ds;
-      l1 += ds * qh;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float su = s[u];
+      for (int o = L >> 1; o > 0; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
+      const long long p = base + u * stride + grp;
+      if (lig == 0 && live[u]) {
+        const float ds = su * ps[u] * (1.f - ps[u]);
+        dsig[p] = ds;
+        const float qh = (__bfloat162float(q[p]) - mu1) * is1;
+        l0 += ds;
+        l1 += ds * qh;
+      }
     }
   }
   block_sum2_atomic(l0, l1, &sums1[0], &sums1[1]);
@@ -170,7 +211,7 @@ __device__ __forceinline__ float gate_dq(float ds, float qv, float g1, float mu1
 }
 
 // backward phase 2: reductions for BN_g, BN_x and the psi conv
-__global__ void __launch_bounds__(256) gate_psi_bwd_reduce_kernel(
+__global__ void __launch_bounds__(256, 2) gate_psi_bwd_reduce_kernel(
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int L, GateBwdCoef c,
     const double* __restrict__ sums1, int training, double* __restrict__ sums, float* __restrict__ dwpsi,
@@ -180,15 +221,15 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_reduce_kernel(
   __syncthreads();
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
   const bool has = lig * 8 < fint;
-  float sg[8], hg[8], mg[8], ig[8], sx[8], hx[8], mx[8], ix[8], wp[8];
+  // per-channel constants kept in registers: BN affine (mask recomputation), means (centred sums), psi weights.
+  // The xhat sums are accumulated as sum da * (v - mean) and scaled by invstd once per block.
+  float sg[8], hg[8], mg[8], sx[8], hx[8], mx[8], wp[8];
   g_load8(c.scale_g + lig * 8, has, sg);
   g_load8(c.shift_g + lig * 8, has, hg);
   g_load8(c.mean_g + lig * 8, has, mg);
-  g_load8(c.invstd_g + lig * 8, has, ig);
   g_load8(c.scale_x + lig * 8, has, sx);
   g_load8(c.shift_x + lig * 8, has, hx);
   g_load8(c.mean_x + lig * 8, has, mx);
-  g_load8(c.invstd_x + lig * 8, has, ix);
   g_load8(c.wpsi + lig * 8, has, wp);
 #pragma unroll
   for (int j = 0; j < 8; ++j) wp[j] = bf16_round(wp[j]);
@@ -198,29 +239,47 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_reduce_kernel(
 #pragma unroll
   for (int j = 0; j < 8; ++j) ab[j] = agg[j] = agx[j] = aw[j] = 0.f;
   if (has) {
-    for (long long p = (long long)blockIdx.x * gpb + grp; p < npix; p += (long long)gridDim.x * gpb) {
-      const float dq = gate_dq(__ldg(dsig + p), __bfloat162float(q[p]), g1, mu1, is1, training, k0, k1);
-      float g[8], x[8];
-      g_unpack8(__ldg(reinterpret_cast<const uint4*>(g1p + p * ld + lig * 8)), g);
-      g_unpack8(__ldg(reinterpret_cast<const uint4*>(x1p + p * ld + lig * 8)), x);
+    const long long stride = (long long)gridDim.x * gpb;
+    constexpr int U = 2;                      // pixels in flight per thread (all loads issued before the math)
+    for (long long p0 = (long long)blockIdx.x * gpb + grp; p0 < npix; p0 += U * stride) {
+      uint4 gv[U], xv[U];
+      float ds[U], qv[U];
+      bool ok[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
-        const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
-        const float a = fmaxf(bf16_round(gb + xb), 0.f);
-        const float da = a > 0.f ? dq * wp[j] : 0.f;
-        ab[j] += da;
-        agg[j] += da * ((g[j] - mg[j]) * ig[j]);
-        agx[j] += da * ((x[j] - mx[j]) * ix[j]);
-        aw[j] = fmaf(dq, a, aw[j]);
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * stride;
+        ok[u] = p < npix;
+        const long long pc = ok[u] ? p : p0;
+        gv[u] = __ldg(reinterpret_cast<const uint4*>(g1p + pc * ld + lig * 8));
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(x1p + pc * ld + lig * 8));
+        ds[u] = __ldg(dsig + pc);
+        qv[u] = __bfloat162float(q[pc]);
       }
-      if (lig == 0) abp += dq;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float dq = ok[u] ? gate_dq(ds[u], qv[u], g1, mu1, is1, training, k0, k1) : 0.f;
+        float g[8], x[8];
+        g_unpack8(gv[u], g);
+        g_unpack8(xv[u], x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
+          const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
+          const float a = fmaxf(bf16_round(gb + xb), 0.f);
+          const float da = a > 0.f ? dq * wp[j] : 0.f;
+          ab[j] += da;
+          agg[j] = fmaf(da, g[j] - mg[j], agg[j]);
+          agx[j] = fmaf(da, x[j] - mx[j], agx[j]);
+          aw[j] = fmaf(dq, a, aw[j]);
+        }
+        if (lig == 0) abp += dq;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&red[0 * fint + lig * 8 + j], ab[j]);
-      atomicAdd(&red[1 * fint + lig * 8 + j], agg[j]);
-      atomicAdd(&red[2 * fint + lig * 8 + j], agx[j]);
+      atomicAdd(&red[1 * fint + lig * 8 + j], agg[j] * __ldg(c.invstd_g + lig * 8 + j));
+      atomicAdd(&red[2 * fint + lig * 8 + j], agx[j] * __ldg(c.invstd_x + lig * 8 + j));
       atomicAdd(&red[3 * fint + lig * 8 + j], aw[j]);
     }
     if (lig == 0) atomicAdd(&red[4 * fint], abp);
@@ -241,7 +300,7 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_reduce_kernel(
 //                                           Cg = -gamma*invstd*dbeta/m - Bg*mean          (same for the x branch)
 // so only the mask coefficients and three constants per branch stay in registers.  Also accumulates the column sums
 // of the ROUNDED outputs = bias gradients of the W_g / W_x convolutions (dbias[0][c], dbias[1][c]).
-__global__ void __launch_bounds__(256) gate_psi_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 2) gate_psi_bwd_apply_kernel(
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int tpp, int rows, GateBwdCoef c,
     const double* __restrict__ sums1, int training, const double* __restrict__ sums,
@@ -290,29 +349,49 @@ __global__ void __launch_bounds__(256) gate_psi_bwd_apply_kernel(
     }
     const float g1 = __ldg(c.gamma1), mu1 = __ldg(c.mean1), is1 = __ldg(c.invstd1);
     const float k0 = (float)(sums1[0] * inv_m), k1 = (float)(sums1[1] * inv_m);
-    for (long long p = (long long)blockIdx.x * rows + r; p < npix; p += (long long)gridDim.x * rows) {
-      const float dq = gate_dq(__ldg(dsig + p), __bfloat162float(q[p]), g1, mu1, is1, training, k0, k1);
-      float g[8], x[8];
-      g_unpack8(__ldg(reinterpret_cast<const uint4*>(g1p + p * ld + gch * 8)), g);
-      g_unpack8(__ldg(reinterpret_cast<const uint4*>(x1p + p * ld + gch * 8)), x);
+    const long long stride = (long long)gridDim.x * rows;
+    constexpr int U = 2;                      // pixels in flight per thread
+    for (long long p0 = (long long)blockIdx.x * rows + r; p0 < npix; p0 += U * stride) {
+      uint4 gv[U], xv[U];
+      float ds[U], qv[U];
+      bool ok[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
-        const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
-        const float dqm = bf16_round(gb + xb) > 0.f ? dq : 0.f;
-        g[j] = fmaf(wg[j], dqm, fmaf(bg[j], g[j], cg[j]));
-        x[j] = fmaf(wx[j], dqm, fmaf(bx[j], x[j], cx[j]));
+      for (int u = 0; u < U; ++u) {
+        const long long p = p0 + u * stride;
+        ok[u] = p < npix;
+        const long long pc = ok[u] ? p : p0;
+        gv[u] = __ldg(reinterpret_cast<const uint4*>(g1p + pc * ld + gch * 8));
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(x1p + pc * ld + gch * 8));
+        ds[u] = __ldg(dsig + pc);
+        qv[u] = __bfloat162float(q[pc]);
       }
-      const uint4 og = g_pack8(g), ox = g_pack8(x);
-      *reinterpret_cast<uint4*>(dg1p + p * ld + gch * 8) = og;
-      *reinterpret_cast<uint4*>(dx1p + p * ld + gch * 8) = ox;
-      if (dbias != nullptr) {
-        g_unpack8(og, g);
-        g_unpack8(ox, x);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const long long p = p0 + u * stride;
+        const float dq = gate_dq(ds[u], qv[u], g1, mu1, is1, training, k0, k1);
+        float g[8], x[8];
+        g_unpack8(gv[u], g);
+        g_unpack8(xv[u], x);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          bsg[j] += g[j];
-          bsx[j] += x[j];
+          const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
+          const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
+          const float dqm = bf16_round(gb + xb) > 0.f ? dq : 0.f;
+          g[j] = fmaf(wg[j], dqm, fmaf(bg[j], g[j], cg[j]));
+          x[j] = fmaf(wx[j], dqm, fmaf(bx[j], x[j], cx[j]));
+        }
+        const uint4 og = g_pack8(g), ox = g_pack8(x);
+        *reinterpret_cast<uint4*>(dg1p + p * ld + gch * 8) = og;
+        *reinterpret_cast<uint4*>(dx1p + p * ld + gch * 8) = ox;
+        if (dbias != nullptr) {
+          g_unpack8(og, g);
+          g_unpack8(ox, x);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            bsg[j] += g[j];
+            bsx[j] += x[j];
+          }
         }
       }
     }

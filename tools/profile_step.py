@@ -25,7 +25,9 @@ kw = {"t": a.t} if a.t is not None else {}
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
 model = getattr(M, a.model)(**kw).to(dev, memory_format=torch.channels_last).train()
-opt = torch.optim.AdamW(model.parameters(), lr=1e-6, weight_decay=5e-4, fused=True)
+from b200seg.optim import FusedClipAdamW  # noqa: E402
+
+opt = FusedClipAdamW(model.parameters(), lr=1e-6, weight_decay=5e-4, max_norm=1.0)     # as utils/helpers.train()
 x, t = xray_batch(a.batch, a.side, a.side, seed=0, device=dev)
 params = list(model.parameters())
 
@@ -34,7 +36,6 @@ def step():
     opt.zero_grad(set_to_none=True)
     loss, _ = ops.seg_loss(model(x), t, 1.0, 0.0, 1.0)
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(params, 1.0)
     opt.step()
     return loss
 
