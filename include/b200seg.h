@@ -203,6 +203,10 @@ int b2_add(const void* a, int32_t lda, const void* b, int32_t ldb, int64_t npix,
 int b2_nchw_f32_to_nhwc_bf16(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* y, int32_t ldy,
                              b2_stream_t stream);
 /* module-boundary adapters for any channel count (input arrives NCHW fp32: utils/helpers.py:318) */
+/* Image stem as a GEMM (AttentionUNet.py:6 basic_block(3,64) first conv, K = 27): xc[N,H,W,32] bf16 = im2col of the
+ * 3x3 neighbourhood of the fp32 NCHW image x[N,c<=3,H,W] (column = tap*c_in + channel, zero padded to 32), consumed by
+ * b2_conv_fprop / b2_conv_wgrad as a 1x1 convolution with 32 input channels. */
+int b2_stem_im2col3x3(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* xc, b2_stream_t stream);
 int b2_layout_nchw_to_nhwc(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* y, int32_t ldy,
                            b2_stream_t stream);
 int b2_layout_nhwc_to_nchw(const void* x, int32_t ldx, int32_t n, int32_t c, int32_t h, int32_t w, float* y,

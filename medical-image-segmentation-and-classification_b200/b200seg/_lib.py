@@ -86,6 +86,7 @@ SIGNATURES = {
     "b2_upsample2x_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2_add": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i32, _vp]),
     "b2_nchw_f32_to_nhwc_bf16": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "b2_stem_im2col3x3": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b2_layout_nchw_to_nhwc": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2_layout_nhwc_to_nchw": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b2_stem7x7_fprop": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp]),

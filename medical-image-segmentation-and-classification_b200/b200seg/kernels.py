@@ -214,6 +214,32 @@ def image_to_nhwc4(x):
     return y
 
 
+STEM_COLS = 32          # im2col columns of the 3x3 stem (27 used for a 3-channel image)
+
+
+def stem_im2col3x3(x):
+    """NCHW fp32 image [N, C<=3, H, W] -> NHWC bf16 [N, H, W, 32]: 3x3 neighbourhood, column = tap * C + c."""
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.shape[1] <= 3
+    n, c, h, w = x.shape
+    xc = torch.empty((n, h, w, STEM_COLS), dtype=BF16, device=x.device)
+    call("b2_stem_im2col3x3", _p(x), n, c, h, w, _p(xc), _stream())
+    return xc
+
+
+def stem_weight_matrix(weight):
+    """fp32 [Cout, Cin<=3, 3, 3] -> fp32 [Cout, 32, 1, 1] with column = tap * Cin + c (the im2col order)."""
+    cout, cin, kh, kw = weight.shape
+    wm = torch.zeros((cout, STEM_COLS), dtype=torch.float32, device=weight.device)
+    wm[:, :kh * kw * cin] = weight.detach().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
+    return wm.view(cout, STEM_COLS, 1, 1)
+
+
+def stem_weight_grad(dwc, cin):
+    """[Cout, 1, 32] gradient of the im2col weight matrix -> [Cout, 9, Cin] (tap-major, as conv_wgrad returns)."""
+    cout = dwc.shape[0]
+    return dwc.reshape(cout, STEM_COLS)[:, :9 * cin].reshape(cout, 9, cin).contiguous()
+
+
 def pack_small_weight(weight):
     """fp32 [Cout, Cin<=4, k, k] -> fp32 [Cout, k*k, 4] (tiny; done with torch indexing on the host stream)."""
     cout, cin, kh, kw = weight.shape

@@ -129,16 +129,29 @@ conv2d.register_autograd(_conv2d_backward, setup_context=_conv2d_setup)
 # image stem: Cin <= 4 direct convolution from the NCHW fp32 batch
 #   AttentionUNet.py:6 (basic_block(3,64) first conv), R2U_Net.py:43 (RRCNN1.conv_1x1, 3 -> 64)
 # ----------------------------------------------------------------------------------------------------------
+_STEM_GEMM = os.environ.get("B200SEG_STEM_GEMM", "1") != "0"     # 0: CUDA-core stem kernels (A/B switch)
+
+
+def _stem_as_gemm(weight) -> bool:
+    """3x3 stem with <= 3 input channels and a tensor-core-sized Cout: im2col (K = 32) + the tcgen05 1x1 kernels."""
+    cout, cin, k, _ = weight.shape
+    return k == 3 and cin <= 3 and cout % 32 == 0 and _STEM_GEMM
+
+
 @custom_op("b200seg::stem_conv", mutates_args=())
 def stem_conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], want_stats: bool) -> Tuple[Tensor, Tensor, Tensor]:
     cout, cin, k, _ = weight.shape
+    stats = (torch.zeros((2, cout), dtype=_F64, device=x.device) if want_stats
+             else torch.empty((0,), dtype=_F64, device=x.device))
+    if _stem_as_gemm(weight):
+        x4 = K.stem_im2col3x3(_c(x))
+        wf, _ = K.pack_weights(K.stem_weight_matrix(weight), want_dgrad=False)
+        y = K.conv_igemm(x4, wf, cout, 1, bias=bias, stats=stats if want_stats else None)
+        return y, stats, x4
     x4 = K.image_to_nhwc4(_c(x))
     y = K.conv_smallc_fprop(x4, K.pack_small_weight(weight), bias, k)
     if want_stats:
-        stats = torch.zeros((2, cout), dtype=_F64, device=x.device)
         K.channel_stats(y, stats)
-    else:
-        stats = torch.empty((0,), dtype=_F64, device=x.device)
     return y, stats, x4
 
 
@@ -146,7 +159,10 @@ def stem_conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], want_stats: boo
 def stem_conv_bwd(dy: Tensor, x4: Tensor, weight: Tensor, need_db: bool) -> Tuple[Tensor, Tensor]:
     cout, cin, k, _ = weight.shape
     dy = _c(dy)
-    dwk = K.conv_smallc_wgrad(dy, x4, k)                       # [cout, taps, 4]
+    if x4.shape[-1] == K.STEM_COLS:
+        dwk = K.stem_weight_grad(K.conv_wgrad(dy, x4, 1), cin)     # [cout, taps, cin]
+    else:
+        dwk = K.conv_smallc_wgrad(dy, x4, k)                       # [cout, taps, 4]
     dw = dwk[:, :, :cin].reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
     db = K.channel_sum(dy) if need_db else torch.empty((0,), device=dy.device)
     return dw, db
@@ -174,7 +190,7 @@ def _(x, weight, bias, want_stats):
     cout = weight.shape[0]
     return (x.new_empty((n, h, w, cout), dtype=torch.bfloat16),
             x.new_empty((2, cout) if want_stats else (0,), dtype=_F64),
-            x.new_empty((n, h, w, 4), dtype=torch.bfloat16))
+            x.new_empty((n, h, w, K.STEM_COLS if _stem_as_gemm(weight) else 4), dtype=torch.bfloat16))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -251,7 +267,11 @@ def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional
     cout, cin, k, _ = weight.shape
     dev = x0.device
     stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
-    if x0.dtype != torch.bfloat16:                        # image stem
+    if x0.dtype != torch.bfloat16 and _stem_as_gemm(weight):   # image stem on the tensor cores (im2col, K = 32)
+        x4 = K.stem_im2col3x3(_c(x0))
+        wf, _ = K.pack_weights(K.stem_weight_matrix(weight), want_dgrad=False)
+        z = K.conv_igemm(x4, wf, cout, 1, bias=bias, stats=stats if training else None)
+    elif x0.dtype != torch.bfloat16:                      # other small-channel stems: CUDA-core kernels
         x4 = K.image_to_nhwc4(_c(x0))
         z = K.conv_smallc_fprop(x4, K.pack_small_weight(weight), bias, k)
         if training:
@@ -275,7 +295,7 @@ def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=Non
     cout = weight.shape[0]
     if x0.dtype != torch.bfloat16:
         n, _, h, w = x0.shape
-        x4 = x0.new_empty((n, h, w, 4), dtype=torch.bfloat16)
+        x4 = x0.new_empty((n, h, w, K.STEM_COLS if _stem_as_gemm(weight) else 4), dtype=torch.bfloat16)
     else:
         n, h, w, _ = x0.shape
         x4 = x0.new_empty((0,), dtype=torch.bfloat16)
@@ -295,7 +315,9 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
     db = res[3] if has_bias else torch.empty((0,), device=dev)
     dx0 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     dx1 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
-    if x4.numel() > 0:                                    # stem: no input gradient
+    if x4.numel() > 0 and x4.shape[-1] == K.STEM_COLS:    # stem as a GEMM: no input gradient
+        dw = K.stem_weight_grad(K.conv_wgrad(dz, x4, 1), cin)
+    elif x4.numel() > 0:                                  # stem: no input gradient
         dwk = K.conv_smallc_wgrad(dz, x4, k)
         dw = dwk[:, :, :cin].reshape(cout, k * k, cin).contiguous()
     else:

@@ -238,6 +238,36 @@ static int ew_grid(long long total, int block) {
 }
 static bool al16(const void* p, int ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 8 == 0; }
 
+// Image stem as a GEMM: im2col of the 3x3 neighbourhood of a <= 3-channel fp32 NCHW image into 32 bf16 columns per
+// pixel (column = tap * CIN + c, zero padded), so that the first convolution (AttentionUNet.py:6, K = 27) and its
+// weight gradient run on the tensor-core kernels as a 1x1 convolution with K = 32.
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_im2col3x3_kernel(const float* __restrict__ x, int n, int h, int w,
+                                                             __nv_bfloat16* __restrict__ xc) {
+  const long long total = (long long)n * h * w;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int xx = (int)(p % w);
+  const int yy = (int)((p / w) % h);
+  const long long img = p / ((long long)w * h);
+  const float* xi = x + img * CIN * (long long)h * w;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int y2 = yy + t / 3 - 1, x2 = xx + t % 3 - 1;
+    const bool in = y2 >= 0 && y2 < h && x2 >= 0 && x2 < w;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) v[t * CIN + c] = in ? __ldg(xi + ((long long)c * h + y2) * w + x2) : 0.f;
+  }
+  uint4* dst = reinterpret_cast<uint4*>(xc + p * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    dst[q] = make_uint4(pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]),
+                        pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+}
+
 }  // namespace b2
 
 using namespace b2;
@@ -424,6 +454,21 @@ extern "C" int b2_layout_nhwc_to_nchw(const void* x, int32_t ldx, int32_t n, int
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n);
   b2::nhwc2nchw_tile_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, c, hw, y);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_stem_im2col3x3(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, void* xc,
+                                 b2_stream_t stream) {
+  B2_REQUIRE(n > 0 && h > 0 && w > 0 && c >= 1 && c <= 3, B2_ERR_SHAPE, "stem im2col: %d channels unsupported (1..3)",
+             c);
+  B2_REQUIRE((reinterpret_cast<uintptr_t>(xc) & 15) == 0, B2_ERR_ALIGN, "xc misaligned");
+  const long long total = (long long)n * h * w;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(xc);
+  if (c == 1) stem_im2col3x3_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, h, w, out);
+  else if (c == 2) stem_im2col3x3_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, h, w, out);
+  else stem_im2col3x3_kernel<3><<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, h, w, out);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -137,6 +137,37 @@ def test_stem_conv(k, cin):
     assert rel(got, refw) < 1e-3
 
 
+@pytest.mark.parametrize("cin", [3, 1, 2])
+def test_stem_conv_as_gemm(cin):
+    """3x3 image stem through im2col (K = 32) + the tcgen05 1x1 kernels: the op the models use (ops.stem_conv)."""
+    from b200seg import kernels as K
+    from b200seg import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, h, w, cout = 2, 64, 128, 64
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.3).requires_grad_(True)
+    b = torch.randn(cout, device="cuda", generator=g).requires_grad_(True)
+    xc = K.stem_im2col3x3(x)
+    assert xc.shape == (n, h, w, 32)
+    cols = F.unfold(x.to(torch.bfloat16).float(), 3, padding=1).reshape(n, cin, 9, h, w)       # [n, c, tap, h, w]
+    want = cols.permute(0, 3, 4, 2, 1).reshape(n, h, w, 9 * cin)                               # column = tap*cin + c
+    assert torch.equal(xc[..., :9 * cin].float(), want) and float(xc[..., 9 * cin:].abs().sum()) == 0.0
+    y, stats, saved = ops.stem_conv(x, wt, b, True)
+    assert saved.shape[-1] == 32
+    xb = x.to(torch.bfloat16).float()
+    wref = wt.detach().to(torch.bfloat16).float().requires_grad_(True)
+    bref = b.detach().clone().requires_grad_(True)
+    ref = F.conv2d(xb, wref, bref, padding=1)
+    assert rel(nchw(y), ref) < 4e-3
+    yf = y.float().reshape(-1, cout)
+    assert rel(stats[0], yf.double().sum(0)) < 1e-5 and rel(stats[1], (yf.double() ** 2).sum(0)) < 1e-5
+    dy = torch.randn(n, cout, h, w, device="cuda", generator=g)
+    y.backward(nhwc(dy))
+    ref.backward(nchw(nhwc(dy)))
+    print(f"stem-as-gemm cin{cin}: dw rel {rel(wt.grad, wref.grad):.2e} db rel {rel(b.grad, bref.grad):.2e}")
+    assert rel(wt.grad, wref.grad) < 1e-3 and rel(b.grad, bref.grad) < 1e-3
+
+
 @pytest.mark.parametrize("cin,cout", [(64, 1), (32, 1), (64, 3)])
 def test_head(cin, cout):
     from b200seg import kernels as K
