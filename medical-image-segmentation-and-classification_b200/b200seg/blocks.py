@@ -41,10 +41,10 @@ def to_internal(x):
     return ops.to_nhwc(check_image(x)) if x.dtype != BF16 else x
 
 
-def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True, addend=None):
+def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True, addend=None, shared_weight=False):
     """conv (3x3 p1 or 1x1) -> BatchNorm -> optional ReLU as ONE fused autograd node.  `x` may be an fp32 NCHW image
     with <= 4 channels (stem), an internal activation, or a tuple of two internal activations (virtual concat)."""
-    return ops.conv_bn_act_module(x, conv, bn, relu, addend)
+    return ops.conv_bn_act_module(x, conv, bn, relu, addend, shared_weight)
 
 
 def conv_plain(x, conv: nn.Conv2d):
@@ -152,7 +152,7 @@ class Recurrent_block(nn.Module):
         x = to_internal(x)
         # t+1 applications of the shared conv+BN+ReLU; every application but the last emits x + f(.) directly from the
         # BatchNorm pass (the un-summed activation is never needed), the last one emits f(.) itself
-        f = lambda v, add: conv_bn_act(v, self.conv[0], self.conv[1], addend=add)
+        f = lambda v, add: conv_bn_act(v, self.conv[0], self.conv[1], addend=add, shared_weight=True)
         if self.t == 0:
             raise ValueError("Recurrent_block needs t >= 1 (the reference leaves x1 undefined for t = 0)")
         s = f(x, x)                       # x + f(x)

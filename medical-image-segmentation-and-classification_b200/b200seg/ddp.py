@@ -11,10 +11,16 @@ the rest of backward.  `finish()` waits and writes the averaged gradients back.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import List
 
 import torch
 import torch.distributed as dist
+
+
+def _wgrad_side_stream():
+    from .kernels import wgrad_side_stream
+    return wgrad_side_stream()
 
 
 class _Bucket:
@@ -67,11 +73,22 @@ class GradReducer:
 
     def _hook(self, p):
         b, i = self._where[p]
-        b.view(i).copy_(p.grad)
-        b.pending -= 1
-        if b.pending == 0:
-            op = dist.ReduceOp.AVG if self.avg_native else dist.ReduceOp.SUM
-            b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+        # weight gradients may still be in flight on the side stream (kernels.wgrad_stream): pack and reduce there,
+        # ordered after both streams, so the main stream never waits for them during backward
+        side = _wgrad_side_stream() if p.grad.is_cuda else None
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            side.wait_event(ev)
+            ctx = torch.cuda.stream(side)
+        else:
+            ctx = contextlib.nullcontext()
+        with ctx:
+            b.view(i).copy_(p.grad)
+            b.pending -= 1
+            if b.pending == 0:
+                op = dist.ReduceOp.AVG if self.avg_native else dist.ReduceOp.SUM
+                b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Wait for every bucket and store the averaged gradients into param.grad."""

@@ -6,7 +6,9 @@ nothing else — torch is used only to allocate outputs.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import os
 
 import torch
 
@@ -36,6 +38,71 @@ def _prof_end(kind, flops, start, alg_scale=1.0, nbytes=0.0):
         end = torch.cuda.Event(enable_timing=True)
         end.record()
         PROFILE.append((kind, flops, flops * alg_scale, nbytes, start, end))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Weight-gradient overlap: dW is only needed after backward, so its kernels can run on a side stream while the main
+# stream goes on with the memory-bound BatchNorm / gate / pooling backward of the next layers (they fit next to the
+# persistent wgrad CTAs on an SM; the tensor-core kernels of the main stream do not, those simply take turns).
+# Opt-in (set_wgrad_overlap / B200SEG_WGRAD_OVERLAP=1): the caller must not touch a weight gradient before
+# loss.backward() has returned — true for utils.helpers.train() and bench.py (zero_grad(set_to_none=True),
+# channels_last parameters, gradients read by GradReducer.finish() / the optimizer) — and weights shared between
+# several autograd nodes (Recurrent_block) are excluded because autograd sums their gradients on the main stream.
+# ----------------------------------------------------------------------------------------------------------
+_OVERLAP = {"enabled": os.environ.get("B200SEG_WGRAD_OVERLAP", "0") == "1", "side": {}, "refs": [], "pending": False}
+
+
+def set_wgrad_overlap(flag: bool) -> None:
+    _OVERLAP["enabled"] = bool(flag)
+
+
+def wgrad_overlap_enabled() -> bool:
+    return _OVERLAP["enabled"]
+
+
+def _join_wgrad_stream():
+    """End of backward (autograd engine callback): the calling stream waits for the side stream, references drop."""
+    main = torch.cuda.current_stream()
+    for side in _OVERLAP["side"].values():
+        main.wait_stream(side)
+    _OVERLAP["refs"].clear()
+    _OVERLAP["pending"] = False
+
+
+def wgrad_side_stream():
+    """The side stream if weight gradients of the running backward pass are in flight on it, else None."""
+    if not _OVERLAP["pending"]:
+        return None
+    return _OVERLAP["side"].get(torch.cuda.current_device())
+
+
+@contextlib.contextmanager
+def wgrad_stream(*keep, allow=True):
+    """Run the enclosed launches on the weight-gradient side stream (ordered after everything already queued on the
+    current stream).  `keep`: tensors produced on the current stream that the side stream reads — references are
+    held until the join so the caching allocator cannot hand their memory out again.  No-op unless enabled, inside a
+    backward pass and `allow`."""
+    if not (allow and _OVERLAP["enabled"] and torch.cuda.is_available()):
+        yield
+        return
+    if not _OVERLAP["pending"]:
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad_stream)
+        except RuntimeError:            # not inside a backward pass: nothing to overlap with
+            yield
+            return
+        _OVERLAP["pending"] = True
+    main = torch.cuda.current_stream()
+    dev = torch.cuda.current_device()
+    side = _OVERLAP["side"].get(dev)
+    if side is None:
+        side = _OVERLAP["side"][dev] = torch.cuda.Stream(device=dev)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    _OVERLAP["refs"].extend(t for t in keep if t is not None)
+    with torch.cuda.stream(side):
+        yield
 
 
 def _stream():

@@ -261,9 +261,11 @@ def batch_norm_act(z: Tensor, stats: Tensor, bn: torch.nn.BatchNorm2d, relu: boo
 @custom_op("b200seg::conv_bn_act", mutates_args=())
 def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], gamma: Tensor,
                 beta: Tensor, running_mean: Tensor, running_var: Tensor, training: bool, eps: float,
-                relu: bool, addend: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                relu: bool, addend: Optional[Tensor] = None,
+                shared_weight: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """`addend`: the first output becomes act(bn(conv(x))) + addend (Recurrent_block's x + x1, R2U_Net.py:19); the
-    un-summed activation is then never written."""
+    un-summed activation is then never written.  `shared_weight`: the weight is used by several autograd nodes
+    (autograd sums those gradients on the main stream, so the weight gradient is not moved to the side stream)."""
     cout, cin, k, _ = weight.shape
     dev = x0.device
     stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
@@ -291,7 +293,7 @@ def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional
 
 
 @conv_bn_act.register_fake
-def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=None):
+def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=None, shared_weight=False):
     cout = weight.shape[0]
     if x0.dtype != torch.bfloat16:
         n, _, h, w = x0.shape
@@ -307,7 +309,7 @@ def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=Non
 @custom_op("b200seg::conv_bn_act_bwd", mutates_args=())
 def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, weight: Tensor, z: Tensor,
                     coef: Tensor, gamma: Tensor, relu: bool, training: bool, need_dx0: bool, need_dx1: bool,
-                    has_bias: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                    has_bias: bool, overlap_ok: bool = True) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     cout, cin, k, _ = weight.shape
     dev = dy.device
     res = K.bn_bwd(_c(dy), z, coef, gamma, relu=relu, training=training, want_dbias=has_bias)
@@ -328,14 +330,16 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
                 dx0 = K.conv_igemm(dz, wd, c0, k, row_offset=0, dgrad=True)
             if need_dx1 and x1 is not None:
                 dx1 = K.conv_igemm(dz, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
-        dw = K.conv_wgrad(dz, x0, k, x1=x1)
+        with K.wgrad_stream(dz, x0, x1, allow=overlap_ok):
+            dw = K.conv_wgrad(dz, x0, k, x1=x1)
     return dx0, dx1, dw, db, dgamma, dbeta
 
 
 def _cba_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
-    x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu, addend = inputs
+    x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu, addend, shared = inputs
     ctx.has_addend = addend is not None
+    ctx.overlap_ok = not shared
     _y, z, coef, _stats, x4 = output
     stem = x0.dtype != torch.bfloat16
     ctx.save_for_backward(None if stem else _c(x0), _c(x1), x4, weight, z, coef, gamma)
@@ -349,10 +353,11 @@ def _cba_backward(ctx, dy, *_unused):
     need0 = bool(need[0]) and not ctx.stem
     need1 = bool(need[1]) and x1 is not None
     dx0, dx1, dw, db, dgamma, dbeta = conv_bn_act_bwd(dy, x0 if x0 is not None else x4, x1, x4, weight, z, coef,
-                                                      gamma, ctx.relu, ctx.training, need0, need1, ctx.has_bias)
+                                                      gamma, ctx.relu, ctx.training, need0, need1, ctx.has_bias,
+                                                      ctx.overlap_ok)
     return (dx0 if need0 else None, dx1 if need1 else None, _dw_as_param_grad(dw, weight),
             db if ctx.has_bias else None, dgamma, dbeta, None, None, None, None, None,
-            dy if (ctx.has_addend and need[11]) else None)      # d(addend) = d(output): the sum is linear
+            dy if (ctx.has_addend and need[11]) else None, None)   # d(addend) = d(output): the sum is linear
 
 
 conv_bn_act.register_autograd(_cba_backward, setup_context=_cba_setup)
@@ -366,7 +371,7 @@ def bn_update_running_(stats: Tensor, count: int, momentum: float, running_mean:
 
 
 def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = True,
-                       addend: Optional[Tensor] = None) -> Tensor:
+                       addend: Optional[Tensor] = None, shared_weight: bool = False) -> Tensor:
     """[Conv2d -> BatchNorm2d -> ReLU] (+ addend) on module objects; x: image | activation | (activation, activation)."""
     x0, x1 = x if isinstance(x, tuple) else (x, None)
     training = bn.training or bn.running_mean is None
@@ -376,7 +381,7 @@ def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu:
             return ops_infer.conv_bn_act_infer(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                                bn.running_var, float(bn.eps), relu, addend)
     y, _z, _coef, stats, _x4 = conv_bn_act(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
-                                           bn.running_var, training, float(bn.eps), relu, addend)
+                                           bn.running_var, training, float(bn.eps), relu, addend, shared_weight)
     if training:
         n, h, w, _ = y.shape
         bn_update_running_(stats.detach(), n * h * w, float(bn.momentum), bn.running_mean, bn.running_var,
@@ -442,10 +447,11 @@ def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Te
                          in_off=(a, b), pad=(a, b), alg_scale=2.25)
     else:
         dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)
-    dweff = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=dev)
-    for ph, (a, b) in enumerate(_PHASES):
-        K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
-    dw = K.fold_upconv_wgrad(dweff)
+    with K.wgrad_stream(dz, x):
+        dweff = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=dev)
+        for ph, (a, b) in enumerate(_PHASES):
+            K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
+        dw = K.fold_upconv_wgrad(dweff)
     return dx, dw, db, dgamma, dbeta
 
 

@@ -50,7 +50,12 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
         raise NotImplementedError("b200seg.train covers the segmentation path only (seg=True)")
     device = torch.device(device)
     model = model.to(device, memory_format=torch.channels_last)            # helpers.py:243
+    from .. import kernels as K
     from ..optim import FusedClipAdamW
+    # weight gradients on a side stream: safe here because gradients are only read after backward() (reducer.finish /
+    # optimizer.step), parameters are channels_last and zero_grad(set_to_none=True) is used
+    overlap_before = K.wgrad_overlap_enabled()
+    K.set_wgrad_overlap(device.type == "cuda" and os.environ.get("B200SEG_WGRAD_OVERLAP", "1") != "0")
     optimizer = FusedClipAdamW(model.parameters(), lr=lr, weight_decay=5e-4, max_norm=1.0)   # helpers.py:251,333
     log(f"Training Segmentation model (all layers unfrozen) with LR: {lr}")
     scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=epochs)   # helpers.py:254
@@ -109,5 +114,6 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
             log(f"Early stopping at epoch {epoch}. Best score: {best_score:.2f}")
             break
 
+    K.set_wgrad_overlap(overlap_before)
     log(f"Training for {name} finished in {(time.time() - start_time) / 60:.2f} minutes.")
     return best_score

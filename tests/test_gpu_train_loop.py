@@ -118,3 +118,57 @@ def test_tester_mirror_matches_oracle_per_sample_metrics():
     mask = T.predict_mask(model, x[:1])
     assert mask.shape == (64, 64) and mask.dtype.name == "uint8"
     assert (mask == ((logits[0, 0] > 0).numpy() * 255)).all()
+
+
+@pytest.mark.parametrize("bn_train", [False, True])
+@pytest.mark.parametrize("name,kw", [("AttentionUNet", {}), ("R2AttU_Net", {"t": 2})])
+def test_wgrad_side_stream_overlap_gives_identical_gradients(name, kw, bn_train):
+    """kernels.set_wgrad_overlap(True): weight gradients computed on the side stream are bit-identical to the
+    single-stream ones once backward() has returned (the engine callback joins the streams)."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle.synthetic import xray_batch
+    from b200seg import kernels as K
+    from b200seg import ops
+    from b200seg.models import segmentation_models as M
+    torch.manual_seed(0)
+    # eval-mode BatchNorm: gradients are reproducible to ~1e-6, so a race would stand out; train-mode BatchNorm on this
+    # tiny batch amplifies the atomic-order noise of the reductions to ~1e-2 and only bounds the error by that noise
+    model = getattr(M, name)(**kw).cuda().to(memory_format=torch.channels_last).train(bn_train)
+    x, y = xray_batch(4, 64, 64, seed=5)
+    x, y = x.cuda(), y.cuda()
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+
+    def grads(flag):
+        model.load_state_dict(state)
+        model.zero_grad(set_to_none=True)
+        K.set_wgrad_overlap(flag)
+        try:
+            loss, _ = ops.seg_loss(model(x), y, 1.0, 0.0, 1.0)
+            loss.backward()
+        finally:
+            K.set_wgrad_overlap(False)
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in model.parameters() if p.grad is not None]
+
+    def worst(u, v):
+        # global relative error (conv biases in front of a BatchNorm have an exactly-zero gradient whose computed
+        # value is rounding noise, so per-tensor ratios are meaningless for them)
+        num = sum(float((gu.double() - gv.double()).pow(2).sum()) for gu, gv in zip(u, v))
+        den = sum(float(gv.double().pow(2).sum()) for gv in v)
+        return (num / den) ** 0.5
+
+    a = grads(False)
+    a2 = grads(False)
+    b = grads(True)
+    b2 = grads(True)
+    assert len(a) == len(b) and len(a) > 100
+    base = worst(a2, a)              # run-to-run noise of the single-stream path (atomic summation order)
+    e1, e2 = worst(b, a), worst(b2, a)
+    print(f"{name}: single-stream run-to-run {base:.2e}; overlap vs single-stream {e1:.2e} {e2:.2e}")
+    if bn_train:
+        assert max(e1, e2) <= max(4.0 * base, 0.1)       # noise-dominated (see above); a race gives O(1)
+    else:
+        assert max(e1, e2) <= 2.0 * base + 1e-5
+    assert not K._OVERLAP["pending"] and not K._OVERLAP["refs"]
