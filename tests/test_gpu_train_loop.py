@@ -172,3 +172,50 @@ def test_wgrad_side_stream_overlap_gives_identical_gradients(name, kw, bn_train)
     else:
         assert max(e1, e2) <= 2.0 * base + 1e-5
     assert not K._OVERLAP["pending"] and not K._OVERLAP["refs"]
+
+
+def test_grad_reducer_on_side_stream_matches_plain_backward():
+    """GradReducer (world size 1, NCCL) with the weight gradients on the side stream: the hook packs and reduces on
+    that stream; after finish() the gradients equal those of a plain backward."""
+    import sys
+    from pathlib import Path
+    import torch.distributed as dist
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from oracle.synthetic import xray_batch
+    from b200seg import kernels as K
+    from b200seg import ops
+    from b200seg.ddp import GradReducer
+    from b200seg.models.segmentation_models import AttentionUNet
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        torch.manual_seed(0)
+        model = AttentionUNet().cuda().to(memory_format=torch.channels_last).eval()   # eval BN: reproducible grads
+        x, y = xray_batch(2, 64, 64, seed=6)
+        x, y = x.cuda(), y.cuda()
+
+        def run(with_reducer):
+            model.zero_grad(set_to_none=True)
+            red = GradReducer(model, bucket_mb=4) if with_reducer else None
+            K.set_wgrad_overlap(with_reducer)
+            try:
+                loss, _ = ops.seg_loss(model(x), y, 1.0, 0.0, 1.0)
+                loss.backward()
+                if red is not None:
+                    red.finish()
+                    red.remove()
+            finally:
+                K.set_wgrad_overlap(False)
+            torch.cuda.synchronize()
+            return [p.grad.clone() for p in model.parameters()]
+
+        a, b = run(False), run(True)
+        num = sum(float((u.double() - v.double()).pow(2).sum()) for u, v in zip(b, a))
+        den = sum(float(v.double().pow(2).sum()) for v in a)
+        assert (num / den) ** 0.5 < 1e-5
+    finally:
+        if created:
+            dist.destroy_process_group()
