@@ -10,8 +10,9 @@
 // The dY tile is loaded once per K chunk and reused by every column block (3x3: 2 X blocks x 3 taps = N 384, issued as
 // two N=192 MMAs into adjacent TMEM columns); the kernel is L2->SM bandwidth bound, so bytes per FLOP is what counts.
 // Cout == 64 ("row pair" mode): instead of leaving half of the 128 MMA rows idle, rows 64..127 hold dY of the NEXT
-// image row, so against the same X row they produce the gradient of the filter row above; with X rows h and h+1 as
-// the two column groups one CTA yields all three filter rows from two MMAs per K step (one quarter is redundant).
+// image row, so against the same X row they produce the gradient of the filter row above.  3x3: with X rows h and
+// h+1 as two column groups one CTA yields all three filter rows from two MMAs per K step (one quarter is redundant);
+// 2x2 (folded UpConv phases): one X row gives both filter rows, nothing is redundant.
 // Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
 #include <stdlib.h>
@@ -42,7 +43,11 @@ struct WgradParams {
   int stages;
   int b_stage_bytes; // smem bytes reserved per stage for the X boxes
   int gy;            // CTAs per (split, channel group): filter rows handled by separate CTAs (1 in row-pair mode)
-  int rowpair;       // Cout == 64, 3x3: M rows 0..63 = dY of image row h, rows 64..127 = dY of row h+1 (see kernel)
+  int rowpair;       // Cout == 64: M rows 0..63 = dY of image row h, rows 64..127 = dY of row h+1 (see kernel);
+                     // value = number of X-row column groups (3x3: 2, 2x2: 1), 0 = off
+  int rp_dir;        // row-pair mode: rows 64..127 hold dY of image row h + rp_dir.  +1 when the filter has a row above
+                     // the centre (pad_h >= 1); -1 for 2x2 taps with pad_h == 0, so that the one product the pairing
+                     // cannot form always involves an out-of-image (zero) X row
   int debug_skip;    // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs
   float* ws;         // [splits][cout][taps][ctot]
 };
@@ -101,7 +106,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   // number of live column blocks for this CTA (1x1 groups may run past the last channel block)
   int live_cb = p.cpb;
   if (cib_base + live_cb > cbt) live_cb = cbt - cib_base;
-  const int ncol_live = p.rowpair ? 6 : live_cb * p.ksize;
+  const int grp_cols = live_cb * p.ksize;                       // columns per X-row group (row-pair mode)
+  const int ncol_live = p.rowpair ? p.rowpair * grp_cols : grp_cols;
 
   if (warp == 0) {
     // TMA producer: warp-uniform loop, one elected lane issues; chunk coordinates advance incrementally
@@ -125,14 +131,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           // dY: both 64-channel blocks of the 128-row M tile in one 5-D box (.., channel block)
           if (p.rowpair) {     // dY rows h0 and h0 + 1 (zero fill below the image)
             tma_load_4d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0);
-            tma_load_4d(sa + kBoxBytes, &tmDY, &full_bar[stage], 0, w0, h0 + 1, n0);
+            tma_load_4d(sa + kBoxBytes, &tmDY, &full_bar[stage], 0, w0, h0 + p.rp_dir, n0);
           } else {
             tma_load_5d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0, co_tile * 2);
           }
           for (int j = 0; j < ncol_live; ++j) {
-            const int cib = p.rowpair ? cib_base : cib_base + j / p.ksize;
+            // row-pair mode: group jg reads X row h0 + (jg + 1) - pad_h (filter row jg + 1 for the top half)
+            const int jg = p.rowpair ? j / grp_cols : 0;
+            const int cib = cib_base + (j - jg * grp_cols) / p.ksize;
             const int xw = p.xstride * w0 + (j % p.ksize) - p.pad_w;
-            const int xh = p.rowpair ? h0 + j / 3 : p.xstride * h0 + rg - p.pad_h;
+            const int xh = p.rowpair ? h0 + (p.rp_dir > 0 ? jg + 1 : 0) - p.pad_h : p.xstride * h0 + rg - p.pad_h;
             if (cib < p.cb0)
               tma_load_4d(sb + j * kBoxBytes, &tmX0, &full_bar[stage], cib * 64, xw, xh, n0);
             else
@@ -209,11 +217,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       int cib = cib_base + j / p.ksize;
       bool live = valid;
       if (p.rowpair) {
-        // X row h (j < 3): dY row h -> filter row 1, dY row h+1 -> filter row 0; X row h+1: dY row h -> filter row 2
-        const int fr = j < 3 ? (row < 64 ? 1 : 0) : (row < 64 ? 2 : -1);
+        // group jg (X row h + jg + 1 - pad): dY row h -> filter row jg + 1, dY row h+1 -> filter row jg; the bottom
+        // half of every group but the first repeats a filter row that the previous group already produced
+        const int jg = j / grp_cols;
+        const int fr = p.rp_dir > 0 ? (row < 64 ? jg + 1 : (jg == 0 ? 0 : -1)) : (row < 64 ? 0 : 1);
         live = fr >= 0;
-        tap = (fr < 0 ? 0 : fr) * 3 + j % 3;
-        cib = cib_base;
+        tap = (fr < 0 ? 0 : fr) * p.ksize + j % p.ksize;
+        cib = cib_base + (j - jg * grp_cols) / p.ksize;
       }
       float* dst = out + (size_t)tap * p.ctot + cib * 64;
       const int cvalid = p.ctot - cib * 64;   // channels left in this block (>= 64 except for a ragged tail)
@@ -310,11 +320,20 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   {
     const char* rp_env = getenv("B200SEG_WG_ROWPAIR");
     const int dm = a->dy_mul == 0 ? 1 : a->dy_mul;
-    p.rowpair = (a->cout == 64 && a->ksize == 3 && xstride == 1 && !a->custom_pad && dm == 1 && p.Hb == 1 &&
-                 p.Nb == 1 && !(rp_env != nullptr && atoi(rp_env) == 0)) ? 1 : 0;
-    if (p.rowpair) {
+    const bool rp_ok = a->cout == 64 && xstride == 1 && p.Hb == 1 && p.Nb == 1 &&
+                       !(rp_env != nullptr && atoi(rp_env) == 0);
+    (void)dm;
+    p.rowpair = 0;
+    p.rp_dir = p.pad_h >= 1 ? 1 : -1;
+    if (rp_ok && a->ksize == 3 && p.pad_h == 1) {              // two X rows x 3 taps x one channel block: N 384
+      p.rowpair = 2;
       p.cpb = 1;
-      p.ncolb = 6;
+    } else if (rp_ok && a->ksize == 2) {       // one X row x 2 taps x two channel blocks: N 256
+      p.rowpair = 1;
+      p.cpb = cbt < 2 ? cbt : 2;
+    }
+    if (p.rowpair) {
+      p.ncolb = p.rowpair * p.ksize * p.cpb;
       p.a_boxes = 2;
       pl->gy = 1;
     }

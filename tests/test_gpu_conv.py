@@ -131,3 +131,30 @@ def test_fprop_two_sources_addend_relu():
     e3 = rel(nchw(dx1), refd)
     print(f"two-source dgrad(src1): rel {e3:.2e}")
     assert e3 < 4e-3
+
+
+@pytest.mark.parametrize("cin", [128, 64, 192])
+def test_wgrad_rowpair_2x2_phase_matches_plain(cin):
+    """Cout = 64 weight gradient of a folded-UpConv phase (2x2 taps, dY read as a sub-lattice): the row-pair layout
+    must reproduce the plain layout (B200SEG_WG_ROWPAIR=0) and the fp32 reference."""
+    import os
+    from b200seg import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, h, w, cout = 2, 64, 128, 64                 # coarse grid; dY lives on the 2x finer grid
+    x = nhwc(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    dz = nhwc(torch.randn(n, cout, 2 * h, 2 * w, device="cuda", generator=g))
+    for a, b in ((0, 0), (0, 1), (1, 0), (1, 1)):
+        os.environ["B200SEG_WG_ROWPAIR"] = "0"
+        plain = K.conv_wgrad(dz, x, 2, dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b))
+        os.environ["B200SEG_WG_ROWPAIR"] = "1"
+        try:
+            pair = K.conv_wgrad(dz, x, 2, dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b))
+        finally:
+            del os.environ["B200SEG_WG_ROWPAIR"]
+        # fp32 reference: dW[co, r, s, ci] = sum_p dY[p, co] * X[p + (r - pad_h, s - pad_w), ci]
+        dys = nchw(dz)[:, :, a::2, b::2]
+        xp = F.pad(nchw(x), (1 - b, b, 1 - a, a))       # (left, right, top, bottom)
+        ref = torch.nn.grad.conv2d_weight(xp, (cout, cin, 2, 2), dys)
+        got = pair.reshape(cout, 2, 2, cin).permute(0, 3, 1, 2)
+        assert rel(got, ref) < 1e-3, (a, b, rel(got, ref))
+        assert rel(pair, plain) < 1e-5
