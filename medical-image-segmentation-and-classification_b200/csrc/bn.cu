@@ -6,6 +6,8 @@
 // Thread mapping shared by every kernel here: a thread owns ONE group of 8 consecutive channels (one uint4 of
 // bf16) and walks over pixels, so per-channel coefficients live in registers and a warp reads consecutive 16-byte
 // chunks of consecutive pixels (fully coalesced for ld == C).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -370,6 +372,179 @@ __global__ void __launch_bounds__(kBlock, 2) bn_bwd_apply_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// "Light" BatchNorm-backward kernels: 4 channels per thread (8-byte loads), four pixels in flight.  Half the
+// per-channel state of the 8-channel kernels -> <= 64 registers, so several blocks fit next to a persistent
+// weight-gradient CTA that runs on the side stream and the kernels overlap with it.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack4(const uint2& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+}
+__device__ __forceinline__ void load4f(const float* p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+}
+// Sum acc[0..3] over the `rows` threads that own the same channel group; result valid in threads with r == 0.
+__device__ __forceinline__ void rows_reduce4(float* acc, int tpp, int rows, int g, int r, bool active, float* red) {
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(r * tpp + g) * 4 + j] = acc[j];
+  }
+  __syncthreads();
+  if (active && r == 0) {
+    for (int rr = 1; rr < rows; ++rr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += red[(rr * tpp + g) * 4 + j];
+    }
+  }
+}
+
+static constexpr int kLightPix = 4;     // pixels in flight per thread
+
+__global__ void __launch_bounds__(kBlock, 4) bn_bwd_reduce_light_kernel(
+    const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
+    int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums) {
+  __shared__ float red[kBlock * 4];
+  const int t = threadIdx.x;
+  const int g = t % m.tpp, r = t / m.tpp;
+  const bool active = r < m.rows;
+  float s0[4], s1[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s0[j] = s1[j] = 0.f;
+  if (active) {
+    float sc[4], sh[4];
+    load4f(scale + g * 4, sc);
+    load4f(shift + g * 4, sh);
+    const long long step = (long long)gridDim.x * m.rows;
+    for (long long p0 = (long long)blockIdx.x * m.rows + r; p0 < npix; p0 += kLightPix * step) {
+      uint2 ud[kLightPix], uz[kLightPix];
+#pragma unroll
+      for (int u = 0; u < kLightPix; ++u) {
+        const long long p = p0 + u * step;
+        const bool ok = p < npix;
+        ud[u] = ok ? __ldg(reinterpret_cast<const uint2*>(dy + p * lddy + g * 4)) : make_uint2(0u, 0u);
+        uz[u] = ok ? __ldg(reinterpret_cast<const uint2*>(z + p * ldz + g * 4)) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < kLightPix; ++u) {
+        float d[4], f[4];
+        unpack4(ud[u], d);          // out-of-range pixels were loaded as dy = 0: they add nothing
+        unpack4(uz[u], f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dd = (!relu || fmaf(f[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+          s0[j] += dd;
+          s1[j] = fmaf(dd, f[j], s1[j]);
+        }
+      }
+    }
+  }
+  rows_reduce4(s0, m.tpp, m.rows, g, r, active, red);
+  float keep0[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) keep0[j] = s0[j];
+  rows_reduce4(s1, m.tpp, m.rows, g, r, active, red);
+  if (active && r == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = g * 4 + j;
+      const double a0 = (double)keep0[j];
+      const double a1 = (double)invstd[c] * ((double)s1[j] - (double)mean[c] * a0);
+      atomicAdd(&sums[c], a0);
+      atomicAdd(&sums[C + c], a1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock, 4) bn_bwd_apply_light_kernel(
+    const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
+    int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
+    int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ float red[kBlock * 4];
+  const int t = threadIdx.x;
+  const int g = t % m.tpp, r = t / m.tpp;
+  const bool active = r < m.rows;
+  float bsum[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bsum[j] = 0.f;
+  if (active) {
+    float sc[4], sh[4], ka[4], kb[4], kc[4];
+    load4f(scale + g * 4, sc);
+    load4f(shift + g * 4, sh);
+    const double inv_m = 1.0 / (double)npix;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = g * 4 + j;
+      const float ga = gamma ? __ldg(gamma + c) : 1.f;
+      const float is = __ldg(invstd + c), mu = __ldg(mean + c);
+      const double a0 = sums[c], a1 = sums[C + c];
+      const float k0 = training ? (float)(a0 * inv_m) : 0.f;
+      const float k1 = training ? (float)(a1 * inv_m) : 0.f;
+      ka[j] = ga * is;
+      kb[j] = -ka[j] * k1 * is;
+      kc[j] = -ka[j] * k0 - kb[j] * mu;
+      if (blockIdx.x == 0 && r == 0) {
+        if (dgamma) dgamma[c] = (float)a1;
+        if (dbeta) dbeta[c] = (float)a0;
+      }
+    }
+    const long long step = (long long)gridDim.x * m.rows;
+    for (long long p0 = (long long)blockIdx.x * m.rows + r; p0 < npix; p0 += kLightPix * step) {
+      uint2 ud[kLightPix], uz[kLightPix];
+#pragma unroll
+      for (int u = 0; u < kLightPix; ++u) {
+        const long long p = p0 + u * step;
+        const bool ok = p < npix;
+        ud[u] = ok ? __ldg(reinterpret_cast<const uint2*>(dy + p * lddy + g * 4)) : make_uint2(0u, 0u);
+        uz[u] = ok ? __ldg(reinterpret_cast<const uint2*>(z + p * ldz + g * 4)) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < kLightPix; ++u) {
+        const long long p = p0 + u * step;
+        if (p >= npix) break;
+        float d[4], f[4];
+        unpack4(ud[u], d);
+        unpack4(uz[u], f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float dd = (!relu || fmaf(f[j], sc[j], sh[j]) > 0.f) ? d[j] : 0.f;
+          f[j] = fmaf(ka[j], dd, fmaf(kb[j], f[j], kc[j]));
+        }
+        const uint2 o = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+        *reinterpret_cast<uint2*>(dz + p * lddz + g * 4) = o;
+        if (dbias != nullptr) {
+          unpack4(o, f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bsum[j] += f[j];
+        }
+      }
+    }
+  }
+  if (dbias != nullptr) {
+    rows_reduce4(bsum, m.tpp, m.rows, g, r, active, red);
+    if (active && r == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) atomicAdd(&dbias[g * 4 + j], bsum[j]);
+    }
+  }
+}
+
+// channel map of the light kernels: C / 4 threads per pixel (C <= 4 * kBlock)
+static bool light_map(int C, ChanMap* m) {
+  static const bool enabled = [] {
+    const char* e = getenv("B200SEG_BN_LIGHT");
+    return !(e != nullptr && atoi(e) == 0);
+  }();
+  if (!enabled || C % 4 != 0 || C / 4 > kBlock) return false;
+  m->tpp = C / 4;
+  m->rows = kBlock / m->tpp;
+  return true;
+}
+
 static int make_map(int C, ChanMap* m) {
   B2_REQUIRE(C > 0 && C % 8 == 0, B2_ERR_SHAPE, "channel count %d must be a positive multiple of 8", C);
   const int cg = C / 8;
@@ -463,6 +638,14 @@ extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int
   int rc = make_map(c, &m);
   if (rc) return rc;
   B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz), B2_ERR_ALIGN, "bn_bwd_reduce operands misaligned");
+  ChanMap lm;
+  if (light_map(c, &lm)) {
+    bn_bwd_reduce_light_kernel<<<chan_grid(npix, lm, 8), kBlock, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, relu,
+        sums);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+  }
   bn_bwd_reduce_kernel<<<chan_grid(npix, m, 4), kBlock, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, relu,
       sums);
@@ -479,6 +662,14 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
   if (rc) return rc;
   B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz) && aligned16(dz, lddz), B2_ERR_ALIGN,
              "bn_bwd_apply operands misaligned");
+  ChanMap lm;
+  if (light_map(c, &lm)) {
+    bn_bwd_apply_light_kernel<<<chan_grid(npix, lm, 8), kBlock, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, gamma,
+        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+  }
   bn_bwd_apply_kernel<<<chan_grid(npix, m, 4), kBlock, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
       relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias);

@@ -431,6 +431,11 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
   static bool attr_set = false;
   if (!attr_set) {
     B2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    // Ask for the full 228 KB shared-memory carveout even when a launch needs less: the driver otherwise picks the
+    // smallest configuration that fits this kernel (196 KB for 194 KB used), and the memory-bound kernels meant to run
+    // next to it on the side-stream schedule (BatchNorm backward, gate) find no shared memory left on the SM.
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   dim3 grid(pl.gy * pl.gz, pl.splits, 1);
