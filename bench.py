@@ -312,16 +312,43 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     _tick("timed region done")
 
-    # end-to-end: pinned host batch -> device, loss -> host, every step
+    # end-to-end: pinned host batch -> device, loss -> host, every step.  As in a real input pipeline the NEXT batch
+    # is copied (copy stream, double-buffered device staging) while the current step computes; every step still
+    # moves one full batch host -> device and reads its loss back.
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty_like(x_dev), torch.empty_like(t_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in consumed:
+        ev.record()
+    pipe = {"i": 0, "primed": False}
+
+    def issue_copy(slot):
+        copy_stream.wait_event(consumed[slot])          # the staging slot has been drained by its previous user
+        with torch.cuda.stream(copy_stream):
+            stage[slot][0].copy_(x_host, non_blocking=True)
+            stage[slot][1].copy_(t_host, non_blocking=True)
+            ready[slot].record()
+
     def e2e_step():
+        slot = pipe["i"] & 1
+        if not pipe["primed"]:
+            issue_copy(slot)
+            pipe["primed"] = True
+        torch.cuda.current_stream().wait_event(ready[slot])
         if graph is not None:
-            x_dev.copy_(x_host, non_blocking=True)
-            t_dev.copy_(t_host, non_blocking=True)
+            x_dev.copy_(stage[slot][0])                 # device-to-device into the graph's static inputs
+            t_dev.copy_(stage[slot][1])
+            consumed[slot].record()
+            issue_copy(slot ^ 1)
             graph.replay()
-            return float(static_loss)
-        x = x_host.to(dev, non_blocking=True)
-        t = t_host.to(dev, non_blocking=True)
-        return float(step(x, t))
+            loss = static_loss
+        else:
+            issue_copy(slot ^ 1)
+            loss = step(stage[slot][0], stage[slot][1])
+            consumed[slot].record()
+        pipe["i"] += 1
+        return float(loss)
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     _tick("e2e done")

@@ -13,9 +13,14 @@
 //   warp 0    TMA producer (smem ring of `stages` A+B slots, full/empty mbarriers)
 //   warp 1    TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem slots and publishes
 //             a finished accumulator (tmem_full); waits on tmem_empty before overwriting a buffer
-//   warps 2-5 epilogue: tcgen05.ld -> +bias (+addend) (ReLU) -> bf16 -> swizzled smem tile -> TMA store;
-//             BatchNorm sum / sum-of-squares of the ROUNDED output are column sums of that smem tile, kept in
-//             fp64 registers across all tiles of the CTA and flushed with one fp64 atomic per channel at the end.
+//   warps 2-5 epilogue group 0, warps 6-9 epilogue group 1 (used when the drain, not the MMAs, paces a tile: small K;
+//             the groups take alternate tiles = alternate TMEM buffers and own one staging tile each):
+//             tcgen05.ld -> +bias (+addend) (ReLU) -> bf16 -> swizzled smem tile -> TMA store; BatchNorm sum /
+//             sum-of-squares of the ROUNDED output are column sums of that smem tile (16-byte reads), kept in fp64
+//             registers across all tiles of the CTA and flushed through shuffles + smem with one fp64 atomic per
+//             channel and group at the end.
+// Optional clusters (B200SEG_CLUSTER=2|4, off by default: no measured gain): the CTAs of a cluster work on
+// consecutive m-tiles of one n-tile and share every weight tile, each fetching 1/cluster of its rows and multicasting.
 // The epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Used for fprop (reference nn.Conv2d call sites, see include/b200seg.h) and for dgrad (flipped/transposed
