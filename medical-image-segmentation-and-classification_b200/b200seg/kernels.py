@@ -49,7 +49,8 @@ def _prof_end(kind, flops, start, alg_scale=1.0, nbytes=0.0):
 # channels_last parameters, gradients read by GradReducer.finish() / the optimizer) — and weights shared between
 # several autograd nodes (Recurrent_block) are excluded because autograd sums their gradients on the main stream.
 # ----------------------------------------------------------------------------------------------------------
-_OVERLAP = {"enabled": os.environ.get("B200SEG_WGRAD_OVERLAP", "0") == "1", "side": {}, "refs": [], "pending": False}
+_OVERLAP = {"enabled": os.environ.get("B200SEG_WGRAD_OVERLAP", "0") == "1", "side": {}, "refs": [], "pending": False,
+            "task": -1}
 
 
 def set_wgrad_overlap(flag: bool) -> None:
@@ -85,13 +86,21 @@ def wgrad_stream(*keep, allow=True):
     if not (allow and _OVERLAP["enabled"] and torch.cuda.is_available()):
         yield
         return
-    if not _OVERLAP["pending"]:
+    task = torch._C._current_graph_task_id()       # -1 outside backward
+    if task < 0:
+        yield                                       # not inside a backward pass: nothing to overlap with
+        return
+    if not _OVERLAP["pending"] or _OVERLAP["task"] != task:
+        if _OVERLAP["pending"]:
+            # a previous backward pass ended without its callback (an exception unwound it): join what it left behind
+            _join_wgrad_stream()
         try:
             torch.autograd.Variable._execution_engine.queue_callback(_join_wgrad_stream)
-        except RuntimeError:            # not inside a backward pass: nothing to overlap with
+        except RuntimeError:
             yield
             return
         _OVERLAP["pending"] = True
+        _OVERLAP["task"] = task
     main = torch.cuda.current_stream()
     dev = torch.cuda.current_device()
     side = _OVERLAP["side"].get(dev)
