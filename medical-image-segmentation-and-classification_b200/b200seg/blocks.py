@@ -41,10 +41,11 @@ def to_internal(x):
     return ops.to_nhwc(check_image(x)) if x.dtype != BF16 else x
 
 
-def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True, addend=None, shared_weight=False):
+def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True, addend=None, share_index=0,
+                share_count=1):
     """conv (3x3 p1 or 1x1) -> BatchNorm -> optional ReLU as ONE fused autograd node.  `x` may be an fp32 NCHW image
     with <= 4 channels (stem), an internal activation, or a tuple of two internal activations (virtual concat)."""
-    return ops.conv_bn_act_module(x, conv, bn, relu, addend, shared_weight)
+    return ops.conv_bn_act_module(x, conv, bn, relu, addend, share_index, share_count)
 
 
 def conv_plain(x, conv: nn.Conv2d):
@@ -152,13 +153,15 @@ class Recurrent_block(nn.Module):
         x = to_internal(x)
         # t+1 applications of the shared conv+BN+ReLU; every application but the last emits x + f(.) directly from the
         # BatchNorm pass (the un-summed activation is never needed), the last one emits f(.) itself
-        f = lambda v, add: conv_bn_act(v, self.conv[0], self.conv[1], addend=add, shared_weight=True)
+        n_uses = self.t + 1               # sequentially dependent applications of the one shared conv weight
+        f = lambda v, add, i: conv_bn_act(v, self.conv[0], self.conv[1], addend=add, share_index=i,
+                                          share_count=n_uses)
         if self.t == 0:
             raise ValueError("Recurrent_block needs t >= 1 (the reference leaves x1 undefined for t = 0)")
-        s = f(x, x)                       # x + f(x)
+        s = f(x, x, 0)                    # x + f(x)
         for i in range(self.t - 1):
-            s = f(s, x)                   # x + f(x + x1)
-        x1 = f(s, None)
+            s = f(s, x, i + 1)            # x + f(x + x1)
+        x1 = f(s, None, self.t)
         return ops.to_nchw(x1) if ext else x1
 
 

@@ -46,8 +46,9 @@ def _prof_end(kind, flops, start, alg_scale=1.0, nbytes=0.0):
 # persistent wgrad CTAs on an SM; the tensor-core kernels of the main stream do not, those simply take turns).
 # Opt-in (set_wgrad_overlap / B200SEG_WGRAD_OVERLAP=1): the caller must not touch a weight gradient before
 # loss.backward() has returned — true for utils.helpers.train() and bench.py (zero_grad(set_to_none=True),
-# channels_last parameters, gradients read by GradReducer.finish() / the optimizer) — and weights shared between
-# several autograd nodes (Recurrent_block) are excluded because autograd sums their gradients on the main stream.
+# channels_last parameters, gradients read by GradReducer.finish() / the optimizer).  Weights shared between several
+# autograd nodes (Recurrent_block) qualify too: their applications accumulate into one buffer inside the wgrad kernel
+# (ops.conv_bn_act, share_index / share_count), so autograd never sums them on the main stream.
 # ----------------------------------------------------------------------------------------------------------
 _OVERLAP = {"enabled": os.environ.get("B200SEG_WGRAD_OVERLAP", "0") == "1", "side": {}, "refs": [], "pending": False,
             "task": -1}

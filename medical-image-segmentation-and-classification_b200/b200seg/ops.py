@@ -261,11 +261,13 @@ def batch_norm_act(z: Tensor, stats: Tensor, bn: torch.nn.BatchNorm2d, relu: boo
 @custom_op("b200seg::conv_bn_act", mutates_args=())
 def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor], gamma: Tensor,
                 beta: Tensor, running_mean: Tensor, running_var: Tensor, training: bool, eps: float,
-                relu: bool, addend: Optional[Tensor] = None,
-                shared_weight: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+                relu: bool, addend: Optional[Tensor] = None, share_index: int = 0,
+                share_count: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """`addend`: the first output becomes act(bn(conv(x))) + addend (Recurrent_block's x + x1, R2U_Net.py:19); the
-    un-summed activation is then never written.  `shared_weight`: the weight is used by several autograd nodes
-    (autograd sums those gradients on the main stream, so the weight gradient is not moved to the side stream)."""
+    un-summed activation is then never written.  `share_index` / `share_count`: this is application number
+    share_index of share_count sequentially dependent applications of the SAME conv weight (Recurrent_block's t+1 uses,
+    R2U_Net.py:15-20): their weight gradients are accumulated by the wgrad kernel into one buffer that the node of
+    application 0 — the last to run in backward — hands to autograd, the others return no weight gradient."""
     cout, cin, k, _ = weight.shape
     dev = x0.device
     stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
@@ -293,7 +295,7 @@ def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional
 
 
 @conv_bn_act.register_fake
-def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=None, shared_weight=False):
+def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=None, share_index=0, share_count=1):
     cout = weight.shape[0]
     if x0.dtype != torch.bfloat16:
         n, _, h, w = x0.shape
@@ -306,10 +308,14 @@ def _(x0, x1, weight, bias, gamma, beta, rm, rv, training, eps, relu, addend=Non
             x0.new_empty((2, cout) if training else (0,), dtype=_F64), x4)
 
 
+_SHARED_DW = {}      # (weight address, device) -> fp32 gradient buffer of a shared conv weight, alive within one backward
+
+
 @custom_op("b200seg::conv_bn_act_bwd", mutates_args=())
 def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, weight: Tensor, z: Tensor,
                     coef: Tensor, gamma: Tensor, relu: bool, training: bool, need_dx0: bool, need_dx1: bool,
-                    has_bias: bool, overlap_ok: bool = True) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                    has_bias: bool, share_index: int = 0,
+                    share_count: int = 1) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     cout, cin, k, _ = weight.shape
     dev = dy.device
     res = K.bn_bwd(_c(dy), z, coef, gamma, relu=relu, training=training, want_dbias=has_bias)
@@ -330,16 +336,32 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
                 dx0 = K.conv_igemm(dz, wd, c0, k, row_offset=0, dgrad=True)
             if need_dx1 and x1 is not None:
                 dx1 = K.conv_igemm(dz, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
-        with K.wgrad_stream(dz, x0, x1, allow=overlap_ok):
-            dw = K.conv_wgrad(dz, x0, k, x1=x1)
+        with K.wgrad_stream(dz, x0, x1):
+            if share_count <= 1:
+                dw = K.conv_wgrad(dz, x0, k, x1=x1)
+            else:
+                # shared weight: backward visits the applications in reverse order (each consumes the previous one's
+                # output), so the last application opens the buffer, the others add to it, application 0 returns it
+                key = (weight.data_ptr(), dz.device.index)
+                buf = None if share_index == share_count - 1 else _SHARED_DW.get(key)
+                if buf is None:
+                    buf = K.conv_wgrad(dz, x0, k, x1=x1)
+                else:
+                    K.conv_wgrad(dz, x0, k, x1=x1, out=buf, accumulate=True)
+                if share_index == 0:
+                    _SHARED_DW.pop(key, None)
+                    dw = buf
+                else:
+                    _SHARED_DW[key] = buf
+                    dw = torch.empty((0,), device=dev)
     return dx0, dx1, dw, db, dgamma, dbeta
 
 
 def _cba_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)      # unused outputs (z, coef, stats, ...) must not get zero-filled grads
-    x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu, addend, shared = inputs
+    (x0, x1, weight, bias, gamma, _beta, _rm, _rv, ctx.training, _eps, ctx.relu, addend, ctx.share_index,
+     ctx.share_count) = inputs
     ctx.has_addend = addend is not None
-    ctx.overlap_ok = not shared
     _y, z, coef, _stats, x4 = output
     stem = x0.dtype != torch.bfloat16
     ctx.save_for_backward(None if stem else _c(x0), _c(x1), x4, weight, z, coef, gamma)
@@ -354,10 +376,11 @@ def _cba_backward(ctx, dy, *_unused):
     need1 = bool(need[1]) and x1 is not None
     dx0, dx1, dw, db, dgamma, dbeta = conv_bn_act_bwd(dy, x0 if x0 is not None else x4, x1, x4, weight, z, coef,
                                                       gamma, ctx.relu, ctx.training, need0, need1, ctx.has_bias,
-                                                      ctx.overlap_ok)
-    return (dx0 if need0 else None, dx1 if need1 else None, _dw_as_param_grad(dw, weight),
+                                                      ctx.share_index, ctx.share_count)
+    return (dx0 if need0 else None, dx1 if need1 else None,
+            _dw_as_param_grad(dw, weight) if dw.numel() > 0 else None,
             db if ctx.has_bias else None, dgamma, dbeta, None, None, None, None, None,
-            dy if (ctx.has_addend and need[11]) else None, None)   # d(addend) = d(output): the sum is linear
+            dy if (ctx.has_addend and need[11]) else None, None, None)   # d(addend) = d(output): the sum is linear
 
 
 conv_bn_act.register_autograd(_cba_backward, setup_context=_cba_setup)
@@ -371,7 +394,7 @@ def bn_update_running_(stats: Tensor, count: int, momentum: float, running_mean:
 
 
 def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu: bool = True,
-                       addend: Optional[Tensor] = None, shared_weight: bool = False) -> Tensor:
+                       addend: Optional[Tensor] = None, share_index: int = 0, share_count: int = 1) -> Tensor:
     """[Conv2d -> BatchNorm2d -> ReLU] (+ addend) on module objects; x: image | activation | (activation, activation)."""
     x0, x1 = x if isinstance(x, tuple) else (x, None)
     training = bn.training or bn.running_mean is None
@@ -381,7 +404,8 @@ def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu:
             return ops_infer.conv_bn_act_infer(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                                bn.running_var, float(bn.eps), relu, addend)
     y, _z, _coef, stats, _x4 = conv_bn_act(x0, x1, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
-                                           bn.running_var, training, float(bn.eps), relu, addend, shared_weight)
+                                           bn.running_var, training, float(bn.eps), relu, addend, share_index,
+                                           share_count)
     if training:
         n, h, w, _ = y.shape
         bn_update_running_(stats.detach(), n * h * w, float(bn.momentum), bn.running_mean, bn.running_var,
