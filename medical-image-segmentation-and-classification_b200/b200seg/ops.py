@@ -98,7 +98,12 @@ def conv2d_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, nee
             dx0 = K.conv_igemm(dy, wd, c0, k, row_offset=0, dgrad=True)
         if need_dx1 and x1 is not None:
             dx1 = K.conv_igemm(dy, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
-    dw = K.conv_wgrad(dy, _c(x0), k, x1=_c(x1)) if need_dw else torch.empty((0,), device=dev)
+    if need_dw:
+        x0c, x1c = _c(x0), _c(x1)
+        with K.wgrad_stream(dy, x0c, x1c):
+            dw = K.conv_wgrad(dy, x0c, k, x1=x1c)
+    else:
+        dw = torch.empty((0,), device=dev)
     db = K.channel_sum(dy) if need_db else torch.empty((0,), device=dev)
     return dx0, dx1, dw, db
 
