@@ -5,6 +5,8 @@
 // (statistics of the psi pre-activation, and of its gradient), hence forward = {psi_fwd, apply_fwd} and
 // backward = {apply_bwd, psi_bwd_reduce, psi_bwd_apply}; `a = relu(..)` is recomputed, never stored.
 // Rounding points mirror autocast: every BN output, the g1+x1 sum, the psi conv output and sigmoid are bf16.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -210,39 +212,64 @@ __device__ __forceinline__ float gate_dq(float ds, float qv, float g1, float mu1
   return training ? g1 * is1 * (ds - k0 - qh * k1) : g1 * is1 * ds;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The two psi-backward kernels are templates on V = channels per thread: V = 8 (16-byte accesses) or V = 4 (8-byte
+// accesses, half the per-channel register state: <= 80 registers, three blocks per SM and room next to a persistent
+// weight-gradient CTA of the side stream).  V = 4 is used whenever F_int / 4 threads per pixel fit a block.
+// ---------------------------------------------------------------------------------------------------------
+template <int V> struct GVec;
+template <> struct GVec<8> { using T = uint4; };
+template <> struct GVec<4> { using T = uint2; };
+template <int V> __device__ __forceinline__ void gv_unpack(const typename GVec<V>::T& u, float* f);
+template <> __device__ __forceinline__ void gv_unpack<8>(const uint4& u, float* f) { g_unpack8(u, f); }
+template <> __device__ __forceinline__ void gv_unpack<4>(const uint2& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+}
+template <int V> __device__ __forceinline__ typename GVec<V>::T gv_pack(const float* f);
+template <> __device__ __forceinline__ uint4 gv_pack<8>(const float* f) { return g_pack8(f); }
+template <> __device__ __forceinline__ uint2 gv_pack<4>(const float* f) {
+  return make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+}
+template <int V> __device__ __forceinline__ void gv_loadf(const float* p, bool has, float* f) {
+#pragma unroll
+  for (int j = 0; j < V; ++j) f[j] = has ? __ldg(p + j) : 0.f;
+}
+
 // backward phase 2: reductions for BN_g, BN_x and the psi conv
-__global__ void __launch_bounds__(256, 2) gate_psi_bwd_reduce_kernel(
+template <int V>
+__global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kernel(
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int L, GateBwdCoef c,
     const double* __restrict__ sums1, int training, double* __restrict__ sums, float* __restrict__ dwpsi,
     float* __restrict__ dbpsi) {
+  using VT = typename GVec<V>::T;
   extern __shared__ float red[];   // [4][fint] + 1
   for (int i = threadIdx.x; i < 4 * fint + 1; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
-  const bool has = lig * 8 < fint;
+  const bool has = lig * V < fint;
   // per-channel constants kept in registers: BN affine (mask recomputation), means (centred sums), psi weights.
   // The xhat sums are accumulated as sum da * (v - mean) and scaled by invstd once per block.
-  float sg[8], hg[8], mg[8], sx[8], hx[8], mx[8], wp[8];
-  g_load8(c.scale_g + lig * 8, has, sg);
-  g_load8(c.shift_g + lig * 8, has, hg);
-  g_load8(c.mean_g + lig * 8, has, mg);
-  g_load8(c.scale_x + lig * 8, has, sx);
-  g_load8(c.shift_x + lig * 8, has, hx);
-  g_load8(c.mean_x + lig * 8, has, mx);
-  g_load8(c.wpsi + lig * 8, has, wp);
+  float sg[V], hg[V], mg[V], sx[V], hx[V], mx[V], wp[V];
+  gv_loadf<V>(c.scale_g + lig * V, has, sg);
+  gv_loadf<V>(c.shift_g + lig * V, has, hg);
+  gv_loadf<V>(c.mean_g + lig * V, has, mg);
+  gv_loadf<V>(c.scale_x + lig * V, has, sx);
+  gv_loadf<V>(c.shift_x + lig * V, has, hx);
+  gv_loadf<V>(c.mean_x + lig * V, has, mx);
+  gv_loadf<V>(c.wpsi + lig * V, has, wp);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) wp[j] = bf16_round(wp[j]);
+  for (int j = 0; j < V; ++j) wp[j] = bf16_round(wp[j]);
   const float g1 = __ldg(c.gamma1), mu1 = __ldg(c.mean1), is1 = __ldg(c.invstd1);
   const float k0 = (float)(sums1[0] / (double)npix), k1 = (float)(sums1[1] / (double)npix);
-  float ab[8], agg[8], agx[8], aw[8], abp = 0.f;
+  float ab[V], agg[V], agx[V], aw[V], abp = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) ab[j] = agg[j] = agx[j] = aw[j] = 0.f;
+  for (int j = 0; j < V; ++j) ab[j] = agg[j] = agx[j] = aw[j] = 0.f;
   if (has) {
     const long long stride = (long long)gridDim.x * gpb;
     constexpr int U = 2;                      // pixels in flight per thread (all loads issued before the math)
     for (long long p0 = (long long)blockIdx.x * gpb + grp; p0 < npix; p0 += U * stride) {
-      uint4 gv[U], xv[U];
+      VT gv[U], xv[U];
       float ds[U], qv[U];
       bool ok[U];
 #pragma unroll
@@ -250,19 +277,19 @@ __global__ void __launch_bounds__(256, 2) gate_psi_bwd_reduce_kernel(
         const long long p = p0 + u * stride;
         ok[u] = p < npix;
         const long long pc = ok[u] ? p : p0;
-        gv[u] = __ldg(reinterpret_cast<const uint4*>(g1p + pc * ld + lig * 8));
-        xv[u] = __ldg(reinterpret_cast<const uint4*>(x1p + pc * ld + lig * 8));
+        gv[u] = __ldg(reinterpret_cast<const VT*>(g1p + pc * ld + lig * V));
+        xv[u] = __ldg(reinterpret_cast<const VT*>(x1p + pc * ld + lig * V));
         ds[u] = __ldg(dsig + pc);
         qv[u] = __bfloat162float(q[pc]);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const float dq = ok[u] ? gate_dq(ds[u], qv[u], g1, mu1, is1, training, k0, k1) : 0.f;
-        float g[8], x[8];
-        g_unpack8(gv[u], g);
-        g_unpack8(xv[u], x);
+        float g[V], x[V];
+        gv_unpack<V>(gv[u], g);
+        gv_unpack<V>(xv[u], x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < V; ++j) {
           const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
           const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
           const float a = fmaxf(bf16_round(gb + xb), 0.f);
@@ -276,11 +303,11 @@ __global__ void __launch_bounds__(256, 2) gate_psi_bwd_reduce_kernel(
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&red[0 * fint + lig * 8 + j], ab[j]);
-      atomicAdd(&red[1 * fint + lig * 8 + j], agg[j] * __ldg(c.invstd_g + lig * 8 + j));
-      atomicAdd(&red[2 * fint + lig * 8 + j], agx[j] * __ldg(c.invstd_x + lig * 8 + j));
-      atomicAdd(&red[3 * fint + lig * 8 + j], aw[j]);
+    for (int j = 0; j < V; ++j) {
+      atomicAdd(&red[0 * fint + lig * V + j], ab[j]);
+      atomicAdd(&red[1 * fint + lig * V + j], agg[j] * __ldg(c.invstd_g + lig * V + j));
+      atomicAdd(&red[2 * fint + lig * V + j], agx[j] * __ldg(c.invstd_x + lig * V + j));
+      atomicAdd(&red[3 * fint + lig * V + j], aw[j]);
     }
     if (lig == 0) atomicAdd(&red[4 * fint], abp);
   }
@@ -300,28 +327,30 @@ __global__ void __launch_bounds__(256, 2) gate_psi_bwd_reduce_kernel(
 //                                           Cg = -gamma*invstd*dbeta/m - Bg*mean          (same for the x branch)
 // so only the mask coefficients and three constants per branch stay in registers.  Also accumulates the column sums
 // of the ROUNDED outputs = bias gradients of the W_g / W_x convolutions (dbias[0][c], dbias[1][c]).
-__global__ void __launch_bounds__(256, 2) gate_psi_bwd_apply_kernel(
+template <int V>
+__global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_apply_kernel(
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int tpp, int rows, GateBwdCoef c,
     const double* __restrict__ sums1, int training, const double* __restrict__ sums,
     __nv_bfloat16* __restrict__ dg1p, __nv_bfloat16* __restrict__ dx1p, float* __restrict__ dgamma_beta,
     float* __restrict__ dbn1, float* __restrict__ dbias) {
-  __shared__ float red[256 * 8];
+  using VT = typename GVec<V>::T;
+  __shared__ float red[256 * V];
   const int gch = threadIdx.x % tpp, r = threadIdx.x / tpp;
   const bool active = r < rows;
-  float bsg[8], bsx[8];
+  float bsg[V], bsx[V];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) bsg[j] = bsx[j] = 0.f;
+  for (int j = 0; j < V; ++j) bsg[j] = bsx[j] = 0.f;
   if (active) {
-    float sg[8], hg[8], sx[8], hx[8], wg[8], bg[8], cg[8], wx[8], bx[8], cx[8];
-    g_load8(c.scale_g + gch * 8, true, sg);
-    g_load8(c.shift_g + gch * 8, true, hg);
-    g_load8(c.scale_x + gch * 8, true, sx);
-    g_load8(c.shift_x + gch * 8, true, hx);
+    float sg[V], hg[V], sx[V], hx[V], wg[V], bg[V], cg[V], wx[V], bx[V], cx[V];
+    gv_loadf<V>(c.scale_g + gch * V, true, sg);
+    gv_loadf<V>(c.shift_g + gch * V, true, hg);
+    gv_loadf<V>(c.scale_x + gch * V, true, sx);
+    gv_loadf<V>(c.shift_x + gch * V, true, hx);
     const double inv_m = 1.0 / (double)npix;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = gch * 8 + j;
+    for (int j = 0; j < V; ++j) {
+      const int ch = gch * V + j;
       const float wp = bf16_round(__ldg(c.wpsi + ch));
       const float igv = __ldg(c.invstd_g + ch), mgv = __ldg(c.mean_g + ch);
       const float ixv = __ldg(c.invstd_x + ch), mxv = __ldg(c.mean_x + ch);
@@ -352,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) gate_psi_bwd_apply_kernel(
     const long long stride = (long long)gridDim.x * rows;
     constexpr int U = 2;                      // pixels in flight per thread
     for (long long p0 = (long long)blockIdx.x * rows + r; p0 < npix; p0 += U * stride) {
-      uint4 gv[U], xv[U];
+      VT gv[U], xv[U];
       float ds[U], qv[U];
       bool ok[U];
 #pragma unroll
@@ -360,8 +389,8 @@ __global__ void __launch_bounds__(256, 2) gate_psi_bwd_apply_kernel(
         const long long p = p0 + u * stride;
         ok[u] = p < npix;
         const long long pc = ok[u] ? p : p0;
-        gv[u] = __ldg(reinterpret_cast<const uint4*>(g1p + pc * ld + gch * 8));
-        xv[u] = __ldg(reinterpret_cast<const uint4*>(x1p + pc * ld + gch * 8));
+        gv[u] = __ldg(reinterpret_cast<const VT*>(g1p + pc * ld + gch * V));
+        xv[u] = __ldg(reinterpret_cast<const VT*>(x1p + pc * ld + gch * V));
         ds[u] = __ldg(dsig + pc);
         qv[u] = __bfloat162float(q[pc]);
       }
@@ -370,25 +399,25 @@ __global__ void __launch_bounds__(256, 2) gate_psi_bwd_apply_kernel(
         if (!ok[u]) continue;
         const long long p = p0 + u * stride;
         const float dq = gate_dq(ds[u], qv[u], g1, mu1, is1, training, k0, k1);
-        float g[8], x[8];
-        g_unpack8(gv[u], g);
-        g_unpack8(xv[u], x);
+        float g[V], x[V];
+        gv_unpack<V>(gv[u], g);
+        gv_unpack<V>(xv[u], x);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < V; ++j) {
           const float gb = bf16_round(fmaf(g[j], sg[j], hg[j]));
           const float xb = bf16_round(fmaf(x[j], sx[j], hx[j]));
           const float dqm = bf16_round(gb + xb) > 0.f ? dq : 0.f;
           g[j] = fmaf(wg[j], dqm, fmaf(bg[j], g[j], cg[j]));
           x[j] = fmaf(wx[j], dqm, fmaf(bx[j], x[j], cx[j]));
         }
-        const uint4 og = g_pack8(g), ox = g_pack8(x);
-        *reinterpret_cast<uint4*>(dg1p + p * ld + gch * 8) = og;
-        *reinterpret_cast<uint4*>(dx1p + p * ld + gch * 8) = ox;
+        const VT og = gv_pack<V>(g), ox = gv_pack<V>(x);
+        *reinterpret_cast<VT*>(dg1p + p * ld + gch * V) = og;
+        *reinterpret_cast<VT*>(dx1p + p * ld + gch * V) = ox;
         if (dbias != nullptr) {
-          g_unpack8(og, g);
-          g_unpack8(ox, x);
+          gv_unpack<V>(og, g);
+          gv_unpack<V>(ox, x);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < V; ++j) {
             bsg[j] += g[j];
             bsx[j] += x[j];
           }
@@ -402,15 +431,15 @@ __global__ void __launch_bounds__(256, 2) gate_psi_bwd_apply_kernel(
       __syncthreads();
       if (active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[(r * tpp + gch) * 8 + j] = v[j];
+        for (int j = 0; j < V; ++j) red[(r * tpp + gch) * V + j] = v[j];
       }
       __syncthreads();
       if (active && r == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < V; ++j) {
           float s = 0.f;
-          for (int rr = 0; rr < rows; ++rr) s += red[(rr * tpp + gch) * 8 + j];
-          atomicAdd(&dbias[which * fint + gch * 8 + j], s);
+          for (int rr = 0; rr < rows; ++rr) s += red[(rr * tpp + gch) * V + j];
+          atomicAdd(&dbias[which * fint + gch * V + j], s);
         }
       }
     }
@@ -421,6 +450,14 @@ static int g_pow2ceil(int v) {
   int p = 1;
   while (p < v) p <<= 1;
   return p;
+}
+// 4 channels per thread when F_int / 4 threads per pixel fit a 256-thread block (B200SEG_GATE_LIGHT=0: always 8)
+static bool gate_light(int fint) {
+  static const bool enabled = [] {
+    const char* e = getenv("B200SEG_GATE_LIGHT");
+    return !(e != nullptr && atoi(e) == 0);
+  }();
+  return enabled && fint % 4 == 0 && fint / 4 <= 256;
 }
 static int g_grid(long long units, int per_block, int waves) {
   long long g = (units + per_block - 1) / per_block;
@@ -493,11 +530,18 @@ extern "C" int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const vo
                                       float* dbpsi, b2_stream_t stream) {
   B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld), B2_ERR_ALIGN, "gate operands misaligned");
-  const int L = g_pow2ceil(fint / 8);
   const size_t smem = (size_t)(4 * fint + 1) * sizeof(float);
-  gate_psi_bwd_reduce_kernel<<<g_grid(npix, 256 / L, 4), 256, smem, (cudaStream_t)stream>>>(
-      dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-      make_coef(coef), sums1, training, sums, dwpsi, dbpsi);
+  if (gate_light(fint)) {
+    const int L = g_pow2ceil(fint / 4);
+    gate_psi_bwd_reduce_kernel<4><<<g_grid(npix, 256 / L, 8), 256, smem, (cudaStream_t)stream>>>(
+        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi);
+  } else {
+    const int L = g_pow2ceil(fint / 8);
+    gate_psi_bwd_reduce_kernel<8><<<g_grid(npix, 256 / L, 4), 256, smem, (cudaStream_t)stream>>>(
+        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi);
+  }
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -510,11 +554,19 @@ extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const voi
   B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld) && g_al(dg1p, ld) && g_al(dx1p, ld), B2_ERR_ALIGN,
              "gate operands misaligned");
-  const int tpp = fint / 8, rows = 256 / tpp;
-  gate_psi_bwd_apply_kernel<<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
-      dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
-      rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-      dbias);
+  if (gate_light(fint)) {
+    const int tpp = fint / 4, rows = 256 / tpp;
+    gate_psi_bwd_apply_kernel<4><<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
+        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
+        rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
+        dbias);
+  } else {
+    const int tpp = fint / 8, rows = 256 / tpp;
+    gate_psi_bwd_apply_kernel<8><<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
+        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
+        rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
+        dbias);
+  }
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
