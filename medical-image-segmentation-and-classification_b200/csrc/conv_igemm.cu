@@ -210,6 +210,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     const uint32_t idesc = umma_idesc_bf16(kTileM, p.block_n, 0, 0);
+    const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);          // K-major SW128 descriptor with start address 0
+    const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
+    const uint32_t desc_lo0 = (uint32_t)desc0;
     int stage = 0;
     uint32_t phase = 0;
     int ti = 0;
@@ -225,6 +228,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + p.a_stage_bytes;
+          if (!p.base_off_mode) {
+            // Descriptors differ only in the 14-bit start-address field (bytes >> 4) of the low word, and smem
+            // addresses are < 256 KB, so stepping a descriptor is one 32-bit add: +2 per 16-element K step (32 B),
+            // +8 per pixel of halo shift (128 B), +8 * BLOCK_N per weight tap.  This keeps the single issuing thread
+            // at a few instructions per MMA — it paces the N <= 128 tiles otherwise.
+            uint32_t a_lo = desc_lo0 + (a_addr >> 4);
+            uint32_t b_lo = desc_lo0 + (b_addr >> 4);
+            const int nsub = (p.debug_skip & 2) ? 0 : sub;
+            for (int s = 0; s < nsub; ++s) {       // (a fully unrolled 12-MMA variant measured slower)
+#pragma unroll
+              for (int k = 0; k < kKBlock / 16; ++k)
+                umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                          (it | s | k) != 0 ? 1u : 0u);
+              a_lo += 8;
+              b_lo += (uint32_t)p.block_n * 8u;
+            }
+          } else {
           for (int s = 0; s < ((p.debug_skip & 2) ? 0 : sub); ++s) {
             const uint32_t a_s = a_addr + s * 128;            // halo mode: shift by s pixels (rows of 128 B)
             const uint32_t b_s = b_addr + s * p.block_n * 128;
@@ -235,6 +255,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               const uint64_t db = umma_desc_sw128(b_s + k * 32, 16, 1024);
               umma_bf16(d_tmem, da, db, idesc, (it | s | k) != 0 ? 1u : 0u);
             }
+          }
           }
           // frees this smem slot (in every CTA that multicasts into it) when the MMAs have read it
           if (C == 1) umma_commit(&empty_bar[stage]);

@@ -170,6 +170,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const int ncol1 = ncol_live - ncol0;
       const uint32_t idesc = umma_idesc_bf16(128, ncol0 * 64, 1, 1);
       const uint32_t idesc1 = ncol1 > 0 ? umma_idesc_bf16(128, ncol1 * 64, 1, 1) : 0u;
+      const uint64_t desc0 = umma_desc_sw128(0, kBoxBytes, 1024);   // MN-major SW128 descriptor, start address 0
+      const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
+      const uint32_t desc_lo0 = (uint32_t)desc0;
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nchunks; ++it) {
@@ -178,15 +181,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + 2 * kBoxBytes;
+          // 16 pixels (K) = two 8-row groups, 1024 B apart (SBO); 64-channel MN blocks 8 KB apart (LBO).  A K step
+          // of 16 pixels moves the start address by 2048 B = +128 in the (bytes >> 4) address field of the low word.
+          uint32_t a_lo = desc_lo0 + (a_addr >> 4);
+          uint32_t b_lo = desc_lo0 + (b_addr >> 4);
+          const uint32_t b1_off = (uint32_t)(ncol0 * kBoxBytes) >> 4;
+          const int nk = (p.debug_skip & 2) ? 0 : kChunkPix / 16;
 #pragma unroll
-          for (int k = 0; k < ((p.debug_skip & 2) ? 0 : kChunkPix / 16); ++k) {
-            // 16 pixels (K) = two 8-row groups, 1024 B apart (SBO); 64-channel MN blocks 8 KB apart (LBO)
-            const uint64_t da = umma_desc_sw128(a_addr + k * 2048, kBoxBytes, 1024);
-            const uint64_t db = umma_desc_sw128(b_addr + k * 2048, kBoxBytes, 1024);
-            umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
-            if (ncol1 > 0) {
-              const uint64_t db1 = umma_desc_sw128(b_addr + ncol0 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-              umma_bf16(tmem_base + (uint32_t)(ncol0 * 64), da, db1, idesc1, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kChunkPix / 16; ++k) {
+            if (k < nk) {
+              const uint64_t da = desc_hi | (uint64_t)(a_lo + 128u * k);
+              umma_bf16(tmem_base, da, desc_hi | (uint64_t)(b_lo + 128u * k), idesc, (it | k) != 0 ? 1u : 0u);
+              if (ncol1 > 0)
+                umma_bf16(tmem_base + (uint32_t)(ncol0 * 64), da, desc_hi | (uint64_t)(b_lo + b1_off + 128u * k),
+                          idesc1, (it | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[stage]);
