@@ -239,6 +239,7 @@ def run_b200(args):
 
     def step(x, t):
         opt.zero_grad(set_to_none=True)
+        K.step_begin()
         logits = model(x)
         loss, _ = ops.seg_loss(logits, t, 1.0, 0.0, 1.0)
         loss.backward()

@@ -115,6 +115,50 @@ def wgrad_stream(*keep, allow=True):
         yield
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Zeroed scratch for the small reduction buffers of a step (BatchNorm statistics, backward sums, loss sums): ~75
+# torch.zeros fills per AttU_Net step become slices of one arena that step_begin() clears with a single memset.
+# Opt-in: without step_begin() (or once the arena is exhausted) zeros_scratch() is torch.zeros.  Slices are only valid
+# until the next step_begin(), so nothing that outlives a step (gradients) is ever taken from it.
+# ----------------------------------------------------------------------------------------------------------
+_ARENA = {"enabled": os.environ.get("B200SEG_ZERO_ARENA", "1") != "0", "bufs": {}, "bytes": 1 << 20}
+
+
+def step_begin():
+    """Start of a training step (train() / bench.py call it): clear what the previous step used of the arena."""
+    if not _ARENA["enabled"] or not torch.cuda.is_available():
+        return
+    dev = torch.cuda.current_device()
+    st = _ARENA["bufs"].get(dev)
+    if st is None:
+        st = _ARENA["bufs"][dev] = {"buf": torch.zeros(_ARENA["bytes"], dtype=torch.uint8, device=f"cuda:{dev}"),
+                                    "off": 0, "high": 0, "armed": False}
+    else:
+        # the high-water mark of all earlier steps: a captured CUDA graph replays this one memset for every step
+        st["high"] = max(st["high"], st["off"])
+        if st["high"]:
+            st["buf"][:st["high"]].zero_()
+    st["off"] = 0
+    st["armed"] = True
+
+
+def zeros_scratch(shape, dtype, device):
+    """Zero-filled reduction buffer that is dead by the end of the step."""
+    st = _ARENA["bufs"].get(device.index if device.index is not None else torch.cuda.current_device()) \
+        if device.type == "cuda" else None
+    if st is None or not st["armed"]:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    off = (st["off"] + 15) & ~15
+    if off + nbytes > st["buf"].numel():
+        return torch.zeros(shape, dtype=dtype, device=device)
+    st["off"] = off + nbytes
+    return st["buf"][off:off + nbytes].view(dtype).view(shape)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -438,7 +482,7 @@ def bn_bwd(dy, z, coef, gamma, relu=True, training=True, want_dbias=False):
     n, h, w, c, lddy = _nhwc(dy)
     ldz = _nhwc(z)[4]
     npix = n * h * w
-    sums = torch.zeros((2, c), dtype=torch.float64, device=z.device)
+    sums = zeros_scratch((2, c), torch.float64, z.device)
     call("b2_bn_bwd_reduce", _p(dy), lddy, _p(z), ldz, npix, c, _p(coef[2]), _p(coef[3]), _p(coef[0]), _p(coef[1]),
          int(relu), _p(sums), _stream())
     dz = new_act(n, h, w, c, z.device)
@@ -514,7 +558,7 @@ def gate_psi_fwd(g1p, x1p, coef_g, coef_x, wpsi, bpsi):
     n, h, w, fint, ld = _nhwc(g1p)
     assert _nhwc(x1p)[4] == ld
     q = torch.empty((n, h, w), dtype=BF16, device=g1p.device)
-    qstats = torch.zeros((2,), dtype=torch.float64, device=g1p.device)
+    qstats = torch.zeros((2,), dtype=torch.float64, device=g1p.device)    # an output of the gate op: not arena memory
     call("b2_gate_psi_fwd", _p(g1p), _p(x1p), ld, n * h * w, fint, _p(coef_g[2]), _p(coef_g[3]), _p(coef_x[2]),
          _p(coef_x[3]), _p(wpsi), _p(bpsi), _p(q), _p(qstats), _stream())
     return q, qstats
@@ -534,7 +578,7 @@ def gate_apply_bwd(dout, x, psi, q, coef1):
     lddo = _nhwc(dout)[4]
     dx = new_act(n, h, w, c, x.device)
     dsig = torch.empty((n, h, w), dtype=torch.float32, device=x.device)
-    sums1 = torch.zeros((2,), dtype=torch.float64, device=x.device)
+    sums1 = zeros_scratch((2,), torch.float64, x.device)
     call("b2_gate_apply_bwd", _p(dout), lddo, _p(x), ldx, _p(psi), _p(q), n * h * w, c, _p(coef1[0]),
          _p(coef1[1]), _p(dx), c, _p(dsig), _p(sums1), _stream())
     return dx, dsig, sums1
@@ -560,7 +604,7 @@ def gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coe
     npix = n * h * w
     dev = g1p.device
     k = _gate_coef(coef_g, gamma_g, coef_x, gamma_x, coef1, gamma1, wpsi)
-    sums = torch.zeros((4, fint), dtype=torch.float64, device=dev)
+    sums = zeros_scratch((4, fint), torch.float64, dev)
     dwpsi = torch.zeros((fint,), dtype=torch.float32, device=dev)
     dbpsi = torch.zeros((1,), dtype=torch.float32, device=dev)
     call("b2_gate_psi_bwd_reduce", _p(dsig), _p(q), _p(g1p), _p(x1p), ld, npix, fint, C.byref(k), _p(sums1),
@@ -582,7 +626,7 @@ def gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coe
 def loss_fwd(z, t, w_bce=1.0, w_dice=0.0, smooth=1.0):
     assert z.dtype == torch.float32 and t.dtype == torch.float32 and z.is_contiguous() and t.is_contiguous()
     assert z.numel() == t.numel()
-    sums = torch.zeros((6,), dtype=torch.float64, device=z.device)
+    sums = zeros_scratch((6,), torch.float64, z.device)
     loss = torch.empty((), dtype=torch.float32, device=z.device)
     call("b2_loss_fwd", _p(z), _p(t), z.numel(), _p(sums), _stream())
     call("b2_loss_finalize", _p(sums), z.numel(), float(w_bce), float(w_dice), float(smooth), _p(loss), _stream())

@@ -275,7 +275,7 @@ def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional
     application 0 — the last to run in backward — hands to autograd, the others return no weight gradient."""
     cout, cin, k, _ = weight.shape
     dev = x0.device
-    stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
+    stats = K.zeros_scratch((2, cout), _F64, dev) if training else torch.empty((0,), dtype=_F64, device=dev)
     if x0.dtype != torch.bfloat16 and _stem_as_gemm(weight):   # image stem on the tensor cores (im2col, K = 32)
         x4 = K.stem_im2col3x3(_c(x0))
         wf, _ = K.pack_weights(K.stem_weight_matrix(weight), want_dgrad=False)
@@ -435,7 +435,7 @@ def upconv_bn_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], gamma: Tens
     x = _c(x)
     n, h, w, _ = x.shape
     dev = x.device
-    stats = torch.zeros((2, cout), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
+    stats = K.zeros_scratch((2, cout), _F64, dev) if training else torch.empty((0,), dtype=_F64, device=dev)
     wf, _ = K.pack_weights_upfold(weight, want_dgrad=False)
     z = K.new_act(n, 2 * h, 2 * w, cout, dev)
     for ph, (a, b) in enumerate(_PHASES):

@@ -36,6 +36,7 @@ def attention_gate(g: Tensor, x: Tensor, wg: Tensor, bg: Tensor, wx: Tensor, bx:
     dev = x.device
 
     def stats_buf():
+        # (several of these are outputs of one op: custom-op outputs may not share a storage, so no arena slices here)
         return torch.zeros((2, fint), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
 
     stats_g, stats_x = stats_buf(), stats_buf()

@@ -71,6 +71,7 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
         for x, y in train_dl:
             x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
             optimizer.zero_grad(set_to_none=True)
+            K.step_begin()                                                # one memset for the step's reduction buffers
             out = model(x)
             if out.dim() == 3:
                 out = out.unsqueeze(1)

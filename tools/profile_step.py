@@ -10,7 +10,7 @@ sys.path.insert(0, str(ROOT / "medical-image-segmentation-and-classification_b20
 
 import torch  # noqa: E402
 
-from b200seg import ops  # noqa: E402
+from b200seg import kernels as K, ops  # noqa: E402
 from b200seg.models import segmentation_models as M  # noqa: E402
 from oracle.synthetic import xray_batch  # noqa: E402
 
@@ -34,6 +34,7 @@ params = list(model.parameters())
 
 def step():
     opt.zero_grad(set_to_none=True)
+    K.step_begin()
     loss, _ = ops.seg_loss(model(x), t, 1.0, 0.0, 1.0)
     loss.backward()
     opt.step()
