@@ -46,6 +46,10 @@ struct IgemmParams {
   int block_n, stages, num_k_iters;
   int cout, n_tiles, m_tiles, m_stride;
   int halo, base_off_mode;
+  int rp;             // row-pair mode (Cout == 64, halo geometry): a tile is 128 pixels of TWO output rows; accumulator
+                      // columns 0..63 = row h0+1, 64..127 = row h0; every input row h0-1+j (j = 0..3) meets the stacked
+                      // taps [W(j-1, s) ; W(j, s)] (one strided TMA box, out-of-range filter rows zero-filled), so the
+                      // MMAs are N = 128 instead of N = 64 and 4 instead of 6 activation rows are fetched per two tiles
   int stride, ksize, pad_h, pad_w;
   long long y_sn, y_sh, y_sw;   // element strides of the output pixel grid (strided placement for ConvT)
   int a_stage_bytes, b_stage_bytes, a_tx_bytes;
@@ -163,11 +167,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       t /= p.tw;
       const int th_i = t % p.th;
       const int tn_i = t / p.th;
-      const int w0 = tw_i * p.Wb, h0 = th_i * p.Hb, n0 = tn_i * p.Nb;
-      const int outer = p.halo ? 3 : p.taps;     // halo mode: one iteration per (filter row, channel block)
+      const int w0 = tw_i * p.Wb, h0 = th_i * (p.rp ? 2 : p.Hb), n0 = tn_i * p.Nb;
+      const int outer = p.rp ? 4 : (p.halo ? 3 : p.taps);   // halo mode: one iteration per (input row, channel block)
       for (int o = 0; o < outer; ++o) {
         int dr = 0, ds = 0, tap0 = o;
-        if (p.halo) {
+        if (p.rp) {
+          dr = o - 1;
+          ds = -1;
+          tap0 = (o - 1) * 3;          // first tap of the stacked pair (filter rows o-1 and o)
+        } else if (p.halo) {
           dr = o - 1;
           ds = -1;
           tap0 = o * 3;
@@ -190,7 +198,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, p.stride * w0 + ds,
                           p.stride * h0 + dr, n0);
             }
-            if (C == 1) {
+            if (p.rp) {
+              for (int tp = 0; tp < 3; ++tp)       // [W(o-1, tp) ; W(o, tp)]: 2 taps, element stride 3, 64 rows each
+                tma_load_3d(sb + tp * (128 * 128), &tmB, &full_bar[stage], cb * kKBlock, 0, tap0 + tp);
+            } else if (C == 1) {
               tma_load_3d(sb, &tmB, &full_bar[stage], cb * kKBlock, n_tile * p.block_n, tap0);
             } else {
               for (int tp = 0; tp < b_taps; ++tp)
@@ -316,7 +327,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) v += red[(w * 2 + which) * p.block_n + c];
-        atomicAdd(&p.stats[which * p.cout + n_tile_ * p.block_n + c], v);
+        atomicAdd(&p.stats[which * p.cout + n_tile_ * p.block_n + (p.rp ? (c & 63) : c)], v);
       }
       // (the staging tile is next written after another group barrier, see the tile loop)
 #pragma unroll
@@ -342,14 +353,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // new output-channel slab: flush the statistics kept for the previous one, reload the bias slice
         if (cur_n_tile >= 0 && p.stats != nullptr) flush_stats(cur_n_tile);
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // everyone is done reading the old bias slice
-        for (int i = et; i < p.block_n; i += 128) s_bias[i] = p.bias ? p.bias[ch_base + i] : 0.f;
+        for (int i = et; i < p.block_n; i += 128)
+          s_bias[i] = p.bias ? p.bias[ch_base + (p.rp ? (i & 63) : i)] : 0.f;
         cur_n_tile = n_tile;
       }
       const int tw_i = t % p.tw;
       t /= p.tw;
       const int th_i = t % p.th;
       const int tn_i = t / p.th;
-      const int w0 = tw_i * p.Wb, h0 = th_i * p.Hb, n0 = tn_i * p.Nb;
+      const int w0 = tw_i * p.Wb, h0 = th_i * (p.rp ? 2 : p.Hb), n0 = tn_i * p.Nb;
       int valid_rows = (p.N - n0) * p.Wb * p.Hb;
       if (valid_rows > kTileM) valid_rows = kTileM;
       const int buf = ti & 1;
@@ -435,7 +447,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
       if (p.tma_store) {
         if (et == 0) {
-          if (p.block_n >= 64) {
+          if (p.rp) {                 // panel 0 = output row h0 + 1, panel 1 = output row h0
+            tma_store_4d(&tmY, ctile, 0, w0, h0 + 1, n0);
+            tma_store_4d(&tmY, ctile + kTileM * 128, 0, w0, h0, n0);
+          } else if (p.block_n >= 64) {
             for (int pn = 0; pn < (p.block_n >> 6); ++pn)
               tma_store_4d(&tmY, ctile + pn * (kTileM * 128), ch_base + pn * 64, w0, h0, n0);
           } else {
@@ -603,7 +618,22 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.halo = (halo_env != 0 && p.taps == 9 && stride == 1 && !a->custom_pad && p.Hb == 1 && p.Nb == 1 &&
             p.Wb == kTileM) ? 1 : 0;
   p.base_off_mode = (halo_env == 2) ? 1 : 0;
-  if (p.halo) {
+  p.tma_store = env_int("B200SEG_TMA_STORE", 1) != 0 ? 1 : 0;
+  p.rp = (p.halo && a->cout == 64 && p.block_n == 64 && a->h % 2 == 0 && a->addend == nullptr && out_mul == 1 &&
+          in_mul == 1 && p.tma_store && env_int("B200SEG_FPROP_ROWPAIR", 0) != 0) ? 1 : 0;   // opt-in, see below
+  // Row-pair mode is parity-tested but off by default: it makes the Cout = 64 MMAs N = 128 (isolated: 64->64 @256^2
+  // 0.390 -> 0.366 ms, 128->64 0.711 -> 0.680 ms) but streams 192 KB of stacked weights per tile pair from L2, and
+  // inside the training step, where the side-stream weight gradients load the same fabric, the gain vanishes.
+  if (p.rp) {
+    p.block_n = 128;                       // two 64-channel panels = two output rows
+    p.n_tiles = 1;
+    p.th = a->h / 2;
+    p.m_tiles = p.tw * p.th * tn;
+    p.a_tx_bytes = (kTileM + 2) * 128;
+    p.a_stage_bytes = ((p.a_tx_bytes + 1023) / 1024) * 1024;
+    p.b_stage_bytes = 3 * 128 * 128;
+    p.num_k_iters = 4 * cbt;
+  } else if (p.halo) {
     p.a_tx_bytes = (kTileM + 2) * 128;
     p.a_stage_bytes = ((p.a_tx_bytes + 1023) / 1024) * 1024;
     p.b_stage_bytes = 3 * p.block_n * 128;
@@ -614,7 +644,6 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     p.b_stage_bytes = p.block_n * 128;
     p.num_k_iters = p.taps * cbt;
   }
-  p.tma_store = env_int("B200SEG_TMA_STORE", 1) != 0 ? 1 : 0;
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int ctile_bytes = kTileM * p.block_n * 2;
   const int tail_bytes = 256 + kMaxEpiGroups * 256 * 4 + 256;
@@ -643,6 +672,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     const int forced_c = env_int("B200SEG_CLUSTER", 0);
     if (forced_c == 1 || forced_c == 2 || forced_c == 4) c = forced_c;
     while (c > 1 && ((p.block_n / c) % 8 != 0 || p.m_tiles < c)) c /= 2;
+    if (p.rp) c = 1;
     p.cluster = c;
   }
   const int budget = 232448 - 1024 - tail_bytes - p.epi_groups * ctile_bytes;
@@ -682,7 +712,13 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
       box[1] = (uint32_t)(p.block_n / p.cluster);
       box[2] = 1u;
     }
-    rc = encode_tmap_bf16(&tmB, a->wpk, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (p.rp) {                   // two taps three apart (filter rows r and r+1 of one column): traversal stride 3
+      uint32_t box_rp[3] = {64, 64, 6};
+      uint32_t est_rp[3] = {1, 1, 3};
+      rc = encode_tmap_bf16(&tmB, a->wpk, 3, dims, str, box_rp, CU_TENSOR_MAP_SWIZZLE_128B, est_rp);
+    } else {
+      rc = encode_tmap_bf16(&tmB, a->wpk, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
     if (rc) return rc;
   }
   // output pixel grid (possibly a strided sub-lattice of a larger image: ConvTranspose pixel shuffle)
