@@ -19,6 +19,9 @@
 //             sum-of-squares of the ROUNDED output are column sums of that smem tile (16-byte reads), kept in fp64
 //             registers across all tiles of the CTA and flushed through shuffles + smem with one fp64 atomic per
 //             channel and group at the end.
+// Double-M work items (BLOCK_N <= 128, large layers): two consecutive m-tiles share every weight stage — two A slots
+// per stage, four accumulators in TMEM, one epilogue group per tile.  The kernel is bound by the bytes each SM pulls
+// through the L2 -> SM fabric, and the weight tile is 75 % of them at N <= 128; sharing it is worth 14-29 % per layer.
 // Optional clusters (B200SEG_CLUSTER=2|4, off by default: no measured gain): the CTAs of a cluster work on
 // consecutive m-tiles of one n-tile and share every weight tile, each fetching 1/cluster of its rows and multicasting.
 // The epilogue of tile i overlaps the main loop of tile i+1.
@@ -46,6 +49,9 @@ struct IgemmParams {
   int block_n, stages, num_k_iters;
   int cout, n_tiles, m_tiles, m_stride;
   int halo, base_off_mode;
+  int dm;             // "double-M" mode: a work item is TWO consecutive m-tiles that share every weight stage (two A
+                      // slots per stage, four accumulators in TMEM): halves the weight bytes a CTA pulls through the
+                      // L2 -> SM fabric per FLOP.  BLOCK_N <= 128.
   int rp;             // row-pair mode (Cout == 64, halo geometry): a tile is 128 pixels of TWO output rows; accumulator
                       // columns 0..63 = row h0+1, 64..127 = row h0; every input row h0-1+j (j = 0..3) meets the stacked
                       // taps [W(j-1, s) ; W(j, s)] (one strided TMA box, out-of-range filter rows zero-filled), so the
@@ -102,16 +108,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int a_slots = p.dm ? 2 : 1;                                    // activation tiles per stage
+  const int nbuf = p.dm ? 4 : 2;                                       // accumulators in TMEM
+  const int stage_bytes = a_slots * p.a_stage_bytes + p.b_stage_bytes;
   const int ctile_bytes = kTileM * p.block_n * 2;
   uint8_t* ctile0 = smem + p.stages * stage_bytes;                     // per group: 128 x block_n bf16, 1024 B aligned
   uint8_t* tail = ctile0 + p.epi_groups * ctile_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full_bar = empty_bar + kMaxStages;                    // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_bias0 = reinterpret_cast<float*>(tail + 256);               // [group][256]
+  uint64_t* tmem_full_bar = empty_bar + kMaxStages;                    // [4]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 4;                        // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
+  float* s_bias0 = reinterpret_cast<float*>(tail + 320);               // [group][256]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,14 +130,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint16_t cmask = (uint16_t)((1u << C) - 1u);
   const int cluster_id = (int)blockIdx.x / C;
   const int num_clusters = (int)gridDim.x / C;
-  const int total_items = ((p.m_tiles + C - 1) / C) * p.n_tiles;
+  const int per_item = p.dm ? 2 : C;                                   // m-tiles per work item
+  const int total_items = ((p.m_tiles + per_item - 1) / per_item) * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], (uint32_t)C);   // every CTA of the cluster reads the shared weight slot
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 4);      // one arrival per epilogue warp
     }
@@ -140,7 +149,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (p.tma_store) tma_prefetch_desc(&tmY);
   }
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.block_n) tmem_cols <<= 1;
+  while ((int)tmem_cols < nbuf * p.block_n) tmem_cols <<= 1;
   if (warp == 1) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
@@ -156,18 +165,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ------------------------------ TMA producer (warp-uniform control flow) ------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx = (uint32_t)(p.a_tx_bytes + p.b_stage_bytes);
+    const uint32_t tx = (uint32_t)(a_slots * p.a_tx_bytes + p.b_stage_bytes);
     const int b_taps = p.halo ? 3 : 1;           // weight taps per stage
     const int b_rows = p.block_n / C;            // weight rows this CTA fetches (and multicasts) per tap
     for (int item = cluster_id; item < total_items; item += num_clusters) {
       const int n_tile = item % p.n_tiles;
-      int t = (item / p.n_tiles) * C + (int)crank;
-      if (t >= p.m_tiles) t = p.m_tiles - 1;     // ragged last group: recompute the last tile (its result is dropped)
-      const int tw_i = t % p.tw;
-      t /= p.tw;
-      const int th_i = t % p.th;
-      const int tn_i = t / p.th;
-      const int w0 = tw_i * p.Wb, h0 = th_i * (p.rp ? 2 : p.Hb), n0 = tn_i * p.Nb;
+      // pixel origin of the item's tile(s); a ragged last item recomputes the last tile (its result is dropped)
+      int w0s[2], h0s[2], n0s[2];
+      for (int q = 0; q < a_slots; ++q) {
+        int t = (item / p.n_tiles) * per_item + (p.dm ? q : (int)crank);
+        if (t >= p.m_tiles) t = p.m_tiles - 1;
+        const int tw_i = t % p.tw;
+        t /= p.tw;
+        const int th_i = t % p.th;
+        const int tn_i = t / p.th;
+        w0s[q] = tw_i * p.Wb;
+        h0s[q] = th_i * (p.rp ? 2 : p.Hb);
+        n0s[q] = tn_i * p.Nb;
+      }
+      const int w0 = w0s[0], h0 = h0s[0], n0 = n0s[0];
       const int outer = p.rp ? 4 : (p.halo ? 3 : p.taps);   // halo mode: one iteration per (input row, channel block)
       for (int o = 0; o < outer; ++o) {
         int dr = 0, ds = 0, tap0 = o;
@@ -187,7 +203,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* sa = smem + stage * stage_bytes;
-            uint8_t* sb = sa + p.a_stage_bytes;
+            uint8_t* sb = sa + a_slots * p.a_stage_bytes;
             if (p.debug_skip & 1) {
               mbar_arrive(&full_bar[stage]);
             } else {
@@ -197,6 +213,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             } else {
               tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, p.stride * w0 + ds,
                           p.stride * h0 + dr, n0);
+            }
+            if (p.dm) {                          // second activation tile of the item, same taps / channel block
+              if (cb < p.cb0)
+                tma_load_4d(sa + p.a_stage_bytes, &tmA0, &full_bar[stage], cb * kKBlock, p.stride * w0s[1] + ds,
+                            p.stride * h0s[1] + dr, n0s[1]);
+              else
+                tma_load_4d(sa + p.a_stage_bytes, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock,
+                            p.stride * w0s[1] + ds, p.stride * h0s[1] + dr, n0s[1]);
             }
             if (p.rp) {
               for (int tp = 0; tp < 3; ++tp)       // [W(o-1, tp) ; W(o, tp)]: 2 taps, element stride 3, 64 rows each
@@ -228,34 +252,42 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     uint32_t phase = 0;
     int ti = 0;
     const int sub = p.halo ? 3 : 1;
+    const int nb_shift = p.dm ? 2 : 1;           // log2(accumulators in TMEM)
     for (int item = cluster_id; item < total_items; item += num_clusters, ++ti) {
-      const int buf = ti & 1;
-      mbar_wait(&tmem_empty_bar[buf], (((uint32_t)ti >> 1) & 1u) ^ 1u);
+      // local tile counter lt = a_slots * ti + q  ->  accumulator lt % nbuf, barrier phase (lt / nbuf) & 1
+      for (int q = 0; q < a_slots; ++q) {
+        const uint32_t lt = (uint32_t)(a_slots * ti + q);
+        mbar_wait(&tmem_empty_bar[lt & (nbuf - 1)], ((lt >> nb_shift) & 1u) ^ 1u);
+      }
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.block_n);
       for (int it = 0; it < p.num_k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+          const uint32_t b_addr = a_addr + a_slots * p.a_stage_bytes;
           if (!p.base_off_mode) {
             // Descriptors differ only in the 14-bit start-address field (bytes >> 4) of the low word, and smem
             // addresses are < 256 KB, so stepping a descriptor is one 32-bit add: +2 per 16-element K step (32 B),
             // +8 per pixel of halo shift (128 B), +8 * BLOCK_N per weight tap.  This keeps the single issuing thread
             // at a few instructions per MMA — it paces the N <= 128 tiles otherwise.
-            uint32_t a_lo = desc_lo0 + (a_addr >> 4);
-            uint32_t b_lo = desc_lo0 + (b_addr >> 4);
             const int nsub = (p.debug_skip & 2) ? 0 : sub;
-            for (int s = 0; s < nsub; ++s) {       // (a fully unrolled 12-MMA variant measured slower)
+            for (int q = 0; q < a_slots; ++q) {
+              const uint32_t lt = (uint32_t)(a_slots * ti + q);
+              const uint32_t d_tmem = tmem_base + (lt & (uint32_t)(nbuf - 1)) * (uint32_t)p.block_n;
+              uint32_t a_lo = desc_lo0 + ((a_addr + (uint32_t)(q * p.a_stage_bytes)) >> 4);
+              uint32_t b_lo = desc_lo0 + (b_addr >> 4);
+              for (int s = 0; s < nsub; ++s) {     // (a fully unrolled 12-MMA variant measured slower)
 #pragma unroll
-              for (int k = 0; k < kKBlock / 16; ++k)
-                umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
-                          (it | s | k) != 0 ? 1u : 0u);
-              a_lo += 8;
-              b_lo += (uint32_t)p.block_n * 8u;
+                for (int k = 0; k < kKBlock / 16; ++k)
+                  umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                            (it | s | k) != 0 ? 1u : 0u);
+                a_lo += 8;
+                b_lo += (uint32_t)p.block_n * 8u;
+              }
             }
           } else {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((ti & 1) * p.block_n);
           for (int s = 0; s < ((p.debug_skip & 2) ? 0 : sub); ++s) {
             const uint32_t a_s = a_addr + s * 128;            // halo mode: shift by s pixels (rows of 128 B)
             const uint32_t b_s = b_addr + s * p.block_n * 128;
@@ -278,7 +310,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&tmem_full_bar[buf]);
+      if (elect_one()) {
+        for (int q = 0; q < a_slots; ++q)
+          umma_commit(&tmem_full_bar[(uint32_t)(a_slots * ti + q) & (uint32_t)(nbuf - 1)]);
+      }
       __syncwarp();
     }
   } else if (((warp - 2) >> 2) < p.epi_groups) {
@@ -335,14 +370,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     };
 
     int cur_n_tile = -1;
-    for (int item = cluster_id + g * num_clusters, ti = g; item < total_items; item += G * num_clusters, ti += G) {
+    const int nb_shift = p.dm ? 2 : 1;           // log2(accumulators in TMEM)
+    // ti = local tile counter of this CTA (group g takes ti = g, g + G, ...); double-M: item = ti / 2, tile ti & 1
+    for (int ti = g;; ti += G) {
+      const int item = cluster_id + (p.dm ? (ti >> 1) : ti) * num_clusters;
+      if (item >= total_items) break;
       const int n_tile = item % p.n_tiles;
       const int ch_base = n_tile * p.block_n;
-      int t = (item / p.n_tiles) * C + (int)crank;
+      int t = (item / p.n_tiles) * per_item + (p.dm ? (ti & 1) : (int)crank);
       if (t >= p.m_tiles || (p.debug_skip & 4)) {
         // ragged last group: this CTA only kept the pipeline protocol going; hand the accumulator straight back
-        const int dbuf = ti & 1;
-        mbar_wait(&tmem_full_bar[dbuf], ((uint32_t)ti >> 1) & 1u);
+        const int dbuf = ti & (nbuf - 1);
+        mbar_wait(&tmem_full_bar[dbuf], ((uint32_t)ti >> nb_shift) & 1u);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
@@ -364,13 +403,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int w0 = tw_i * p.Wb, h0 = th_i * (p.rp ? 2 : p.Hb), n0 = tn_i * p.Nb;
       int valid_rows = (p.N - n0) * p.Wb * p.Hb;
       if (valid_rows > kTileM) valid_rows = kTileM;
-      const int buf = ti & 1;
+      const int buf = ti & (nbuf - 1);
 
       // the group's previous TMA store must have finished READING the staging tile before it is overwritten
       if (p.tma_store && et == 0) tma_store_wait_read();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 
-      mbar_wait(&tmem_full_bar[buf], ((uint32_t)ti >> 1) & 1u);
+      mbar_wait(&tmem_full_bar[buf], ((uint32_t)ti >> nb_shift) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.block_n);
       const bool valid = row < valid_rows;
@@ -644,9 +683,20 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     p.b_stage_bytes = p.block_n * 128;
     p.num_k_iters = p.taps * cbt;
   }
-  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int ctile_bytes = kTileM * p.block_n * 2;
-  const int tail_bytes = 256 + kMaxEpiGroups * 256 * 4 + 256;
+  const int tail_bytes = 320 + kMaxEpiGroups * 256 * 4 + 192;
+  // Double-M: two consecutive m-tiles per work item share every weight stage (see IgemmParams::dm).  Needs four
+  // accumulators in TMEM (BLOCK_N <= 128), two A slots per stage and still >= 2 (>= 3 for thin stages) stages.
+  {
+    const int want = env_int("B200SEG_DM", 2);      // 0 = off, 1 = only with two epilogue groups, 2 = also with one
+    p.dm = 0;
+    if (want != 0 && p.block_n <= 128 && !p.rp && p.m_tiles >= env_int("B200SEG_DM_MIN_TILES", 4 * num_sms())) {
+      const int sb2 = 2 * p.a_stage_bytes + p.b_stage_bytes;
+      const int g2 = 232448 - 1024 - tail_bytes - 2 * ctile_bytes, g1 = g2 + ctile_bytes;
+      if (g2 / sb2 >= 2 || (want == 2 && g1 / sb2 >= 2)) p.dm = 1;
+    }
+  }
+  const int stage_bytes = (p.dm ? 2 : 1) * p.a_stage_bytes + p.b_stage_bytes;
   // Two epilogue groups (two staging tiles) when the accumulator drain, not the MMA, paces a tile: the drain costs
   // about 1750 + 36 * BLOCK_N clocks per tile per group (measured), the MMAs K/16 * BLOCK_N/2.  A second group is
   // not worth giving up pipeline stages for when the main loop is the longer of the two anyway.
@@ -656,6 +706,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     const int forced_g = env_int("B200SEG_EPI_GROUPS", 0);
     p.epi_groups = forced_g > 0 ? (forced_g > kMaxEpiGroups ? kMaxEpiGroups : forced_g)
                                 : (mma_clk * 5 < epi_clk * 6 ? 2 : 1);
+    if (p.dm) p.epi_groups = 2;        // the two tiles of an item finish together: one group each
     const int budget2 = 232448 - 1024 - tail_bytes - 2 * ctile_bytes;
     if (p.epi_groups == 2 && budget2 / stage_bytes < 2) p.epi_groups = 1;
   }
@@ -672,7 +723,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     const int forced_c = env_int("B200SEG_CLUSTER", 0);
     if (forced_c == 1 || forced_c == 2 || forced_c == 4) c = forced_c;
     while (c > 1 && ((p.block_n / c) % 8 != 0 || p.m_tiles < c)) c /= 2;
-    if (p.rp) c = 1;
+    if (p.rp || p.dm) c = 1;
     p.cluster = c;
   }
   const int budget = 232448 - 1024 - tail_bytes - p.epi_groups * ctile_bytes;
@@ -772,7 +823,8 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     }
     if (clusters > max_clusters[C]) clusters = max_clusters[C];
   }
-  const long long total = (long long)((p.m_tiles + C - 1) / C) * p.n_tiles;
+  const int per_item = p.dm ? 2 : C;
+  const long long total = (long long)((p.m_tiles + per_item - 1) / per_item) * p.n_tiles;
   B2_REQUIRE(total < (1ll << 31), B2_ERR_SHAPE, "too many tiles");
   if (clusters > total) clusters = (int)total;
   if (clusters > p.n_tiles && (total / clusters) >= 16) clusters = (clusters / p.n_tiles) * p.n_tiles;
