@@ -690,7 +690,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   {
     const int want = env_int("B200SEG_DM", 2);      // 0 = off, 1 = only with two epilogue groups, 2 = also with one
     p.dm = 0;
-    if (want != 0 && p.block_n <= 128 && !p.rp && p.m_tiles >= env_int("B200SEG_DM_MIN_TILES", 4 * num_sms())) {
+    if (want != 0 && p.block_n <= 128 && p.m_tiles >= env_int("B200SEG_DM_MIN_TILES", 4 * num_sms())) {
       const int sb2 = 2 * p.a_stage_bytes + p.b_stage_bytes;
       const int g2 = 232448 - 1024 - tail_bytes - 2 * ctile_bytes, g1 = g2 + ctile_bytes;
       if (g2 / sb2 >= 2 || (want == 2 && g1 / sb2 >= 2)) p.dm = 1;
