@@ -13,6 +13,11 @@
 // image row, so against the same X row they produce the gradient of the filter row above.  3x3: with X rows h and
 // h+1 as two column groups one CTA yields all three filter rows from two MMAs per K step (one quarter is redundant);
 // 2x2 (folded UpConv phases): one X row gives both filter rows, nothing is redundant.
+// X-halo mode (3x3, unit stride — the default): one (Wb+2)-pixel-wide box per X block replaces the three tap-shifted
+// boxes; tap s is an MMA whose B descriptor starts s pixels (s * 128 B) into the box — the 128B swizzle is a function
+// of the absolute shared-memory address, so the shifted view reads the right bytes.  The kernel is bound by the bytes
+// it pulls through the L2 -> SM fabric; this halves them (64 -> 33 KB per chunk): 128->128 @128^2 0.378 -> 0.226 ms
+// (1367 TFLOP/s), 64->64 @256^2 0.720 -> 0.308 ms.
 // Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
 #include <stdlib.h>
@@ -29,6 +34,7 @@ int encode_act_tmap_ex(CUtensorMap* tm, const void* base, int c, int n, int h, i
 static constexpr int kChunkPix = 64;            // K per pipeline stage
 static constexpr int kBoxBytes = kChunkPix * 128;  // 8 KB: 64 pixels x 64 channels bf16
 static constexpr int kWgThreads = 192;
+static constexpr int kXhBox = 9 * 1024;         // X-halo box slot: 66 pixels x 128 B = 8448 B, padded to 1 KB
 
 struct WgradParams {
   int Wb, Hb, Nb, tw, th;
@@ -48,6 +54,11 @@ struct WgradParams {
   int rp_dir;        // row-pair mode: rows 64..127 hold dY of image row h + rp_dir.  +1 when the filter has a row above
                      // the centre (pad_h >= 1); -1 for 2x2 taps with pad_h == 0, so that the one product the pairing
                      // cannot form always involves an out-of-image (zero) X row
+  int xh;            // X-halo mode (3x3, chunk = 64 pixels of one image row): ONE (64+2)-pixel box per X block / row
+                     // instead of three tap-shifted ones; tap s is an MMA whose B descriptor starts s*128 B into
+                     // the box (the 128B swizzle is a function of the absolute smem address).  Halves the bytes a
+                     // CTA pulls through the L2 -> SM fabric.  nbox = boxes per stage (2), kXhBox bytes apart.
+  int nbox;
   int debug_skip;    // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs
   float* ws;         // [splits][cout][taps][ctot]
 };
@@ -108,13 +119,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   if (cib_base + live_cb > cbt) live_cb = cbt - cib_base;
   const int grp_cols = live_cb * p.ksize;                       // columns per X-row group (row-pair mode)
   const int ncol_live = p.rowpair ? p.rowpair * grp_cols : grp_cols;
+  const int xh_live = p.rowpair ? p.rowpair : live_cb;           // X-halo mode: boxes this CTA fills per stage
 
   if (warp == 0) {
     // TMA producer: warp-uniform loop, one elected lane issues; chunk coordinates advance incrementally
     if (nchunks > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = (uint32_t)((p.a_boxes + ncol_live) * kBoxBytes);
+      const uint32_t tx = p.xh ? (uint32_t)(p.a_boxes * kBoxBytes + xh_live * (p.Wb + 2) * p.Hb * 128)
+                               : (uint32_t)((p.a_boxes + ncol_live) * kBoxBytes);
       int tw_i = chunk_begin % p.tw;
       int th_i = (chunk_begin / p.tw) % p.th;
       int tn_i = chunk_begin / (p.tw * p.th);
@@ -135,6 +148,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           } else {
             tma_load_5d(sa, &tmDY, &full_bar[stage], 0, w0, h0, n0, co_tile * 2);
           }
+          if (p.xh) {
+            // one box per (X block | X row): pixels w0-1 .. w0+Wb of the chunk's Hb rows, shifted by the filter row
+            for (int b = 0; b < xh_live; ++b) {
+              const int cib = p.rowpair ? cib_base : cib_base + b;
+              const int xh_row = p.rowpair ? h0 + (p.rp_dir > 0 ? b + 1 : 0) - p.pad_h : h0 + rg - p.pad_h;
+              if (cib < p.cb0)
+                tma_load_4d(sb + b * kXhBox, &tmX0, &full_bar[stage], cib * 64, w0 - p.pad_w, xh_row, n0);
+              else
+                tma_load_4d(sb + b * kXhBox, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, w0 - p.pad_w, xh_row, n0);
+            }
+          } else
           for (int j = 0; j < ncol_live; ++j) {
             // row-pair mode: group jg reads X row h0 + (jg + 1) - pad_h (filter row jg + 1 for the top half)
             const int jg = p.rowpair ? j / grp_cols : 0;
@@ -173,6 +197,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       const uint64_t desc0 = umma_desc_sw128(0, kBoxBytes, 1024);   // MN-major SW128 descriptor, start address 0
       const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
       const uint32_t desc_lo0 = (uint32_t)desc0;
+      const uint64_t descx0 = umma_desc_sw128(0, kXhBox, 1024);     // X-halo boxes: MN blocks kXhBox apart
+      const uint64_t descx_hi = descx0 & 0xFFFFFFFF00000000ull;
+      const uint32_t descx_lo0 = (uint32_t)descx0;
+      const uint32_t idescx = umma_idesc_bf16(128, xh_live * 64, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < nchunks; ++it) {
@@ -187,6 +215,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           uint32_t b_lo = desc_lo0 + (b_addr >> 4);
           const uint32_t b1_off = (uint32_t)(ncol0 * kBoxBytes) >> 4;
           const int nk = (p.debug_skip & 2) ? 0 : kChunkPix / 16;
+          if (p.xh) {
+            // three taps = three MMAs on the same halo boxes, B start shifted by one pixel (128 B = +8) per tap;
+            // N = all boxes of the stage (kXhBox apart), accumulator columns [tap][box][64]
+            const uint32_t bx_lo = descx_lo0 + (b_addr >> 4);
+            const uint32_t ncx = (uint32_t)(xh_live * 64);
+#pragma unroll
+            for (int k = 0; k < kChunkPix / 16; ++k) {
+              if (k < nk) {
+                const uint64_t da = desc_hi | (uint64_t)(a_lo + 128u * k);
+#pragma unroll
+                // the 16 pixels of this K step sit in box row (16k / Wb), (Wb + 2)-pixel rows, 8 x 16 B per pixel
+                const uint32_t koff = (uint32_t)(((16 * k) / p.Wb) * (p.Wb + 2) + (16 * k) % p.Wb) * 8u;
+#pragma unroll
+                for (int tp = 0; tp < 3; ++tp)
+                  umma_bf16(tmem_base + tp * ncx, da, descx_hi | (uint64_t)(bx_lo + 8u * tp + koff), idescx,
+                            (it | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < kChunkPix / 16; ++k) {
             if (k < nk) {
@@ -220,11 +267,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       tc_fence_after();
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int j = 0; j < ncol_live; ++j) {
+    const int ncol_epi = p.xh ? 3 * xh_live : ncol_live;
+    for (int j = 0; j < ncol_epi; ++j) {
       int tap = rg * p.ksize + (j % p.ksize);
       int cib = cib_base + j / p.ksize;
       bool live = valid;
-      if (p.rowpair) {
+      if (p.xh) {
+        // accumulator columns are [tap s][box b][64]: b = X block (plain) or X row group (row-pair mode)
+        const int sx = j / xh_live, b = j % xh_live;
+        if (p.rowpair) {
+          const int fr = row < 64 ? b + 1 : (b == 0 ? 0 : -1);
+          live = fr >= 0;
+          tap = (fr < 0 ? 0 : fr) * 3 + sx;
+          cib = cib_base;
+        } else {
+          tap = rg * 3 + sx;
+          cib = cib_base + b;
+        }
+      } else if (p.rowpair) {
         // group jg (X row h + jg + 1 - pad): dY row h -> filter row jg + 1, dY row h+1 -> filter row jg; the bottom
         // half of every group but the first repeats a filter row that the previous group already produced
         const int jg = j / grp_cols;
@@ -368,7 +428,16 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   splits = (p.num_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   pl->splits = splits;
   pl->count = (long long)a->cout * p.taps * p.ctot;
-  p.b_stage_bytes = p.ncolb * kBoxBytes;
+  {
+    // X-halo mode: 3x3, unit stride, chunk = 64 consecutive pixels of one image row
+    const char* xe = getenv("B200SEG_WG_XHALO");
+    const int want = xe ? atoi(xe) : 1;
+    // chunk = Hb rows of Wb pixels (64 x 1, 32 x 2, 16 x 4): the halo box has Hb rows of Wb + 2 pixels <= 72 rows
+    p.xh = (want != 0 && a->ksize == 3 && xstride == 1 && !a->custom_pad && p.Nb == 1 && p.Wb >= 16 &&
+            (p.Wb + 2) * p.Hb * 128 <= kXhBox) ? 1 : 0;
+    p.nbox = p.rowpair ? p.rowpair : p.cpb;
+  }
+  p.b_stage_bytes = p.xh ? p.nbox * kXhBox : p.ncolb * kBoxBytes;
   const int stage_bytes = 2 * kBoxBytes + p.b_stage_bytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -424,7 +493,7 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     }
     if (rc) return rc;
   }
-  const int xboxw = pl.p.Wb;
+  const int xboxw = pl.p.xh ? pl.p.Wb + 2 : pl.p.Wb;
   const int xs = pl.p.xstride, xh = a->h * xs, xw = a->w * xs;     // X extent (2x the dY grid for ConvTranspose)
   rc = encode_act_tmap_ex(&tmX0, a->x0, a->c0, a->n, xh, xw, a->ldx0, (long long)a->ldx0 * xw,
                           (long long)a->ldx0 * xw * xh, xboxw, pl.p.Hb, pl.p.Nb, xs);
