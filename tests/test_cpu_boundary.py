@@ -89,3 +89,20 @@ def test_fake_kernels_give_reference_shapes():
         assert ops.upsample2x(y).shape == (2, 64, 64, 128)
         hw = torch.empty(1, 128, 1, 1, device="cuda")
         assert ops.head(y, hw, None).shape == (2, 1, 32, 32)
+
+
+def test_host_side_helpers_degrade_gracefully_without_a_gpu():
+    """kernels.zeros_scratch / step_begin / wgrad_stream are no-ops (plain torch.zeros, same stream) on a machine
+    without CUDA and outside a backward pass — they never touch the library."""
+    import torch
+    from b200seg import kernels as K
+    K.step_begin()
+    z = K.zeros_scratch((2, 8), torch.float64, torch.device("cpu"))
+    assert z.shape == (2, 8) and z.dtype == torch.float64 and float(z.abs().sum()) == 0.0
+    K.set_wgrad_overlap(True)
+    try:
+        with K.wgrad_stream(z):
+            pass
+        assert K.wgrad_side_stream() is None
+    finally:
+        K.set_wgrad_overlap(False)
