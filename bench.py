@@ -131,13 +131,16 @@ class ClockSampler:
 # CPU arm: the oracle port of the reference on the host cores
 # ----------------------------------------------------------------------------------------------------------
 def cpu_reference_steps(model_name, kw, batch, side, steps, warmup, with_optimizer=True):
+    import numpy as np
     import torch
-    from oracle import unet_oracle as O
+    from oracle import unet_oracle as O           # the CPU arm is the one place bench.py may execute oracle/
     from oracle.synthetic import xray_batch
-    from b200seg.models import segmentation_models as M
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
-    sd = {k: v.detach().clone() for k, v in getattr(M, model_name)(**kw).state_dict().items()}
+    # weights: the reference's state_dict layout (recorded from the real modules in tests/golden/) + synthetic fill;
+    # nothing of the CUDA package is imported on this arm
+    lay = np.load(ROOT / "tests" / "golden" / f"{model_name}.npz", allow_pickle=True)
+    sd = O.state_dict_from_layout(lay["keys"], lay["shapes"], lay["dtypes"], seed=0)
     frozen = ("encoder",) if model_name == "ResNetUnet" else ()      # reference default freeze=True
     params = {k: v.requires_grad_(True) for k, v in sd.items()
               if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))
@@ -206,7 +209,7 @@ def run_b200(args):
     from b200seg import _lib, kernels as K, ops
     from b200seg.models import segmentation_models as M
     from b200seg.ddp import GradReducer
-    from oracle.synthetic import xray_batch
+    from b200seg.utils.synthetic import xray_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

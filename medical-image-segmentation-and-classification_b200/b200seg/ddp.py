@@ -43,15 +43,23 @@ class _Bucket:
 class GradReducer:
     """Usage:  reducer = GradReducer(model); ...; loss.backward(); reducer.finish(); optimizer.step()"""
 
-    def __init__(self, model: torch.nn.Module, bucket_mb: float = 32.0, group=None):
+    def __init__(self, model: torch.nn.Module, bucket_mb: float = 32.0, group=None, broadcast: bool = True):
         if not dist.is_initialized():
             raise RuntimeError("GradReducer needs an initialised torch.distributed process group")
         self.group = group
         self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
         self.avg_native = dist.get_backend(group) == "nccl"
         params = [p for p in model.parameters() if p.requires_grad]
         if not params:
             raise ValueError("model has no trainable parameters")
+        if broadcast and self.world > 1:
+            # replicas start identical whatever each rank's seed was (torch DDP does the same): parameters and
+            # buffers (BatchNorm running statistics, num_batches_tracked) come from rank 0 of the group
+            src = dist.get_global_rank(group, 0) if group is not None else 0
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, src=src, group=group)
         device = params[0].device
         cap = int(bucket_mb * (1 << 20) / 4)
         self.buckets: List[_Bucket] = []
@@ -86,12 +94,19 @@ class GradReducer:
         with ctx:
             b.view(i).copy_(p.grad)
             b.pending -= 1
+            assert b.pending >= 0, "two backward passes without GradReducer.finish() in between"
             if b.pending == 0:
                 op = dist.ReduceOp.AVG if self.avg_native else dist.ReduceOp.SUM
                 b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
     def finish(self):
         """Wait for every bucket and store the averaged gradients into param.grad."""
+        if self.buckets[0].flat.is_cuda:
+            # gradients may have been packed on the weight-gradient side stream: what follows on the current stream
+            # (the fallback reductions, the copy-back) is ordered after it, whether or not backward's own join ran
+            from .kernels import wgrad_side_streams
+            for side in wgrad_side_streams():
+                torch.cuda.current_stream().wait_stream(side)
         for b in self.buckets:
             if b.pending != 0:
                 # parameters that received no gradient this step (unused branch): reduce what we have

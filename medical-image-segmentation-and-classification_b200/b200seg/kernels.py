@@ -78,6 +78,24 @@ def wgrad_side_stream():
     return _OVERLAP["side"].get(torch.cuda.current_device())
 
 
+def wgrad_side_streams():
+    """every side stream created so far on the current device (for callers that must order work after them)"""
+    side = _OVERLAP["side"].get(torch.cuda.current_device())
+    return [side] if side is not None else []
+
+
+def grad_is_stolen(weight) -> bool:
+    """True when autograd's AccumulateGrad will adopt the [Cout, taps, Cin] weight-gradient buffer as `weight.grad`
+    without touching it on the main stream: no gradient accumulated yet and the parameter's memory order is the
+    buffer's (channels_last; size-1 dims are free).  Otherwise AccumulateGrad clones / adds on the main stream and a
+    side-stream wgrad kernel would race it — callers then keep the weight gradient on the main stream."""
+    if weight.grad is not None or weight.dim() != 4:
+        return False
+    cout, cin, kh, kw = weight.shape
+    want = (kh * kw * cin, 1, kw * cin, cin)
+    return all(d == 1 or s == w for d, s, w in zip(weight.shape, weight.stride(), want))
+
+
 @contextlib.contextmanager
 def wgrad_stream(*keep, allow=True):
     """Run the enclosed launches on the weight-gradient side stream (ordered after everything already queued on the
@@ -626,7 +644,7 @@ def gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coe
 def loss_fwd(z, t, w_bce=1.0, w_dice=0.0, smooth=1.0):
     assert z.dtype == torch.float32 and t.dtype == torch.float32 and z.is_contiguous() and t.is_contiguous()
     assert z.numel() == t.numel()
-    sums = zeros_scratch((6,), torch.float64, z.device)
+    sums = torch.zeros((6,), dtype=torch.float64, device=z.device)   # an output of seg_loss the caller may keep: not arena memory
     loss = torch.empty((), dtype=torch.float32, device=z.device)
     call("b2_loss_fwd", _p(z), _p(t), z.numel(), _p(sums), _stream())
     call("b2_loss_finalize", _p(sums), z.numel(), float(w_bce), float(w_dice), float(smooth), _p(loss), _stream())

@@ -100,7 +100,7 @@ def conv2d_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, nee
             dx1 = K.conv_igemm(dy, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
     if need_dw:
         x0c, x1c = _c(x0), _c(x1)
-        with K.wgrad_stream(dy, x0c, x1c):
+        with K.wgrad_stream(dy, x0c, x1c, allow=K.grad_is_stolen(weight)):
             dw = K.conv_wgrad(dy, x0c, k, x1=x1c)
     else:
         dw = torch.empty((0,), device=dev)
@@ -341,7 +341,7 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
                 dx0 = K.conv_igemm(dz, wd, c0, k, row_offset=0, dgrad=True)
             if need_dx1 and x1 is not None:
                 dx1 = K.conv_igemm(dz, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
-        with K.wgrad_stream(dz, x0, x1):
+        with K.wgrad_stream(dz, x0, x1, allow=K.grad_is_stolen(weight)):
             if share_count <= 1:
                 dw = K.conv_wgrad(dz, x0, k, x1=x1)
             else:
@@ -476,7 +476,7 @@ def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Te
                          in_off=(a, b), pad=(a, b), alg_scale=2.25)
     else:
         dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)
-    with K.wgrad_stream(dz, x):
+    with K.wgrad_stream(dz, x, allow=K.grad_is_stolen(weight)):
         dweff = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=dev)
         for ph, (a, b) in enumerate(_PHASES):
             K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)

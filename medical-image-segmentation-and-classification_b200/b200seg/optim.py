@@ -6,8 +6,10 @@ Drop-in for the optimizer half of the reference's hot loop (utils/helpers.py:251
     opt = FusedClipAdamW(model.parameters(), lr=lr, weight_decay=5e-4, max_norm=1.0)
     loss.backward(); opt.step()                     # == clip_grad_norm_(params, 1.0); AdamW.step()
 
-It is a torch.optim.Optimizer (param_groups / state_dict / LR schedulers work; the learning rate is mirrored into a
-device scalar so a captured CUDA graph sees scheduler updates).  Gradients may be re-allocated every step
+It is a torch.optim.Optimizer (param_groups / state_dict / load_state_dict / LR schedulers work; the learning rate is
+mirrored into a device scalar so a captured CUDA graph sees scheduler updates).  The moments live in buffers whose
+addresses are baked into the device-side pointer table, so load_state_dict() copies the loaded moments INTO those
+buffers (and restores the step counter, kept as state[p]["step"] like torch.optim.AdamW) instead of swapping tensors.  Gradients may be re-allocated every step
 (zero_grad(set_to_none=True)): the device-side pointer table is refreshed from a pinned staging buffer when any
 pointer changed; inside a CUDA-graph capture the upload is captured too, from a private snapshot of the table.
 """
@@ -40,6 +42,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
             st = self.state[p]
             st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] = torch.zeros((), dtype=torch.float32)        # host mirror, refreshed by state_dict()
         # block -> (tensor, chunk) map
         bt, bc = [], []
         for i, p in enumerate(self._params):
@@ -55,7 +58,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
         self._grad_ptrs = [0] * n
         self._captured_tables = []
         self._sqnorm = torch.zeros((), dtype=torch.float64, device=dev)
-        self._step = torch.zeros((), dtype=torch.float32, device=dev)
+        self._step = torch.zeros((), dtype=torch.float32, device=dev)    # device-side step counter (bias correction)
         self._lr = torch.full((), float(lr), dtype=torch.float32, device=dev)
         self._lr_host = float(lr)
         self.total_norm = torch.zeros((), dtype=torch.float32, device=dev)
@@ -65,6 +68,47 @@ class FusedClipAdamW(torch.optim.Optimizer):
             self._refs_host[i, 2] = st["exp_avg"].data_ptr()
             self._refs_host[i, 3] = st["exp_avg_sq"].data_ptr()
             self._refs_host[i, 4] = p.numel()
+
+    def _moment_buffers(self):
+        return [(self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p in self._params]
+
+    def state_dict(self):
+        """torch.optim.Optimizer.state_dict() with the per-parameter `step` entries filled from the device counter"""
+        step = float(self._step)
+        for p in self._params:
+            self.state[p]["step"] = torch.tensor(step, dtype=torch.float32)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        """The kernels read the moments through a table of raw addresses captured at construction (and possibly baked
+        into a CUDA graph), so the loaded moments are copied into the EXISTING buffers; the step counter is restored
+        from the saved per-parameter `step`."""
+        keep = self._moment_buffers()
+        super().load_state_dict(state_dict)
+        params_now = [p for p in self.param_groups[0]["params"] if p.requires_grad]
+        if len(params_now) != len(self._params):
+            raise ValueError("loaded optimizer state does not match the parameter list")
+        steps = set()
+        for p, (m, v) in zip(self._params, keep):
+            st = self.state[p]
+            if "exp_avg" in st:
+                if st["exp_avg"].shape != m.shape:
+                    raise ValueError("loaded optimizer state has a different parameter shape")
+                if st["exp_avg"].data_ptr() != m.data_ptr():
+                    m.copy_(st["exp_avg"])
+                    v.copy_(st["exp_avg_sq"])
+                steps.add(float(st.get("step", 0.0)))
+            else:                       # a state dict saved before the first step
+                m.zero_()
+                v.zero_()
+                steps.add(0.0)
+            st["exp_avg"], st["exp_avg_sq"] = m, v
+        if len(steps) > 1:
+            raise ValueError(f"FusedClipAdamW keeps one step counter; the loaded state has {sorted(steps)}")
+        self._step.fill_(steps.pop() if steps else 0.0)
+        g = self.param_groups[0]
+        self._lr_host = float(g["lr"])
+        self._lr.fill_(self._lr_host)
 
     def _grad_for(self, p):
         g = p.grad

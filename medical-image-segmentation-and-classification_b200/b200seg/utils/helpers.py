@@ -43,6 +43,14 @@ def iou(pred, mask, t=0.5):
     return (inter / (union + 1e-7)).item()
 
 
+def _dataset_len(dl, fallback):
+    """len(dl.dataset) as the reference divides by (helpers.py:361,367); `fallback` for loaders without a dataset"""
+    try:
+        return len(dl.dataset)
+    except (AttributeError, TypeError):
+        return fallback
+
+
 def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False, cls_head_name=None,
           reducer=None, log=print):
     """helpers.py:231-412, segmentation branch.  Returns the best validation loss."""
@@ -64,57 +72,73 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
     params = [p for p in model.parameters() if p.requires_grad]
     start_time = time.time()
 
-    for epoch in range(1, epochs + 1):
-        model.train()
-        running = torch.zeros((), dtype=torch.float64, device=device)     # no per-step .item() (helpers.py:337)
-        seen = 0
-        for x, y in train_dl:
-            x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
-            optimizer.zero_grad(set_to_none=True)
-            K.step_begin()                                                # one memset for the step's reduction buffers
-            out = model(x)
-            if out.dim() == 3:
-                out = out.unsqueeze(1)
-            loss, _ = ops.seg_loss(out, y, 1.0, 0.0, 1.0)
-            loss.backward()
-            if reducer is not None:
-                reducer.finish()
-            optimizer.step()                                              # clip_grad_norm_(1.0) + AdamW, fused
-            running += loss.detach().double() * x.size(0)
-            seen += x.size(0)
-
-        model.eval()
-        val_loss = torch.zeros((), dtype=torch.float64, device=device)
-        val_iou = torch.zeros((), dtype=torch.float64, device=device)
-        n_val, n_batches = 0, 0
-        with torch.no_grad():
-            for x, y in val_dl:
-                x, y = x.to(device), y.to(device)
+    try:
+        for epoch in range(1, epochs + 1):
+            model.train()
+            running = torch.zeros((), dtype=torch.float64, device=device)     # no per-step .item() (helpers.py:337)
+            seen = 0
+            for x, y in train_dl:
+                x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+                optimizer.zero_grad(set_to_none=True)
+                K.step_begin()                                                # one memset for the step's reduction buffers
                 out = model(x)
                 if out.dim() == 3:
                     out = out.unsqueeze(1)
-                loss, sums = ops.seg_loss(out, y, 1.0, 0.0, 1.0)
-                val_loss += loss.double() * x.size(0)
-                val_iou += sums[4] / (sums[5] + 1e-7)                     # helpers.py:223-227 per batch
-                n_val += x.size(0)
-                n_batches += 1
-        val_loss = float(val_loss) / max(n_val, 1)
-        val_iou_f = float(val_iou) / max(n_batches, 1)
-        log(f"[{name}] Ep{epoch}: TrainLoss {float(running) / max(seen, 1):.3f} | ValLoss {val_loss:.3f} | "
-            f"IoU {val_iou_f:.3f}")
-        improved = val_loss < best_score
-        scheduler.step()
-        if improved:
-            best_score = val_loss
-            patience_counter = 0
-            os.makedirs(save_dir, exist_ok=True)
-            torch.save(model.state_dict(), os.path.join(save_dir, f"{name}_best_loss.pt"))   # helpers.py:394-400
-        else:
-            patience_counter += 1
-        if patience_counter >= patience:
-            log(f"Early stopping at epoch {epoch}. Best score: {best_score:.2f}")
-            break
+                loss, _ = ops.seg_loss(out, y, 1.0, 0.0, 1.0)
+                loss.backward()
+                if reducer is not None:
+                    reducer.finish()
+                optimizer.step()                                              # clip_grad_norm_(1.0) + AdamW, fused
+                running += loss.detach().double() * x.size(0)
+                seen += x.size(0)
 
-    K.set_wgrad_overlap(overlap_before)
+            model.eval()
+            val_loss = torch.zeros((), dtype=torch.float64, device=device)
+            val_iou = torch.zeros((), dtype=torch.float64, device=device)
+            n_val, n_batches = 0, 0
+            with torch.no_grad():
+                for x, y in val_dl:
+                    x, y = x.to(device), y.to(device)
+                    out = model(x)
+                    if out.dim() == 3:
+                        out = out.unsqueeze(1)
+                    loss, sums = ops.seg_loss(out, y, 1.0, 0.0, 1.0)
+                    val_loss += loss.double() * x.size(0)
+                    val_iou += sums[4] / (sums[5] + 1e-7)                     # helpers.py:223-227 per batch
+                    n_val += x.size(0)
+                    n_batches += 1
+            if reducer is not None:
+                # data parallel: every rank must take the SAME improved / patience / early-stop decision (BatchNorm
+                # running statistics are per rank, so local validation losses differ) — decide on the global means
+                import torch.distributed as dist
+                tot = torch.stack([val_loss, val_iou, torch.tensor(float(n_val), dtype=torch.float64, device=device),
+                                   torch.tensor(float(n_batches), dtype=torch.float64, device=device)])
+                dist.all_reduce(tot, group=reducer.group)
+                val_loss, val_iou, n_val, n_batches = tot[0], tot[1], float(tot[2]), float(tot[3])
+                n_train = seen                                   # per-rank shard: samples this rank saw
+            else:
+                # the reference divides by len(dataset) / len(loader) (helpers.py:361-367) — differs from the number of
+                # samples seen when the loader drops the last batch
+                n_val, n_batches = _dataset_len(val_dl, n_val), max(n_batches, 1)
+                n_train = _dataset_len(train_dl, seen)
+            val_loss = float(val_loss) / max(n_val, 1)
+            val_iou_f = float(val_iou) / max(n_batches, 1)
+            log(f"[{name}] Ep{epoch}: TrainLoss {float(running) / max(n_train, 1):.3f} | ValLoss {val_loss:.3f} | "
+                f"IoU {val_iou_f:.3f}")
+            improved = val_loss < best_score
+            scheduler.step()
+            if improved:
+                best_score = val_loss
+                patience_counter = 0
+                if reducer is None or reducer.rank == 0:      # one writer (rank 0's replica, its own BN statistics)
+                    os.makedirs(save_dir, exist_ok=True)
+                    torch.save(model.state_dict(), os.path.join(save_dir, f"{name}_best_loss.pt"))   # helpers.py:394-400
+            else:
+                patience_counter += 1
+            if patience_counter >= patience:
+                log(f"Early stopping at epoch {epoch}. Best score: {best_score:.2f}")
+                break
+    finally:
+        K.set_wgrad_overlap(overlap_before)
     log(f"Training for {name} finished in {(time.time() - start_time) / 60:.2f} minutes.")
     return best_score

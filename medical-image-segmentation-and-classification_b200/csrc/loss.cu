@@ -23,9 +23,10 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
     a[1] += s * ti;
     a[2] += s;
     a[3] += ti;
-    const bool pr = zi > 0.f, tg = ti > 0.5f;
-    a[4] += (pr && tg) ? 1.f : 0.f;
-    a[5] += (pr || tg) ? 1.f : 0.f;
+    // iou() of utils/helpers.py:223-227 on the RAW mask: inter = sum(p * mask), union = #((p + mask) > 0), p in {0,1}
+    const float pf = zi > 0.f ? 1.f : 0.f;
+    a[4] += pf * ti;
+    a[5] += (pf + ti > 0.f) ? 1.f : 0.f;
   }
   __shared__ float sh[6][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -204,6 +204,18 @@ def rrcnn_block(sd, x, prefix, t=2, training=True):
     return _rrcnn_block(c, x, prefix, t), c.new_buffers
 
 
+def recurrent_block(sd, x, prefix, t=2, training=True):
+    """Recurrent_block on its own (R2U_Net.py:4-20)"""
+    c = _Ctx(sd, training)
+    return _recurrent_block(c, x, prefix, t), c.new_buffers
+
+
+def decoder_block(sd, down, skip, prefix, training=True):
+    """DecoderBlock on its own (ResnetUnet.py:17-27)"""
+    c = _Ctx(sd, training)
+    return _decoder_block(c, down, skip, prefix), c.new_buffers
+
+
 # ----------------------------------------------------------------------------------------------------------
 # losses
 # ----------------------------------------------------------------------------------------------------------
@@ -272,3 +284,16 @@ def train_step_grads(name, sd, x, target, training=True, loss="bce", **fw_kwargs
     lval = lf(logits.to(target.dtype) if logits.dtype != target.dtype else logits, target)
     grads = torch.autograd.grad(lval, list(params.values()), allow_unused=True)
     return logits.detach(), lval.detach(), OrderedDict(zip(params.keys(), grads)), newb
+
+
+def state_dict_from_layout(keys, shapes, dtypes, seed=0, float_dtype=torch.float32):
+    """A state_dict with the reference's layout (key order / shapes as stored in tests/golden/<model>.npz by
+    make_golden.py from the real reference modules; shapes are 'd0,d1,..' strings, '' for scalars) and the
+    deterministic synthetic fill — lets the CPU arm of bench.py build its weights without touching the CUDA package's
+    modules.  Floating-point entries get `float_dtype` (the reference's parameters are fp32), integer ones int64."""
+    from .synthetic import fill_state_dict_
+    sd = OrderedDict()
+    for k, shp, dt in zip(keys, shapes, dtypes):
+        dims = tuple(int(d) for d in str(shp).split(",") if d != "")
+        sd[str(k)] = torch.zeros(dims, dtype=float_dtype if "float" in str(dt) else torch.int64)
+    return fill_state_dict_(sd, seed)

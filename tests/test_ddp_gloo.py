@@ -10,8 +10,8 @@ import torch.multiprocessing as mp
 import torch.nn as nn
 
 
-def _model():
-    torch.manual_seed(0)
+def _model(seed=0):
+    torch.manual_seed(seed)
     return nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.BatchNorm2d(8), nn.ReLU(), nn.Conv2d(8, 8, 3, padding=1),
                          nn.BatchNorm2d(8), nn.ReLU(), nn.Conv2d(8, 1, 1))
 
@@ -24,9 +24,13 @@ def _data(rank):
 def _worker(rank, world, initfile, out):
     from b200seg.ddp import GradReducer
     dist.init_process_group("gloo", init_method=f"file://{initfile}", rank=rank, world_size=world)
-    m = _model()
+    m = _model(seed=rank)                           # ranks seed differently: the reducer must broadcast rank 0's replica
+    m[1].running_mean.fill_(float(rank))
     red = GradReducer(m, bucket_mb=0.0005)          # tiny buckets -> several all-reduces, exercising the ordering
     assert len(red.buckets) >= 2
+    ref0 = _model(seed=0)
+    for (k, a), (_, b) in zip(m.state_dict().items(), ref0.state_dict().items()):
+        assert torch.equal(a, b), f"rank {rank}: {k} was not broadcast from rank 0"
     for step in range(2):                           # two steps: buckets must reset correctly
         m.zero_grad(set_to_none=True)
         x, t = _data(rank)

@@ -1,0 +1,171 @@
+"""GPU parity, level (ii) of the pyramid: every building block of the reference on its own, in
+TRAIN mode (batch-statistics BatchNorm), against the fp64 oracle on identical block inputs and a random upstream
+gradient:
+
+    basic_block      AttentionUNet.py:4-13   (also ResnetUnet.py:5-14)
+    Recurrent_block  R2U_Net.py:4-20         t = 2 and the ctor default of the R2 models, t = 5
+    RRCNN_block      R2U_Net.py:36-48
+    DecoderBlock     ResnetUnet.py:17-27
+
+(UpConv and AttentionGate have their block tests in test_gpu_models.py.)
+
+Gates.  Forward <= 1e-2 rel-L2 absolute (north_star).  Gradients: train-mode block gradients are dominated by ReLU-mask
+flips (the reference's OWN bf16 autocast sits at 3e-2 .. 1.4e-1), so they are gated against the
+reference's bf16-autocast deviation measured in the same run on the same inputs: ours <= 1.25x that (+ an absolute
+floor of 2e-2, the north_star gradient tolerance).  Side effects: num_batches_tracked exact (t+1 per Recurrent_block
+forward), running_var within 1e-2.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _sd(module, prefix, dtype):
+    return {prefix + k: (v.detach().to(dtype) if v.is_floating_point() else v.detach().clone())
+            for k, v in module.state_dict().items()}
+
+
+def _is_pre_bn_bias(k):
+    # conv biases that feed a train-mode BatchNorm have an exactly-zero true gradient: rel-L2 is meaningless there
+    return k.endswith(("conv.0.bias", ".0.bias", ".3.bias")) and "conv_1x1" not in k and "up_sample" not in k
+
+
+def _oracle_run(fn, sd, inputs, dy, autocast):
+    """fn(work_sd, *inputs) -> (y, new_buffers); returns y, input grads, param grads, new buffers"""
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and "running" not in k}
+    xs = [x.clone().requires_grad_(True) for x in inputs]
+    work = {**sd, **params}
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y, newb = fn(work, *xs)
+    else:
+        y, newb = fn(work, *xs)
+    grads = torch.autograd.grad(y, xs + list(params.values()), dy.to(y.dtype), allow_unused=True)
+    return y.detach(), list(grads[:len(xs)]), dict(zip(params.keys(), grads[len(xs):])), newb
+
+
+def _check_block(label, module, prefix, fn, inputs, dy, fwd_tol=1e-2):
+    """runs the CUDA module, the fp64 oracle and the bf16-autocast oracle on the same data and applies the gates"""
+    module.train()
+    sd64, sd32 = _sd(module, prefix, torch.float64), _sd(module, prefix, torch.float32)   # BEFORE the forward updates buffers
+    xs = [x.clone().requires_grad_(True) for x in inputs]
+    y = module(*xs)
+    y.backward(dy)
+    ref_y, ref_dx, ref_dp, newb = _oracle_run(fn, sd64, [x.double() for x in inputs], dy.double(), False)
+    fl_y, fl_dx, fl_dp, _ = _oracle_run(fn, sd32, inputs, dy, True)
+    e_y, f_y = rel(y, ref_y), rel(fl_y.float(), ref_y)
+    print(f"{label}: y ours {e_y:.2e} ref-bf16 {f_y:.2e}")
+    assert e_y < fwd_tol, (label, e_y)
+    for i, (xi, r, f) in enumerate(zip(xs, ref_dx, fl_dx)):
+        e, fl = rel(xi.grad, r), rel(f.float(), r)
+        print(f"{label}: d(input{i}) ours {e:.2e} ref-bf16 {fl:.2e}")
+        assert e < max(1.25 * fl, 2e-2), (label, i, e, fl)
+    mine = dict(module.named_parameters())
+    num = den = fnum = 0.0
+    wmax = max(float(g.abs().max()) for k, g in ref_dp.items() if g is not None and k.endswith("weight") and g.dim() == 4)
+    for k, g in ref_dp.items():
+        if g is None:
+            continue
+        m = mine[k[len(prefix):]].grad
+        assert m is not None, k
+        if _is_pre_bn_bias(k):
+            assert float(m.abs().max()) < 1e-2 * wmax + 1e-3, (k, float(m.abs().max()))
+            continue
+        num += float((m.double() - g).norm() ** 2)
+        fnum += float((fl_dp[k].double() - g).norm() ** 2)
+        den += float(g.norm() ** 2)
+    glob, gfloor = (num / den) ** 0.5, (fnum / den) ** 0.5
+    print(f"{label}: global param-grad ours {glob:.2e} ref-bf16 {gfloor:.2e}")
+    assert glob < max(1.25 * gfloor, 2e-2), (label, glob, gfloor)
+    msd = module.state_dict()
+    for k, v in newb.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(msd[k[len(prefix):]]) == int(v), k
+        elif k.endswith("running_var"):
+            assert rel(msd[k[len(prefix):]], v) < 1e-2, k
+        elif k.endswith("running_mean"):
+            assert float((msd[k[len(prefix):]].double() - v).abs().max()) < 1e-2 * (1.0 + float(v.abs().max())), k
+
+
+def _randn(shape, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, device="cuda", generator=g)
+
+
+@pytest.mark.parametrize("cin,cout,h", [(64, 128, 64), (128, 64, 128), (512, 1024, 16), (3, 64, 128)])
+def test_basic_block_train(cin, cout, h):
+    from b200seg import blocks
+    from oracle import unet_oracle as O
+    torch.manual_seed(7)
+    m = blocks.basic_block(cin, cout).cuda()
+    x, dy = _randn((2, cin, h, h), 11), _randn((2, cout, h, h), 12)
+    inputs = [x]
+    if cin == 3:                       # the image stem takes no input gradient on the CUDA path (it is the data)
+        m.train()
+        sd64 = _sd(m, "b.", torch.float64)
+        y = m(x)
+        ref, _ = O.basic_block(sd64, x.double(), "b", training=True)
+        assert rel(y, ref) < 1e-2
+        return
+    _check_block(f"basic_block({cin},{cout})@{h}", m, "b.", lambda sd, v: O.basic_block(sd, v, "b", training=True),
+                 inputs, dy)
+
+
+@pytest.mark.parametrize("c,h,t", [(64, 64, 2), (128, 32, 2), (64, 64, 5), (256, 16, 5)])
+def test_recurrent_block_train(c, h, t):
+    from b200seg import blocks
+    from oracle import unet_oracle as O
+    torch.manual_seed(8)
+    m = blocks.Recurrent_block(c, c, t=t).cuda()
+    x, dy = _randn((2, c, h, h), 13).relu(), _randn((2, c, h, h), 14)
+    _check_block(f"Recurrent_block({c},t={t})@{h}", m, "r.",
+                 lambda sd, v: O.recurrent_block(sd, v, "r", t=t, training=True), [x], dy)
+    assert int(m.conv[1].num_batches_tracked) == t + 1
+
+
+@pytest.mark.parametrize("cin,cout,h,t", [(64, 128, 64, 2), (256, 128, 32, 2), (128, 64, 64, 5)])
+def test_rrcnn_block_train(cin, cout, h, t):
+    from b200seg import blocks
+    from oracle import unet_oracle as O
+    torch.manual_seed(9)
+    m = blocks.RRCNN_block(cin, cout, t=t).cuda()
+    x, dy = _randn((2, cin, h, h), 15), _randn((2, cout, h, h), 16)
+    _check_block(f"RRCNN_block({cin},{cout},t={t})@{h}", m, "q.",
+                 lambda sd, v: O.rrcnn_block(sd, v, "q", t=t, training=True), [x], dy)
+
+
+@pytest.mark.parametrize("cdown,cskip,cout,h", [(256, 64, 64, 32), (512, 256, 256, 16), (2048, 1024, 1024, 8)])
+def test_decoder_block_train(cdown, cskip, cout, h):
+    """DecoderBlock(cin = cdown + cskip, cout): ConvTranspose2d(cdown, cdown, 2, 2) on `down`, cat([up, skip])"""
+    from b200seg.models.segmentation_models.ResnetUnet import DecoderBlock
+    from oracle import unet_oracle as O
+    torch.manual_seed(10)
+    m = DecoderBlock(cdown + cskip, cout).cuda()
+    assert m.up_sample.in_channels == cdown
+    down, skip = _randn((2, cdown, h, h), 17), _randn((2, cskip, 2 * h, 2 * h), 18)
+    dy = _randn((2, cout, 2 * h, 2 * h), 19)
+
+    class Wrap(torch.nn.Module):        # NCHW fp32 in/out around the internal-layout block
+        def __init__(self, blk):
+            super().__init__()
+            self.blk = blk
+
+        def forward(self, d, s):
+            from b200seg import ops
+            return ops.to_nchw(self.blk(ops.to_nhwc(d.contiguous()), ops.to_nhwc(s.contiguous())))
+
+        def named_parameters(self, *a, **k):
+            return self.blk.named_parameters(*a, **k)
+
+        def state_dict(self, *a, **k):
+            return self.blk.state_dict(*a, **k)
+
+    _check_block(f"DecoderBlock({cdown}+{cskip},{cout})@{h}", Wrap(m), "d.",
+                 lambda sd, d, s: O.decoder_block(sd, d, s, "d", training=True), [down, skip], dy)

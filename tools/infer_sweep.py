@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT / "medical-image-segmentation-and-classification_b20
 import torch  # noqa: E402
 
 from b200seg.models.segmentation_models import R2U_Net  # noqa: E402
-from oracle.synthetic import xray_batch  # noqa: E402
+from b200seg.utils.synthetic import xray_batch  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--t", type=int, default=2)

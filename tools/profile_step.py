@@ -12,7 +12,7 @@ import torch  # noqa: E402
 
 from b200seg import kernels as K, ops  # noqa: E402
 from b200seg.models import segmentation_models as M  # noqa: E402
-from oracle.synthetic import xray_batch  # noqa: E402
+from b200seg.utils.synthetic import xray_batch  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="AttentionUNet")
