@@ -41,6 +41,16 @@ int b2_abi_version(void);
 int b2_arch_check(void);   /* 0 iff the current device is sm_100; B2_ERR_ARCH otherwise */
 int b2_num_sms(void);
 
+/* Deterministic-reduction mode (cuDNN's BatchNorm in the reference, AttentionUNet.py:7, is
+ * run-to-run reproducible; fp64/fp32 atomics are not).  With a workspace registered for the current device every
+ * kernel that would end in cross-block atomics — the BatchNorm statistics of the conv epilogue, the BatchNorm /
+ * gate backward sums, bias and head gradients, the loss sums, the gradient norm — writes one row of per-block
+ * partials into it and a second tiny kernel adds the rows in block order, so two runs on the same inputs are
+ * bit-identical.  The workspace (>= 1 MiB, 64 MiB covers every shape of the four models) is used by the launches
+ * of ONE compute stream at a time; NULL switches the mode off.  b2_get_deterministic() -> 0 | 1. */
+int b2_set_deterministic(void* workspace, int64_t bytes);
+int b2_get_deterministic(void);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution, ksize in {1,3} with 'same' padding (stride 1 or 2) or ksize 2 / stride 2 / no padding (the input
  * gradient of ConvTranspose2d(k=2,s=2)): implicit GEMM on tcgen05 (TMA -> 128B-swizzled smem ->

@@ -177,7 +177,42 @@ def zeros_scratch(shape, dtype, device):
     return st["buf"][off:off + nbytes].view(dtype).view(shape)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Deterministic-reduction mode (b2_set_deterministic): per-block partials + fixed-order second stage instead of
+# atomics, so that two runs on the same inputs are bit-identical (set_deterministic(True) or B200SEG_DETERMINISTIC=1).
+# The workspace belongs to the launches of one compute stream at a time; the weight-gradient side stream only runs
+# the (always deterministic) wgrad kernels and never touches it.
+# ----------------------------------------------------------------------------------------------------------
+_DET = {"want": os.environ.get("B200SEG_DETERMINISTIC", "0") == "1", "bufs": {}, "bytes": 64 << 20}
+
+
+def set_deterministic(flag: bool) -> None:
+    _DET["want"] = bool(flag)
+    if torch.cuda.is_available():
+        _sync_deterministic()
+
+
+def deterministic_enabled() -> bool:
+    return _DET["want"]
+
+
+def _sync_deterministic():
+    """register / drop the workspace of the current device so that the library state follows _DET['want']"""
+    dev = torch.cuda.current_device()
+    have = dev in _DET["bufs"]
+    if _DET["want"] and not have:
+        buf = torch.empty(_DET["bytes"], dtype=torch.uint8, device=f"cuda:{dev}")
+        _lib.check(_lib.load().b2_set_deterministic(C.c_void_p(buf.data_ptr()), buf.numel()), "b2_set_deterministic")
+        _DET["bufs"][dev] = buf
+    elif not _DET["want"] and have:
+        _lib.check(_lib.load().b2_set_deterministic(C.c_void_p(0), 0), "b2_set_deterministic")
+        torch.cuda.synchronize(dev)          # no launch may still be writing partials when the buffer is freed
+        del _DET["bufs"][dev]
+
+
 def _stream():
+    if _DET["want"] != (torch.cuda.current_device() in _DET["bufs"]):
+        _sync_deterministic()
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -54,7 +54,7 @@ __device__ __forceinline__ void rows_reduce8(float* acc, int tpp, int rows, int 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) channel_stats_kernel(const __nv_bfloat16* __restrict__ z, int ldz,
                                                                long long npix, int C, ChanMap m,
-                                                               double* __restrict__ stats, int want_sq) {
+                                                               double* __restrict__ stats, int want_sq, DetBuf det) {
   __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(kBlock) channel_stats_kernel(const __nv_bfloat
   rows_reduce8(s, m.tpp, m.rows, g, r, active, red);
   if (active && r == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&stats[g * 8 + j], (double)s[j]);
+    for (int j = 0; j < 8; ++j) red_out(stats, det, g * 8 + j, (double)s[j]);
   }
   if (want_sq) {
     rows_reduce8(q, m.tpp, m.rows, g, r, active, red);
     if (active && r == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&stats[C + g * 8 + j], (double)q[j]);
+      for (int j = 0; j < 8; ++j) red_out(stats, det, C + g * 8 + j, (double)q[j]);
     }
   }
 }
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kBlock) channel_stats_kernel(const __nv_bfloat
 // db[c] = sum_p dy[p][c]  (two-stage: fp64 scratch is avoided by a single-block-per-channel-slab final pass)
 __global__ void __launch_bounds__(kBlock) channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                              long long npix, int C, ChanMap m,
-                                                             float* __restrict__ db) {
+                                                             float* __restrict__ db, DetBuf det) {
   __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kBlock) channel_sum_kernel(const __nv_bfloat16
   rows_reduce8(s, m.tpp, m.rows, g, r, active, red);
   if (active && r == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&db[g * 8 + j], s[j]);
+    for (int j = 0; j < 8; ++j) red_out(db, det, g * 8 + j, s[j]);
   }
 }
 
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* _
 __global__ void __launch_bounds__(kBlock, 3) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
-    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums) {
+    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums,
+    DetBuf det) {
   __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -278,8 +279,8 @@ __global__ void __launch_bounds__(kBlock, 3) bn_bwd_reduce_kernel(
       const int c = g * 8 + j;
       const double a0 = (double)keep0[j];
       const double a1 = (double)invstd[c] * ((double)s1[j] - (double)mean[c] * a0);
-      atomicAdd(&sums[c], a0);
-      atomicAdd(&sums[C + c], a1);
+      red_out(sums, det, c, a0);
+      red_out(sums, det, C + c, a1);
     }
   }
 }
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kBlock, 2) bn_bwd_apply_kernel(
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
     int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, DetBuf det) {
   __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kBlock, 2) bn_bwd_apply_kernel(
     rows_reduce8(bsum, m.tpp, m.rows, g, r, active, red);
     if (active && r == 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&dbias[g * 8 + j], bsum[j]);
+      for (int j = 0; j < 8; ++j) red_out(dbias, det, g * 8 + j, bsum[j]);
     }
   }
 }
@@ -405,7 +406,8 @@ static constexpr int kLightPix = 4;     // pixels in flight per thread
 __global__ void __launch_bounds__(kBlock, 4) bn_bwd_reduce_light_kernel(
     const __nv_bfloat16* __restrict__ dy, int lddy, const __nv_bfloat16* __restrict__ z, int ldz, long long npix,
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
-    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums) {
+    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums,
+    DetBuf det) {
   __shared__ float red[kBlock * 4];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -452,8 +454,8 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_reduce_light_kernel(
       const int c = g * 4 + j;
       const double a0 = (double)keep0[j];
       const double a1 = (double)invstd[c] * ((double)s1[j] - (double)mean[c] * a0);
-      atomicAdd(&sums[c], a0);
-      atomicAdd(&sums[C + c], a1);
+      red_out(sums, det, c, a0);
+      red_out(sums, det, C + c, a1);
     }
   }
 }
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_apply_light_kernel(
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
     int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, DetBuf det) {
   __shared__ float red[kBlock * 4];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_apply_light_kernel(
     rows_reduce4(bsum, m.tpp, m.rows, g, r, active, red);
     if (active && r == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(&dbias[g * 4 + j], bsum[j]);
+      for (int j = 0; j < 4; ++j) red_out(dbias, det, g * 4 + j, bsum[j]);
     }
   }
 }
@@ -572,9 +574,14 @@ extern "C" int b2_channel_stats(const void* z, int32_t ldz, int64_t npix, int32_
   int rc = make_map(c, &m);
   if (rc) return rc;
   B2_REQUIRE(aligned16(z, ldz), B2_ERR_ALIGN, "z misaligned");
-  channel_stats_kernel<<<chan_grid(npix, m, 8), kBlock, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)z, ldz, npix, c, m, stats, 1);
+  const int grid = chan_grid(npix, m, 8);
+  DetBuf det;
+  rc = det_begin(&det, grid, 2 * c, (cudaStream_t)stream);
+  if (rc) return rc;
+  channel_stats_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, ldz, npix, c, m, stats, 1,
+                                                                  det);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, 2 * c, stats, (cudaStream_t)stream);
   return B2_OK;
 }
 
@@ -585,9 +592,13 @@ extern "C" int b2_channel_sum(const void* dy, int32_t lddy, int64_t npix, int32_
   if (rc) return rc;
   B2_REQUIRE(aligned16(dy, lddy), B2_ERR_ALIGN, "dy misaligned");
   B2_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, (cudaStream_t)stream));
-  channel_sum_kernel<<<chan_grid(npix, m, 8), kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
-                                                                                 npix, c, m, db);
+  const int grid = chan_grid(npix, m, 8);
+  DetBuf det;
+  rc = det_begin(&det, grid, c, (cudaStream_t)stream);
+  if (rc) return rc;
+  channel_sum_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy, npix, c, m, db, det);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, c, db, (cudaStream_t)stream);
   return B2_OK;
 }
 
@@ -639,17 +650,22 @@ extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int
   if (rc) return rc;
   B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz), B2_ERR_ALIGN, "bn_bwd_reduce operands misaligned");
   ChanMap lm;
-  if (light_map(c, &lm)) {
-    bn_bwd_reduce_light_kernel<<<chan_grid(npix, lm, 8), kBlock, 0, (cudaStream_t)stream>>>(
+  const bool light = light_map(c, &lm);
+  const int grid = light ? chan_grid(npix, lm, 8) : chan_grid(npix, m, 4);
+  DetBuf det;
+  rc = det_begin(&det, grid, 2 * c, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (light) {
+    bn_bwd_reduce_light_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, relu,
-        sums);
-    B2_LAUNCH_CHECK();
-    return B2_OK;
+        sums, det);
+  } else {
+    bn_bwd_reduce_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, relu,
+        sums, det);
   }
-  bn_bwd_reduce_kernel<<<chan_grid(npix, m, 4), kBlock, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, relu,
-      sums);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, 2 * c, sums, (cudaStream_t)stream);
   return B2_OK;
 }
 
@@ -663,16 +679,25 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
   B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz) && aligned16(dz, lddz), B2_ERR_ALIGN,
              "bn_bwd_apply operands misaligned");
   ChanMap lm;
-  if (light_map(c, &lm)) {
-    bn_bwd_apply_light_kernel<<<chan_grid(npix, lm, 8), kBlock, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, gamma,
-        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias);
-    B2_LAUNCH_CHECK();
-    return B2_OK;
+  const bool light = light_map(c, &lm);
+  const int grid = light ? chan_grid(npix, lm, 8) : chan_grid(npix, m, 4);
+  DetBuf det;
+  det.partial = nullptr;
+  det.n = c;
+  if (dbias != nullptr) {
+    rc = det_begin(&det, grid, c, (cudaStream_t)stream);
+    if (rc) return rc;
   }
-  bn_bwd_apply_kernel<<<chan_grid(npix, m, 4), kBlock, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
-      relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias);
+  if (light) {
+    bn_bwd_apply_light_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, gamma,
+        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det);
+  } else {
+    bn_bwd_apply_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
+        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det);
+  }
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, c, dbias, (cudaStream_t)stream);
   return B2_OK;
 }

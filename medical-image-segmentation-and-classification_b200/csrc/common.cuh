@@ -39,10 +39,33 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
                      const uint32_t* elem_strides = nullptr);
 
+// ---------------------------------------------------------------------------------------------
+// Deterministic-reduction mode (b2_set_deterministic, include/b200seg.h).  Kernels whose last step is a cross-block
+// atomicAdd write ONE ROW of per-block partials into the registered workspace instead; det_finish adds the rows to the
+// destination in block order.  With the mode off (`partial == nullptr`) the kernels use their atomics.
+// ---------------------------------------------------------------------------------------------
+struct DetBuf {
+  double* partial;   // [rows][n] or nullptr
+  int n;             // row length in doubles
+};
+// Reserve (and zero) rows*n doubles of the workspace for a launch on `stream`.  out->partial stays nullptr when the
+// mode is off.  Consecutive reservations of ONE entry point may coexist (`keep` = doubles already reserved by it).
+int det_begin(DetBuf* out, long long rows, int n, cudaStream_t stream, long long keep = 0);
+// dst[i] += sum over rows r (in order) of partial[r * row_stride + i], i < count
+int det_finish(const double* partial, long long rows, int row_stride, int count, double* dst, cudaStream_t stream);
+int det_finish(const double* partial, long long rows, int row_stride, int count, float* dst, cudaStream_t stream);
+bool det_enabled();
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
+// final cross-block accumulation of a per-block value: atomics, or this block's slot of the partial rows
+template <typename T>
+__device__ __forceinline__ void red_out(T* dst, const DetBuf& d, int idx, T v) {
+  if (d.partial != nullptr) d.partial[(size_t)blockIdx.x * d.n + idx] = (double)v;
+  else atomicAdd(dst + idx, v);
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }

@@ -70,6 +70,7 @@ struct IgemmParams {
   const __nv_bfloat16* addend;
   int ldadd;
   double* stats;
+  double* stats_partial;   // deterministic mode: [gridDim.x * epi_groups][2 * cout] rows, one per (CTA, epilogue group)
   int relu;
   int add_after_act;
 };
@@ -362,7 +363,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) v += red[(w * 2 + which) * p.block_n + c];
-        atomicAdd(&p.stats[which * p.cout + n_tile_ * p.block_n + (p.rp ? (c & 63) : c)], v);
+        const int sidx = which * p.cout + n_tile_ * p.block_n + (p.rp ? (c & 63) : c);
+        if (p.stats_partial != nullptr)      // this thread owns slot sidx of this (CTA, group) row for the whole launch
+          p.stats_partial[(size_t)(blockIdx.x * p.epi_groups + g) * (2 * p.cout) + sidx] += v;
+        else
+          atomicAdd(&p.stats[sidx], v);
       }
       // (the staging tile is next written after another group barrier, see the tile loop)
 #pragma unroll
@@ -659,7 +664,8 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.base_off_mode = (halo_env == 2) ? 1 : 0;
   p.tma_store = env_int("B200SEG_TMA_STORE", 1) != 0 ? 1 : 0;
   p.rp = (p.halo && a->cout == 64 && p.block_n == 64 && a->h % 2 == 0 && a->addend == nullptr && out_mul == 1 &&
-          in_mul == 1 && p.tma_store && env_int("B200SEG_FPROP_ROWPAIR", 0) != 0) ? 1 : 0;   // opt-in, see below
+          in_mul == 1 && p.tma_store && env_int("B200SEG_FPROP_ROWPAIR", 0) != 0 &&
+          !(a->stats != nullptr && det_enabled())) ? 1 : 0;   // opt-in, see below (two columns share a statistics slot)
   // Row-pair mode is parity-tested but off by default: it makes the Cout = 64 MMAs N = 128 (isolated: 64->64 @256^2
   // 0.390 -> 0.366 ms, 128->64 0.711 -> 0.680 ms) but streams 192 KB of stacked weights per tile pair from L2, and
   // inside the training step, where the side-stream weight gradients load the same fabric, the gain vanishes.
@@ -841,11 +847,20 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  DetBuf det;
+  det.partial = nullptr;
+  const long long det_rows = (long long)clusters * C * p.epi_groups;
+  if (p.stats != nullptr) {
+    rc = det_begin(&det, det_rows, 2 * p.cout, stream);
+    if (rc) return rc;
+  }
+  p.stats_partial = det.partial;
   if (p.addend != nullptr)
     B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmA0, tmA1, tmB, tmY, p));
   else
     B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA0, tmA1, tmB, tmY, p));
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, det_rows, 2 * p.cout, 2 * p.cout, p.stats, stream);
   return B2_OK;
 }
 

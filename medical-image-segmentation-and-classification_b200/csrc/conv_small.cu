@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) smallc_fprop_kernel(const uint2* __restri
 template <int KS>
 __global__ void __launch_bounds__(256) smallc_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                            const uint2* __restrict__ x4, int n, int h, int w,
-                                                           float* __restrict__ dw) {
+                                                           float* __restrict__ dw, DetBuf det) {
   constexpr int TAPS = KS * KS;
   constexpr int NC = TAPS * 4;                 // im2col columns
   constexpr int CPG = (NC + 3) / 4;            // columns per thread group (9 or 1)
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) smallc_wgrad_kernel(const __nv_bfloat16* 
 #pragma unroll
   for (int k = 0; k < CPG; ++k) {
     const int col = grp * CPG + k;
-    if (col < NC) atomicAdd(&dw[(size_t)co * NC + col], acc[k]);
+    if (col < NC) red_out(dw, det, co * NC + col, acc[k]);
   }
 }
 
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        long long npix, int hw, int cin,
                                                        const float* __restrict__ w, int cout, int L,
                                                        __nv_bfloat16* __restrict__ dx, int lddx,
-                                                       float* __restrict__ dw, float* __restrict__ db) {
+                                                       float* __restrict__ dw, float* __restrict__ db, DetBuf det) {
   extern __shared__ float sacc[];   // [cout][cin] + [cout]
   for (int i = threadIdx.x; i < cout * cin + cout; i += blockDim.x) sacc[i] = 0.f;
   __syncthreads();
@@ -233,19 +233,40 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                      pack_bf16x2(g[6], g[7]));
     }
   }
-  if (has) {
+  if (det.partial == nullptr) {
+    if (has) {
 #pragma unroll
-    for (int co = 0; co < CO; ++co) {
-      if (co < cout) {
+      for (int co = 0; co < CO; ++co) {
+        if (co < cout) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&sacc[co * cin + lig * 8 + j], aw[co][j]);
-        if (lig == 0) atomicAdd(&sacc[cout * cin + co], ab[co]);
+          for (int j = 0; j < 8; ++j) atomicAdd(&sacc[co * cin + lig * 8 + j], aw[co][j]);
+          if (lig == 0) atomicAdd(&sacc[cout * cin + co], ab[co]);
+        }
       }
+    }
+  } else {
+    // deterministic mode: the pixel groups of the block add their sums one after the other (fixed order)
+    for (int gsel = 0; gsel < gpb; ++gsel) {
+      if (grp == gsel && has) {
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          if (co < cout) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sacc[co * cin + lig * 8 + j] += aw[co][j];
+            if (lig == 0) sacc[cout * cin + co] += ab[co];
+          }
+        }
+      }
+      __syncthreads();
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) atomicAdd(&dw[i], sacc[i]);
-  for (int i = threadIdx.x; i < cout; i += blockDim.x) atomicAdd(&db[i], sacc[cout * cin + i]);
+  // partial-row layout in deterministic mode: [0, cout*cin) = dw, [cout*cin, cout*cin + cout) = db
+  for (int i = threadIdx.x; i < cout * cin + cout; i += blockDim.x) {
+    if (det.partial != nullptr) det.partial[(size_t)blockIdx.x * det.n + i] = (double)sacc[i];
+    else if (i < cout * cin) atomicAdd(&dw[i], sacc[i]);
+    else atomicAdd(&db[i - cout * cin], sacc[i]);
+  }
 }
 
 static int pow2ceil(int v) {
@@ -288,13 +309,18 @@ extern "C" int b2_conv_smallc_wgrad(const void* dy, int32_t lddy, const void* x4
   const long long tiles = ((long long)n * h * w + 127) / 128;
   long long grid = (long long)num_sms() * 5;
   if (grid > tiles) grid = tiles;
+  const int ncol = cout * ksize * ksize * 4;
+  DetBuf det;
+  int rc = det_begin(&det, grid, ncol, (cudaStream_t)stream);
+  if (rc) return rc;
   if (ksize == 3)
     smallc_wgrad_kernel<3><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
-                                                                             (const uint2*)x4, n, h, w, dw);
+                                                                             (const uint2*)x4, n, h, w, dw, det);
   else
     smallc_wgrad_kernel<1><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy,
-                                                                             (const uint2*)x4, n, h, w, dw);
+                                                                             (const uint2*)x4, n, h, w, dw, det);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, ncol, dw, (cudaStream_t)stream);
   return B2_OK;
 }
 
@@ -330,10 +356,18 @@ extern "C" int b2_head_bwd(const float* dy, const void* x, int32_t ldx, int64_t 
   const long long cap = (long long)num_sms() * 16;
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)(cout * cin + cout) * sizeof(float);
+  DetBuf det;
+  int rc = det_begin(&det, grid, cout * cin + cout, (cudaStream_t)stream);
+  if (rc) return rc;
 #define B2_HEAD_BWD(CO) head_bwd_kernel<CO><<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>( \
-      dy, (const __nv_bfloat16*)x, ldx, npix, hw, cin, w, cout, L, (__nv_bfloat16*)dx, lddx, dw, db)
+      dy, (const __nv_bfloat16*)x, ldx, npix, hw, cin, w, cout, L, (__nv_bfloat16*)dx, lddx, dw, db, det)
   if (cout == 1) B2_HEAD_BWD(1); else if (cout == 2) B2_HEAD_BWD(2); else if (cout <= 4) B2_HEAD_BWD(4); else B2_HEAD_BWD(8);
 #undef B2_HEAD_BWD
   B2_LAUNCH_CHECK();
+  if (det.partial) {
+    rc = det_finish(det.partial, grid, det.n, cout * cin, dw, (cudaStream_t)stream);
+    if (rc) return rc;
+    return det_finish(det.partial + cout * cin, grid, det.n, cout, db, (cudaStream_t)stream);
+  }
   return B2_OK;
 }

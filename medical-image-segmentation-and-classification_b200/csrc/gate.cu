@@ -25,8 +25,8 @@ __device__ __forceinline__ void g_load8(const float* p, bool has, float* f) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// block-wide sum of two floats held by arbitrary threads -> fp64 atomics
-__device__ __forceinline__ void block_sum2_atomic(float a, float b, double* out0, double* out1) {
+// block-wide sum of two floats held by arbitrary threads -> dst[0], dst[1] (fp64 atomics, or the block's partial row)
+__device__ __forceinline__ void block_sum2_out(float a, float b, double* dst, const DetBuf& det) {
   __shared__ float sh[2][8];
   a = warp_sum(a);
   b = warp_sum(b);
@@ -42,8 +42,8 @@ __device__ __forceinline__ void block_sum2_atomic(float a, float b, double* out0
       ta += sh[0][i];
       tb += sh[1][i];
     }
-    atomicAdd(out0, (double)ta);
-    atomicAdd(out1, (double)tb);
+    red_out(dst, det, 0, (double)ta);
+    red_out(dst, det, 1, (double)tb);
   }
 }
 
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
     const __nv_bfloat16* __restrict__ g1p, const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint,
     int L, const float* __restrict__ scale_g, const float* __restrict__ shift_g, const float* __restrict__ scale_x,
     const float* __restrict__ shift_x, const float* __restrict__ wpsi, const float* __restrict__ bpsi,
-    __nv_bfloat16* __restrict__ q, double* __restrict__ qstats) {
+    __nv_bfloat16* __restrict__ q, double* __restrict__ qstats, DetBuf det) {
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
   const bool has = lig * 8 < fint;
   float sg[8], hg[8], sx[8], hx[8], wp[8];
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
       lsq += qf * qf;
     }
   }
-  block_sum2_atomic(lsum, lsq, &qstats[0], &qstats[1]);
+  block_sum2_out(lsum, lsq, qstats, det);
 }
 
 // forward phase C: psi = sigmoid(bn1(q)); out = x * psi      (thread owns an 8-channel group, walks pixels)
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
     const __nv_bfloat16* __restrict__ dout, int lddout, const __nv_bfloat16* __restrict__ x, int ldx,
     const __nv_bfloat16* __restrict__ psi, const __nv_bfloat16* __restrict__ q, long long npix, int cg, int L,
     const float* __restrict__ mean1, const float* __restrict__ invstd1, __nv_bfloat16* __restrict__ dx, int lddx,
-    float* __restrict__ dsig, double* __restrict__ sums1) {
+    float* __restrict__ dsig, double* __restrict__ sums1, DetBuf det) {
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
   const float mu1 = __ldg(mean1), is1 = __ldg(invstd1);
   float l0 = 0.f, l1 = 0.f;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
       }
     }
   }
-  block_sum2_atomic(l0, l1, &sums1[0], &sums1[1]);
+  block_sum2_out(l0, l1, sums1, det);
 }
 
 struct GateBwdCoef {
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kerne
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int L, GateBwdCoef c,
     const double* __restrict__ sums1, int training, double* __restrict__ sums, float* __restrict__ dwpsi,
-    float* __restrict__ dbpsi) {
+    float* __restrict__ dbpsi, DetBuf det) {
   using VT = typename GVec<V>::T;
   extern __shared__ float red[];   // [4][fint] + 1
   for (int i = threadIdx.x; i < 4 * fint + 1; i += blockDim.x) red[i] = 0.f;
@@ -302,24 +302,47 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kerne
         if (lig == 0) abp += dq;
       }
     }
+    if (det.partial == nullptr) {
 #pragma unroll
-    for (int j = 0; j < V; ++j) {
-      atomicAdd(&red[0 * fint + lig * V + j], ab[j]);
-      atomicAdd(&red[1 * fint + lig * V + j], agg[j] * __ldg(c.invstd_g + lig * V + j));
-      atomicAdd(&red[2 * fint + lig * V + j], agx[j] * __ldg(c.invstd_x + lig * V + j));
-      atomicAdd(&red[3 * fint + lig * V + j], aw[j]);
+      for (int j = 0; j < V; ++j) {
+        atomicAdd(&red[0 * fint + lig * V + j], ab[j]);
+        atomicAdd(&red[1 * fint + lig * V + j], agg[j] * __ldg(c.invstd_g + lig * V + j));
+        atomicAdd(&red[2 * fint + lig * V + j], agx[j] * __ldg(c.invstd_x + lig * V + j));
+        atomicAdd(&red[3 * fint + lig * V + j], aw[j]);
+      }
+      if (lig == 0) atomicAdd(&red[4 * fint], abp);
     }
-    if (lig == 0) atomicAdd(&red[4 * fint], abp);
+  }
+  if (det.partial != nullptr) {
+    // deterministic mode: the pixel groups of the block add their sums one after the other (fixed order)
+    for (int gsel = 0; gsel < gpb; ++gsel) {
+      if (grp == gsel && has) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          red[0 * fint + lig * V + j] += ab[j];
+          red[1 * fint + lig * V + j] += agg[j] * __ldg(c.invstd_g + lig * V + j);
+          red[2 * fint + lig * V + j] += agx[j] * __ldg(c.invstd_x + lig * V + j);
+          red[3 * fint + lig * V + j] += aw[j];
+        }
+        if (lig == 0) red[4 * fint] += abp;
+      }
+      __syncthreads();
+    }
   }
   __syncthreads();
+  // partial-row layout in deterministic mode: [0, 4 fint) = sums, [4 fint, 5 fint) = dwpsi, [5 fint] = dbpsi
   for (int i = threadIdx.x; i < fint; i += blockDim.x) {
-    atomicAdd(&sums[0 * fint + i], (double)red[0 * fint + i]);   // dbeta_g
-    atomicAdd(&sums[1 * fint + i], (double)red[1 * fint + i]);   // dgamma_g
-    atomicAdd(&sums[2 * fint + i], (double)red[0 * fint + i]);   // dbeta_x (same upstream gradient)
-    atomicAdd(&sums[3 * fint + i], (double)red[2 * fint + i]);   // dgamma_x
-    atomicAdd(&dwpsi[i], red[3 * fint + i]);
+    red_out(sums, det, 0 * fint + i, (double)red[0 * fint + i]);   // dbeta_g
+    red_out(sums, det, 1 * fint + i, (double)red[1 * fint + i]);   // dgamma_g
+    red_out(sums, det, 2 * fint + i, (double)red[0 * fint + i]);   // dbeta_x (same upstream gradient)
+    red_out(sums, det, 3 * fint + i, (double)red[2 * fint + i]);   // dgamma_x
+    if (det.partial != nullptr) det.partial[(size_t)blockIdx.x * det.n + 4 * fint + i] = (double)red[3 * fint + i];
+    else atomicAdd(&dwpsi[i], red[3 * fint + i]);
   }
-  if (threadIdx.x == 0) atomicAdd(dbpsi, red[4 * fint]);
+  if (threadIdx.x == 0) {
+    if (det.partial != nullptr) det.partial[(size_t)blockIdx.x * det.n + 5 * fint] = (double)red[4 * fint];
+    else atomicAdd(dbpsi, red[4 * fint]);
+  }
 }
 
 // backward phase 3: gradients w.r.t. the two pre-BN GEMM outputs.  Per channel the BatchNorm backward collapses to
@@ -333,7 +356,7 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_apply_kernel
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int tpp, int rows, GateBwdCoef c,
     const double* __restrict__ sums1, int training, const double* __restrict__ sums,
     __nv_bfloat16* __restrict__ dg1p, __nv_bfloat16* __restrict__ dx1p, float* __restrict__ dgamma_beta,
-    float* __restrict__ dbn1, float* __restrict__ dbias) {
+    float* __restrict__ dbn1, float* __restrict__ dbias, DetBuf det) {
   using VT = typename GVec<V>::T;
   __shared__ float red[256 * V];
   const int gch = threadIdx.x % tpp, r = threadIdx.x / tpp;
@@ -439,7 +462,7 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_apply_kernel
         for (int j = 0; j < V; ++j) {
           float s = 0.f;
           for (int rr = 0; rr < rows; ++rr) s += red[(rr * tpp + gch) * V + j];
-          atomicAdd(&dbias[which * fint + gch * V + j], s);
+          red_out(dbias, det, which * fint + gch * V + j, s);
         }
       }
     }
@@ -479,10 +502,15 @@ extern "C" int b2_gate_psi_fwd(const void* g1p, const void* x1p, int32_t ld, int
   B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld), B2_ERR_ALIGN, "gate operands misaligned");
   const int L = g_pow2ceil(fint / 8);
-  gate_psi_fwd_kernel<<<g_grid(npix, 256 / L, 8), 256, 0, (cudaStream_t)stream>>>(
+  const int grid = g_grid(npix, 256 / L, 8);
+  DetBuf det;
+  int rc = det_begin(&det, grid, 2, (cudaStream_t)stream);
+  if (rc) return rc;
+  gate_psi_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L, scale_g, shift_g, scale_x, shift_x,
-      wpsi, bpsi, (__nv_bfloat16*)q, qstats);
+      wpsi, bpsi, (__nv_bfloat16*)q, qstats, det);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, 2, qstats, (cudaStream_t)stream);
   return B2_OK;
 }
 
@@ -506,10 +534,15 @@ extern "C" int b2_gate_apply_bwd(const void* dout, int32_t lddout, const void* x
   B2_REQUIRE(g_al(dout, lddout) && g_al(x, ldx) && g_al(dx, lddx), B2_ERR_ALIGN, "gate operands misaligned");
   int L = g_pow2ceil(c / 8);
   if (L > 32) L = 32;
-  gate_apply_bwd_kernel<<<g_grid(npix, 256 / L, 8), 256, 0, (cudaStream_t)stream>>>(
+  const int grid = g_grid(npix, 256 / L, 8);
+  DetBuf det;
+  int rc = det_begin(&det, grid, 2, (cudaStream_t)stream);
+  if (rc) return rc;
+  gate_apply_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)dout, lddout, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)psi,
-      (const __nv_bfloat16*)q, npix, c / 8, L, mean1, invstd1, (__nv_bfloat16*)dx, lddx, dsig, sums1);
+      (const __nv_bfloat16*)q, npix, c / 8, L, mean1, invstd1, (__nv_bfloat16*)dx, lddx, dsig, sums1, det);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, 2, sums1, (cudaStream_t)stream);
   return B2_OK;
 }
 
@@ -531,18 +564,29 @@ extern "C" int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const vo
   B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld), B2_ERR_ALIGN, "gate operands misaligned");
   const size_t smem = (size_t)(4 * fint + 1) * sizeof(float);
-  if (gate_light(fint)) {
-    const int L = g_pow2ceil(fint / 4);
-    gate_psi_bwd_reduce_kernel<4><<<g_grid(npix, 256 / L, 8), 256, smem, (cudaStream_t)stream>>>(
+  const bool light = gate_light(fint);
+  const int L = g_pow2ceil(fint / (light ? 4 : 8));
+  const int grid = g_grid(npix, 256 / L, light ? 8 : 4);
+  DetBuf det;
+  int rc = det_begin(&det, grid, 5 * fint + 1, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (light) {
+    gate_psi_bwd_reduce_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi);
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, det);
   } else {
-    const int L = g_pow2ceil(fint / 8);
-    gate_psi_bwd_reduce_kernel<8><<<g_grid(npix, 256 / L, 4), 256, smem, (cudaStream_t)stream>>>(
+    gate_psi_bwd_reduce_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi);
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, det);
   }
   B2_LAUNCH_CHECK();
+  if (det.partial) {
+    rc = det_finish(det.partial, grid, det.n, 4 * fint, sums, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = det_finish(det.partial + 4 * fint, grid, det.n, fint, dwpsi, (cudaStream_t)stream);
+    if (rc) return rc;
+    return det_finish(det.partial + 5 * fint, grid, det.n, 1, dbpsi, (cudaStream_t)stream);
+  }
   return B2_OK;
 }
 
@@ -554,19 +598,28 @@ extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const voi
   B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld) && g_al(dg1p, ld) && g_al(dx1p, ld), B2_ERR_ALIGN,
              "gate operands misaligned");
-  if (gate_light(fint)) {
-    const int tpp = fint / 4, rows = 256 / tpp;
-    gate_psi_bwd_apply_kernel<4><<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
+  const bool light = gate_light(fint);
+  const int tpp = fint / (light ? 4 : 8), rows = 256 / tpp;
+  const int grid = g_grid(npix, rows, 16);
+  DetBuf det;
+  det.partial = nullptr;
+  det.n = 2 * fint;
+  if (dbias != nullptr) {
+    int rc = det_begin(&det, grid, 2 * fint, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  if (light) {
+    gate_psi_bwd_apply_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
         rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias);
+        dbias, det);
   } else {
-    const int tpp = fint / 8, rows = 256 / tpp;
-    gate_psi_bwd_apply_kernel<8><<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
+    gate_psi_bwd_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
         rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias);
+        dbias, det);
   }
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, det.n, 2 * fint, dbias, (cudaStream_t)stream);
   return B2_OK;
 }

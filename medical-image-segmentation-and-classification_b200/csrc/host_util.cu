@@ -32,6 +32,66 @@ int num_sms() {
   return cached[dev];
 }
 
+// ---------------------------------------------------------------------------------------------
+// deterministic-reduction workspace
+// ---------------------------------------------------------------------------------------------
+static std::mutex g_det_mu;
+static double* g_det_ws[64] = {nullptr};       // per device
+static long long g_det_doubles[64] = {0};
+
+static bool det_lookup(double** ws, long long* n) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  std::lock_guard<std::mutex> lk(g_det_mu);
+  *ws = g_det_ws[dev];
+  *n = g_det_doubles[dev];
+  return *ws != nullptr;
+}
+
+bool det_enabled() {
+  double* ws;
+  long long n;
+  return det_lookup(&ws, &n);
+}
+
+int det_begin(DetBuf* out, long long rows, int n, cudaStream_t stream, long long keep) {
+  out->partial = nullptr;
+  out->n = n;
+  double* ws;
+  long long cap;
+  if (!det_lookup(&ws, &cap)) return B2_OK;
+  const long long need = rows * (long long)n;
+  B2_REQUIRE(keep + need <= cap, B2_ERR_WORKSPACE,
+             "deterministic workspace too small: need %lld B, have %lld B (b2_set_deterministic)",
+             (keep + need) * 8, cap * 8);
+  out->partial = ws + keep;
+  B2_CHECK_CUDA(cudaMemsetAsync(out->partial, 0, (size_t)need * sizeof(double), stream));
+  return B2_OK;
+}
+
+template <typename T>
+__global__ void det_finish_kernel(const double* __restrict__ partial, long long rows, int row_stride, int count,
+                                  T* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double s = 0.0;
+  for (long long r = 0; r < rows; ++r) s += partial[r * row_stride + i];     // fixed order: bit-reproducible
+  dst[i] = (T)((double)dst[i] + s);
+}
+
+int det_finish(const double* partial, long long rows, int row_stride, int count, double* dst, cudaStream_t stream) {
+  if (count <= 0) return B2_OK;
+  det_finish_kernel<double><<<(count + 127) / 128, 128, 0, stream>>>(partial, rows, row_stride, count, dst);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+int det_finish(const double* partial, long long rows, int row_stride, int count, float* dst, cudaStream_t stream) {
+  if (count <= 0) return B2_OK;
+  det_finish_kernel<float><<<(count + 127) / 128, 128, 0, stream>>>(partial, rows, row_stride, count, dst);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -90,6 +150,21 @@ extern "C" {
 const char* b2_last_error(void) { return b2::g_err; }
 int b2_abi_version(void) { return B2_ABI_VERSION; }
 int b2_num_sms(void) { return b2::num_sms(); }
+
+int b2_set_deterministic(void* workspace, int64_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return b2::cuda_fail(e, "cudaGetDevice");
+  B2_REQUIRE(dev >= 0 && dev < 64, B2_ERR_SHAPE, "device index %d out of range", dev);
+  B2_REQUIRE(workspace == nullptr || (bytes >= (1 << 20) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0),
+             B2_ERR_WORKSPACE, "deterministic workspace must be 16 B aligned and >= 1 MiB");
+  std::lock_guard<std::mutex> lk(b2::g_det_mu);
+  b2::g_det_ws[dev] = static_cast<double*>(workspace);
+  b2::g_det_doubles[dev] = workspace ? bytes / 8 : 0;
+  return B2_OK;
+}
+
+int b2_get_deterministic(void) { return b2::det_enabled() ? 1 : 0; }
 
 int b2_arch_check(void) {
   int dev = 0;

@@ -13,7 +13,7 @@ __device__ __forceinline__ float stable_sigmoid(float z) {
 }
 
 __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
-                                                       long long count, double* __restrict__ sums) {
+                                                       long long count, double* __restrict__ sums, DetBuf det) {
   float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (long long)gridDim.x * blockDim.x) {
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(const float* __restrict__
   if (threadIdx.x < 6) {
     float s = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
-    atomicAdd(&sums[threadIdx.x], (double)s);
+    red_out(sums, det, (int)threadIdx.x, (double)s);
   }
 }
 
@@ -148,8 +148,13 @@ using namespace b2;
 
 extern "C" int b2_loss_fwd(const float* z, const float* t, int64_t count, double* sums, b2_stream_t stream) {
   B2_REQUIRE(count > 0, B2_ERR_SHAPE, "empty loss input");
-  loss_fwd_kernel<<<l_grid(count), 256, 0, (cudaStream_t)stream>>>(z, t, count, sums);
+  const int grid = l_grid(count);
+  DetBuf det;
+  int rc = det_begin(&det, grid, 6, (cudaStream_t)stream);
+  if (rc) return rc;
+  loss_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, t, count, sums, det);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, grid, 6, 6, sums, (cudaStream_t)stream);
   return B2_OK;
 }
 

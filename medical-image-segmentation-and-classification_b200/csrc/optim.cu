@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(kOptThreads) grad_sqnorm_kernel(const TensorRe
                                                                   const int* __restrict__ block_tensor,
                                                                   const int* __restrict__ block_chunk,
                                                                   int chunk_elems, double* __restrict__ sqnorm,
-                                                                  float* __restrict__ step) {
+                                                                  float* __restrict__ step, DetBuf det) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && step != nullptr) *step += 1.f;
   const TensorRef r = refs[block_tensor[blockIdx.x]];
   const long long base = (long long)block_chunk[blockIdx.x] * chunk_elems;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kOptThreads) grad_sqnorm_kernel(const TensorRe
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < kOptThreads / 32; ++i) t += sh[i];
-    atomicAdd(sqnorm, (double)t);
+    red_out(sqnorm, det, 0, (double)t);
   }
 }
 
@@ -88,9 +88,13 @@ extern "C" int b2_grad_sqnorm_multi(const b2_tensor_ref* refs, const int32_t* bl
                                     b2_stream_t stream) {
   B2_REQUIRE(nblocks > 0 && chunk_elems > 0, B2_ERR_SHAPE, "empty optimizer launch");
   B2_CHECK_CUDA(cudaMemsetAsync(sqnorm, 0, sizeof(double), (cudaStream_t)stream));
+  DetBuf det;
+  int rc = det_begin(&det, nblocks, 1, (cudaStream_t)stream);
+  if (rc) return rc;
   grad_sqnorm_kernel<<<nblocks, kOptThreads, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const TensorRef*>(refs), block_tensor, block_chunk, chunk_elems, sqnorm, step);
+      reinterpret_cast<const TensorRef*>(refs), block_tensor, block_chunk, chunk_elems, sqnorm, step, det);
   B2_LAUNCH_CHECK();
+  if (det.partial) return det_finish(det.partial, nblocks, 1, 1, sqnorm, (cudaStream_t)stream);
   return B2_OK;
 }
 

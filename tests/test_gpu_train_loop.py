@@ -172,6 +172,15 @@ def test_wgrad_side_stream_overlap_gives_identical_gradients(name, kw, bn_train)
     else:
         assert max(e1, e2) <= 2.0 * base + 1e-5
     assert not K._OVERLAP["pending"] and not K._OVERLAP["refs"]
+    # deterministic-reduction mode removes the atomic-order noise: the comparison becomes BITWISE, train mode included,
+    # so a race that corrupts even one element of one gradient is caught
+    K.set_deterministic(True)
+    try:
+        c, c2, d, d2 = grads(False), grads(False), grads(True), grads(True)
+    finally:
+        K.set_deterministic(False)
+    for u, v, w_, z in zip(c, c2, d, d2):
+        assert torch.equal(u, v) and torch.equal(u, w_) and torch.equal(u, z)
 
 
 def test_grad_reducer_on_side_stream_matches_plain_backward():
