@@ -240,7 +240,7 @@ def run_b200(args):
     x_dev, t_dev = x_host.to(dev), t_host.to(dev)
     params = [p for p in model.parameters() if p.requires_grad]
 
-    def step(x, t):
+    def step(x, t):      # the eager step, used by the instrumented roofline pass below
         opt.zero_grad(set_to_none=True)
         K.step_begin()
         logits = model(x)
@@ -271,91 +271,74 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    # warm-up (eager) on a side stream, then optionally capture the whole step — forward, loss, backward, clip, AdamW —
-    # in ONE CUDA graph: every kernel of the step is replayed without any Python / launch overhead
-    # Everything below runs on ONE non-default stream (the autograd AccumulateGrad nodes bind to the stream of their
-    # first use; mixing streams between warm-up and timing would add synchronisation).
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    torch.cuda.set_stream(side)
+    # The package's own fast step (b200seg.engine.GraphedTrainStep — the same object utils.helpers.train() drives):
+    # the first calls run eagerly (warm-up), then the whole step — forward, loss, backward, bucketed NCCL all-reduces,
+    # clip, AdamW, weight re-pack — is captured in ONE CUDA graph and every later call is a replay.
+    from b200seg.engine import GraphedTrainStep, PinnedPrefetcher
+    n_warm = max(args.warmup, 3)
+    stepper = GraphedTrainStep(model, opt, reducer=reducer, graph=use_graph, warmup=n_warm,
+                               wgrad_overlap=bool(args.wgrad_overlap),
+                               clip_fn=None if args.optimizer == "fused"
+                               else (lambda: torch.nn.utils.clip_grad_norm_(params, 1.0)))
+    run_stream = stepper.stream           # everything below runs on the stepper's stream (no per-step stream hops)
+    run_stream.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(run_stream)
     _tick("model built, warm-up begins")
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, t_dev)
+    for _ in range(n_warm):
+        stepper(x_dev, t_dev)
     torch.cuda.synchronize()
     _tick("warm-up done")
-    graph, static_loss, launches_per_step = None, None, None
-    if use_graph:
-        try:
-            opt.zero_grad(set_to_none=True)
-            l_before = _lib.launch_count
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_loss = step(x_dev, t_dev)
-            launches_per_step = _lib.launch_count - l_before
-            graph.replay()
-            torch.cuda.synchronize()
-            _tick("graph captured and replayed once")
-        except Exception as e:   # keep the eager path measurable if capture is refused
-            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
-                  file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
+    stepper(x_dev, t_dev)                 # captures (if enabled) and replays once
+    torch.cuda.synchronize()
+    graphed = stepper.graph_for(x_dev, t_dev) is not None
+    if use_graph and not graphed:
+        print(f"[bench] CUDA graph capture failed ({stepper.capture_error}); timing eager launches", file=sys.stderr)
+    static = stepper.static_inputs(x_dev.shape, t_dev.shape)
+    if static is not None:
+        x_run, t_run = static             # batch resident in the graph's input buffers when the timed region starts
+    else:
+        x_run, t_run = x_dev, t_dev
+    launches_per_step = stepper.launches_per_replay.get((tuple(x_dev.shape), tuple(t_dev.shape)))
+    _tick("graph captured and replayed once" if graphed else "eager mode")
 
     def run_step():
-        if graph is not None:
-            graph.replay()
-            return static_loss
-        return step(x_dev, t_dev)
+        return stepper(x_run, t_run, inputs_are_static=graphed)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = _lib.launch_count
     ms = timed(run_step, args.steps)
-    launches = (_lib.launch_count - l0) if graph is None else launches_per_step * args.steps
+    launches = (_lib.launch_count - l0) if not graphed else launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     _tick("timed region done")
 
-    # end-to-end: pinned host batch -> device, loss -> host, every step.  As in a real input pipeline the NEXT batch
-    # is copied (copy stream, double-buffered device staging) while the current step computes; every step still
-    # moves one full batch host -> device and reads its loss back.
-    copy_stream = torch.cuda.Stream()
-    stage = [(torch.empty_like(x_dev), torch.empty_like(t_dev)) for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    for ev in consumed:
-        ev.record()
-    pipe = {"i": 0, "primed": False}
+    # end-to-end through the package API: every step's batch starts in pinned HOST memory (as DataLoader(pin_memory=True)
+    # delivers it), PinnedPrefetcher copies batch i+1 on its copy stream while step i computes, the stepper copies it
+    # into the graph's inputs and replays, and the loss is read back to the host — every step moves one full batch
+    # host -> device and 4 bytes device -> host inside the timed region.
+    class _HostBatches:
+        def __init__(self, n):
+            self.n = n
 
-    def issue_copy(slot):
-        copy_stream.wait_event(consumed[slot])          # the staging slot has been drained by its previous user
-        with torch.cuda.stream(copy_stream):
-            stage[slot][0].copy_(x_host, non_blocking=True)
-            stage[slot][1].copy_(t_host, non_blocking=True)
-            ready[slot].record()
+        def __len__(self):
+            return self.n
+
+        def __iter__(self):
+            for _ in range(self.n):
+                yield x_host, t_host
+
+    pre = PinnedPrefetcher(_HostBatches(args.steps + 1), dev)
+    e2e_iter = iter(pre)
 
     def e2e_step():
-        slot = pipe["i"] & 1
-        if not pipe["primed"]:
-            issue_copy(slot)
-            pipe["primed"] = True
-        torch.cuda.current_stream().wait_event(ready[slot])
-        if graph is not None:
-            x_dev.copy_(stage[slot][0])                 # device-to-device into the graph's static inputs
-            t_dev.copy_(stage[slot][1])
-            consumed[slot].record()
-            issue_copy(slot ^ 1)
-            graph.replay()
-            loss = static_loss
-        else:
-            issue_copy(slot ^ 1)
-            loss = step(stage[slot][0], stage[slot][1])
-            consumed[slot].record()
-        pipe["i"] += 1
-        return float(loss)
+        xb, tb = next(e2e_iter)
+        return float(stepper(xb, tb))
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    h2d_per_step = pre.h2d_bytes // (args.steps + 1)
     _tick("e2e done")
+    graph = stepper if graphed else None
 
     # instrumented pass for the roofline of the tensor-core kernels
     # (single stream: with the weight gradients on the side stream the per-launch event times would include the
@@ -413,7 +396,7 @@ def run_b200(args):
                    "l2": "working set per step (>10 GB of activations) far exceeds the 126 MB L2",
                    "model_kwargs": kw, "cuda_graph": graph is not None, "optimizer": args.optimizer,
                    "wgrad_side_stream": bool(args.wgrad_overlap)},
-        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(x_host.numel() * 4 + t_host.numel() * 4),
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(h2d_per_step),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -103,6 +103,7 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b2_grad_sqnorm_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2_adamw_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    "b2_pack_weights_multi": (C.c_int, [_vp, _i32, _i32, _vp]),
     "b2_loss_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "b2_loss_finalize": (C.c_int, [_vp, _i64, _f32, _f32, _f32, _vp, _vp]),
     "b2_loss_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp, _vp, _vp]),

@@ -51,7 +51,6 @@ class GraphedTrainStep:
         self.replays = 0
         self.eager_steps = 0
         self.capture_error: Optional[str] = None
-        self.last_iou_sums = None
 
     # -- one eager step on the current stream --------------------------------------------------------------
     def _step(self, x, t):
@@ -83,7 +82,6 @@ class GraphedTrainStep:
 
     def __call__(self, x: torch.Tensor, t: torch.Tensor, inputs_are_static: bool = False) -> torch.Tensor:
         """`inputs_are_static`: x / t ARE the graph's static buffers (see static_inputs) — skip the device copy."""
-        from . import _lib
         key = (tuple(x.shape), tuple(t.shape))
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)
@@ -103,6 +101,7 @@ class GraphedTrainStep:
                         ts.copy_(t, non_blocking=True)
                     self._sync_lr()
                     graph.replay()
+                    K.bump_param_epoch()             # the replayed optimizer step rewrote the parameters
                     self.replays += 1
                     loss = loss_s
                 else:
@@ -116,7 +115,6 @@ class GraphedTrainStep:
             if self.wgrad_overlap is not None:
                 K.set_wgrad_overlap(prev_overlap)
         cur.wait_stream(self.stream)
-        del _lib
         return loss
 
     def _capture(self, key, x, t):
@@ -162,6 +160,7 @@ class PinnedPrefetcher:
         self._pinned: Dict[Tuple, list] = {}
         self._slots: Dict[Tuple, list] = {}
         self._turn: Dict[Tuple, int] = {}
+        self._hold: Dict[Tuple, list] = {}
         self.h2d_bytes = 0
 
     def __len__(self):
@@ -180,13 +179,18 @@ class PinnedPrefetcher:
                                  torch.empty(y.shape, dtype=y.dtype, device=self.device), torch.cuda.Event(),
                                  torch.cuda.Event()) for _ in range(self.depth)]
             self._turn[key] = 0
+            self._hold[key] = [None] * self.depth
         i = self._turn[key]
         self._turn[key] = (i + 1) % self.depth
-        px, py = self._pinned[key][i]
         xd, yd, ready, consumed = self._slots[key][i]
-        ready.synchronize()                       # the previous H2D out of this pinned pair has finished
-        px.copy_(x)
-        py.copy_(y)
+        if x.is_pinned() and y.is_pinned():       # DataLoader(pin_memory=True): copy straight out of the batch
+            px, py = x, y
+            self._hold[key][i] = (x, y)           # keep the source alive until its H2D has run
+        else:
+            px, py = self._pinned[key][i]
+            ready.synchronize()                   # the previous H2D out of this pinned pair has finished
+            px.copy_(x)
+            py.copy_(y)
         self.copy_stream.wait_event(consumed)     # the slot's previous consumer is done with it
         with torch.cuda.stream(self.copy_stream):
             xd.copy_(px, non_blocking=True)
@@ -200,9 +204,13 @@ class PinnedPrefetcher:
         nxt = None
         try:
             x, y = next(it)
-            nxt = self._stage(x, y)
         except StopIteration:
             return
+        if x.is_cuda:                             # already on the device: nothing to stage
+            yield x, y
+            yield from it
+            return
+        nxt = self._stage(x, y)
         while nxt is not None:
             xd, yd, ready, consumed = nxt
             try:

@@ -236,9 +236,110 @@ def new_act(n, h, w, c, device):
 # ----------------------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------------------
+# Packed (bf16, MMA-layout) copies of the convolution weights are cached per parameter and kept fresh by the optimizer:
+# FusedClipAdamW re-packs every registered weight in ONE multi-tensor launch right after its AdamW kernel
+# (b2_pack_weights_multi), so the conv calls of a training step pack nothing.  Any other writer goes through torch
+# (in-place ops bump Tensor._version) and simply invalidates the entry.
+#
+# Entries are keyed by (data_ptr, kind) and validated against a weak reference to the parameter object: a freed
+# parameter whose address is reused by another tensor can never alias a stale entry (the old object is dead).
+_PACKS = {"cache": {}, "serial": 0, "epoch": 0}
+
+
+class _Pack:
+    __slots__ = ("ref", "ptr", "version", "kind", "wf", "wd", "cout", "cin", "ksize", "strides", "code")
+
+
 def invalidate_pack_cache():
-    """kept for API compatibility: packed weights are never cached across calls (a cache keyed on storage address
-    and version counter is unsafe: freed parameters get their addresses reused)"""
+    """drop every cached packed weight (they are rebuilt on next use)"""
+    _PACKS["cache"].clear()
+    _PACKS["serial"] += 1
+
+
+def bump_param_epoch():
+    """called by whoever updated parameters through raw pointers (FusedClipAdamW.step, a graph replay of it): derived
+    caches that the optimizer does NOT refresh itself (BN-folded inference weights) become stale"""
+    _PACKS["epoch"] += 1
+
+
+def param_epoch() -> int:
+    return _PACKS["epoch"]
+
+
+def pack_serial() -> int:
+    return _PACKS["serial"]
+
+
+def _pack_valid(pk, weight):
+    o = pk.ref()
+    return (o is not None and pk.ptr == weight.data_ptr() and o.data_ptr() == pk.ptr
+            and o._version == pk.version and weight._version == pk.version)
+
+
+_PACK_KINDS = {"plain": 0, "upfold": 1, "stem": 2, "convT_f": 0, "convT_d": 0}
+
+
+def packed(weight, kind="plain", want_dgrad=False):
+    """Cached packed copies of a conv weight: (wf, wd) with wd None unless a dgrad layout was ever requested.
+    kind: 'plain'   [Cout,Cin,k,k] -> wf [k*k,Cout,Cin], wd [k*k,Cin,Cout] (flipped taps)
+          'upfold'  [Cout,Cin,3,3] -> wf [4,4,Cout,Cin], wd [4,4,Cin,Cout]           (UpConv folding)
+          'stem'    [Cout,<=3,3,3] -> wf [1,Cout,32] im2col matrix                   (image stem as a GEMM)
+          'convT_f' ConvTranspose weight [Cin,Cout,2,2] -> wf [4,Cout,Cin]           (forward: rows = Cout)
+          'convT_d' ConvTranspose weight [Cin,Cout,2,2] -> wf [4,Cin,Cout]           (input gradient: rows = Cin)"""
+    key = (weight.data_ptr(), kind)
+    pk = _PACKS["cache"].get(key)
+    if pk is not None and _pack_valid(pk, weight) and (pk.wd is not None or not want_dgrad):
+        return pk.wf, pk.wd
+    import weakref
+    view = weight.permute(1, 0, 2, 3) if kind == "convT_f" else weight
+    cout, cin, kh, kw = view.shape
+    assert kh == kw and weight.dtype == torch.float32
+    dev = weight.device
+    reuse = pk is not None and pk.ref() is weight and pk.ptr == weight.data_ptr() and pk.strides == tuple(view.stride())
+    wf = pk.wf if reuse else None
+    wd = pk.wd if reuse else None
+    need_wd = want_dgrad or wd is not None
+    if kind == "upfold":
+        wf = wf if wf is not None else torch.empty((4, 4, cout, cin), dtype=BF16, device=dev)
+        if need_wd and wd is None:
+            wd = torch.empty((4, 4, cin, cout), dtype=BF16, device=dev)
+        sv = view.stride()
+        call("b2_pack_weights_upfold", _p(view), cout, cin, sv[0], sv[1], sv[2], sv[3], _p(wf), _p(wd), _stream())
+    elif kind == "stem":
+        wf = wf if wf is not None else torch.empty((1, cout, STEM_COLS), dtype=BF16, device=dev)
+        wm = stem_weight_matrix(weight)
+        sm = wm.stride()
+        call("b2_pack_weights", _p(wm), cout, STEM_COLS, 1, sm[0], sm[1], sm[2], sm[3], _p(wf), _p(None), _stream())
+    else:
+        taps = kh * kw
+        wf = wf if wf is not None else torch.empty((taps, cout, cin), dtype=BF16, device=dev)
+        if need_wd and wd is None:
+            wd = torch.empty((taps, cin, cout), dtype=BF16, device=dev)
+        sv = view.stride()
+        call("b2_pack_weights", _p(view), cout, cin, kh, sv[0], sv[1], sv[2], sv[3], _p(wf), _p(wd), _stream())
+    new = _Pack()
+    new.ref, new.ptr, new.version, new.kind = weakref.ref(weight), weight.data_ptr(), weight._version, kind
+    new.wf, new.wd, new.cout, new.cin, new.ksize = wf, wd, cout, cin, kh
+    new.strides, new.code = tuple(view.stride()), _PACK_KINDS[kind]
+    cache = _PACKS["cache"]
+    if len(cache) > 4096:
+        for k in [k for k, v in cache.items() if v.ref() is None]:
+            del cache[k]
+    cache[key] = new
+    if not (reuse and wd is pk.wd and wf is pk.wf):
+        _PACKS["serial"] += 1          # new buffers: optimizers rebuild their re-pack tables
+    return wf, wd
+
+
+def packs_of(params):
+    """every live cached pack whose master is one of `params` (FusedClipAdamW builds its re-pack table from this)"""
+    ptrs = {p.data_ptr(): p for p in params}
+    out = []
+    for (ptr, _kind), pk in _PACKS["cache"].items():
+        p = ptrs.get(ptr)
+        if p is not None and _pack_valid(pk, p):
+            out.append(pk)
+    return out
 
 
 def pack_weights(weight, want_dgrad=True):

@@ -1,7 +1,8 @@
 """torch.library custom ops (namespace `b200seg`) with autograd, built on the C ABI wrappers in kernels.py.
 
 Internal activation format: NHWC bf16 tensors [N, H, W, C].  Parameters stay ordinary fp32 nn.Parameters in the
-reference's shapes; weights are re-packed to bf16 MMA layouts inside the ops (a few MB per step).
+reference's shapes; their bf16 MMA-layout copies are cached per parameter (kernels.packed) and refreshed by the fused
+optimizer in one multi-tensor launch per step.
 
 Each op cites the reference lines whose ATen dispatch it replaces.  There is no fallback: every op launches
 kernels of libb200seg.so or raises.
@@ -67,7 +68,7 @@ def _(x):
 def conv2d(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional[Tensor],
            want_stats: bool) -> Tuple[Tensor, Tensor]:
     cout, cin, k, _ = weight.shape
-    wf, _ = K.pack_weights(weight, want_dgrad=False)
+    wf, _ = K.packed(weight)
     stats = torch.zeros((2, cout), dtype=_F64, device=x0.device) if want_stats else \
         torch.empty((0,), dtype=_F64, device=x0.device)
     y = K.conv_igemm(_c(x0), wf, cout, k, x1=_c(x1), bias=bias, stats=stats if want_stats else None)
@@ -93,7 +94,7 @@ def conv2d_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, nee
     dx0 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     dx1 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     if need_dx0 or need_dx1:
-        _, wd = K.pack_weights(weight, want_dgrad=True)
+        _, wd = K.packed(weight, want_dgrad=True)
         if need_dx0:
             dx0 = K.conv_igemm(dy, wd, c0, k, row_offset=0, dgrad=True)
         if need_dx1 and x1 is not None:
@@ -150,7 +151,7 @@ def stem_conv(x: Tensor, weight: Tensor, bias: Optional[Tensor], want_stats: boo
              else torch.empty((0,), dtype=_F64, device=x.device))
     if _stem_as_gemm(weight):
         x4 = K.stem_im2col3x3(_c(x))
-        wf, _ = K.pack_weights(K.stem_weight_matrix(weight), want_dgrad=False)
+        wf, _ = K.packed(weight, "stem")
         y = K.conv_igemm(x4, wf, cout, 1, bias=bias, stats=stats if want_stats else None)
         return y, stats, x4
     x4 = K.image_to_nhwc4(_c(x))
@@ -278,7 +279,7 @@ def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional
     stats = K.zeros_scratch((2, cout), _F64, dev) if training else torch.empty((0,), dtype=_F64, device=dev)
     if x0.dtype != torch.bfloat16 and _stem_as_gemm(weight):   # image stem on the tensor cores (im2col, K = 32)
         x4 = K.stem_im2col3x3(_c(x0))
-        wf, _ = K.pack_weights(K.stem_weight_matrix(weight), want_dgrad=False)
+        wf, _ = K.packed(weight, "stem")
         z = K.conv_igemm(x4, wf, cout, 1, bias=bias, stats=stats if training else None)
     elif x0.dtype != torch.bfloat16:                      # other small-channel stems: CUDA-core kernels
         x4 = K.image_to_nhwc4(_c(x0))
@@ -287,7 +288,7 @@ def conv_bn_act(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Optional
             K.channel_stats(z, stats)
     else:
         x4 = torch.empty((0,), dtype=torch.bfloat16, device=dev)
-        wf, _ = K.pack_weights(weight, want_dgrad=False)
+        wf, _ = K.packed(weight)
         z = K.conv_igemm(_c(x0), wf, cout, k, x1=_c(x1), bias=bias, stats=stats if training else None)
     n, h, w, _ = z.shape
     if training:
@@ -336,7 +337,7 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
     else:
         c0 = x0.shape[3]
         if need_dx0 or need_dx1:
-            _, wd = K.pack_weights(weight, want_dgrad=True)
+            _, wd = K.packed(weight, want_dgrad=True)
             if need_dx0:
                 dx0 = K.conv_igemm(dz, wd, c0, k, row_offset=0, dgrad=True)
             if need_dx1 and x1 is not None:
@@ -436,7 +437,7 @@ def upconv_bn_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], gamma: Tens
     n, h, w, _ = x.shape
     dev = x.device
     stats = K.zeros_scratch((2, cout), _F64, dev) if training else torch.empty((0,), dtype=_F64, device=dev)
-    wf, _ = K.pack_weights_upfold(weight, want_dgrad=False)
+    wf, _ = K.packed(weight, "upfold")
     z = K.new_act(n, 2 * h, 2 * w, cout, dev)
     for ph, (a, b) in enumerate(_PHASES):
         K.conv_igemm(x, wf[ph], cout, 2, bias=bias, stats=stats if training else None, out=z, out_mul=2,
@@ -467,7 +468,7 @@ def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Te
     db = res[3] if has_bias else torch.empty((0,), device=dev)
     n, h, w, _ = x.shape
     if need_dx:
-        _, wd = K.pack_weights_upfold(weight, want_dgrad=True)
+        _, wd = K.packed(weight, "upfold", want_dgrad=True)
         dx = K.new_act(n, h, w, cin, dev)
         for ph, (a, b) in enumerate(_PHASES):
             # 2x2 conv of the (a,b) sub-lattice of dz with the flipped/transposed phase weights, chained through the

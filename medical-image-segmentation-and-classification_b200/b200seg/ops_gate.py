@@ -40,8 +40,8 @@ def attention_gate(g: Tensor, x: Tensor, wg: Tensor, bg: Tensor, wx: Tensor, bx:
         return torch.zeros((2, fint), dtype=_F64, device=dev) if training else torch.empty((0,), dtype=_F64, device=dev)
 
     stats_g, stats_x = stats_buf(), stats_buf()
-    wgf, _ = K.pack_weights(wg, want_dgrad=False)
-    wxf, _ = K.pack_weights(wx, want_dgrad=False)
+    wgf, _ = K.packed(wg)
+    wxf, _ = K.packed(wx)
     g1p = K.conv_igemm(g, wgf, fint, 1, bias=bg, stats=stats_g if training else None)
     x1p = K.conv_igemm(x, wxf, fint, 1, bias=bx, stats=stats_x if training else None)
     if training:
@@ -83,12 +83,12 @@ def attention_gate_bwd(dout: Tensor, g: Tensor, x: Tensor, wg: Tensor, wx: Tenso
     dg1p, dx1p, dgb, dbn1, dwpsi, dbpsi, dbias = K.gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x,
                                                                 gamma_x, coef_1, gamma_1, wpsi, training=training)
     if need_dg:
-        _, wgd = K.pack_weights(wg, want_dgrad=True)
+        _, wgd = K.packed(wg, want_dgrad=True)
         dg = K.conv_igemm(dg1p, wgd, g.shape[3], 1, dgrad=True)
     else:
         dg = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     if need_dx:
-        _, wxd = K.pack_weights(wx, want_dgrad=True)
+        _, wxd = K.packed(wx, want_dgrad=True)
         K.conv_igemm(dx1p, wxd, x.shape[3], 1, addend=dx, out=dx, dgrad=True)     # dx += dx1p . W_x (epilogue add)
     with K.wgrad_stream(dg1p, dx1p, g, x, allow=K.grad_is_stolen(wg) and K.grad_is_stolen(wx)):
         dwg = K.conv_wgrad(dg1p, g, 1)

@@ -12,8 +12,32 @@ import torch
 from torch import Tensor
 from torch.library import custom_op
 
+import weakref
+
 from . import kernels as K
 from .ops import _PHASES, _c
+
+# BN-folded weights are a pure function of (conv weight, conv bias, BN affine, BN running statistics): they are cached
+# per conv weight and rebuilt only when one of those tensors changed — torch writers bump Tensor._version, the fused
+# optimizer (raw-pointer writes) bumps kernels.param_epoch().  Batch-1 inference no longer re-folds and re-packs every
+# conv on every call (pipeline.py:340-357 runs one image per call).
+_FOLDED = {}
+
+
+def _folded(weight, bias, gamma, beta, rm, rv, eps, upfold):
+    tensors = (weight, bias, gamma, beta, rm, rv)
+    stamp = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (K.param_epoch(), float(eps))
+    key = (weight.data_ptr(), bool(upfold))
+    hit = _FOLDED.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == stamp:
+        return hit[2], hit[3]
+    coef = K.bn_eval_coeffs(gamma, beta, rm, rv, eps)
+    wf, bf = K.pack_weights_folded(weight, bias, coef, upfold=upfold)
+    if len(_FOLDED) > 4096:
+        for k in [k for k, v in _FOLDED.items() if v[0]() is None]:
+            del _FOLDED[k]
+    _FOLDED[key] = (weakref.ref(weight), stamp, wf, bf)
+    return wf, bf
 
 
 @custom_op("b200seg::conv_bn_act_infer", mutates_args=())
@@ -22,8 +46,7 @@ def conv_bn_act_infer(x0: Tensor, x1: Optional[Tensor], weight: Tensor, bias: Op
                       addend: Optional[Tensor]) -> Tensor:
     """y = act(conv(x; W*s) + (b*s + t)) [+ addend]  with s = gamma/sqrt(running_var+eps), t = beta - running_mean*s"""
     cout, cin, k, _ = weight.shape
-    coef = K.bn_eval_coeffs(gamma, beta, running_mean, running_var, eps)
-    wf, bf = K.pack_weights_folded(weight, bias, coef)
+    wf, bf = _folded(weight, bias, gamma, beta, running_mean, running_var, eps, False)
     return K.conv_igemm(_c(x0), wf, cout, k, x1=_c(x1), bias=bf, relu=relu, addend=_c(addend),
                         add_after_act=addend is not None)
 
@@ -40,8 +63,7 @@ def upconv_bn_act_infer(x: Tensor, weight: Tensor, bias: Optional[Tensor], gamma
     cout = weight.shape[0]
     x = _c(x)
     n, h, w, _ = x.shape
-    coef = K.bn_eval_coeffs(gamma, beta, running_mean, running_var, eps)
-    wf, bf = K.pack_weights_folded(weight, bias, coef, upfold=True)
+    wf, bf = _folded(weight, bias, gamma, beta, running_mean, running_var, eps, True)
     y = K.new_act(n, 2 * h, 2 * w, cout, x.device)
     for ph, (a, b) in enumerate(_PHASES):
         K.conv_igemm(x, wf[ph], cout, 2, bias=bf, relu=relu, out=y, out_mul=2, out_off=(a, b), pad=(1 - a, 1 - b))

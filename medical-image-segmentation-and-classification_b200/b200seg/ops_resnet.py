@@ -62,7 +62,7 @@ def enc_conv_bn(x: Tensor, weight: Tensor, gamma: Tensor, beta: Tensor, running_
     """bias-free conv (1x1 or 3x3, stride 1|2) -> BatchNorm (batch stats when training) -> [+identity] -> [ReLU];
     returns (y, stats) — the caller applies the running-stat update."""
     cout, cin, k, _ = weight.shape
-    wf, _ = K.pack_weights(weight, want_dgrad=False)
+    wf, _ = K.packed(weight)
     stats = torch.zeros((2, cout), dtype=_F64, device=x.device) if training else \
         torch.empty((0,), dtype=_F64, device=x.device)
     z = K.conv_igemm(_c(x), wf, cout, k, stats=stats if training else None, stride=stride)
@@ -91,7 +91,7 @@ def conv_transpose2x2(x: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tens
     cin, cout = weight.shape[0], weight.shape[1]
     x = _c(x)
     n, h, w, _ = x.shape
-    wf, _ = K.pack_weights(weight.permute(1, 0, 2, 3), want_dgrad=False)       # [4][Cout][Cin]
+    wf, _ = K.packed(weight, "convT_f")                                          # [4][Cout][Cin]
     y = K.new_act(n, 2 * h, 2 * w, cout, x.device)
     for i in range(2):
         for j in range(2):
@@ -115,7 +115,7 @@ def conv_transpose2x2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool,
     if need_dx:
         # dx[n,h,w,ci] = sum_{i,j,co} dy[n,2h+i,2w+j,co] W[ci,co,i,j]: a 2x2 / stride-2 conv of dy whose
         # "output channels" are ci — W already has the [rows=ci][K=co][2][2] shape the fprop packing expects
-        wd, _ = K.pack_weights(weight, want_dgrad=False)                        # [4][Cin][Cout]
+        wd, _ = K.packed(weight, "convT_d")                                       # [4][Cin][Cout]
         dx = K.conv_igemm(dy, wd, cin, 2, stride=2, dgrad=True)
     else:
         dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)

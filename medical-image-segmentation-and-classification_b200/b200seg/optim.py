@@ -20,6 +20,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from . import kernels as K
 from .kernels import _p, _stream
 
 _CHUNK = 1 << 16          # elements per block
@@ -68,6 +69,13 @@ class FusedClipAdamW(torch.optim.Optimizer):
             self._refs_host[i, 2] = st["exp_avg"].data_ptr()
             self._refs_host[i, 3] = st["exp_avg_sq"].data_ptr()
             self._refs_host[i, 4] = p.numel()
+        # re-pack table (b2_pack_ref rows: 10 x int64) for the cached bf16 copies of the conv weights
+        self._pack_serial = -1
+        self._pack_dev = None
+        self._pack_n = 0
+        self._pack_items = 0
+        self._pack_keep = []
+        self._pack_hosts = []
 
     def _moment_buffers(self):
         return [(self.state[p]["exp_avg"], self.state[p]["exp_avg_sq"]) for p in self._params]
@@ -138,15 +146,49 @@ class FusedClipAdamW(torch.optim.Optimizer):
             else:
                 self._refs_dev.copy_(self._refs_host, non_blocking=True)
 
+    def sync_lr(self):
+        """mirror param_groups[0]['lr'] into the device scalar the kernels read (call outside graph capture / replay)"""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_host:
+            self._lr_host = lr
+            self._lr.fill_(lr)
+
+    def _refresh_pack_table(self):
+        """device table of every cached packed copy (kernels.packed) of the parameters this optimizer updates"""
+        if self._pack_serial == K.pack_serial():
+            return
+        packs = K.packs_of(self._params)
+        rows, start = [], 0
+        for pk in packs:
+            tco, tci = (pk.cout + 31) // 32, (pk.cin + 31) // 32
+            items = tco if pk.code == 2 else (16 if pk.code == 1 else pk.ksize * pk.ksize) * tco * tci
+            lo = (pk.cout & 0xFFFFFFFF) | (pk.cin << 32)
+            hi = (pk.ksize & 0xFFFFFFFF) | (pk.code << 32)
+            rows.append([pk.ptr, pk.wf.data_ptr(), pk.wd.data_ptr() if pk.wd is not None else 0, lo, hi,
+                         pk.strides[0], pk.strides[1], pk.strides[2], pk.strides[3], start])   # one b2_pack_ref (80 B)
+            start += items
+        self._pack_n, self._pack_items = len(rows), start
+        self._pack_keep = packs
+        if rows:
+            host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+            self._pack_hosts.append(host)          # a captured graph may replay this upload: never freed
+            dev = self._refs_dev.device
+            if len(rows) > 4096:
+                raise RuntimeError("FusedClipAdamW: more than 4096 packed weight copies")
+            if self._pack_dev is None:      # fixed size: its address is baked into captured graphs
+                self._pack_dev = torch.zeros((4096, 10), dtype=torch.int64, device=dev)
+            self._pack_dev[:len(rows)].copy_(host, non_blocking=True)
+        self._pack_serial = K.pack_serial()
+
     @torch.no_grad()
     def step(self, closure=None):
         if closure is not None:
             raise ValueError("closures are not supported")
         g = self.param_groups[0]
-        if float(g["lr"]) != self._lr_host and not torch.cuda.is_current_stream_capturing():
-            self._lr_host = float(g["lr"])
-            self._lr.fill_(self._lr_host)
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
         self._refresh_refs()
+        self._refresh_pack_table()
         b1, b2 = g["betas"]
         refs = C.c_void_p(self._refs_dev.data_ptr())
         _lib.call("b2_grad_sqnorm_multi", refs, _p(self._block_tensor), _p(self._block_chunk), self._nblocks, _CHUNK,
@@ -154,4 +196,9 @@ class FusedClipAdamW(torch.optim.Optimizer):
         _lib.call("b2_adamw_multi", refs, _p(self._block_tensor), _p(self._block_chunk), self._nblocks, _CHUNK,
                   _p(self._sqnorm), self.max_norm, _p(self._lr), float(b1), float(b2), float(g["eps"]),
                   float(g["weight_decay"]), _p(self._step), _p(self.total_norm), _stream())
+        if self._pack_n:
+            # the fp32 masters just changed through raw pointers: refresh every bf16 MMA-layout copy in ONE launch
+            _lib.call("b2_pack_weights_multi", C.c_void_p(self._pack_dev.data_ptr()), self._pack_n, self._pack_items,
+                      _stream())
+        K.bump_param_epoch()
         return None

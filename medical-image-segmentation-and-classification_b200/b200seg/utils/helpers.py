@@ -6,7 +6,10 @@ Differences from the reference, all forced by the B200 path and listed in DESIGN
     fp32's exponent range); the autocast context is not used either — the modules always run bf16;
   * the loss is the fused b200seg::seg_loss op (BCEWithLogits, helpers.py:245), which also yields the IoU counts,
     so validation does not launch per-sample reductions (iou() below is kept for API compatibility);
-  * only `seg=True` is supported (the classification branch, helpers.py:257-283, is outside the hot path).
+  * only `seg=True` is supported (the classification branch, helpers.py:257-283, is outside the hot path);
+  * the training step (zero_grad .. optimizer.step, helpers.py:317-337) is captured once per batch shape in a CUDA graph
+    and replayed (engine.GraphedTrainStep; B200SEG_TRAIN_GRAPH=0 launches eagerly), and CPU batches are staged through
+    pinned memory and copied on a copy stream while the previous step computes (engine.PinnedPrefetcher).
 """
 from __future__ import annotations
 
@@ -69,7 +72,11 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
     scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=epochs)   # helpers.py:254
     best_score = float("inf")
     patience, patience_counter = 10, 0
-    params = [p for p in model.parameters() if p.requires_grad]
+    from ..engine import GraphedTrainStep, PinnedPrefetcher
+    on_gpu = device.type == "cuda"
+    stepper = GraphedTrainStep(model, optimizer, reducer=reducer, loss_weights=(1.0, 0.0, 1.0),     # helpers.py:245
+                               graph=on_gpu and os.environ.get("B200SEG_TRAIN_GRAPH", "1") != "0")
+    train.last_stepper = stepper          # introspection for tests / tools: replays, eager steps, capture errors
     start_time = time.time()
 
     try:
@@ -77,18 +84,13 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
             model.train()
             running = torch.zeros((), dtype=torch.float64, device=device)     # no per-step .item() (helpers.py:337)
             seen = 0
-            for x, y in train_dl:
-                x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
-                optimizer.zero_grad(set_to_none=True)
-                K.step_begin()                                                # one memset for the step's reduction buffers
-                out = model(x)
-                if out.dim() == 3:
-                    out = out.unsqueeze(1)
-                loss, _ = ops.seg_loss(out, y, 1.0, 0.0, 1.0)
-                loss.backward()
-                if reducer is not None:
-                    reducer.finish()
-                optimizer.step()                                              # clip_grad_norm_(1.0) + AdamW, fused
+            batches = PinnedPrefetcher(train_dl, device) if on_gpu else train_dl
+            for x, y in batches:
+                if not x.is_cuda:
+                    x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+                # zero_grad -> forward -> BCEWithLogits -> backward -> (all-reduce) -> clip_grad_norm_(1.0) + AdamW,
+                # replayed from a CUDA graph after the first few (eager) steps of each batch shape
+                loss = stepper(x.float(), y.float())
                 running += loss.detach().double() * x.size(0)
                 seen += x.size(0)
 

@@ -79,9 +79,104 @@ __global__ void __launch_bounds__(kOptThreads) adamw_kernel(const TensorRef* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Multi-tensor weight re-pack: ONE launch refreshes the bf16 MMA-layout copies of every convolution weight after the
+// optimizer step (SURVEY.md §8f N1 "... + bf16 weight re-pack"), instead of one pack launch per conv call in forward
+// and again in backward.  A work item is a 32 x 32 (cout x cin) tile of one tap of one tensor, moved through shared
+// memory so that the reads of w, the writes of the fprop layout [tap][cout][cin] and the writes of the transposed /
+// flipped dgrad layout [taps-1-tap][cin][cout] are all row-contiguous.
+//   kind 0  plain:   wf[tap][co][ci] = w[co][ci][kh][kw],  wd[taps-1-tap][ci][co]
+//   kind 1  UpConv folding (AttentionUNet.py:15-27): 4 phases x 4 taps of summed 3x3 taps (pack_weights_upfold_kernel)
+//   kind 2  3x3 image stem as a K = 32 GEMM: wf[co][tap * cin + c], zero padded (kernels.stem_weight_matrix)
+// ------------------------------------------------------------------------------------------------------------
+struct PackRef {       // mirrors b2_pack_ref
+  const float* w;
+  __nv_bfloat16* wf;
+  __nv_bfloat16* wd;
+  int cout, cin, ksize, kind;
+  long long s_co, s_ci, s_kh, s_kw;
+  int item_start, pad_;
+};
+
+__device__ __forceinline__ bool upfold_member_(int a, int u, int r) {
+  return a == 0 ? (u == 0 ? r == 0 : r >= 1) : (u == 0 ? r <= 1 : r == 2);
+}
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackRef* __restrict__ refs, int nrefs) {
+  __shared__ float tile[32][33];
+  // find the tensor of this work item: last ref with item_start <= blockIdx.x
+  int lo = 0, hi = nrefs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (refs[mid].item_start <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackRef r = refs[lo];
+  int item = (int)blockIdx.x - r.item_start;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tco = (r.cout + 31) / 32;
+  if (r.kind == 2) {                                    // stem matrix [cout][32]
+    const int co0 = item * 32;
+    const int ncol = r.ksize * r.ksize * r.cin;
+    for (int rr = ty; rr < 32; rr += 8) {
+      const int co = co0 + rr;
+      if (co >= r.cout) continue;
+      float v = 0.f;
+      if (tx < ncol) {
+        const int tap = tx / r.cin, c = tx % r.cin;
+        v = r.w[co * r.s_co + c * r.s_ci + (tap / r.ksize) * r.s_kh + (tap % r.ksize) * r.s_kw];
+      }
+      r.wf[(long long)co * 32 + tx] = __float2bfloat16_rn(v);
+    }
+    return;
+  }
+  const int tci = (r.cin + 31) / 32;
+  const int ci_t = item % tci;
+  item /= tci;
+  const int co_t = item % tco;
+  const int slab = item / tco;                          // tap (kind 0) or phase * 4 + tap (kind 1)
+  const int co0 = co_t * 32, ci0 = ci_t * 32;
+  const int taps = r.ksize * r.ksize;
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int co = co0 + rr, ci = ci0 + tx;
+    float v = 0.f;
+    if (co < r.cout && ci < r.cin) {
+      const float* base = r.w + co * r.s_co + ci * r.s_ci;
+      if (r.kind == 0) {
+        v = base[(slab / r.ksize) * r.s_kh + (slab % r.ksize) * r.s_kw];
+      } else {
+        const int phase = slab >> 2, tap = slab & 3;
+        const int a = phase >> 1, b = phase & 1, u = tap >> 1, vv = tap & 1;
+        for (int rw = 0; rw < 3; ++rw)
+          for (int c = 0; c < 3; ++c)
+            if (upfold_member_(a, u, rw) && upfold_member_(b, vv, c)) v += base[rw * r.s_kh + c * r.s_kw];
+      }
+      if (r.wf != nullptr) r.wf[((long long)slab * r.cout + co) * r.cin + ci] = __float2bfloat16_rn(v);
+    }
+    tile[rr][tx] = v;
+  }
+  if (r.wd == nullptr) return;
+  __syncthreads();
+  const int dslab = r.kind == 0 ? (taps - 1 - slab) : ((slab & ~3) + (3 - (slab & 3)));
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int ci = ci0 + rr, co = co0 + tx;
+    if (co < r.cout && ci < r.cin)
+      r.wd[((long long)dslab * r.cin + ci) * r.cout + co] = __float2bfloat16_rn(tile[tx][rr]);
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int b2_pack_weights_multi(const b2_pack_ref* refs, int32_t nrefs, int32_t total_items,
+                                     b2_stream_t stream) {
+  static_assert(sizeof(PackRef) == sizeof(b2_pack_ref), "PackRef must mirror b2_pack_ref");
+  B2_REQUIRE(nrefs > 0 && total_items > 0, B2_ERR_SHAPE, "empty pack launch");
+  pack_weights_multi_kernel<<<total_items, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackRef*>(refs),
+                                                                           nrefs);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
 
 extern "C" int b2_grad_sqnorm_multi(const b2_tensor_ref* refs, const int32_t* block_tensor, const int32_t* block_chunk,
                                     int32_t nblocks, int32_t chunk_elems, double* sqnorm, float* step,
