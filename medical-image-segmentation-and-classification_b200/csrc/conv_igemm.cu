@@ -24,6 +24,9 @@
 // through the L2 -> SM fabric, and the weight tile is 75 % of them at N <= 128; sharing it is worth 14-29 % per layer.
 // Optional clusters (B200SEG_CLUSTER=2|4, off by default: no measured gain): the CTAs of a cluster work on
 // consecutive m-tiles of one n-tile and share every weight tile, each fetching 1/cluster of its rows and multicasting.
+// CTA pairs (cta_group::2, IgemmParams::pair): the two CTAs of a 2-cluster share one M = 256 MMA, each holding its own
+// 128-pixel activation tile and half of the weight rows, which halves the weight bytes every SM pulls through the
+// L2 -> SM fabric without needing a second set of accumulators (the N = 256 layers fill TMEM with two buffers already).
 // The epilogue of tile i overlaps the main loop of tile i+1.
 //
 // Used for fprop (reference nn.Conv2d call sites, see include/b200seg.h) and for dgrad (flipped/transposed
@@ -64,6 +67,10 @@ struct IgemmParams {
   int debug_skip;     // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs, 4 = no drain
   int cluster;        // CTAs per cluster (1, 2 or 4): they work on consecutive m-tiles of one n-tile and share the
                       // weight tiles, each CTA fetching 1/cluster of the rows and multicasting them
+  int pair;           // CTA-pair mode (cluster == 2): ONE tcgen05.mma.cta_group::2 with M = 256 covers the two m-tiles of
+                      // the pair; each CTA stages its own activation tile and HALF of the weight rows in its own shared
+                      // memory (no multicast: each SM receives half the weight bytes), the rank-0 CTA issues the MMAs,
+                      // every CTA drains its own 128 accumulator rows
   __nv_bfloat16* y;
   int ldy;
   const float* bias;
@@ -137,11 +144,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], (uint32_t)C);   // every CTA of the cluster reads the shared weight slot
+      // multicast mode: every CTA of the cluster reads the shared weight slot; pair mode: one (multicast) commit of
+      // the leader's MMAs frees the slot in both CTAs
+      mbar_init(&empty_bar[s], p.pair ? 1u : (uint32_t)C);
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);      // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], p.pair ? 8u : 4u);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA0);
@@ -152,8 +161,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < nbuf * p.block_n) tmem_cols <<= 1;
   if (warp == 1) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if (p.pair) {
+      tmem_alloc_pair(tmem_slot, tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -166,7 +180,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ------------------------------ TMA producer (warp-uniform control flow) ------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx = (uint32_t)(a_slots * p.a_tx_bytes + p.b_stage_bytes);
+    // pair mode: the leader's barrier collects the bytes of BOTH CTAs (own A tile + half of B each)
+    const uint32_t tx = (uint32_t)(a_slots * p.a_tx_bytes + p.b_stage_bytes) * (p.pair ? 2u : 1u);
     const int b_taps = p.halo ? 3 : 1;           // weight taps per stage
     const int b_rows = p.block_n / C;            // weight rows this CTA fetches (and multicasts) per tap
     for (int item = cluster_id; item < total_items; item += num_clusters) {
@@ -205,7 +220,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (elect_one()) {
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + a_slots * p.a_stage_bytes;
-            if (p.debug_skip & 1) {
+            if (p.pair) {
+              // both CTAs load into their own smem; completion is counted on the LEADER's barrier, which only the
+              // leader arms (its arrive + expect_tx may come after the peer's bytes: the phase needs both)
+              const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
+              if (cb < p.cb0)
+                tma_load_4d_pair(sa, &tmA0, lbar, cb * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
+              else
+                tma_load_4d_pair(sa, &tmA1, lbar, (cb - p.cb0) * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
+              tma_load_3d_pair(sb, &tmB, lbar, cb * kKBlock, n_tile * p.block_n + (int)crank * b_rows, tap0);
+            } else if (p.debug_skip & 1) {
               mbar_arrive(&full_bar[stage]);
             } else {
             mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -243,9 +268,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    const uint32_t idesc = umma_idesc_bf16(kTileM, p.block_n, 0, 0);
+  } else if (warp == 1 && !(p.pair && crank != 0)) {
+    // ------------------------------ MMA issuer (pair mode: the leader CTA only) ------------------------------
+    const uint32_t idesc = umma_idesc_bf16(p.pair ? 2 * kTileM : kTileM, p.block_n, 0, 0);
+    const uint32_t b_tap_step = (uint32_t)(p.pair ? p.block_n / 2 : p.block_n) * 8u;   // descriptor units between taps
     const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);          // K-major SW128 descriptor with start address 0
     const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo0 = (uint32_t)desc0;
@@ -279,12 +305,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               uint32_t a_lo = desc_lo0 + ((a_addr + (uint32_t)(q * p.a_stage_bytes)) >> 4);
               uint32_t b_lo = desc_lo0 + (b_addr >> 4);
               for (int s = 0; s < nsub; ++s) {     // (a fully unrolled 12-MMA variant measured slower)
+                if (p.pair) {
 #pragma unroll
-                for (int k = 0; k < kKBlock / 16; ++k)
-                  umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
-                            (it | s | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < kKBlock / 16; ++k)
+                    umma_bf16_pair(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                                   (it | s | k) != 0 ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < kKBlock / 16; ++k)
+                    umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
+                              (it | s | k) != 0 ? 1u : 0u);
+                }
                 a_lo += 8;
-                b_lo += (uint32_t)p.block_n * 8u;
+                b_lo += b_tap_step;
               }
             }
           } else {
@@ -302,7 +335,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           }
           // frees this smem slot (in every CTA that multicasts into it) when the MMAs have read it
-          if (C == 1) umma_commit(&empty_bar[stage]);
+          if (p.pair) umma_commit_pair(&empty_bar[stage], 3);
+          else if (C == 1) umma_commit(&empty_bar[stage]);
           else umma_commit_mc(&empty_bar[stage], cmask);
         }
         __syncwarp();
@@ -312,12 +346,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
       if (elect_one()) {
-        for (int q = 0; q < a_slots; ++q)
-          umma_commit(&tmem_full_bar[(uint32_t)(a_slots * ti + q) & (uint32_t)(nbuf - 1)]);
+        for (int q = 0; q < a_slots; ++q) {
+          uint64_t* fb = &tmem_full_bar[(uint32_t)(a_slots * ti + q) & (uint32_t)(nbuf - 1)];
+          if (p.pair) umma_commit_pair(fb, 3);      // both CTAs drain their half of the M = 256 accumulator
+          else umma_commit(fb);
+        }
       }
       __syncwarp();
     }
-  } else if (((warp - 2) >> 2) < p.epi_groups) {
+  } else if (warp >= 2 && ((warp - 2) >> 2) < p.epi_groups) {
     // ---------------- epilogue: group 0 = warps 2..5, group 1 = warps 6..9 (tiles alternate between groups) ----------------
     const int g = (warp - 2) >> 2;
     const int G = p.epi_groups;
@@ -390,7 +427,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[dbuf]);
+        if (lane == 0) {
+          if (p.pair) mbar_arrive_remote(&tmem_empty_bar[dbuf], 0);
+          else mbar_arrive(&tmem_empty_bar[dbuf]);
+        }
         continue;
       }
       if (n_tile != cur_n_tile) {
@@ -485,7 +525,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if (p.pair) mbar_arrive_remote(&tmem_empty_bar[buf], 0);    // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(&tmem_empty_bar[buf]);
+      }
       fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA store
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 
@@ -548,7 +591,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (C > 1) cluster_sync_all();       // no CTA leaves while a peer may still signal its barriers
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 1) {
+    if (p.pair) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 // Tile geometry shared with the wgrad kernel: split `tile_pix` pixels into a (Wb, Hb, Nb) box.
@@ -702,6 +748,19 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
       if (g2 / sb2 >= 2 || (want == 2 && g1 / sb2 >= 2)) p.dm = 1;
     }
   }
+  // CTA pairs (cta_group::2): B200SEG_PAIR = 0 off, 1 the N = 256 tiles (no room in TMEM for the double-M sharing),
+  // 2 every eligible layer (replaces double-M there).
+  {
+    const int want = env_int("B200SEG_PAIR", 0);
+    p.pair = 0;
+    if (want != 0 && !p.rp && p.m_tiles >= 2 && p.block_n % 16 == 0 && (want >= 2 || p.block_n == 256) &&
+        env_int("B200SEG_CLUSTER", 0) <= 1 && env_int("B200SEG_DEBUG_SKIP", 0) == 0) {
+      p.pair = 1;
+      p.dm = 0;
+      p.base_off_mode = 0;
+      p.b_stage_bytes /= 2;          // each CTA of the pair stages half of the weight rows
+    }
+  }
   const int stage_bytes = (p.dm ? 2 : 1) * p.a_stage_bytes + p.b_stage_bytes;
   // Two epilogue groups (two staging tiles) when the accumulator drain, not the MMA, paces a tile: the drain costs
   // about 1750 + 36 * BLOCK_N clocks per tile per group (measured), the MMAs K/16 * BLOCK_N/2.  A second group is
@@ -730,6 +789,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     if (forced_c == 1 || forced_c == 2 || forced_c == 4) c = forced_c;
     while (c > 1 && ((p.block_n / c) % 8 != 0 || p.m_tiles < c)) c /= 2;
     if (p.rp || p.dm) c = 1;
+    if (p.pair) c = 2;
     p.cluster = c;
   }
   const int budget = 232448 - 1024 - tail_bytes - p.epi_groups * ctile_bytes;
@@ -765,7 +825,9 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     uint64_t dims[3] = {(uint64_t)(a->c0 + a->c1), (uint64_t)a->cout, (uint64_t)p.taps};
     uint64_t str[3] = {2, (uint64_t)a->ktot * 2, (uint64_t)a->w_tap_stride * 2};
     uint32_t box[3] = {64, (uint32_t)p.block_n, p.halo ? 3u : 1u};
-    if (p.cluster > 1) {          // one multicast box per tap: this CTA's share of the rows
+    if (p.pair) {                 // this CTA's half of the rows, all taps of the stage in one box
+      box[1] = (uint32_t)(p.block_n / 2);
+    } else if (p.cluster > 1) {   // one multicast box per tap: this CTA's share of the rows
       box[1] = (uint32_t)(p.block_n / p.cluster);
       box[2] = 1u;
     }
