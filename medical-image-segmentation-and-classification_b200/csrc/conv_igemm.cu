@@ -109,7 +109,9 @@ __device__ __forceinline__ uint32_t ctile_off(int block_n, int row, int ch) {
   return (uint32_t)(row * 64 + ((((ch >> 3) ^ ((row >> 1) & 3))) << 4) + ((ch & 7) << 1));
 }
 
-template <bool kHasAdd>
+// kPair: the CTA-pair variant is a separate instantiation — a kernel that contains cta_group::2 instructions can only
+// be launched as (multiples of) 2-CTA clusters, so the single-CTA kernel must not contain them.
+template <bool kHasAdd, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
@@ -161,7 +163,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < nbuf * p.block_n) tmem_cols <<= 1;
   if (warp == 1) {
-    if (p.pair) {
+    if constexpr (kPair) {
       tmem_alloc_pair(tmem_slot, tmem_cols);
       tmem_relinquish_pair();
     } else {
@@ -220,7 +222,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (elect_one()) {
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + a_slots * p.a_stage_bytes;
-            if (p.pair) {
+            if constexpr (kPair) {
               // both CTAs load into their own smem; completion is counted on the LEADER's barrier, which only the
               // leader arms (its arrive + expect_tx may come after the peer's bytes: the phase needs both)
               const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
@@ -230,7 +232,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               else
                 tma_load_4d_pair(sa, &tmA1, lbar, (cb - p.cb0) * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
               tma_load_3d_pair(sb, &tmB, lbar, cb * kKBlock, n_tile * p.block_n + (int)crank * b_rows, tap0);
-            } else if (p.debug_skip & 1) {
+            } else {
+            if (p.debug_skip & 1) {
               mbar_arrive(&full_bar[stage]);
             } else {
             mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -259,6 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                                cb * kKBlock, n_tile * p.block_n + (int)crank * b_rows, tap0 + tp, cmask);
             }
             }
+            }
           }
           __syncwarp();
           if (++stage == p.stages) {
@@ -268,10 +272,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 && !(p.pair && crank != 0)) {
+  } else if (warp == 1 && !(kPair && crank != 0)) {
     // ------------------------------ MMA issuer (pair mode: the leader CTA only) ------------------------------
-    const uint32_t idesc = umma_idesc_bf16(p.pair ? 2 * kTileM : kTileM, p.block_n, 0, 0);
-    const uint32_t b_tap_step = (uint32_t)(p.pair ? p.block_n / 2 : p.block_n) * 8u;   // descriptor units between taps
+    const uint32_t idesc = umma_idesc_bf16(kPair ? 2 * kTileM : kTileM, p.block_n, 0, 0);
+    const uint32_t b_tap_step = (uint32_t)(kPair ? p.block_n / 2 : p.block_n) * 8u;   // descriptor units between taps
     const uint64_t desc0 = umma_desc_sw128(0, 16, 1024);          // K-major SW128 descriptor with start address 0
     const uint64_t desc_hi = desc0 & 0xFFFFFFFF00000000ull;
     const uint32_t desc_lo0 = (uint32_t)desc0;
@@ -305,7 +309,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               uint32_t a_lo = desc_lo0 + ((a_addr + (uint32_t)(q * p.a_stage_bytes)) >> 4);
               uint32_t b_lo = desc_lo0 + (b_addr >> 4);
               for (int s = 0; s < nsub; ++s) {     // (a fully unrolled 12-MMA variant measured slower)
-                if (p.pair) {
+                if constexpr (kPair) {
 #pragma unroll
                   for (int k = 0; k < kKBlock / 16; ++k)
                     umma_bf16_pair(d_tmem, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc,
@@ -335,9 +339,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           }
           // frees this smem slot (in every CTA that multicasts into it) when the MMAs have read it
-          if (p.pair) umma_commit_pair(&empty_bar[stage], 3);
-          else if (C == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_mc(&empty_bar[stage], cmask);
+          if constexpr (kPair) {
+            umma_commit_pair(&empty_bar[stage], 3);
+          } else {
+            if (C == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_mc(&empty_bar[stage], cmask);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -348,7 +355,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (elect_one()) {
         for (int q = 0; q < a_slots; ++q) {
           uint64_t* fb = &tmem_full_bar[(uint32_t)(a_slots * ti + q) & (uint32_t)(nbuf - 1)];
-          if (p.pair) umma_commit_pair(fb, 3);      // both CTAs drain their half of the M = 256 accumulator
+          if constexpr (kPair) umma_commit_pair(fb, 3);      // both CTAs drain their half of the M = 256 accumulator
           else umma_commit(fb);
         }
       }
@@ -428,7 +435,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (p.pair) mbar_arrive_remote(&tmem_empty_bar[dbuf], 0);
+          if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[dbuf], 0);
           else mbar_arrive(&tmem_empty_bar[dbuf]);
         }
         continue;
@@ -526,7 +533,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.pair) mbar_arrive_remote(&tmem_empty_bar[buf], 0);    // the leader's MMA thread waits for both CTAs
+        if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[buf], 0);    // the leader's MMA thread waits for both CTAs
         else mbar_arrive(&tmem_empty_bar[buf]);
       }
       fence_proxy_async();                       // generic-proxy smem writes -> visible to the TMA store
@@ -592,7 +599,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __syncthreads();
   if (C > 1) cluster_sync_all();       // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
-    if (p.pair) tmem_dealloc_pair(tmem_base, tmem_cols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, tmem_cols);
     else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
@@ -749,9 +756,11 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     }
   }
   // CTA pairs (cta_group::2): B200SEG_PAIR = 0 off, 1 the N = 256 tiles (no room in TMEM for the double-M sharing),
-  // 2 every eligible layer (replaces double-M there).
+  // 2 (default) every eligible layer (replaces double-M there).  Measured at batch 64 (profiles/r02_conv_layers_pair*):
+  // N = 256 layers 1224 -> 1460 ... 1385 -> 1637 TFLOP/s, 64 -> 128 @128^2 944 -> 1218, 64 -> 64 @256^2 853 -> 910;
+  // conv_igemm time inside the training step 16.3 -> 14.7 ms.
   {
-    const int want = env_int("B200SEG_PAIR", 0);
+    const int want = env_int("B200SEG_PAIR", 2);
     p.pair = 0;
     if (want != 0 && !p.rp && p.m_tiles >= 2 && p.block_n % 16 == 0 && (want >= 2 || p.block_n == 256) &&
         env_int("B200SEG_CLUSTER", 0) <= 1 && env_int("B200SEG_DEBUG_SKIP", 0) == 0) {
@@ -862,8 +871,10 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
   // persistent grid: one CTA per SM.  When the number of clusters is a multiple of n_tiles every CTA keeps one n-tile
@@ -885,7 +896,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
       qc.attrs = qa;
       qc.numAttrs = 1;
       int n = 0;
-      B2_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_igemm_kernel<false>, &qc));
+      B2_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_igemm_kernel<false, false>, &qc));
       B2_REQUIRE(n > 0, B2_ERR_CUDA, "no cluster of %d CTAs can be resident", C);
       max_clusters[C] = n;
     }
@@ -917,10 +928,16 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   p.stats_partial = det.partial;
-  if (p.addend != nullptr)
-    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tmA0, tmA1, tmB, tmY, p));
-  else
-    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tmA0, tmA1, tmB, tmY, p));
+  if (p.pair) {
+    if (p.addend != nullptr)
+      B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, tmA0, tmA1, tmB, tmY, p));
+    else
+      B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, tmA0, tmA1, tmB, tmY, p));
+  } else if (p.addend != nullptr) {
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, tmA0, tmA1, tmB, tmY, p));
+  } else {
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, tmA0, tmA1, tmB, tmY, p));
+  }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, det_rows, 2 * p.cout, 2 * p.cout, p.stats, stream);
   return B2_OK;

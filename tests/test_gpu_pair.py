@@ -105,8 +105,8 @@ def test_pair_mode_two_sources_stride_and_placement(mode):
 
 def test_pair_mode_whole_model_step():
     """AttentionUNet eval-mode forward + backward with every eligible layer in pair mode == the default path, bitwise
-    (eval mode: no batch statistics, so nothing depends on summation order except the bias / BN-affine gradient sums,
-    which are compared to fp32 rounding)"""
+    (eval mode: no batch statistics, so nothing depends on summation order except the bias / BN-affine / head / psi
+    gradient sums (atomics), which are compared to fp32 rounding)"""
     from b200seg import ops
     from b200seg.models.segmentation_models import AttentionUNet
     from b200seg.utils.synthetic import xray_batch
@@ -127,7 +127,7 @@ def test_pair_mode_whole_model_step():
         l1, g1 = run()
     assert torch.equal(l0, l1)
     for k in g0:
-        if g0[k].dim() == 4:
-            assert torch.equal(g0[k], g1[k]), k              # weight gradients: deterministic kernels on identical inputs
+        if g0[k].dim() == 4 and g0[k].shape[0] >= 32:
+            assert torch.equal(g0[k], g1[k]), k              # tensor-core weight gradients: deterministic on identical inputs
         else:
             assert torch.allclose(g0[k], g1[k], rtol=1e-4, atol=1e-7), k
