@@ -331,6 +331,37 @@ def packed(weight, kind="plain", want_dgrad=False):
     return wf, wd
 
 
+# ----------------------------------------------------------------------------------------------------------
+# Gradient slots: a data-parallel reducer (ddp.GradReducer) registers, per conv weight, the slice of its flat bucket
+# where that weight's gradient belongs.  The weight-gradient kernels then write straight into the bucket and autograd
+# adopts a view of it as `weight.grad` — no pack copy before the all-reduce, no copy back after it.
+# ----------------------------------------------------------------------------------------------------------
+_GRAD_SLOTS = {}
+
+
+def register_grad_slot(weight, flat_slice):
+    """flat_slice: 1-D fp32 view (weight.numel() elements) of the bucket; memory order = [Cout][taps][Cin]"""
+    import weakref
+    assert flat_slice.dtype == torch.float32 and flat_slice.numel() == weight.numel() and flat_slice.is_contiguous()
+    _GRAD_SLOTS[weight.data_ptr()] = (weakref.ref(weight), flat_slice)
+
+
+def unregister_grad_slots(weights=None):
+    if weights is None:
+        _GRAD_SLOTS.clear()
+        return
+    for w in weights:
+        _GRAD_SLOTS.pop(w.data_ptr(), None)
+
+
+def grad_slot(weight, shape):
+    """a FRESH tensor (so AccumulateGrad can adopt it) viewing the registered bucket slice as `shape`, or None"""
+    hit = _GRAD_SLOTS.get(weight.data_ptr())
+    if hit is None or hit[0]() is not weight or not grad_is_stolen(weight):
+        return None
+    return hit[1].view(shape)
+
+
 def packs_of(params):
     """every live cached pack whose master is one of `params` (FusedClipAdamW builds its re-pack table from this)"""
     ptrs = {p.data_ptr(): p for p in params}
@@ -377,10 +408,11 @@ def pack_weights_folded(weight, bias, coef, upfold=False):
     return wf, bf
 
 
-def fold_upconv_wgrad(dweff):
+def fold_upconv_wgrad(dweff, out=None):
     """fp32 [4 phases, Cout, 4 taps, Cin] -> fp32 [Cout, 9, Cin]"""
     _, cout, _, cin = dweff.shape
-    dw = torch.empty((cout, 9, cin), dtype=torch.float32, device=dweff.device)
+    dw = out if out is not None else torch.empty((cout, 9, cin), dtype=torch.float32, device=dweff.device)
+    assert dw.is_contiguous() and dw.numel() == cout * 9 * cin
     call("b2_fold_upconv_wgrad", _p(dweff), cout, cin, _p(dw), _stream())
     return dw
 

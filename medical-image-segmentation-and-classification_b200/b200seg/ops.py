@@ -102,7 +102,7 @@ def conv2d_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], weight: Tensor, nee
     if need_dw:
         x0c, x1c = _c(x0), _c(x1)
         with K.wgrad_stream(dy, x0c, x1c, allow=K.grad_is_stolen(weight)):
-            dw = K.conv_wgrad(dy, x0c, k, x1=x1c)
+            dw = K.conv_wgrad(dy, x0c, k, x1=x1c, out=K.grad_slot(weight, (cout, k * k, cin)))
     else:
         dw = torch.empty((0,), device=dev)
     db = K.channel_sum(dy) if need_db else torch.empty((0,), device=dev)
@@ -344,14 +344,14 @@ def conv_bn_act_bwd(dy: Tensor, x0: Tensor, x1: Optional[Tensor], x4: Tensor, we
                 dx1 = K.conv_igemm(dz, wd, x1.shape[3], k, row_offset=c0, dgrad=True)
         with K.wgrad_stream(dz, x0, x1, allow=K.grad_is_stolen(weight)):
             if share_count <= 1:
-                dw = K.conv_wgrad(dz, x0, k, x1=x1)
+                dw = K.conv_wgrad(dz, x0, k, x1=x1, out=K.grad_slot(weight, (cout, k * k, cin)))
             else:
                 # shared weight: backward visits the applications in reverse order (each consumes the previous one's
                 # output), so the last application opens the buffer, the others add to it, application 0 returns it
                 key = (weight.data_ptr(), dz.device.index)
                 buf = None if share_index == share_count - 1 else _SHARED_DW.get(key)
                 if buf is None:
-                    buf = K.conv_wgrad(dz, x0, k, x1=x1)
+                    buf = K.conv_wgrad(dz, x0, k, x1=x1, out=K.grad_slot(weight, (cout, k * k, cin)))
                 else:
                     K.conv_wgrad(dz, x0, k, x1=x1, out=buf, accumulate=True)
                 if share_index == 0:
@@ -481,7 +481,7 @@ def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Te
         dweff = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=dev)
         for ph, (a, b) in enumerate(_PHASES):
             K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
-        dw = K.fold_upconv_wgrad(dweff)
+        dw = K.fold_upconv_wgrad(dweff, out=K.grad_slot(weight, (cout, 9, cin)))
     return dx, dw, db, dgamma, dbeta
 
 

@@ -91,8 +91,8 @@ def attention_gate_bwd(dout: Tensor, g: Tensor, x: Tensor, wg: Tensor, wx: Tenso
         _, wxd = K.packed(wx, want_dgrad=True)
         K.conv_igemm(dx1p, wxd, x.shape[3], 1, addend=dx, out=dx, dgrad=True)     # dx += dx1p . W_x (epilogue add)
     with K.wgrad_stream(dg1p, dx1p, g, x, allow=K.grad_is_stolen(wg) and K.grad_is_stolen(wx)):
-        dwg = K.conv_wgrad(dg1p, g, 1)
-        dwx = K.conv_wgrad(dx1p, x, 1)
+        dwg = K.conv_wgrad(dg1p, g, 1, out=K.grad_slot(wg, (fint, 1, g.shape[3])))
+        dwx = K.conv_wgrad(dx1p, x, 1, out=K.grad_slot(wx, (fint, 1, x.shape[3])))
     return dg, dx, dwg, dwx, dgb, dbn1, dwpsi, dbpsi, dbias
 
 

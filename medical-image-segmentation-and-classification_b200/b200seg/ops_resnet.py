@@ -120,7 +120,7 @@ def conv_transpose2x2_bwd(dy: Tensor, x: Tensor, weight: Tensor, need_dx: bool,
     else:
         dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     with K.wgrad_stream(x, dy, allow=K.grad_is_stolen(weight)):
-        dw = K.conv_wgrad(x, dy, 2, x_stride=2)                                 # [Cin][4][Cout]
+        dw = K.conv_wgrad(x, dy, 2, x_stride=2, out=K.grad_slot(weight, (cin, 4, cout)))   # [Cin][4][Cout]
     db = K.channel_sum(dy) if has_bias else torch.empty((0,), device=dev)
     return dx, dw, db
 
