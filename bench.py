@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fixed GLOBAL batch split over the ranks (strong scaling: BASELINE.json configs[2] R2AttU b32, "
+                         "configs[3] ResNetUnet b128); overrides --batch")
     ap.add_argument("--model", default="AttentionUNet", choices=["AttentionUNet", "R2U_Net", "R2AttU_Net", "ResNetUnet"])
     ap.add_argument("--t", type=int, default=None, help="recurrence depth for the R2 models (reference default 5)")
     ap.add_argument("--side", type=int, default=256)
@@ -234,6 +237,9 @@ def run_b200(args):
     else:
         opt = torch.optim.AdamW(trainable, lr=1e-6, weight_decay=5e-4, fused=True, capturable=use_graph)
     reducer = GradReducer(model, bucket_mb=32) if world > 1 else None
+    if args.global_batch:
+        assert args.global_batch % world == 0, "--global-batch must be divisible by the number of ranks"
+        args.batch = args.global_batch // world
     B, S = args.batch, args.side
     x_host, t_host = xray_batch(B, S, S, seed=100 + rank)
     x_host, t_host = x_host.pin_memory(), t_host.pin_memory()
@@ -338,6 +344,8 @@ def run_b200(args):
     ms_e2e = timed(e2e_step, args.steps)
     h2d_per_step = pre.h2d_bytes // (args.steps + 1)
     _tick("e2e done")
+    # data-parallel sanity inside the measured run: after all those steps every replica must hold the same parameters
+    replicas_in_sync = (reducer.param_checksum() == 0.0) if reducer is not None else None
     graph = stepper if graphed else None
 
     # instrumented pass for the roofline of the tensor-core kernels
@@ -388,7 +396,8 @@ def run_b200(args):
     line = {
         "metric": METRIC if args.model == "AttentionUNet" else f"{args.model} {S}x{S} train images/sec",
         "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "strong" if args.global_batch else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.model} {S}x{S} training step (fwd + BCEWithLogits + bwd + clip_grad_norm + "
                                f"AdamW), batch {B} per GPU, random init, synthetic X-ray-shaped inputs",
@@ -399,6 +408,7 @@ def run_b200(args):
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(h2d_per_step),
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "replicas_in_sync": replicas_in_sync,
         "clocks": clocks,
         "roofline": {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM; fprop + dgrad launches)",
                      "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
