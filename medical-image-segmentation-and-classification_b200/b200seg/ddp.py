@@ -35,7 +35,7 @@ class _Bucket:
         off = 0
         for p in params:
             self.offsets.append(off)
-            off += p.numel()
+            off += (p.numel() + 63) // 64 * 64      # 256 B aligned slices: kernels write gradients straight into them
         self.flat = torch.zeros(off, dtype=torch.float32, device=device)
         self.pending = len(params)
         self.work = None
