@@ -329,6 +329,45 @@ typedef struct b2_pack_ref {
 
 int b2_pack_weights_multi(const b2_pack_ref* refs, int32_t nrefs, int32_t total_items, b2_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 parity mode (BASELINE.json north_star: "fp32-accumulate mode within 1e-4"): the inference path with fp32
+ * activation storage and fp32 FMA accumulation on the CUDA cores, for callers that need the reference's own fp32
+ * results — utils/pipeline.py:340-357 runs `logits = model(img)` in fp32 without autocast and thresholds
+ * sigmoid(logits) > 0.5.  Activations are NHWC fp32 [N, H, W, C] (channel stride ld*); weights are packed by
+ * b2_f32_pack_weights to [tap][cin][cout] with the eval-mode BatchNorm folded in (W * scale[co], bias * scale + shift;
+ * AttentionUNet.py:7-8 etc.).  b2_f32_conv covers every convolution of the four models: ksize <= 7, stride 1|2,
+ * explicit padding, K from two tensors (elided torch.cat), + bias (+ addend before or after the ReLU), and the strided
+ * output placement that turns ConvTranspose2d(k2, s2) (ResnetUnet.py:21,53) into four 1x1 convolutions.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b2_f32_conv_args {
+  const float* x0;        /* NHWC fp32 */
+  const float* x1;        /* optional second K source */
+  int32_t c0, c1, ldx0, ldx1;
+  int32_t n, hi, wi;      /* input extent */
+  int32_t ho, wo;         /* output grid extent (before out_mul) */
+  int32_t ksize, stride, pad_h, pad_w;
+  const float* w;         /* [ksize*ksize][c0 + c1][cout] */
+  const float* bias;      /* [cout] or NULL */
+  const float* addend;    /* optional NHWC fp32 [.., cout] on the OUTPUT grid (dense pixels, channel stride ldadd) */
+  int32_t ldadd, add_after_act, relu, cout;
+  float* y;               /* NHWC fp32 */
+  int32_t ldy, out_mul, out_off_h, out_off_w;
+} b2_f32_conv_args;
+
+int b2_f32_conv(const b2_f32_conv_args* args, b2_stream_t stream);
+int b2_f32_pack_weights(const float* w, int32_t cout, int32_t cin, int32_t ksize, int64_t s_co, int64_t s_ci,
+                        int64_t s_kh, int64_t s_kw, const float* scale, const float* shift, const float* bias,
+                        float* w_out, float* bias_out, b2_stream_t stream);
+/* out = x * sigmoid(scale1 * (bpsi + wpsi . relu(g1 + x1)) + shift1): the attention gate after its two 1x1
+ * convolutions (AttentionUNet.py:48-54); g1, x1 dense [npix][fint] */
+int b2_f32_gate_tail(const float* g1, const float* x1, int32_t fint, const float* wpsi, const float* bpsi,
+                     const float* scale1, const float* shift1, const float* x, int32_t ldx, int32_t c, int64_t npix,
+                     float* out, int32_t ldo, b2_stream_t stream);
+int b2_f32_maxpool(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t ksize, int32_t stride,
+                   int32_t pad, float* y, b2_stream_t stream);         /* nn.MaxPool2d(2,2) / (3,2,1) */
+int b2_f32_upsample2x(const float* x, int32_t n, int32_t h, int32_t w, int32_t c, float* y, b2_stream_t stream);
+int b2_f32_layout(const float* x, int32_t n, int32_t c, int64_t hw, int32_t to_nchw, float* y, b2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,3 +10,12 @@ Layout
   ddp.py       bucketed NCCL gradient all-reduce
 """
 __version__ = "0.1.0"
+
+
+def __getattr__(name):
+    # b200seg.precision("fp32") / set_precision / get_precision: the fp32 parity mode switch (ops_fp32.py), resolved
+    # lazily so that importing the package stays free of torch.library / ctypes work
+    if name in ("precision", "set_precision", "get_precision"):
+        from . import ops_fp32
+        return getattr(ops_fp32, name)
+    raise AttributeError(f"module 'b200seg' has no attribute {name!r}")

@@ -45,6 +45,16 @@ class WgradArgs(C.Structure):
                 ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32)]
 
 
+class F32ConvArgs(C.Structure):
+    """struct b2_f32_conv_args"""
+    _fields_ = [("x0", _vp), ("x1", _vp), ("c0", _i32), ("c1", _i32), ("ldx0", _i32), ("ldx1", _i32),
+                ("n", _i32), ("hi", _i32), ("wi", _i32), ("ho", _i32), ("wo", _i32),
+                ("ksize", _i32), ("stride", _i32), ("pad_h", _i32), ("pad_w", _i32),
+                ("w", _vp), ("bias", _vp), ("addend", _vp),
+                ("ldadd", _i32), ("add_after_act", _i32), ("relu", _i32), ("cout", _i32),
+                ("y", _vp), ("ldy", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32)]
+
+
 class GateCoef(C.Structure):
     """struct b2_gate_coef"""
     _fields_ = [(k, _vp) for k in (
@@ -104,6 +114,12 @@ SIGNATURES = {
     "b2_grad_sqnorm_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2_adamw_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "b2_pack_weights_multi": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "b2_f32_conv": (C.c_int, [C.POINTER(F32ConvArgs), _vp]),
+    "b2_f32_pack_weights": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_f32_gate_tail": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _i32, _vp]),
+    "b2_f32_maxpool": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b2_f32_upsample2x": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "b2_f32_layout": (C.c_int, [_vp, _i32, _i32, _i64, _i32, _vp, _vp]),
     "b2_loss_fwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "b2_loss_finalize": (C.c_int, [_vp, _i64, _f32, _f32, _f32, _vp, _vp]),
     "b2_loss_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _f32, _f32, _f32, _vp, _vp, _vp]),

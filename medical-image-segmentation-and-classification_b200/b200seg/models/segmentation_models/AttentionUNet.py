@@ -61,5 +61,8 @@ class AttentionUNet(nn.Module):
         return d2
 
     def forward(self, x: torch.Tensor):
+        from ... import ops_fp32
+        if ops_fp32.active(self):                 # fp32 parity mode (inference): b200seg.precision("fp32")
+            return ops_fp32.attention_unet(self, check_image(x))
         d2 = self.features(check_image(x))
         return ops.head(d2, self.out.weight, self.out.bias)    # raw logits, fp32 NCHW

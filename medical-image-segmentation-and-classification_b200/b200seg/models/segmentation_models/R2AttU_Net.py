@@ -60,5 +60,8 @@ class R2AttU_Net(nn.Module):
         return d2
 
     def forward(self, x):
+        from ... import ops_fp32
+        if ops_fp32.active(self):                 # fp32 parity mode (inference): b200seg.precision("fp32")
+            return ops_fp32.r2_net(self, check_image(x), gates=True)
         d2 = self.features(check_image(x))
         return ops.head(d2, self.conv_1x1.weight, self.conv_1x1.bias)

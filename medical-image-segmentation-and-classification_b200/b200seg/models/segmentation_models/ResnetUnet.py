@@ -112,6 +112,9 @@ class ResNetUnet(nn.Module):
 
     def forward(self, x):
         x = check_image(x)
+        from ... import ops_fp32
+        if ops_fp32.active(self):                 # fp32 parity mode (inference): b200seg.precision("fp32")
+            return ops_fp32.resnet_unet(self, x)
         e1, e2, e3, e4, e5 = self._encode(x)
         d5 = self.decoder5(e5, e4)
         d4 = self.decoder4(d5, e3)

@@ -43,8 +43,10 @@ def noise_batch(n, h=256, w=256, seed=1234, device="cpu", dtype=torch.float32):
     return x.to(device=device, dtype=dtype), t.to(device=device, dtype=dtype)
 
 
-def fill_state_dict_(sd, seed=0):
-    """In-place deterministic fill of a state_dict (keys visited in sorted order; each key has its own stream)."""
+def fill_state_dict_(sd, seed=0, conv_gain=1.0):
+    """In-place deterministic fill of a state_dict (keys visited in sorted order; each key has its own stream).
+    conv_gain scales the He-normal convolution weights (< 1 keeps eval-mode activations of the recurrent models, whose
+    x + x1 re-injection doubles the variance at every application, in range)."""
     for idx, k in enumerate(sorted(sd.keys())):
         v = sd[k]
         g = torch.Generator().manual_seed(seed * 100003 + idx)
@@ -56,7 +58,7 @@ def fill_state_dict_(sd, seed=0):
             v.copy_(1.0 + 0.2 * torch.rand(v.shape, generator=g))
         elif v.dim() == 4:                                          # conv / conv-transpose weight
             fan_in = v.shape[1] * v.shape[2] * v.shape[3]
-            v.copy_(torch.randn(v.shape, generator=g) * math.sqrt(2.0 / fan_in))
+            v.copy_(torch.randn(v.shape, generator=g) * (conv_gain * math.sqrt(2.0 / fan_in)))
         elif k.endswith("weight"):                                  # BatchNorm gamma
             v.copy_(1.0 + 0.1 * torch.randn(v.shape, generator=g))
         else:                                                       # conv bias / BatchNorm beta

@@ -107,12 +107,16 @@ def test_segmentation_model(model, test_loader, device, model_name, log=print):
 test_segmentation_model.__test__ = False      # not a pytest test
 
 
-def predict_mask(model, img_tensor, threshold=0.5):
+def predict_mask(model, img_tensor, threshold=0.5, precision=None):
     """pipeline.py:340-357 (_predict_segmentation, U-Net branch): logits -> uint8 {0,255} mask on the host.
-    `img_tensor`: [1,3,H,W] (or [N,3,H,W]) normalised image; returns a numpy array [H,W] (or [N,H,W])."""
+    `img_tensor`: [1,3,H,W] (or [N,3,H,W]) normalised image; returns a numpy array [H,W] (or [N,H,W]).
+    precision="fp32": run the fp32 parity mode (ops_fp32.py) — the reference computes this path in fp32, and its masks
+    are reproduced bit for bit only at that precision; None: whatever b200seg.get_precision() says (default bf16)."""
+    import contextlib
+    from .. import ops_fp32
     model.eval()
     dev = next(model.parameters()).device
-    with torch.no_grad():
+    with torch.no_grad(), (ops_fp32.precision(precision) if precision else contextlib.nullcontext()):
         logits = model(img_tensor.to(dev)).float().contiguous()
         mask = K.logits_to_mask(logits, threshold)
     mask = mask.cpu()

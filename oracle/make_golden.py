@@ -154,6 +154,51 @@ def golden_metrics():
     return out
 
 
+FP32_CASES = ("AttentionUNet", "R2U_Net", "R2AttU_Net", "ResNetUnet")
+FP32_SIDE = 128
+FP32_GAIN = {"AttentionUNet": 1.0, "R2U_Net": 0.62, "R2AttU_Net": 0.8, "ResNetUnet": 1.0}   # see fill_state_dict_
+
+
+def golden_fp32_masks():
+    """The reference's own inference path (utils/pipeline.py:340-357: model.eval(), torch.no_grad(), fp32, no autocast,
+    mask = sigmoid(logits) > 0.5) on one synthetic X-ray per model, with the deterministic weights of
+    fill_state_dict_.  Stored: the fp32 logits and the packed {0,1} mask.  The input seed of each model is the one
+    (of 24) whose logits stay farthest from the threshold, so that 'bit-equal masks' is a meaningful gate for an
+    implementation that sums in a different order (fp32 summation-order noise is ~1e-6 relative) — the margin
+    min |logit| actually found is recorded."""
+    out = OrderedDict()
+    for case in FP32_CASES:
+        m = build_reference(case)
+        fill_state_dict_(m.state_dict(), SEED, conv_gain=FP32_GAIN[case])
+        m = m.float().eval()
+        best = None
+        for seed in range(40, 64):
+            x, _ = xray_batch(1, FP32_SIDE, FP32_SIDE, seed=seed)
+            with torch.no_grad():
+                lg = m(x.float())
+            margin = float(lg.abs().min())
+            frac = float((lg > 0).float().mean())
+            if not (0.02 <= frac <= 0.98):
+                continue                          # a degenerate (all / nothing) mask tests nothing
+            if best is None or margin > best[0]:
+                best = (margin, seed, lg)
+        if best is None:
+            raise RuntimeError(f"{case}: every candidate mask is degenerate; adjust FP32_GAIN")
+        margin, seed, logits = best
+        mask = (torch.sigmoid(logits).squeeze(0).squeeze(0).numpy() > 0.5).astype(np.uint8)      # pipeline.py:352-354
+        out[f"{case}::seed"] = np.array(seed)
+        out[f"{case}::margin"] = np.array(margin)
+        out[f"{case}::logits"] = logits.numpy().astype(np.float32)
+        out[f"{case}::mask_bits"] = np.packbits(mask.reshape(-1))
+        out[f"{case}::positives"] = np.array(int(mask.sum()))
+        print(f"  fp32 mask {case}: seed {seed}, margin {margin:.2e}, {int(mask.sum())} positive pixels", flush=True)
+    for case in FP32_CASES:
+        out[f"{case}::conv_gain"] = np.array(FP32_GAIN[case])
+    out["side"] = np.array(FP32_SIDE)
+    out["weight_seed"] = np.array(SEED)
+    return out
+
+
 def main():
     dst = ROOT / "tests" / "golden"
     dst.mkdir(parents=True, exist_ok=True)
@@ -165,7 +210,12 @@ def main():
     print("wrote losses")
     np.savez_compressed(dst / "metrics.npz", **golden_metrics())
     print("wrote metrics")
+    np.savez_compressed(dst / "fp32_masks.npz", **golden_fp32_masks())
+    print("wrote fp32_masks")
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fp32_masks":       # only the fp32 inference fixture
+        np.savez_compressed(ROOT / "tests" / "golden" / "fp32_masks.npz", **golden_fp32_masks())
+    else:
+        main()
