@@ -330,6 +330,26 @@ typedef struct b2_pack_ref {
 int b2_pack_weights_multi(const b2_pack_ref* refs, int32_t nrefs, int32_t total_items, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * ResNetUnet(freeze=False) (ResnetUnet.py:29-30: the torchvision ResNet-50 encoder trains too): what the encoder's
+ * backward needs beyond the entry points above.
+ *   b2_stem_im2col      the 7x7 / stride-2 / pad-3 stem (backbone.conv1) as a GEMM: fp32 NCHW image -> bf16 im2col
+ *                       [N, Ho, Wo, cols] (column = tap * C + c, zero padded to `cols`), so that fprop (with the BN
+ *                       statistics epilogue) and wgrad run on b2_conv_fprop / b2_conv_wgrad as a 1x1 convolution
+ *   b2_maxpool3x3s2_bwd backward of backbone.maxpool = MaxPool2d(3, 2, 1): gather form, first maximum wins (ATen)
+ *   b2_zero_insert2x    y[2h, 2w] = x[h, w], zero elsewhere: dY of a stride-2 convolution on the stride-1 grid — dgrad
+ *                       and wgrad of the strided 3x3 / 1x1 convolutions then are the ordinary stride-1 kernels
+ *   b2_relu_mask        g = out > 0 ? dy : 0, the gradient of relu(bn3(z) + identity) (torchvision Bottleneck)
+ * ---------------------------------------------------------------------------------------------------------- */
+int b2_stem_im2col(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, int32_t ksize, int32_t stride,
+                   int32_t pad, int32_t cols, void* xc, b2_stream_t stream);
+int b2_maxpool3x3s2_bwd(const void* dy, int32_t lddy, const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w,
+                        int32_t c, void* dx, int32_t lddx, b2_stream_t stream);
+int b2_zero_insert2x(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w, int32_t c, void* y, int32_t ldy,
+                     b2_stream_t stream);
+int b2_relu_mask(const void* dy, int32_t lddy, const void* out, int32_t ldo, int64_t npix, int32_t c, void* g,
+                 int32_t ldg, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * fp32 parity mode (BASELINE.json north_star: "fp32-accumulate mode within 1e-4"): the inference path with fp32
  * activation storage and fp32 FMA accumulation on the CUDA cores, for callers that need the reference's own fp32
  * results — utils/pipeline.py:340-357 runs `logits = model(img)` in fp32 without autocast and thresholds

@@ -90,9 +90,17 @@ def attention_gate_bwd(dout: Tensor, g: Tensor, x: Tensor, wg: Tensor, wx: Tenso
     if need_dx:
         _, wxd = K.packed(wx, want_dgrad=True)
         K.conv_igemm(dx1p, wxd, x.shape[3], 1, addend=dx, out=dx, dgrad=True)     # dx += dx1p . W_x (epilogue add)
+    # gradient slots (data-parallel buckets): both weights usually live in ONE flat bucket, and two outputs of a custom
+    # op may not share a storage — so slot-resident gradients are written as a side effect and returned as empty
+    # placeholders; the autograd formula below hands autograd fresh views of the slots
+    slot_g, slot_x = K.grad_slot(wg, (fint, 1, g.shape[3])), K.grad_slot(wx, (fint, 1, x.shape[3]))
     with K.wgrad_stream(dg1p, dx1p, g, x, allow=K.grad_is_stolen(wg) and K.grad_is_stolen(wx)):
-        dwg = K.conv_wgrad(dg1p, g, 1, out=K.grad_slot(wg, (fint, 1, g.shape[3])))
-        dwx = K.conv_wgrad(dx1p, x, 1, out=K.grad_slot(wx, (fint, 1, x.shape[3])))
+        dwg = K.conv_wgrad(dg1p, g, 1, out=slot_g)
+        dwx = K.conv_wgrad(dx1p, x, 1, out=slot_x)
+    if slot_g is not None:
+        dwg = torch.empty((0,), device=dev)
+    if slot_x is not None:
+        dwx = torch.empty((0,), device=dev)
     return dg, dx, dwg, dwx, dgb, dbn1, dwpsi, dbpsi, dbias
 
 
@@ -111,6 +119,11 @@ def _backward(ctx, dout, *_unused):
     dg, dx, dwg, dwx, dgb, dbn1, dwpsi, dbpsi, dbias = attention_gate_bwd(
         dout, g, x, wg, wx, psi, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coef_1, gamma_1, wpsi, ctx.training,
         bool(need[0]), bool(need[1]))
+    fint = wg.shape[0]
+    if dwg.numel() == 0:
+        dwg = K.grad_slot(wg, (fint, 1, wg.shape[1]))
+    if dwx.numel() == 0:
+        dwx = K.grad_slot(wx, (fint, 1, wx.shape[1]))
     return (dg if need[0] else None, dx if need[1] else None,
             _dw_as_param_grad(dwg, wg), dbias[0], _dw_as_param_grad(dwx, wx), dbias[1],
             dgb[0], dgb[1], None, None, dgb[2], dgb[3], None, None,
