@@ -316,15 +316,16 @@ int b2_adamw_multi(const b2_tensor_ref* refs, const int32_t* block_tensor, const
  * b2_pack_weights / b2_pack_weights_upfold / the im2col stem matrix) of EVERY convolution weight, right after
  * b2_adamw_multi updated the fp32 masters (utils/helpers.py:333-335), so that no conv call of the next step packs
  * anything.  `refs` is a DEVICE array; item_start = exclusive prefix sum of the per-tensor work items
- * (kind 0: taps * ceil(cout/32) * ceil(cin/32); kind 1: 16 * ...; kind 2: ceil(cout/32)); total_items = their sum.
+ * (kind 0: taps * ceil(cout/32) * ceil(cin/32); kind 1: 16 * ...; kind 2: ceil(cout/32) * ceil(cols/32));
+ * total_items = their sum.
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct b2_pack_ref {
   const float* w;      /* fp32 [cout][cin][k][k] master, any strides */
   void* wf;            /* bf16 fprop layout (may be NULL) */
   void* wd;            /* bf16 dgrad layout (may be NULL) */
-  int32_t cout, cin, ksize, kind;   /* kind: 0 plain, 1 UpConv-folded (ksize 3), 2 3x3-stem im2col matrix (K = 32) */
+  int32_t cout, cin, ksize, kind;   /* kind: 0 plain, 1 UpConv-folded (ksize 3), 2 image-stem im2col matrix */
   int64_t s_co, s_ci, s_kh, s_kw;   /* element strides of w */
-  int32_t item_start, pad_;
+  int32_t item_start, pad_;         /* pad_: kind 2 -> columns of the stem matrix (multiple of 8) */
 } b2_pack_ref;
 
 int b2_pack_weights_multi(const b2_pack_ref* refs, int32_t nrefs, int32_t total_items, b2_stream_t stream);

@@ -247,7 +247,7 @@ _PACKS = {"cache": {}, "serial": 0, "epoch": 0}
 
 
 class _Pack:
-    __slots__ = ("ref", "ptr", "version", "kind", "wf", "wd", "cout", "cin", "ksize", "strides", "code")
+    __slots__ = ("ref", "ptr", "version", "kind", "wf", "wd", "cout", "cin", "ksize", "strides", "code", "cols")
 
 
 def invalidate_pack_cache():
@@ -306,10 +306,11 @@ def packed(weight, kind="plain", want_dgrad=False):
         sv = view.stride()
         call("b2_pack_weights_upfold", _p(view), cout, cin, sv[0], sv[1], sv[2], sv[3], _p(wf), _p(wd), _stream())
     elif kind == "stem":
-        wf = wf if wf is not None else torch.empty((1, cout, STEM_COLS), dtype=BF16, device=dev)
+        cols = stem_cols(weight)
+        wf = wf if wf is not None else torch.empty((1, cout, cols), dtype=BF16, device=dev)
         wm = stem_weight_matrix(weight)
         sm = wm.stride()
-        call("b2_pack_weights", _p(wm), cout, STEM_COLS, 1, sm[0], sm[1], sm[2], sm[3], _p(wf), _p(None), _stream())
+        call("b2_pack_weights", _p(wm), cout, cols, 1, sm[0], sm[1], sm[2], sm[3], _p(wf), _p(None), _stream())
     else:
         taps = kh * kw
         wf = wf if wf is not None else torch.empty((taps, cout, cin), dtype=BF16, device=dev)
@@ -321,6 +322,7 @@ def packed(weight, kind="plain", want_dgrad=False):
     new.ref, new.ptr, new.version, new.kind = weakref.ref(weight), weight.data_ptr(), weight._version, kind
     new.wf, new.wd, new.cout, new.cin, new.ksize = wf, wd, cout, cin, kh
     new.strides, new.code = tuple(view.stride()), _PACK_KINDS[kind]
+    new.cols = stem_cols(weight) if kind == "stem" else 0
     cache = _PACKS["cache"]
     if len(cache) > 4096:
         for k in [k for k, v in cache.items() if v.ref() is None]:
@@ -533,18 +535,60 @@ def stem_im2col3x3(x):
     return xc
 
 
-def stem_weight_matrix(weight):
-    """fp32 [Cout, Cin<=3, 3, 3] -> fp32 [Cout, 32, 1, 1] with column = tap * Cin + c (the im2col order)."""
+def stem_cols(weight):
+    """im2col columns of an image stem: 32 for the 3x3 stems, ks*ks*cin rounded up to 8 otherwise (7x7: 152)"""
     cout, cin, kh, kw = weight.shape
-    wm = torch.zeros((cout, STEM_COLS), dtype=torch.float32, device=weight.device)
+    return STEM_COLS if kh == 3 else (kh * kw * cin + 7) // 8 * 8
+
+
+def stem_weight_matrix(weight):
+    """fp32 [Cout, Cin<=3, k, k] -> fp32 [Cout, cols, 1, 1] with column = tap * Cin + c (the im2col order)."""
+    cout, cin, kh, kw = weight.shape
+    cols = stem_cols(weight)
+    wm = torch.zeros((cout, cols), dtype=torch.float32, device=weight.device)
     wm[:, :kh * kw * cin] = weight.detach().permute(0, 2, 3, 1).reshape(cout, kh * kw * cin)
-    return wm.view(cout, STEM_COLS, 1, 1)
+    return wm.view(cout, cols, 1, 1)
 
 
-def stem_weight_grad(dwc, cin):
-    """[Cout, 1, 32] gradient of the im2col weight matrix -> [Cout, 9, Cin] (tap-major, as conv_wgrad returns)."""
+def stem_im2col(x, ksize, stride, pad, cols):
+    """NCHW fp32 image -> NHWC bf16 [N, Ho, Wo, cols] im2col (column = tap * C + c) for any stem geometry"""
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+    n, c, h, w = x.shape
+    ho, wo = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+    xc = torch.empty((n, ho, wo, cols), dtype=BF16, device=x.device)
+    call("b2_stem_im2col", _p(x), n, c, h, w, ksize, stride, pad, cols, _p(xc), _stream())
+    return xc
+
+
+def maxpool3x3s2_bwd(dy, x):
+    n, h, w, c, ld = _nhwc(x)
+    lddy = _nhwc(dy)[4]
+    dx = new_act(n, h, w, c, x.device)
+    call("b2_maxpool3x3s2_bwd", _p(dy), lddy, _p(x), ld, n, h, w, c, _p(dx), c, _stream())
+    return dx
+
+
+def zero_insert2x(x):
+    """y[2h, 2w] = x[h, w], zero elsewhere"""
+    n, h, w, c, ld = _nhwc(x)
+    y = new_act(n, 2 * h, 2 * w, c, x.device)
+    call("b2_zero_insert2x", _p(x), ld, n, h, w, c, _p(y), c, _stream())
+    return y
+
+
+def relu_mask(dy, out):
+    """g = out > 0 ? dy : 0"""
+    n, h, w, c, lddy = _nhwc(dy)
+    ldo = _nhwc(out)[4]
+    g = new_act(n, h, w, c, dy.device)
+    call("b2_relu_mask", _p(dy), lddy, _p(out), ldo, n * h * w, c, _p(g), c, _stream())
+    return g
+
+
+def stem_weight_grad(dwc, cin, taps=9):
+    """[Cout, 1, cols] gradient of the im2col weight matrix -> [Cout, taps, Cin] (tap-major, as conv_wgrad returns)."""
     cout = dwc.shape[0]
-    return dwc.reshape(cout, STEM_COLS)[:, :9 * cin].reshape(cout, 9, cin).contiguous()
+    return dwc.reshape(cout, -1)[:, :taps * cin].reshape(cout, taps, cin).contiguous()
 
 
 def pack_small_weight(weight):

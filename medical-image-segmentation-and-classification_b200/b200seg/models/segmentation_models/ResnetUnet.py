@@ -5,7 +5,8 @@ Differences forced by the environment, not by the design:
   * the reference builds `models.resnet50(weights=ResNet50_Weights.DEFAULT)` (ResnetUnet.py:32), which downloads a
     checkpoint; offline that raises, so this module falls back to random init with a warning (load the reference's
     checkpoint with load_state_dict to get the pretrained encoder);
-  * only the reference default `freeze=True` is supported on the CUDA path: the encoder kernels are forward-only.
+  * `freeze=True` (the reference default) runs the encoder through forward-only kernels under no_grad; `freeze=False`
+    (ResnetUnet.py:29-30) trains it through the res_* autograd ops of ops_resnet.py.
 """
 import warnings
 
@@ -37,6 +38,21 @@ def _bottleneck(blk, x):
     o = _enc_conv_bn(o, blk.conv2, blk.bn2, True)
     idt = x if blk.downsample is None else _enc_conv_bn(x, blk.downsample[0], blk.downsample[1], False)
     return _enc_conv_bn(o, blk.conv3, blk.bn3, True, identity=idt)
+
+
+def _res_conv_bn(x, conv, bn, relu, identity=None):
+    """the same layer with autograd (trainable encoder)"""
+    y, _z, _coef, stats = R.res_conv_bn(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, identity,
+                                        conv.stride[0], bn.training, float(bn.eps), relu)
+    _bn_update(bn, stats.detach(), y)
+    return y
+
+
+def _res_bottleneck(blk, x):
+    o = _res_conv_bn(x, blk.conv1, blk.bn1, True)
+    o = _res_conv_bn(o, blk.conv2, blk.bn2, True)
+    idt = x if blk.downsample is None else _res_conv_bn(x, blk.downsample[0], blk.downsample[1], False)
+    return _res_conv_bn(o, blk.conv3, blk.bn3, True, identity=idt)
 
 
 class DecoderBlock(nn.Module):
@@ -91,10 +107,25 @@ class ResNetUnet(nn.Module):
             for param in layer.parameters():
                 param.requires_grad = False
 
+    def _encode_trainable(self, x):
+        """freeze=False: the encoder is part of the autograd graph"""
+        conv1, bn1 = self.encoder1[0], self.encoder1[1]
+        e1, _z, _coef, stats, _xcol = R.res_stem(x, conv1.weight, bn1.weight, bn1.bias, bn1.running_mean,
+                                                 bn1.running_var, bn1.training, float(bn1.eps))
+        _bn_update(bn1, stats.detach(), e1)
+        feats = [e1]
+        t = R.res_maxpool3x3s2(e1)
+        for layer in (self.encoder2, self.encoder3, self.encoder4, self.encoder5):
+            for blk in layer:
+                t = _res_bottleneck(blk, t)
+            feats.append(t)
+        return feats
+
     def _encode(self, x):
-        if any(p.requires_grad for p in self.encoder1.parameters()):
-            raise NotImplementedError("b200seg ResNetUnet supports the reference default freeze=True only "
-                                      "(the ResNet-50 encoder kernels are forward-only)")
+        enc_params = [p for layer in (self.encoder1, self.encoder2, self.encoder3, self.encoder4, self.encoder5)
+                      for p in layer.parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in enc_params):
+            return self._encode_trainable(x)
         with torch.no_grad():
             conv1, bn1 = self.encoder1[0], self.encoder1[1]
             z, stats = R.enc_stem(x, conv1.weight)

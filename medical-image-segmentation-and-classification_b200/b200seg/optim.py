@@ -161,11 +161,13 @@ class FusedClipAdamW(torch.optim.Optimizer):
         rows, start = [], 0
         for pk in packs:
             tco, tci = (pk.cout + 31) // 32, (pk.cin + 31) // 32
-            items = tco if pk.code == 2 else (16 if pk.code == 1 else pk.ksize * pk.ksize) * tco * tci
+            items = tco * ((pk.cols + 31) // 32) if pk.code == 2 else \
+                (16 if pk.code == 1 else pk.ksize * pk.ksize) * tco * tci
             lo = (pk.cout & 0xFFFFFFFF) | (pk.cin << 32)
             hi = (pk.ksize & 0xFFFFFFFF) | (pk.code << 32)
             rows.append([pk.ptr, pk.wf.data_ptr(), pk.wd.data_ptr() if pk.wd is not None else 0, lo, hi,
-                         pk.strides[0], pk.strides[1], pk.strides[2], pk.strides[3], start])   # one b2_pack_ref (80 B)
+                         pk.strides[0], pk.strides[1], pk.strides[2], pk.strides[3],
+                         (start & 0xFFFFFFFF) | (pk.cols << 32)])                               # one b2_pack_ref (80 B)
             start += items
         self._pack_n, self._pack_items = len(rows), start
         self._pack_keep = packs

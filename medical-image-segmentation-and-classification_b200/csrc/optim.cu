@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kOptThreads) adamw_kernel(const TensorRef* __r
 // flipped dgrad layout [taps-1-tap][cin][cout] are all row-contiguous.
 //   kind 0  plain:   wf[tap][co][ci] = w[co][ci][kh][kw],  wd[taps-1-tap][ci][co]
 //   kind 1  UpConv folding (AttentionUNet.py:15-27): 4 phases x 4 taps of summed 3x3 taps (pack_weights_upfold_kernel)
-//   kind 2  3x3 image stem as a K = 32 GEMM: wf[co][tap * cin + c], zero padded (kernels.stem_weight_matrix)
+//   kind 2  image stem as a GEMM (3x3: K = 32, 7x7/s2: K = 152): wf[co][tap * cin + c], zero padded to pad_ columns
 // ------------------------------------------------------------------------------------------------------------
 struct PackRef {       // mirrors b2_pack_ref
   const float* w;
@@ -114,18 +114,21 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackRef* 
   int item = (int)blockIdx.x - r.item_start;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int tco = (r.cout + 31) / 32;
-  if (r.kind == 2) {                                    // stem matrix [cout][32]
-    const int co0 = item * 32;
+  if (r.kind == 2) {                                    // stem matrix [cout][cols], cols = r.pad_ (a multiple of 8)
+    const int cols = r.pad_;
+    const int ctiles = (cols + 31) / 32;
+    const int co0 = (item / ctiles) * 32, col = (item % ctiles) * 32 + tx;
     const int ncol = r.ksize * r.ksize * r.cin;
+    if (col >= cols) return;
     for (int rr = ty; rr < 32; rr += 8) {
       const int co = co0 + rr;
       if (co >= r.cout) continue;
       float v = 0.f;
-      if (tx < ncol) {
-        const int tap = tx / r.cin, c = tx % r.cin;
+      if (col < ncol) {
+        const int tap = col / r.cin, c = col % r.cin;
         v = r.w[co * r.s_co + c * r.s_ci + (tap / r.ksize) * r.s_kh + (tap % r.ksize) * r.s_kw];
       }
-      r.wf[(long long)co * 32 + tx] = __float2bfloat16_rn(v);
+      r.wf[(long long)co * cols + col] = __float2bfloat16_rn(v);
     }
     return;
   }
