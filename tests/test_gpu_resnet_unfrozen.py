@@ -120,7 +120,7 @@ def test_res_conv_bn_block_gradients(k, stride, cin, cout):
     gr, br = gamma.detach().double().requires_grad_(True), beta.detach().double().requires_grad_(True)
     ir = idt.detach().double().permute(0, 3, 1, 2).requires_grad_(True)
     z = F.conv2d(xr, wr, stride=stride, padding=k // 2)
-    z = z.to(torch.bfloat16).double() + (z - z.detach())            # the CUDA path stores z in bf16 (straight-through)
+    z = z.detach().to(torch.bfloat16).double() + (z - z.detach())   # the CUDA path stores z in bf16 (straight-through)
     yr = F.relu(F.batch_norm(z, rm.double(), rv.double(), gr, br, False, 0.1, 1e-5) + ir)
     yr.backward(dy.double().permute(0, 3, 1, 2))
     assert rel(y.permute(0, 3, 1, 2), yr) < 1e-2
