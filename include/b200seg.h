@@ -331,6 +331,33 @@ typedef struct b2_pack_ref {
 int b2_pack_weights_multi(const b2_pack_ref* refs, int32_t nrefs, int32_t total_items, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Attention gate, eval mode, ONE kernel (north_star (2); AttentionUNet.py:29-54 / R2AttU_Net.py:61-86 with the three
+ * BatchNorms folded into weights, biases and two scalars):
+ *     out = x * sigmoid(scale1 * (bpsi + wpsi . relu(W_g' g + W_x' x + bias')) + shift1)
+ * runs as one tcgen05 GEMM with K = [g | x] (2C) and N = F_int whose epilogue reduces every accumulator row to psi
+ * and writes x * psi — g1, x1, q and psi never touch HBM.  wpk = bf16 [1][fint][2C] = [s_g W_g | s_x W_x],
+ * bias = s_g b_g + t_g + s_x b_x + t_x (fp32 [fint]); wpsi fp32 [fint]; bpsi / scale1 / shift1 device scalars.
+ * Requires C % 64 == 0 and F_int in {32, 64, 128, 256}.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b2_gate_args {
+  int32_t n, h, w, c, fint;
+  const void* g;        /* NHWC bf16 [.., c] */
+  int32_t ldg;
+  const void* x;        /* NHWC bf16 [.., c] */
+  int32_t ldx;
+  const void* wpk;
+  const float* bias;
+  const float* wpsi;
+  const float* bpsi;
+  const float* scale1;
+  const float* shift1;
+  void* out;            /* NHWC bf16 [.., c] */
+  int32_t ldo;
+} b2_gate_args;
+
+int b2_gate_fused(const b2_gate_args* args, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * ResNetUnet(freeze=False) (ResnetUnet.py:29-30: the torchvision ResNet-50 encoder trains too): what the encoder's
  * backward needs beyond the entry points above.
  *   b2_stem_im2col      the 7x7 / stride-2 / pad-3 stem (backbone.conv1) as a GEMM: fp32 NCHW image -> bf16 im2col

@@ -55,6 +55,14 @@ class F32ConvArgs(C.Structure):
                 ("y", _vp), ("ldy", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32)]
 
 
+class GateArgs(C.Structure):
+    """struct b2_gate_args"""
+    _fields_ = [("n", _i32), ("h", _i32), ("w", _i32), ("c", _i32), ("fint", _i32),
+                ("g", _vp), ("ldg", _i32), ("x", _vp), ("ldx", _i32),
+                ("wpk", _vp), ("bias", _vp), ("wpsi", _vp), ("bpsi", _vp), ("scale1", _vp), ("shift1", _vp),
+                ("out", _vp), ("ldo", _i32)]
+
+
 class GateCoef(C.Structure):
     """struct b2_gate_coef"""
     _fields_ = [(k, _vp) for k in (
@@ -114,6 +122,7 @@ SIGNATURES = {
     "b2_grad_sqnorm_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2_adamw_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "b2_pack_weights_multi": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "b2_gate_fused": (C.c_int, [C.POINTER(GateArgs), _vp]),
     "b2_stem_im2col": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b2_maxpool3x3s2_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "b2_zero_insert2x": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),

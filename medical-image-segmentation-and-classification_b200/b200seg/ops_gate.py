@@ -136,6 +136,11 @@ attention_gate.register_autograd(_backward, setup_context=_setup)
 def attention_gate_module(gate, g: Tensor, x: Tensor) -> Tensor:
     """gate: an AttentionGate module (W_g, W_x, psi Sequentials with the reference's layout)"""
     bn_g, bn_x, bn_1 = gate.W_g[1], gate.W_x[1], gate.psi[1]
+    import os
+    if os.environ.get("B200SEG_FOLD_BN", "1") != "0" and os.environ.get("B200SEG_GATE_FUSED", "1") != "0":
+        from . import ops_infer
+        if ops_infer.inference_mode(bn_g) and ops_infer.gate_fusable(gate, g, x):
+            return ops_infer.attention_gate_fused(gate, g, x)          # eval + no_grad: the whole gate in ONE kernel
     training = bn_g.training
     res = attention_gate(g, x, gate.W_g[0].weight, gate.W_g[0].bias, gate.W_x[0].weight, gate.W_x[0].bias,
                          bn_g.weight, bn_g.bias, bn_g.running_mean, bn_g.running_var,

@@ -64,6 +64,7 @@ struct IgemmParams {
   int a_stage_bytes, b_stage_bytes, a_tx_bytes;
   int tma_store;
   int epi_groups;     // 1 or 2 epilogue warp groups (two staging tiles)
+  int ctile_bytes;    // bytes of one staging tile (128 x block_n bf16; at least one 64-channel panel in gate mode)
   int debug_skip;     // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs, 4 = no drain
   int cluster;        // CTAs per cluster (1, 2 or 4): they work on consecutive m-tiles of one n-tile and share the
                       // weight tiles, each CTA fetching 1/cluster of the rows and multicasting them
@@ -80,6 +81,15 @@ struct IgemmParams {
   double* stats_partial;   // deterministic mode: [gridDim.x * epi_groups][2 * cout] rows, one per (CTA, epilogue group)
   int relu;
   int add_after_act;
+  // fused eval-mode attention gate (b2_gate_fused): the GEMM is [g | x] . [s_g W_g ; s_x W_x]^T (+ folded biases), the
+  // epilogue turns each accumulator ROW (one pixel, all F_int columns — one thread) into
+  //   psi = sigmoid(s1 * (bpsi + sum_f wpsi[f] * relu(acc[f])) + h1)   and stores   out[pixel, :] = x[pixel, :] * psi
+  const __nv_bfloat16* gate_x;    // nullptr: ordinary convolution epilogue
+  int gate_ldx, gate_c;           // channel stride / channel count of x and out (tmY describes out, 64-channel boxes)
+  const float* gate_wpsi;         // [F_int]
+  const float* gate_k;            // device scalars: bpsi, scale1, shift1 (three pointers packed below)
+  const float* gate_s1;
+  const float* gate_h1;
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem, int c0, int c1, int c2, int c3) {
@@ -121,7 +131,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int a_slots = p.dm ? 2 : 1;                                    // activation tiles per stage
   const int nbuf = p.dm ? 4 : 2;                                       // accumulators in TMEM
   const int stage_bytes = a_slots * p.a_stage_bytes + p.b_stage_bytes;
-  const int ctile_bytes = kTileM * p.block_n * 2;
+  const int ctile_bytes = p.ctile_bytes;
   uint8_t* ctile0 = smem + p.stages * stage_bytes;                     // per group: 128 x block_n bf16, 1024 B aligned
   uint8_t* tail = ctile0 + p.epi_groups * ctile_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
@@ -130,6 +140,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* tmem_empty_bar = tmem_full_bar + 4;                        // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
   float* s_bias0 = reinterpret_cast<float*>(tail + 320);               // [group][256]
+  float* s_psi0 = s_bias0 + kMaxEpiGroups * 256;                       // [group][256] (fused gate: psi weights)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -368,6 +379,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int et = (threadIdx.x - 64) & 127;   // 0..127 within the group
     uint8_t* ctile = ctile0 + g * ctile_bytes;
     float* s_bias = s_bias0 + g * 256;
+    float* s_psi = s_psi0 + g * 256;
     const int bar_id = 1 + g;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;          // accumulator row == pixel within the tile
@@ -444,8 +456,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // new output-channel slab: flush the statistics kept for the previous one, reload the bias slice
         if (cur_n_tile >= 0 && p.stats != nullptr) flush_stats(cur_n_tile);
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // everyone is done reading the old bias slice
-        for (int i = et; i < p.block_n; i += 128)
+        for (int i = et; i < p.block_n; i += 128) {
           s_bias[i] = p.bias ? p.bias[ch_base + (p.rp ? (i & 63) : i)] : 0.f;
+          if (p.gate_x != nullptr) s_psi[i] = p.gate_wpsi[i];
+        }
         cur_n_tile = n_tile;
       }
       const int tw_i = t % p.tw;
@@ -471,6 +485,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (kHasAdd) {
         const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
         arow = valid ? p.addend + pix * p.ldadd + ch_base : nullptr;
+      }
+      if (p.gate_x != nullptr) {
+        // ---------------- fused attention-gate epilogue (eval mode) ----------------
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // s_bias / s_psi of this slab are in place
+        float q = 0.f;
+        for (int c = 0; c < p.block_n; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) q = fmaf(fmaxf(v[e] + s_bias[c + e], 0.f), s_psi[c + e], q);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+          else mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        const float qn = fmaf(q + __ldg(p.gate_k), __ldg(p.gate_s1), __ldg(p.gate_h1));
+        const float ps = 1.f / (1.f + __expf(-qn));
+        const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
+        const __nv_bfloat16* xrow = valid ? p.gate_x + pix * p.gate_ldx : nullptr;
+        for (int pn = 0; pn < (p.gate_c >> 6); ++pn) {
+          if (pn > 0) {                      // the previous panel's TMA store must have read the staging tile
+            if (et == 0) tma_store_wait_read();
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          }
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8) {
+            uint4 u = xrow != nullptr ? __ldg(reinterpret_cast<const uint4*>(xrow + pn * 64) + q8) : make_uint4(0, 0, 0, 0);
+            u.x = pack_bf16x2(bf16lo(u.x) * ps, bf16hi(u.x) * ps);
+            u.y = pack_bf16x2(bf16lo(u.y) * ps, bf16hi(u.y) * ps);
+            u.z = pack_bf16x2(bf16lo(u.z) * ps, bf16hi(u.z) * ps);
+            u.w = pack_bf16x2(bf16lo(u.w) * ps, bf16hi(u.w) * ps);
+            *reinterpret_cast<uint4*>(ctile + (uint32_t)row * 128u + (((uint32_t)q8 ^ (uint32_t)(row & 7)) << 4)) = u;
+          }
+          fence_proxy_async();
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (et == 0) {
+            tma_store_4d(&tmY, ctile, pn * 64, w0, h0, n0);
+            tma_store_commit();
+          }
+        }
+        continue;
       }
       for (int c = 0; c < p.block_n; c += 32) {
         float v[32];
@@ -661,7 +719,13 @@ static int pick_block_n(int cout, bool wide_rows) {
   return 0;
 }
 
-static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
+struct GateExtra {            // fused eval-mode attention gate (b2_gate_fused): see IgemmParams::gate_x
+  const void* x;
+  int ldx, c;
+  const float *wpsi, *bpsi, *scale1, *shift1;
+};
+
+static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const GateExtra* gate = nullptr) {
   B2_REQUIRE(a != nullptr, B2_ERR_SHAPE, "null args");
   const int stride = a->stride == 0 ? 1 : a->stride;
   const int out_mul = a->out_mul == 0 ? 1 : a->out_mul;
@@ -742,8 +806,23 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
     p.b_stage_bytes = p.block_n * 128;
     p.num_k_iters = p.taps * cbt;
   }
-  const int ctile_bytes = kTileM * p.block_n * 2;
-  const int tail_bytes = 320 + kMaxEpiGroups * 256 * 4 + 192;
+  int ctile_bytes = kTileM * p.block_n * 2;
+  if (gate != nullptr) {
+    B2_REQUIRE(p.n_tiles == 1 && !p.rp && out_mul == 1 && in_mul == 1 && stride == 1 && a->ksize == 1 && p.tma_store,
+               B2_ERR_SHAPE, "fused gate: F_int=%d must be one tile (32 | 64 | 128 | 256) of a plain 1x1 GEMM", a->cout);
+    B2_REQUIRE(gate->c % 64 == 0 && gate->ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(gate->x) & 15) == 0, B2_ERR_SHAPE,
+               "fused gate: C=%d must be a multiple of 64, x 16 B aligned", gate->c);
+    if (ctile_bytes < kTileM * 128) ctile_bytes = kTileM * 128;       // one 64-channel output panel
+    p.gate_x = static_cast<const __nv_bfloat16*>(gate->x);
+    p.gate_ldx = gate->ldx;
+    p.gate_c = gate->c;
+    p.gate_wpsi = gate->wpsi;
+    p.gate_k = gate->bpsi;
+    p.gate_s1 = gate->scale1;
+    p.gate_h1 = gate->shift1;
+  }
+  p.ctile_bytes = ctile_bytes;
+  const int tail_bytes = 320 + 2 * kMaxEpiGroups * 256 * 4 + 192;      // barriers, bias + psi slices, slack
   // Double-M: two consecutive m-tiles per work item share every weight stage (see IgemmParams::dm).  Needs four
   // accumulators in TMEM (BLOCK_N <= 128), two A slots per stage and still >= 2 (>= 3 for thin stages) stages.
   {
@@ -856,7 +935,9 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.y_sn = oh * ow * a->ldy;
   p.y = static_cast<__nv_bfloat16*>(a->y) + ((long long)a->out_off_h * ow + a->out_off_w) * a->ldy;
   if (p.tma_store) {
-    if (p.block_n >= 64) {
+    if (gate != nullptr) {        // the gate's output has C channels (64-channel boxes), not F_int
+      rc = encode_act_tmap_ex(&tmY, p.y, gate->c, a->n, a->h, a->w, p.y_sw, p.y_sh, p.y_sn, p.Wb, p.Hb, p.Nb, 1);
+    } else if (p.block_n >= 64) {
       rc = encode_act_tmap_ex(&tmY, p.y, a->cout, a->n, a->h, a->w, p.y_sw, p.y_sh, p.y_sn, p.Wb, p.Hb, p.Nb, 1);
     } else {
       // 32-channel tiles are staged as 64 B rows with chunk ^= (row >> 1) & 3 == TMA's 64B swizzle
@@ -955,4 +1036,25 @@ extern "C" int b2_conv_dgrad(const b2_conv_args* a, b2_stream_t stream) {
   int rc = b2_arch_check();
   if (rc) return rc;
   return b2::conv_igemm_launch(a, static_cast<cudaStream_t>(stream));
+}
+
+// Eval-mode attention gate in ONE launch (AttentionUNet.py:48-54 with the three BatchNorms folded):
+//   out = x * sigmoid(s1 * (bpsi + wpsi . relu([g | x] . W^T + bias)) + h1)
+extern "C" int b2_gate_fused(const b2_gate_args* g, b2_stream_t stream) {
+  int rc = b2_arch_check();
+  if (rc) return rc;
+  B2_REQUIRE(g != nullptr && g->c > 0 && g->fint > 0, B2_ERR_SHAPE, "bad gate args");
+  b2_conv_args a;
+  memset(&a, 0, sizeof(a));
+  a.n = g->n; a.h = g->h; a.w = g->w; a.ksize = 1;
+  a.x0 = g->g; a.c0 = g->c; a.ldx0 = g->ldg;
+  a.x1 = g->x; a.c1 = g->c; a.ldx1 = g->ldx;
+  a.wpk = g->wpk; a.ktot = 2 * g->c; a.w_tap_stride = (int64_t)g->fint * 2 * g->c;
+  a.cout = g->fint;
+  a.y = g->out; a.ldy = g->ldo;
+  a.bias = g->bias;
+  b2::GateExtra gx;
+  gx.x = g->x; gx.ldx = g->ldx; gx.c = g->c;
+  gx.wpsi = g->wpsi; gx.bpsi = g->bpsi; gx.scale1 = g->scale1; gx.shift1 = g->shift1;
+  return b2::conv_igemm_launch(&a, static_cast<cudaStream_t>(stream), &gx);
 }

@@ -208,3 +208,44 @@ def test_attention_gate_block(c, fint, h):
             assert int(msd[k[4:]]) == int(v)
         elif k.endswith("running_var"):
             assert rel(msd[k[4:]], v) < 1e-2, k
+
+
+@pytest.mark.parametrize("c,fint,h,n", [(512, 256, 32, 2), (256, 128, 64, 2), (128, 64, 128, 2), (64, 32, 256, 1),
+                                        (64, 32, 16, 3)])
+def test_attention_gate_eval_is_one_fused_kernel(c, fint, h, n):
+    """north_star (2): in eval mode (BatchNorms fold) the whole gate runs as ONE kernel — b2_gate_fused: a tcgen05 GEMM
+    over K = [g | x] whose epilogue does ReLU -> psi dot -> sigmoid -> multiply.  Checked against the fp64 oracle
+    (<= 1e-2) and against the unfused eval path, and that exactly one kernel launch happens."""
+    import os
+    from b200seg import _lib, blocks, ops
+    from oracle import unet_oracle as O
+    torch.manual_seed(12)
+    m = blocks.AttentionGate(c, c, fint).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    for bn in (m.W_g[1], m.W_x[1], m.psi[1]):            # non-trivial running statistics and affine parameters
+        bn.running_mean.copy_(0.2 * torch.randn(bn.running_mean.shape, device="cuda", generator=gen))
+        bn.running_var.copy_(0.5 + torch.rand(bn.running_var.shape, device="cuda", generator=gen))
+        bn.weight.data.copy_(0.5 + torch.rand(bn.weight.shape, device="cuda", generator=gen))
+        bn.bias.data.copy_(0.2 * torch.randn(bn.bias.shape, device="cuda", generator=gen))
+    m.eval()
+    g = torch.randn(n, c, h, h, device="cuda", generator=gen)
+    x = torch.randn(n, c, h, h, device="cuda", generator=gen)
+    gi, xi = ops.to_nhwc(g), ops.to_nhwc(x)
+    with torch.no_grad():
+        m(g=gi, x=xi)                                    # builds the folded-weight cache
+        torch.cuda.synchronize()
+        before = _lib.launch_count
+        y = m(g=gi, x=xi)
+        launches = _lib.launch_count - before
+        os.environ["B200SEG_GATE_FUSED"] = "0"
+        try:
+            y_unfused = m(g=gi, x=xi)
+        finally:
+            del os.environ["B200SEG_GATE_FUSED"]
+        sd = {("att." + k): v.detach().double() if v.is_floating_point() else v.detach().clone()
+              for k, v in m.state_dict().items()}
+        ref, _ = O.attention_gate(sd, g.to(torch.bfloat16).double(), x.to(torch.bfloat16).double(), "att", training=False)
+    assert launches == 1, f"{launches} kernel launches for the eval-mode gate"
+    e, e_un = rel(ops.to_nchw(y), ref), rel(ops.to_nchw(y_unfused), ref)
+    print(f"fused eval gate C={c} F_int={fint} @{h}: fused {e:.2e}  unfused {e_un:.2e}")
+    assert e < 1e-2 and e <= 1.5 * e_un + 1e-3
