@@ -331,6 +331,27 @@ typedef struct b2_pack_ref {
 int b2_pack_weights_multi(const b2_pack_ref* refs, int32_t nrefs, int32_t total_items, b2_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * GPU input pipeline: the reference's segmentation training transform (utils/trainer.py:88-101:
+ * A.Resize(256,256) -> ShiftScaleRotate -> HorizontalFlip -> RandomBrightnessContrast -> Normalize -> ToTensorV2) and the
+ * mask's / 255 (utils/dataset.py:124-126) in ONE kernel per batch: uint8 [N, Hs, Ws, 3] images + uint8 [N, Hs, Ws] masks
+ * -> normalised fp32 NCHW [N, 3, S, S] + fp32 [N, 1, S, S], with the CPU pipeline's uint8 rounding points.  The random
+ * draw stays on the host: `params` (DEVICE array, one entry per image) carries the inverse affine matrix in the resized
+ * image's pixel coordinates, the flip flag and the brightness / contrast coefficients.  mean3 / std3 are HOST arrays.
+ * Third-party arithmetic restated here: Albumentations 2.0.8 + OpenCV 4.12 (requirements.txt pins; neither is vendored
+ * in the reference) — cv2.resize INTER_LINEAR (INTER_NEAREST for masks when mask_nearest_resize), cv2.warpAffine with
+ * 1/32-pixel coordinate quantisation, BORDER_CONSTANT(0) or BORDER_REFLECT_101, the truncating uint8 LUT.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct b2_aug_params {
+  float m[6];            /* inverse affine: xs = m0*x + m1*y + m2, ys = m3*x + m4*y + m5 */
+  float alpha, beta;     /* v' = clip(alpha * v + beta * 255) */
+  int32_t flip, warp, adjust, border;   /* border: 0 constant(0), 1 reflect-101 */
+} b2_aug_params;
+
+int b2_seg_augment(const uint8_t* img, const uint8_t* mask, int32_t n, int32_t hs, int32_t ws, int32_t size,
+                   const b2_aug_params* params, const float* mean3, const float* std3, int32_t mask_nearest_resize,
+                   float* x, float* t, b2_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Attention gate, eval mode, ONE kernel (north_star (2); AttentionUNet.py:29-54 / R2AttU_Net.py:61-86 with the three
  * BatchNorms folded into weights, biases and two scalars):
  *     out = x * sigmoid(scale1 * (bpsi + wpsi . relu(W_g' g + W_x' x + bias')) + shift1)

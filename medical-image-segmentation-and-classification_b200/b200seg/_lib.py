@@ -122,6 +122,8 @@ SIGNATURES = {
     "b2_grad_sqnorm_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "b2_adamw_multi": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _f32, _vp, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "b2_pack_weights_multi": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "b2_seg_augment": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, C.POINTER(_f32), C.POINTER(_f32), _i32, _vp, _vp,
+                                 _vp]),
     "b2_gate_fused": (C.c_int, [C.POINTER(GateArgs), _vp]),
     "b2_stem_im2col": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "b2_maxpool3x3s2_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),

@@ -154,8 +154,11 @@ class PinnedPrefetcher:
 
     Yields (x_dev, y_dev); the tensors stay valid until the SECOND next batch is requested."""
 
-    def __init__(self, loader, device, depth: int = 2):
+    def __init__(self, loader, device, depth: int = 2, device_transform=None):
+        """device_transform(x_dev, y_dev) -> (x, y): applied on the consumer's stream when a batch is handed out, e.g.
+        data.GpuSegAugment turning raw uint8 image / mask batches into normalised fp32 tensors on the device"""
         self.loader, self.device, self.depth = loader, torch.device(device), max(int(depth), 2)
+        self.device_transform = device_transform
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._pinned: Dict[Tuple, list] = {}
         self._slots: Dict[Tuple, list] = {}
@@ -219,6 +222,9 @@ class PinnedPrefetcher:
             except StopIteration:
                 following = None
             torch.cuda.current_stream(self.device).wait_event(ready)
-            yield xd, yd
+            if self.device_transform is not None:
+                yield self.device_transform(xd, yd)
+            else:
+                yield xd, yd
             consumed.record(torch.cuda.current_stream(self.device))
             nxt = following

@@ -1,0 +1,64 @@
+"""GPU: the input pipeline kernel (b2_seg_augment, b200seg.data.GpuSegAugment) against OpenCV's own
+results for the reference's transform chain (tests/golden/augment.npz, written by oracle/make_golden_aug.py with
+cv2.resize / cv2.warpAffine / cv2.flip / cv2.LUT): images within one uint8 level on >= 99.5 % of the pixels (OpenCV
+interpolates in fixed point), masks identical on >= 99.5 %, exact for the resize-only (validation) transform."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden" / "augment.npz"
+LEVEL = 1.0 / 255.0 / 0.224      # one uint8 level in normalised units (largest of the three channels)
+
+
+def _samples(gold):
+    keys = [str(k) for k in gold["param_keys"]]
+    out = []
+    for row in gold["params"]:
+        d = {k: v for k, v in zip(keys, row) if not np.isnan(v)}
+        d["flip"] = bool(d.get("flip", 0.0))
+        out.append(d)
+    return out
+
+
+@pytest.mark.parametrize("border", ["constant", "reflect101"])
+def test_augment_matches_opencv(border):
+    from b200seg.data import GpuSegAugment
+    gold = np.load(GOLD)
+    aug = GpuSegAugment(size=int(gold["size"]), border=border)
+    img, msk = torch.from_numpy(gold["img"]), torch.from_numpy(gold["mask"])
+    x, t = aug(img, msk, samples=_samples(gold))
+    x, t = x.cpu().numpy(), t.cpu().numpy()
+    rx, rt = gold[f"x_{border}"], gold[f"t_{border}"]
+    assert x.shape == rx.shape and t.shape == rt.shape
+    for i in range(x.shape[0]):
+        d = np.abs(x[i] - rx[i])
+        frac1 = float((d <= 1.01 * LEVEL).mean())
+        mfrac = float((t[i] == rt[i]).mean())
+        print(f"case {i} ({border}): exact {float((d < 1e-5).mean()):.4f}, within 1 level {frac1:.4f}, "
+              f"max {d.max() / LEVEL:.1f} levels, mask equal {mfrac:.4f}")
+        assert frac1 >= 0.995 and mfrac >= 0.995
+        assert float(d.mean()) < 0.2 * LEVEL
+    # the validation transform (resize + normalise): OpenCV's resize differs from exact bilinear by at most one level
+    assert float((np.abs(x[0] - rx[0]) <= 1.01 * LEVEL).mean()) == 1.0 and (t[0] == rt[0]).all()
+
+
+def test_augment_sampling_and_prefetcher():
+    """train-mode random draw: shapes, value ranges, determinism under a seed; the prefetcher applies the transform"""
+    from b200seg.data import GpuSegAugment
+    from b200seg.engine import PinnedPrefetcher
+    gold = np.load(GOLD)
+    img, msk = torch.from_numpy(gold["img"]), torch.from_numpy(gold["mask"])
+    a1, a2 = GpuSegAugment(size=64, seed=5), GpuSegAugment(size=64, seed=5)
+    x1, t1 = a1(img, msk)
+    x2, t2 = a2(img, msk)
+    assert torch.equal(x1, x2) and torch.equal(t1, t2)
+    assert x1.shape == (5, 3, 64, 64) and t1.shape == (5, 1, 64, 64) and x1.dtype == torch.float32
+    assert float(t1.min()) >= 0.0 and float(t1.max()) <= 1.0 and torch.isfinite(x1).all()
+    val = GpuSegAugment(size=64, train=False)
+    loader = [(img[:3], msk[:3]), (img[3:], msk[3:])]
+    got = [xb.clone() for xb, _ in PinnedPrefetcher(loader, "cuda", device_transform=val)]
+    ref, _ = val(img, msk)
+    assert torch.equal(torch.cat(got), ref)
