@@ -467,8 +467,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int th_i = t % p.th;
       const int tn_i = t / p.th;
       const int w0 = tw_i * p.Wb, h0 = th_i * (p.rp ? 2 : p.Hb), n0 = tn_i * p.Nb;
-      int valid_rows = (p.N - n0) * p.Wb * p.Hb;
-      if (valid_rows > kTileM) valid_rows = kTileM;
+      // pixels of the tile that exist (tiles at the right / bottom / batch edge are clipped): row r of the tile is pixel
+      // (n0 + r / (Wb Hb), h0 + (r / Wb) % Hb, w0 + r % Wb); all three box extents are powers of two
+      const bool tile_full = w0 + p.Wb <= p.W && h0 + (p.rp ? 2 : p.Hb) <= p.H && n0 + p.Nb <= p.N;
+      auto row_valid = [&](int r) {
+        return tile_full || (w0 + r % p.Wb < p.W && h0 + (r / p.Wb) % p.Hb < p.H && n0 + r / (p.Wb * p.Hb) < p.N);
+      };
       const int buf = ti & (nbuf - 1);
 
       // the group's previous TMA store must have finished READING the staging tile before it is overwritten
@@ -478,7 +482,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)ti >> nb_shift) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.block_n);
-      const bool valid = row < valid_rows;
+      const bool valid = row_valid(row);
       const uint32_t row_off = p.block_n >= 64 ? (uint32_t)row * 128u : (uint32_t)row * 64u;
       const uint32_t row_x = p.block_n >= 64 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
       const __nv_bfloat16* arow = nullptr;
@@ -614,7 +618,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // coalesced copy-out: consecutive threads write consecutive 16 B of consecutive pixels
         for (int idx = et; idx < kTileM * nchunks; idx += 128) {
           const int r = idx / nchunks, ck = idx % nchunks;
-          if (r < valid_rows) {
+          if (row_valid(r)) {
             const int rwl = r % p.Wb, rhl = (r / p.Wb) % p.Hb, rnl = r / (p.Wb * p.Hb);
             const long long ro = (n0 + rnl) * p.y_sn + (h0 + rhl) * p.y_sh + (w0 + rwl) * p.y_sw;
             const uint4 u = *reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, ck * 8));
@@ -628,9 +632,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
         const int r_begin = sgrp * nchunks;
-        int r_end = r_begin + nchunks;
-        if (r_end > valid_rows) r_end = valid_rows;
+        const int r_end = r_begin + nchunks;
         for (int r = r_begin; r < r_end; ++r) {
+          if (!row_valid(r)) continue;
           const uint4 u = *reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, schunk * 8));
           const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -662,25 +666,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
 }
 
-// Tile geometry shared with the wgrad kernel: split `tile_pix` pixels into a (Wb, Hb, Nb) box.
+// Tile geometry shared with the wgrad kernel: split `tile_pix` pixels into a (Wb, Hb, Nb) box of power-of-two extents,
+// Wb * Hb * Nb == tile_pix.  Any image extent is accepted (the reference is fully convolutional, AttentionUNet.py:86-121:
+// 224^2, 320^2, 384^2 ...): tiles at the right / bottom / batch edge are CLIPPED — TMA loads zero-fill the pixels outside
+// the tensor (they add nothing to a weight gradient), TMA stores drop them, and the epilogue masks them out of the
+// BatchNorm statistics.  For extents that are powers of two or multiples of 128 nothing is clipped.
+static int pow2ceil_i(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
 int conv_tile_geometry(int n, int h, int w, int tile_pix, int* Wb, int* Hb, int* Nb, int* tw, int* th, int* tn) {
-  if (w >= tile_pix) {
-    B2_REQUIRE(w % tile_pix == 0, B2_ERR_SHAPE, "W=%d must be a multiple of %d", w, tile_pix);
-    *Wb = tile_pix; *Hb = 1; *Nb = 1;
-  } else {
-    B2_REQUIRE(tile_pix % w == 0, B2_ERR_SHAPE, "W=%d must divide %d", w, tile_pix);
-    *Wb = w;
-    const int rows = tile_pix / w;
-    if (h >= rows) {
-      B2_REQUIRE(h % rows == 0, B2_ERR_SHAPE, "H=%d must be a multiple of %d (W=%d)", h, rows, w);
-      *Hb = rows; *Nb = 1;
-    } else {
-      B2_REQUIRE(rows % h == 0, B2_ERR_SHAPE, "H=%d must divide %d (W=%d)", h, rows, w);
-      *Hb = h; *Nb = rows / h;
-    }
-  }
-  *tw = w / *Wb;
-  *th = h / *Hb;
+  B2_REQUIRE(n > 0 && h > 0 && w > 0, B2_ERR_SHAPE, "bad extent n=%d h=%d w=%d", n, h, w);
+  int wb = pow2ceil_i(w);
+  if (wb > tile_pix) wb = tile_pix;
+  const int rows = tile_pix / wb;
+  int hb = pow2ceil_i(h);
+  if (hb > rows) hb = rows;
+  *Wb = wb;
+  *Hb = hb;
+  *Nb = rows / hb;
+  *tw = (w + wb - 1) / wb;
+  *th = (h + hb - 1) / hb;
   *tn = (n + *Nb - 1) / *Nb;
   return B2_OK;
 }
