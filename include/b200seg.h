@@ -96,6 +96,12 @@ typedef struct b2_conv_args {
   int32_t in_mul, in_off_h, in_off_w;
   int32_t custom_pad, pad_h, pad_w;
   int32_t add_after_act;  /* 1: y = act(conv + bias) + addend (Recurrent_block's x + x1 in the folded inference path) */
+  /* merged launches of the folded UpConv (ksize 2; wpk = the 16 packed taps [4 phases][4 taps][rows][ktot]):
+   *   1 = fprop:  x0 is the coarse input [n, h, w, c0], y the FINE output [n, 2h, 2w, cout] — all four phase
+   *               convolutions in one launch (phase = extra tile dimension, pixel-shuffle stores);
+   *   2 = dgrad:  x0 is the FINE gradient dz [n, 2h, 2w, c0], y the coarse dx [n, h, w, cout] — the four phases are
+   *               one K loop of 16 taps over the sub-lattices of dz (no addend chain). */
+  int32_t fold_mode;
 } b2_conv_args;
 
 int b2_conv_fprop(const b2_conv_args* a, b2_stream_t stream);

@@ -30,7 +30,8 @@ class ConvArgs(C.Structure):
                 ("stats", _vp), ("relu", _i32),
                 ("stride", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32),
                 ("in_mul", _i32), ("in_off_h", _i32), ("in_off_w", _i32),
-                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32), ("add_after_act", _i32)]
+                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32), ("add_after_act", _i32),
+                ("fold_mode", _i32)]
 
 
 class WgradArgs(C.Structure):

@@ -424,20 +424,27 @@ def fold_upconv_wgrad(dweff, out=None):
 # ----------------------------------------------------------------------------------------------------------
 def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None, relu=False, out=None,
                row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0), in_mul=1, in_off=(0, 0), pad=None,
-               alg_scale=1.0, add_after_act=False):
+               alg_scale=1.0, add_after_act=False, fold=0):
     """y = conv(x0 | x1; wpk) (+bias) (+addend) (relu); wpk is [taps, rows, ktot] bf16, rows [row_offset,
     row_offset+cout) are used.  `stats` (fp64 [2, cout]) accumulates sum / sumsq of the rounded output.
     stride=2 samples the input on a 2x finer grid (strided conv / ConvTranspose dgrad); out_mul=2 places the result
-    at pixels (2h+off_h, 2w+off_w) of `out` (ConvTranspose pixel shuffle)."""
+    at pixels (2h+off_h, 2w+off_w) of `out` (ConvTranspose pixel shuffle).
+    fold: merged launches of the folded UpConv, wpk = its 16 packed taps [16, rows, ktot] — 1: x0 coarse -> y on the 2x
+    grid (all four phases, one launch); 2: x0 = dz on the 2x grid -> coarse dx (16-tap K loop, one launch)."""
     n, hi, wi, c0, ld0 = _nhwc(x0)
-    assert hi % (stride * in_mul) == 0 and wi % (stride * in_mul) == 0
-    h, w = hi // (stride * in_mul), wi // (stride * in_mul)     # output grid (in_mul: x0 is read as a sub-lattice)
+    if fold:
+        assert ksize == 2 and x1 is None and addend is None and stride == 1 and out_mul == 1 and in_mul == 1
+        out_mul = 2 if fold == 1 else 1
+        h, w = (hi, wi) if fold == 1 else (hi // 2, wi // 2)
+    else:
+        assert hi % (stride * in_mul) == 0 and wi % (stride * in_mul) == 0
+        h, w = hi // (stride * in_mul), wi // (stride * in_mul)     # output grid (in_mul: x0 is read as a sub-lattice)
     c1, ld1 = 0, 0
     if x1 is not None:
         n1, h1, w1, c1, ld1 = _nhwc(x1)
         assert (n1, h1, w1) == (n, hi, wi)
     taps, rows, ktot = wpk.shape
-    assert taps == ksize * ksize and wpk.dtype == BF16 and wpk.is_contiguous()
+    assert taps == (16 if fold else ksize * ksize) and wpk.dtype == BF16 and wpk.is_contiguous()
     assert ktot >= c0 + c1 and row_offset + cout <= rows
     y = out if out is not None else new_act(n, h * out_mul, w * out_mul, cout, x0.device)
     ny, hy, wy, cy, ldy = _nhwc(y)
@@ -460,16 +467,18 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
         assert stats.dtype == torch.float64 and stats.numel() == 2 * cout
         a.stats = stats.data_ptr()
     a.relu = int(relu)
-    a.stride, a.out_mul, a.out_off_h, a.out_off_w = stride, out_mul, out_off[0], out_off[1]
+    a.stride, a.out_mul, a.out_off_h, a.out_off_w = stride, (1 if fold else out_mul), out_off[0], out_off[1]
     a.in_mul, a.in_off_h, a.in_off_w = in_mul, in_off[0], in_off[1]
     a.add_after_act = int(add_after_act)
+    a.fold_mode = int(fold)
     if pad is not None:
         a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
     t0 = _prof_begin()
     call("b2_conv_dgrad" if dgrad else "b2_conv_fprop", C.byref(a), _stream())
     # algorithmic DRAM bytes of the launch: every input element once, every output element once, the weights once
     _prof_end("conv_igemm", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale,
-              2.0 * (n * hi * wi * (c0 + c1) // (in_mul * in_mul) + n * h * w * cout + taps * cout * (c0 + c1)))
+              2.0 * (n * hi * wi * (c0 + c1) // (in_mul * in_mul) + n * h * w * cout * (4 if fold == 1 else 1)
+                     + taps * cout * (c0 + c1)))
     return y
 
 

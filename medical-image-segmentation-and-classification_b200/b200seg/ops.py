@@ -426,6 +426,7 @@ def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu:
 # the only numerical difference is that the 3x3 taps are summed in fp32 before the bf16 rounding of the weights.
 # ----------------------------------------------------------------------------------------------------------
 _PHASES = ((0, 0), (0, 1), (1, 0), (1, 1))
+_UPFOLD_MERGED = os.environ.get("B200SEG_UPFOLD_MERGED", "1") != "0"     # 0: four launches per direction (A/B switch)
 
 
 @custom_op("b200seg::upconv_bn_act", mutates_args=())
@@ -439,9 +440,14 @@ def upconv_bn_act(x: Tensor, weight: Tensor, bias: Optional[Tensor], gamma: Tens
     stats = K.zeros_scratch((2, cout), _F64, dev) if training else torch.empty((0,), dtype=_F64, device=dev)
     wf, _ = K.packed(weight, "upfold")
     z = K.new_act(n, 2 * h, 2 * w, cout, dev)
-    for ph, (a, b) in enumerate(_PHASES):
-        K.conv_igemm(x, wf[ph], cout, 2, bias=bias, stats=stats if training else None, out=z, out_mul=2,
-                     out_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
+    if _UPFOLD_MERGED and cout % 64 == 0 and cin % 64 == 0:
+        # all four phase convolutions in ONE launch (the phase is an extra tile dimension, pixel-shuffle TMA stores)
+        K.conv_igemm(x, wf.view(16, cout, cin), cout, 2, bias=bias, stats=stats if training else None, out=z, fold=1,
+                     alg_scale=2.25)
+    else:
+        for ph, (a, b) in enumerate(_PHASES):
+            K.conv_igemm(x, wf[ph], cout, 2, bias=bias, stats=stats if training else None, out=z, out_mul=2,
+                         out_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
     if training:
         coef = K.bn_finalize(stats, n * 4 * h * w, gamma, beta, eps, 0.0, None, None, None)
     else:
@@ -470,11 +476,15 @@ def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Te
     if need_dx:
         _, wd = K.packed(weight, "upfold", want_dgrad=True)
         dx = K.new_act(n, h, w, cin, dev)
-        for ph, (a, b) in enumerate(_PHASES):
-            # 2x2 conv of the (a,b) sub-lattice of dz with the flipped/transposed phase weights, chained through the
-            # epilogue's addend so the four phases sum into one dx
-            K.conv_igemm(dz, wd[ph], cin, 2, addend=dx if ph > 0 else None, out=dx, dgrad=True, in_mul=2,
-                         in_off=(a, b), pad=(a, b), alg_scale=2.25)
+        if _UPFOLD_MERGED and cout % 64 == 0 and cin % 64 == 0:
+            # the four phases as ONE K loop of 16 taps over the sub-lattices of dz: one launch, one epilogue per tile
+            K.conv_igemm(dz, wd.view(16, cin, cout), cin, 2, out=dx, dgrad=True, fold=2, alg_scale=2.25)
+        else:
+            for ph, (a, b) in enumerate(_PHASES):
+                # 2x2 conv of the (a,b) sub-lattice of dz with the flipped/transposed phase weights, chained through
+                # the epilogue's addend so the four phases sum into one dx
+                K.conv_igemm(dz, wd[ph], cin, 2, addend=dx if ph > 0 else None, out=dx, dgrad=True, in_mul=2,
+                             in_off=(a, b), pad=(a, b), alg_scale=2.25)
     else:
         dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     with K.wgrad_stream(dz, x, allow=K.grad_is_stolen(weight)):

@@ -65,8 +65,13 @@ def upconv_bn_act_infer(x: Tensor, weight: Tensor, bias: Optional[Tensor], gamma
     n, h, w, _ = x.shape
     wf, bf = _folded(weight, bias, gamma, beta, running_mean, running_var, eps, True)
     y = K.new_act(n, 2 * h, 2 * w, cout, x.device)
-    for ph, (a, b) in enumerate(_PHASES):
-        K.conv_igemm(x, wf[ph], cout, 2, bias=bf, relu=relu, out=y, out_mul=2, out_off=(a, b), pad=(1 - a, 1 - b))
+    from . import ops as _ops
+    cin = x.shape[3]
+    if _ops._UPFOLD_MERGED and cout % 64 == 0 and cin % 64 == 0:
+        K.conv_igemm(x, wf.view(16, cout, cin), cout, 2, bias=bf, relu=relu, out=y, fold=1)
+    else:
+        for ph, (a, b) in enumerate(_PHASES):
+            K.conv_igemm(x, wf[ph], cout, 2, bias=bf, relu=relu, out=y, out_mul=2, out_off=(a, b), pad=(1 - a, 1 - b))
     return y
 
 

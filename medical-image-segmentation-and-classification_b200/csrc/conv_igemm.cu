@@ -68,6 +68,15 @@ struct IgemmParams {
   int debug_skip;     // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs, 4 = no drain
   int cluster;        // CTAs per cluster (1, 2 or 4): they work on consecutive m-tiles of one n-tile and share the
                       // weight tiles, each CTA fetching 1/cluster of the rows and multicasting them
+  int fold;           // folded-UpConv launches (AttentionUNet.py:15-27 as four 2x2 phase convolutions) merged into ONE:
+                      //   1 = fprop: the phase (a, b) is an extra tile dimension; tile t belongs to phase t / m_tiles_phase,
+                      //       uses weight taps 4*phase .. 4*phase+3 with tap offsets (u - (1-a), v - (1-b)) and stores to
+                      //       y[n, 2h+a, 2w+b, :] through a 5-D view (b*C + c, w, a, h, n) of the fine grid;
+                      //   2 = dgrad: the four phases are ONE K loop of 16 taps, tap o = 4*phase + 2u + v reading the
+                      //       (a, b) sub-lattice of dz at offset (u - a, v - b) through the same kind of 5-D view — no
+                      //       addend chain, one epilogue per output tile instead of four.
+  int fold_c;         // channel count of the fine-grid tensor behind the 5-D view (fprop: Cout, dgrad: C of dz)
+  int m_tiles_phase;  // fold == 1: m-tiles per phase
   int pair;           // CTA-pair mode (cluster == 2): ONE tcgen05.mma.cta_group::2 with M = 256 covers the two m-tiles of
                       // the pair; each CTA stages its own activation tile and HALF of the weight rows in its own shared
                       // memory (no multicast: each SM receives half the weight bytes), the rank-0 CTA issues the MMAs,
@@ -97,6 +106,21 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* 
                    reinterpret_cast<uint64_t>(tm)),
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, const void* smem, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(void* smem, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1,
+                                                 int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() {
@@ -201,9 +225,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int n_tile = item % p.n_tiles;
       // pixel origin of the item's tile(s); a ragged last item recomputes the last tile (its result is dropped)
       int w0s[2], h0s[2], n0s[2];
+      int tph = 0;                                 // fold == 1: the phase of the item's tile(s)
       for (int q = 0; q < a_slots; ++q) {
         int t = (item / p.n_tiles) * per_item + (p.dm ? q : (int)crank);
         if (t >= p.m_tiles) t = p.m_tiles - 1;
+        if (p.fold == 1) {
+          tph = t / p.m_tiles_phase;
+          t -= tph * p.m_tiles_phase;
+        }
         const int tw_i = t % p.tw;
         t /= p.tw;
         const int th_i = t % p.th;
@@ -216,7 +245,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int outer = p.rp ? 4 : (p.halo ? 3 : p.taps);   // halo mode: one iteration per (input row, channel block)
       for (int o = 0; o < outer; ++o) {
         int dr = 0, ds = 0, tap0 = o;
-        if (p.rp) {
+        int fa = 0, fb = 0;                        // fold == 2: sub-lattice (a, b) of dz this tap reads
+        if (p.fold == 2) {
+          fa = o >> 3;
+          fb = (o >> 2) & 1;
+          dr = ((o >> 1) & 1) - fa;
+          ds = (o & 1) - fb;
+        } else if (p.fold == 1) {
+          dr = (o >> 1) - (1 - (tph >> 1));
+          ds = (o & 1) - (1 - (tph & 1));
+          tap0 = tph * 4 + o;
+        } else if (p.rp) {
           dr = o - 1;
           ds = -1;
           tap0 = (o - 1) * 3;          // first tap of the stacked pair (filter rows o-1 and o)
@@ -233,35 +272,32 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (elect_one()) {
             uint8_t* sa = smem + stage * stage_bytes;
             uint8_t* sb = sa + a_slots * p.a_stage_bytes;
+            // one activation box (4-D NHWC box, or the 5-D sub-lattice view of the merged UpConv dgrad)
+            auto load_a = [&](uint8_t* dst, int qw0, int qh0, int qn0, uint32_t lbar) {
+              const CUtensorMap* tm = cb < p.cb0 ? &tmA0 : &tmA1;
+              const int c = (cb < p.cb0 ? cb : cb - p.cb0) * kKBlock;
+              if (p.fold == 2) {
+                if constexpr (kPair) tma_load_5d_pair(dst, tm, lbar, fb * p.fold_c + c, qw0 + ds, fa, qh0 + dr, qn0);
+                else tma_load_5d(dst, tm, &full_bar[stage], fb * p.fold_c + c, qw0 + ds, fa, qh0 + dr, qn0);
+              } else {
+                if constexpr (kPair) tma_load_4d_pair(dst, tm, lbar, c, p.stride * qw0 + ds, p.stride * qh0 + dr, qn0);
+                else tma_load_4d(dst, tm, &full_bar[stage], c, p.stride * qw0 + ds, p.stride * qh0 + dr, qn0);
+              }
+            };
             if constexpr (kPair) {
               // both CTAs load into their own smem; completion is counted on the LEADER's barrier, which only the
               // leader arms (its arrive + expect_tx may come after the peer's bytes: the phase needs both)
               const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
               if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
-              if (cb < p.cb0)
-                tma_load_4d_pair(sa, &tmA0, lbar, cb * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
-              else
-                tma_load_4d_pair(sa, &tmA1, lbar, (cb - p.cb0) * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
+              load_a(sa, w0, h0, n0, lbar);
               tma_load_3d_pair(sb, &tmB, lbar, cb * kKBlock, n_tile * p.block_n + (int)crank * b_rows, tap0);
             } else {
             if (p.debug_skip & 1) {
               mbar_arrive(&full_bar[stage]);
             } else {
             mbar_arrive_expect_tx(&full_bar[stage], tx);
-            if (cb < p.cb0) {
-              tma_load_4d(sa, &tmA0, &full_bar[stage], cb * kKBlock, p.stride * w0 + ds, p.stride * h0 + dr, n0);
-            } else {
-              tma_load_4d(sa, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock, p.stride * w0 + ds,
-                          p.stride * h0 + dr, n0);
-            }
-            if (p.dm) {                          // second activation tile of the item, same taps / channel block
-              if (cb < p.cb0)
-                tma_load_4d(sa + p.a_stage_bytes, &tmA0, &full_bar[stage], cb * kKBlock, p.stride * w0s[1] + ds,
-                            p.stride * h0s[1] + dr, n0s[1]);
-              else
-                tma_load_4d(sa + p.a_stage_bytes, &tmA1, &full_bar[stage], (cb - p.cb0) * kKBlock,
-                            p.stride * w0s[1] + ds, p.stride * h0s[1] + dr, n0s[1]);
-            }
+            load_a(sa, w0, h0, n0, 0u);
+            if (p.dm) load_a(sa + p.a_stage_bytes, w0s[1], h0s[1], n0s[1], 0u);   // second tile of the item
             if (p.rp) {
               for (int tp = 0; tp < 3; ++tp)       // [W(o-1, tp) ; W(o, tp)]: 2 taps, element stride 3, 64 rows each
                 tma_load_3d(sb + tp * (128 * 128), &tmB, &full_bar[stage], cb * kKBlock, 0, tap0 + tp);
@@ -439,6 +475,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int n_tile = item % p.n_tiles;
       const int ch_base = n_tile * p.block_n;
       int t = (item / p.n_tiles) * per_item + (p.dm ? (ti & 1) : (int)crank);
+      int eph = 0;                                 // fold == 1: phase of this tile
+      if (p.fold == 1 && t < p.m_tiles) {
+        eph = t / p.m_tiles_phase;
+      }
       if (t >= p.m_tiles || (p.debug_skip & 4)) {
         // ragged last group: this CTA only kept the pipeline protocol going; hand the accumulator straight back
         const int dbuf = ti & (nbuf - 1);
@@ -462,6 +502,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         cur_n_tile = n_tile;
       }
+      if (p.fold == 1) t -= eph * p.m_tiles_phase;
       const int tw_i = t % p.tw;
       t /= p.tw;
       const int th_i = t % p.th;
@@ -606,6 +647,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (p.rp) {                 // panel 0 = output row h0 + 1, panel 1 = output row h0
             tma_store_4d(&tmY, ctile, 0, w0, h0 + 1, n0);
             tma_store_4d(&tmY, ctile + kTileM * 128, 0, w0, h0, n0);
+          } else if (p.fold == 1) {    // phase (a, b) of the fine grid: 5-D view (b*C + c, w, a, h, n)
+            for (int pn = 0; pn < (p.block_n >> 6); ++pn)
+              tma_store_5d(&tmY, ctile + pn * (kTileM * 128), (eph & 1) * p.fold_c + ch_base + pn * 64, w0, eph >> 1, h0,
+                           n0);
           } else if (p.block_n >= 64) {
             for (int pn = 0; pn < (p.block_n >> 6); ++pn)
               tma_store_4d(&tmY, ctile + pn * (kTileM * 128), ch_base + pn * 64, w0, h0, n0);
@@ -737,9 +782,18 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   const int stride = a->stride == 0 ? 1 : a->stride;
   const int out_mul = a->out_mul == 0 ? 1 : a->out_mul;
   B2_REQUIRE(a->ksize >= 1 && a->ksize <= 3, B2_ERR_SHAPE, "ksize %d unsupported (1, 2 or 3)", a->ksize);
+  const int fold = a->fold_mode;
+  B2_REQUIRE(fold >= 0 && fold <= 2, B2_ERR_SHAPE, "fold_mode %d unsupported", fold);
+  if (fold != 0) {
+    B2_REQUIRE(gate == nullptr && a->ksize == 2 && a->c1 == 0 && a->addend == nullptr && (a->stride == 0 || a->stride == 1) &&
+                   (a->out_mul == 0 || a->out_mul == 1) && (a->in_mul == 0 || a->in_mul == 1) && a->c0 % 64 == 0 &&
+                   a->cout % 64 == 0,
+               B2_ERR_SHAPE, "merged UpConv launch: plain 2x2 taps, one K source, channels multiples of 64");
+    B2_REQUIRE(a->ldx0 == a->c0 && a->ldy == a->cout, B2_ERR_SHAPE, "merged UpConv launch needs dense tensors");
+  }
   B2_REQUIRE(stride == 1 || stride == 2, B2_ERR_SHAPE, "stride %d unsupported (1 or 2)", stride);
   const int in_mul = a->in_mul == 0 ? 1 : a->in_mul;
-  B2_REQUIRE(a->ksize != 2 || stride == 2 || a->custom_pad != 0, B2_ERR_SHAPE,
+  B2_REQUIRE(a->ksize != 2 || stride == 2 || a->custom_pad != 0 || fold != 0, B2_ERR_SHAPE,
              "ksize 2 needs stride 2 or explicit tap offsets");
   B2_REQUIRE(in_mul >= 1 && (in_mul == 1 || stride == 1) && a->in_off_h >= 0 && a->in_off_h < in_mul &&
                  a->in_off_w >= 0 && a->in_off_w < in_mul,
@@ -762,13 +816,17 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   int rc = conv_tile_geometry(a->n, a->h, a->w, kTileM, &p.Wb, &p.Hb, &p.Nb, &p.tw, &p.th, &tn);
   if (rc) return rc;
   p.H = a->h; p.W = a->w; p.N = a->n;
-  p.taps = a->ksize * a->ksize;
+  p.taps = fold == 2 ? 16 : a->ksize * a->ksize;
+  p.fold = fold;
+  p.fold_c = fold == 1 ? a->cout : a->c0;
   p.cb0 = (a->c0 + 63) / 64;
   p.cb1 = (a->c1 + 63) / 64;
   const int cbt = p.cb0 + p.cb1;
   p.cout = a->cout;
   p.n_tiles = a->cout / p.block_n;
   p.m_tiles = p.tw * p.th * tn;
+  p.m_tiles_phase = p.m_tiles;
+  if (fold == 1) p.m_tiles *= 4;                 // the four phases are an extra tile dimension
   p.y = static_cast<__nv_bfloat16*>(a->y);
   p.ldy = a->ldy;
   p.bias = a->bias;
@@ -835,7 +893,8 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   {
     const int want = env_int("B200SEG_DM", 2);      // 0 = off, 1 = only with two epilogue groups, 2 = also with one
     p.dm = 0;
-    if (want != 0 && p.block_n <= 128 && p.m_tiles >= env_int("B200SEG_DM_MIN_TILES", 4 * num_sms())) {
+    if (want != 0 && p.block_n <= 128 && p.m_tiles >= env_int("B200SEG_DM_MIN_TILES", 4 * num_sms()) &&
+        !(fold == 1 && p.m_tiles_phase % 2 != 0)) {
       const int sb2 = 2 * p.a_stage_bytes + p.b_stage_bytes;
       const int g2 = 232448 - 1024 - tail_bytes - 2 * ctile_bytes, g1 = g2 + ctile_bytes;
       if (g2 / sb2 >= 2 || (want == 2 && g1 / sb2 >= 2)) p.dm = 1;
@@ -849,6 +908,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
     const int want = env_int("B200SEG_PAIR", 2);
     p.pair = 0;
     if (want != 0 && !p.rp && p.m_tiles >= 2 && p.block_n % 16 == 0 && (want >= 2 || p.block_n == 256) &&
+        !(fold == 1 && p.m_tiles_phase % 2 != 0) &&
         env_int("B200SEG_CLUSTER", 0) <= 1 && env_int("B200SEG_DEBUG_SKIP", 0) == 0) {
       p.pair = 1;
       p.dm = 0;
@@ -899,7 +959,15 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   CUtensorMap tmA0, tmA1, tmB, tmY;
   const int boxw = p.halo ? p.Wb + 2 : p.Wb;
   const int ih = a->h * stride, iw = a->w * stride;      // extent of the sampled input grid
-  {
+  if (fold == 2) {
+    // dz [n, 2h, 2w, C] as (b*C + c, w, a, h, n): the (a, b) sub-lattices become coordinates of one 5-D map
+    const uint64_t Cc = (uint64_t)a->c0, W2 = (uint64_t)a->w, H2 = (uint64_t)a->h;
+    uint64_t dims[5] = {2 * Cc, W2, 2, H2, (uint64_t)a->n};
+    uint64_t str[5] = {2, 2 * Cc * 2, 2 * W2 * Cc * 2, 4 * W2 * Cc * 2, 4 * H2 * W2 * Cc * 2};
+    uint32_t box[5] = {64, (uint32_t)p.Wb, 1, (uint32_t)p.Hb, (uint32_t)p.Nb};
+    rc = encode_tmap_bf16(&tmA0, a->x0, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  } else {
     // underlying image is (ih*in_mul) x (iw*in_mul); the operand is its (in_off_h, in_off_w) sub-lattice
     const long long fw = (long long)iw * in_mul, fh = (long long)ih * in_mul;
     const long long off0 = ((long long)a->in_off_h * fw + a->in_off_w) * a->ldx0;
@@ -917,7 +985,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
     tmA1 = tmA0;
   }
   {
-    uint64_t dims[3] = {(uint64_t)(a->c0 + a->c1), (uint64_t)a->cout, (uint64_t)p.taps};
+    uint64_t dims[3] = {(uint64_t)(a->c0 + a->c1), (uint64_t)a->cout, (uint64_t)(fold == 1 ? 16 : p.taps)};
     uint64_t str[3] = {2, (uint64_t)a->ktot * 2, (uint64_t)a->w_tap_stride * 2};
     uint32_t box[3] = {64, (uint32_t)p.block_n, p.halo ? 3u : 1u};
     if (p.pair) {                 // this CTA's half of the rows, all taps of the stage in one box
@@ -942,7 +1010,14 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   p.y_sn = oh * ow * a->ldy;
   p.y = static_cast<__nv_bfloat16*>(a->y) + ((long long)a->out_off_h * ow + a->out_off_w) * a->ldy;
   if (p.tma_store) {
-    if (gate != nullptr) {        // the gate's output has C channels (64-channel boxes), not F_int
+    if (fold == 1) {              // y [n, 2h, 2w, Cout] as (b*C + c, w, a, h, n)
+      B2_REQUIRE(p.block_n >= 64, B2_ERR_SHAPE, "merged UpConv fprop needs cout >= 64");
+      const uint64_t Cc = (uint64_t)a->cout, W2 = (uint64_t)a->w, H2 = (uint64_t)a->h;
+      uint64_t dims[5] = {2 * Cc, W2, 2, H2, (uint64_t)a->n};
+      uint64_t str[5] = {2, 2 * Cc * 2, 2 * W2 * Cc * 2, 4 * W2 * Cc * 2, 4 * H2 * W2 * Cc * 2};
+      uint32_t box[5] = {64, (uint32_t)p.Wb, 1, (uint32_t)p.Hb, (uint32_t)p.Nb};
+      rc = encode_tmap_bf16(&tmY, a->y, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else if (gate != nullptr) { // the gate's output has C channels (64-channel boxes), not F_int
       rc = encode_act_tmap_ex(&tmY, p.y, gate->c, a->n, a->h, a->w, p.y_sw, p.y_sh, p.y_sn, p.Wb, p.Hb, p.Nb, 1);
     } else if (p.block_n >= 64) {
       rc = encode_act_tmap_ex(&tmY, p.y, a->cout, a->n, a->h, a->w, p.y_sw, p.y_sh, p.y_sn, p.Wb, p.Hb, p.Nb, 1);
