@@ -73,7 +73,7 @@ def measured_peaks():
 def measured_traffic():
     """mean DRAM bytes per launch of the tensor-core kernels, from the committed ncu capture of one training step of
     the default workload (tools/profile_step.py + tools/summarize_traffic.py); {} if the capture is absent"""
-    p = ROOT / "profiles" / "r01_final_traffic.json"
+    p = ROOT / "profiles" / "r02_traffic.json"
     if not p.exists():
         return {}
     d = json.loads(p.read_text())
@@ -416,7 +416,7 @@ def run_b200(args):
                      "note": "achieved = FLOPs the launches executed / their CUDA-event time; achieved_algorithmic "
                              "counts the folded UpConv launches at the reference's 3x3-on-the-fine-grid FLOPs (x2.25)",
                      "traffic": traffic.get("conv_igemm"), "traffic_unit": "bytes per launch (mean over the step's "
-                     "launches; ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_final_traffic.json)",
+                     "launches; ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_traffic.json)",
                      "algorithmic_bytes_per_launch": by_i / max(n, 1),
                      "peak_source": peak_src, "launches_per_step": n // 2,
                      "ms_per_step_in_kernel": tms / 2, "share_of_step": (tms / 2) / step_ms},
