@@ -102,10 +102,6 @@ typedef struct b2_conv_args {
    *   2 = dgrad:  x0 is the FINE gradient dz [n, 2h, 2w, c0], y the coarse dx [n, h, w, cout] — the four phases are
    *               one K loop of 16 taps over the sub-lattices of dz (no addend chain). */
   int32_t fold_mode;
-  /* optional fp32 scratch of n*h*w*cout*4 bytes (16 B aligned).  When given, layers with fewer tiles than half the SMs
-   * (batch 1 ... 4 per GPU) split their K loop over several SMs through it (split-K + finalize pass); NULL = never. */
-  void* workspace;
-  int64_t workspace_bytes;
 } b2_conv_args;
 
 int b2_conv_fprop(const b2_conv_args* a, b2_stream_t stream);

@@ -31,7 +31,7 @@ class ConvArgs(C.Structure):
                 ("stride", _i32), ("out_mul", _i32), ("out_off_h", _i32), ("out_off_w", _i32),
                 ("in_mul", _i32), ("in_off_h", _i32), ("in_off_w", _i32),
                 ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32), ("add_after_act", _i32),
-                ("fold_mode", _i32), ("workspace", _vp), ("workspace_bytes", _i64)]
+                ("fold_mode", _i32)]
 
 
 class WgradArgs(C.Structure):

@@ -422,11 +422,6 @@ def fold_upconv_wgrad(dweff, out=None):
 # ----------------------------------------------------------------------------------------------------------
 # tcgen05 convolutions
 # ----------------------------------------------------------------------------------------------------------
-# fp32 scratch for split-K launches of small-M layers (one per device; consumed by the finalize pass of the same call,
-# so consecutive convolutions of one stream can share it)
-_SPLITK = {"bufs": {}, "bytes": 16 << 20}
-
-
 def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None, relu=False, out=None,
                row_offset=0, dgrad=False, stride=1, out_mul=1, out_off=(0, 0), in_mul=1, in_off=(0, 0), pad=None,
                alg_scale=1.0, add_after_act=False, fold=0):
@@ -476,14 +471,6 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
     a.in_mul, a.in_off_h, a.in_off_w = in_mul, in_off[0], in_off[1]
     a.add_after_act = int(add_after_act)
     a.fold_mode = int(fold)
-    if addend is None and not fold and out_mul == 1:
-        # small outputs: offer the split-K scratch (the library uses it only when the layer has fewer tiles than SMs)
-        need = n * h * w * cout * 4
-        if need <= _SPLITK["bytes"]:
-            ws = _SPLITK["bufs"].get(x0.device.index)
-            if ws is None:
-                ws = _SPLITK["bufs"][x0.device.index] = torch.empty(_SPLITK["bytes"], dtype=torch.uint8, device=x0.device)
-            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     if pad is not None:
         a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
     t0 = _prof_begin()

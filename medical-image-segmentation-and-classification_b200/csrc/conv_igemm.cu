@@ -68,11 +68,6 @@ struct IgemmParams {
   int debug_skip;     // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs, 4 = no drain
   int cluster;        // CTAs per cluster (1, 2 or 4): they work on consecutive m-tiles of one n-tile and share the
                       // weight tiles, each CTA fetching 1/cluster of the rows and multicasting them
-  int ksplit;         // split-K (small-M layers: fewer tiles than SMs): a work item is (tile, n-tile, K range); the ranges
-                      // of one tile run on different SMs and add their fp32 partial accumulators into `ws` with red.add,
-                      // a finalize kernel applies bias / ReLU / bf16 rounding / statistics.  1 = off.
-  int k_per_split;    // K iterations (of num_k_iters) per range
-  float* ws;          // [pixels][cout] fp32, zeroed by the host
   int fold;           // folded-UpConv launches (AttentionUNet.py:15-27 as four 2x2 phase convolutions) merged into ONE:
                       //   1 = fprop: the phase (a, b) is an extra tile dimension; tile t belongs to phase t / m_tiles_phase,
                       //       uses weight taps 4*phase .. 4*phase+3 with tap offsets (u - (1-a), v - (1-b)) and stores to
@@ -181,7 +176,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int cluster_id = (int)blockIdx.x / C;
   const int num_clusters = (int)gridDim.x / C;
   const int per_item = p.dm ? 2 : C;                                   // m-tiles per work item
-  const int total_items = ((p.m_tiles + per_item - 1) / per_item) * p.n_tiles * p.ksplit;
+  const int total_items = ((p.m_tiles + per_item - 1) / per_item) * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -226,10 +221,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t tx = (uint32_t)(a_slots * p.a_tx_bytes + p.b_stage_bytes) * (p.pair ? 2u : 1u);
     const int b_taps = p.halo ? 3 : 1;           // weight taps per stage
     const int b_rows = p.block_n / C;            // weight rows this CTA fetches (and multicasts) per tap
-    for (int witem = cluster_id; witem < total_items; witem += num_clusters) {
-      const int item = witem / p.ksplit;           // (m-group, n-tile); witem % ksplit = the K range of this work item
-      const int it0 = (witem % p.ksplit) * p.k_per_split;
-      const int it1 = it0 + p.k_per_split < p.num_k_iters ? it0 + p.k_per_split : p.num_k_iters;
+    for (int item = cluster_id; item < total_items; item += num_clusters) {
       const int n_tile = item % p.n_tiles;
       // pixel origin of the item's tile(s); a ragged last item recomputes the last tile (its result is dropped)
       int w0s[2], h0s[2], n0s[2];
@@ -250,9 +242,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         n0s[q] = tn_i * p.Nb;
       }
       const int w0 = w0s[0], h0 = h0s[0], n0 = n0s[0];
-      // K iterations: (tap | input row in halo mode) x channel block, flattened so that a split-K item takes a range
-      for (int it = it0; it < it1; ++it) {
-        const int o = it / cbt, cb = it - o * cbt;
+      const int outer = p.rp ? 4 : (p.halo ? 3 : p.taps);   // halo mode: one iteration per (input row, channel block)
+      for (int o = 0; o < outer; ++o) {
         int dr = 0, ds = 0, tap0 = o;
         int fa = 0, fb = 0;                        // fold == 2: sub-lattice (a, b) of dz this tap reads
         if (p.fold == 2) {
@@ -276,7 +267,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           dr = o / p.ksize - p.pad_h;
           ds = o % p.ksize - p.pad_w;
         }
-        {
+        for (int cb = 0; cb < cbt; ++cb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
             uint8_t* sa = smem + stage * stage_bytes;
@@ -340,16 +331,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int ti = 0;
     const int sub = p.halo ? 3 : 1;
     const int nb_shift = p.dm ? 2 : 1;           // log2(accumulators in TMEM)
-    for (int witem = cluster_id; witem < total_items; witem += num_clusters, ++ti) {
-      const int it0 = (witem % p.ksplit) * p.k_per_split;
-      const int n_iters = (it0 + p.k_per_split < p.num_k_iters ? it0 + p.k_per_split : p.num_k_iters) - it0;
+    for (int item = cluster_id; item < total_items; item += num_clusters, ++ti) {
       // local tile counter lt = a_slots * ti + q  ->  accumulator lt % nbuf, barrier phase (lt / nbuf) & 1
       for (int q = 0; q < a_slots; ++q) {
         const uint32_t lt = (uint32_t)(a_slots * ti + q);
         mbar_wait(&tmem_empty_bar[lt & (nbuf - 1)], ((lt >> nb_shift) & 1u) ^ 1u);
       }
       tc_fence_after();
-      for (int it = 0; it < n_iters; ++it) {
+      for (int it = 0; it < p.num_k_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -481,9 +470,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int nb_shift = p.dm ? 2 : 1;           // log2(accumulators in TMEM)
     // ti = local tile counter of this CTA (group g takes ti = g, g + G, ...); double-M: item = ti / 2, tile ti & 1
     for (int ti = g;; ti += G) {
-      const int witem = cluster_id + (p.dm ? (ti >> 1) : ti) * num_clusters;
-      if (witem >= total_items) break;
-      const int item = witem / p.ksplit;
+      const int item = cluster_id + (p.dm ? (ti >> 1) : ti) * num_clusters;
+      if (item >= total_items) break;
       const int n_tile = item % p.n_tiles;
       const int ch_base = n_tile * p.block_n;
       int t = (item / p.n_tiles) * per_item + (p.dm ? (ti & 1) : (int)crank);
@@ -542,27 +530,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (kHasAdd) {
         const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
         arow = valid ? p.addend + pix * p.ldadd + ch_base : nullptr;
-      }
-      if (p.ksplit > 1) {
-        // ---------------- split-K: add this K range's partial accumulator into the fp32 workspace ----------------
-        const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
-        float* wrow = p.ws + pix * p.cout + ch_base;
-        for (int c = 0; c < p.block_n; c += 32) {
-          float v[32];
-          tmem_ld32(taddr + c, v);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) atomicAdd(wrow + c + e, v[e]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if constexpr (kPair) mbar_arrive_remote(&tmem_empty_bar[buf], 0);
-          else mbar_arrive(&tmem_empty_bar[buf]);
-        }
-        continue;
       }
       if (p.gate_x != nullptr) {
         // ---------------- fused attention-gate epilogue (eval mode) ----------------
@@ -741,29 +708,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 1) {
     if constexpr (kPair) tmem_dealloc_pair(tmem_base, tmem_cols);
     else tmem_dealloc(tmem_base, tmem_cols);
-  }
-}
-
-// split-K finalize: y = bf16(act(ws + bias)); 8 channels per thread
-__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, long long npix, int cout,
-                                                              const float* __restrict__ bias, int relu,
-                                                              __nv_bfloat16* __restrict__ y, int ldy) {
-  const int cg = cout / 8;
-  const long long total = npix * cg;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const long long pix = i / cg;
-    const float4 a = *reinterpret_cast<const float4*>(ws + pix * cout + g * 8);
-    const float4 b = *reinterpret_cast<const float4*>(ws + pix * cout + g * 8 + 4);
-    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] += bias ? __ldg(bias + g * 8 + j) : 0.f;
-      if (relu) v[j] = fmaxf(v[j], 0.f);
-    }
-    *reinterpret_cast<uint4*>(y + pix * ldy + g * 8) =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
@@ -1098,32 +1042,6 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   }
   // persistent grid: one CTA per SM.  When the number of clusters is a multiple of n_tiles every CTA keeps one n-tile
   // for its whole life and its BN statistics stay in registers; otherwise they are flushed whenever the slab changes.
-  // split-K for small-M layers: with fewer work items than half the machine, split the K loop of every tile over
-  // several SMs (fp32 partials added into the caller's workspace, finalized below).  Needs a plain convolution epilogue.
-  p.ksplit = 1;
-  p.k_per_split = p.num_k_iters;
-  p.ws = nullptr;
-  {
-    const int per_item0 = p.dm ? 2 : p.cluster;
-    const long long items0 = (long long)((p.m_tiles + per_item0 - 1) / per_item0) * p.n_tiles;
-    const int slots = num_sms() / p.cluster;
-    const long long ws_need = (long long)a->n * a->h * a->w * a->cout * 4;
-    if (env_int("B200SEG_SPLITK", 1) != 0 && a->workspace != nullptr && a->workspace_bytes >= ws_need &&
-        items0 * 2 <= slots && p.num_k_iters >= 8 && gate == nullptr && fold == 0 && a->addend == nullptr &&
-        out_mul == 1 && !p.rp && !p.dm && a->cout % 8 == 0 && a->cout <= 2048 && !det_enabled() &&
-        (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0) {
-      int want = (int)(slots / items0);
-      if (want > p.num_k_iters / 4) want = p.num_k_iters / 4;       // at least 4 K iterations per range
-      if (want > 16) want = 16;
-      if (want >= 2) {
-        p.k_per_split = (p.num_k_iters + want - 1) / want;
-        p.ksplit = (p.num_k_iters + p.k_per_split - 1) / p.k_per_split;
-        p.ws = static_cast<float*>(a->workspace);
-        p.stats = nullptr;                                          // taken by the finalize pass
-        B2_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, (size_t)ws_need, stream));
-      }
-    }
-  }
   const int C = p.cluster;
   int clusters = num_sms() / C;
   if (C > 1) {
@@ -1148,7 +1066,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
     if (clusters > max_clusters[C]) clusters = max_clusters[C];
   }
   const int per_item = p.dm ? 2 : C;
-  const long long total = (long long)((p.m_tiles + per_item - 1) / per_item) * p.n_tiles * p.ksplit;
+  const long long total = (long long)((p.m_tiles + per_item - 1) / per_item) * p.n_tiles;
   B2_REQUIRE(total < (1ll << 31), B2_ERR_SHAPE, "too many tiles");
   if (clusters > total) clusters = (int)total;
   if (clusters > p.n_tiles && (total / clusters) >= 16) clusters = (clusters / p.n_tiles) * p.n_tiles;
@@ -1184,17 +1102,6 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
     B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, tmA0, tmA1, tmB, tmY, p));
   }
   B2_LAUNCH_CHECK();
-  if (p.ksplit > 1) {
-    const long long npix = (long long)a->n * a->h * a->w;
-    long long grid = (npix * (a->cout / 8) + 255) / 256;
-    const long long cap = (long long)num_sms() * 8;
-    if (grid > cap) grid = cap;
-    splitk_finalize_kernel<<<(unsigned)grid, 256, 0, stream>>>(p.ws, npix, a->cout, a->bias, a->relu,
-                                                              static_cast<__nv_bfloat16*>(a->y), a->ldy);
-    B2_LAUNCH_CHECK();
-    if (a->stats != nullptr) return b2_channel_stats(a->y, a->ldy, npix, a->cout, a->stats, stream);
-    return B2_OK;
-  }
   if (det.partial) return det_finish(det.partial, det_rows, 2 * p.cout, 2 * p.cout, p.stats, stream);
   return B2_OK;
 }

@@ -194,45 +194,3 @@ def test_fprop_dgrad_rowpair_mode_matches_plain(n, h, w, cin):
     assert rel(res["1"][0].float(), res["0"][0].float()) < 2e-3 and rel(res["1"][2].float(), res["0"][2].float()) < 2e-3
     yf = res["1"][0].float().reshape(-1, cout)
     assert rel(res["1"][1][0], yf.double().sum(0)) < 1e-5 and rel(res["1"][1][1], (yf.double() ** 2).sum(0)) < 1e-5
-
-
-@pytest.mark.parametrize("n,h,w,cin,cout,k,relu", [
-    (1, 16, 16, 512, 1024, 3, False), (1, 16, 16, 1024, 1024, 3, True), (2, 8, 8, 256, 256, 3, False),
-    (1, 32, 32, 256, 512, 3, True), (4, 16, 16, 1024, 512, 1, False), (1, 16, 16, 3072, 1024, 3, False),
-    (3, 14, 14, 512, 512, 3, True)])
-def test_split_k_small_m(n, h, w, cin, cout, k, relu):
-    """small-M layers (fewer tiles than SMs: batch 1 ... 4 per GPU) split their K loop over several SMs through an fp32
-    workspace + finalize pass (B200SEG_SPLITK, on by default): same result as the single-pass kernel up to the fp32
-    summation order, statistics of the rounded output included"""
-    import os
-    from b200seg import kernels as K
-    g = torch.Generator(device="cuda").manual_seed(9)
-    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
-    wt = torch.randn(cout, cin, k, k, device="cuda", generator=g) / (cin * k * k) ** 0.5
-    b = torch.randn(cout, device="cuda", generator=g)
-    xb = nhwc(x)
-    wf, wd = K.pack_weights(wt)
-
-    def run():
-        stats = torch.zeros(2, cout, dtype=torch.float64, device="cuda")
-        y = K.conv_igemm(xb, wf, cout, k, bias=b, stats=stats, relu=relu)
-        dx = K.conv_igemm(nhwc(torch.randn(n, cout, h, w, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))),
-                          wd, cin, k, dgrad=True)
-        torch.cuda.synchronize()
-        return y, stats, dx
-
-    y1, s1, dx1 = run()
-    os.environ["B200SEG_SPLITK"] = "0"
-    try:
-        y0, s0, dx0 = run()
-    finally:
-        del os.environ["B200SEG_SPLITK"]
-    ref = F.conv2d(nchw(xb), wt.to(torch.bfloat16).float(), b, padding=k // 2)
-    if relu:
-        ref = F.relu(ref)
-    e1, e0 = rel(nchw(y1), ref), rel(nchw(y0), ref)
-    print(f"split-K {n}x{h}x{w} {cin}->{cout} k{k}: with {e1:.2e} without {e0:.2e}; dgrad diff {rel(dx1, dx0):.1e}")
-    assert e1 < 4e-3 and e0 < 4e-3
-    assert rel(dx1, dx0) < 3e-3                  # (both round the same fp32 sums to bf16; order differs in the last bits)
-    yf = nchw(y1).double()
-    assert rel(s1[0], yf.sum((0, 2, 3))) < 1e-6 and rel(s1[1], (yf * yf).sum((0, 2, 3))) < 1e-6
