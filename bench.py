@@ -219,10 +219,14 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL prints its version banner on stdout from native code: park fd 1 on stderr until the JSON line is due, so
+        # that rank 0's stdout carries exactly ONE line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().b2_arch_check(), "b2_arch_check")
     K.set_wgrad_overlap(bool(args.wgrad_overlap))
@@ -438,6 +442,9 @@ def run_b200(args):
             "sample": f"oracle port of the reference, {args.model} batch {args.cpu_batch} fp32 train step "
                       f"(fwd+BCE+bwd+clip+AdamW), best of 3 after 1 warm-up, {os.cpu_count()} threads",
             "median_s_per_step": statistics.median(times)}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     leave()
 

@@ -1,0 +1,86 @@
+"""CPU: host-side logic added in round 2 that needs no GPU — the augmentation parameter packing (against OpenCV's own
+matrix routines), the layout contract check behind the side-stream / gradient-slot paths, the precision switch, and the
+header <-> ctypes agreement of the new argument structs."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_affine_matrices_match_opencv():
+    cv2 = pytest.importorskip("cv2")
+    from b200seg.data import affine_matrix, invert_affine, pack_params
+    for size, ang, sc, dx, dy in [(256, 11.0, 1.04, 0.03, -0.05), (64, -15.0, 0.95, -0.05, 0.02), (128, 0.0, 1.0, 0.0, 0.0)]:
+        m = affine_matrix(size, ang, sc, dx, dy)
+        ref = cv2.getRotationMatrix2D((size / 2 - 0.5, size / 2 - 0.5), ang, sc)
+        ref[0, 2] += dx * size
+        ref[1, 2] += dy * size
+        assert np.allclose(m, ref, atol=1e-12)
+        assert np.allclose(invert_affine(m), cv2.invertAffineTransform(ref), atol=1e-10)
+    p = pack_params(64, [{"angle": 5.0, "scale": 1.0, "dx": 0.0, "dy": 0.0, "flip": True, "alpha": 1.1, "beta": -0.05},
+                         {"flip": False}], border="reflect101")
+    assert p.shape == (2, 12) and p.dtype == np.float32
+    iv = p.view(np.int32)
+    assert list(iv[0, 8:12]) == [1, 1, 1, 1] and list(iv[1, 8:12]) == [0, 0, 0, 1]
+    assert np.allclose(p[1, 0:6], [1, 0, 0, 0, 1, 0]) and p[1, 6] == 1.0 and p[1, 7] == 0.0
+
+
+def test_grad_is_stolen_layout_contract():
+    from b200seg.kernels import grad_is_stolen
+    w = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+    assert not grad_is_stolen(w)                                   # contiguous 3x3: AccumulateGrad would clone
+    w_cl = torch.nn.Parameter(torch.randn(8, 4, 3, 3).contiguous(memory_format=torch.channels_last))
+    assert grad_is_stolen(w_cl)
+    w_cl.grad = torch.zeros_like(w_cl)
+    assert not grad_is_stolen(w_cl)                                # a gradient is already there: accumulation
+    w11 = torch.nn.Parameter(torch.randn(8, 4, 1, 1))
+    assert grad_is_stolen(w11)                                     # 1x1: both layouts coincide (size-1 dims are free)
+
+
+def test_precision_switch_and_inference_only_guard():
+    import b200seg
+    from b200seg import ops_fp32
+    assert b200seg.get_precision() == "bf16"
+    with b200seg.precision("fp32"):
+        assert b200seg.get_precision() == "fp32"
+        m = torch.nn.Linear(2, 2).train()
+        with pytest.raises(RuntimeError, match="inference path only"):
+            ops_fp32.active(m)
+        with torch.no_grad():
+            assert ops_fp32.active(m.eval())
+    assert b200seg.get_precision() == "bf16"
+    with pytest.raises(ValueError):
+        b200seg.set_precision("fp16")
+
+
+def _struct_fields(name):
+    text = (ROOT / "include" / "b200seg.h").read_text()
+    body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    n = 0
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(",")
+        arr = re.search(r"\[(\d+)\]", names[0])
+        n += int(arr.group(1)) if arr else len(names)
+    return n
+
+
+@pytest.mark.parametrize("cname,pyname", [("b2_conv_args", "ConvArgs"), ("b2_wgrad_args", "WgradArgs"),
+                                          ("b2_gate_args", "GateArgs"), ("b2_f32_conv_args", "F32ConvArgs")])
+def test_ctypes_structs_have_the_headers_field_count(cname, pyname):
+    from b200seg import _lib
+    assert len(getattr(_lib, pyname)._fields_) == _struct_fields(cname)
+
+
+def test_aug_params_size_matches_header():
+    from b200seg.data import PARAM_FLOATS
+    assert _struct_fields("b2_aug_params") == PARAM_FLOATS          # 6 + 2 floats + 4 ints, 4 bytes each
+    assert C.sizeof(C.c_float) == 4
