@@ -51,6 +51,10 @@ int b2_num_sms(void);
 int b2_set_deterministic(void* workspace, int64_t bytes);
 int b2_get_deterministic(void);
 
+/* The B200SEG_* environment switches are read once and cached behind a mutex; call this after
+ * changing the environment of a running process (tests do) to have them re-read. */
+int b2_reload_env(void);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution, ksize in {1,3} with 'same' padding (stride 1 or 2) or ksize 2 / stride 2 / no padding (the input
  * gradient of ConvTranspose2d(k=2,s=2)): implicit GEMM on tcgen05 (TMA -> 128B-swizzled smem ->

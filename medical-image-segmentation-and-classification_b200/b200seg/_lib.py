@@ -80,6 +80,7 @@ SIGNATURES = {
     "b2_num_sms": (C.c_int, []),
     "b2_set_deterministic": (C.c_int, [_vp, _i64]),
     "b2_get_deterministic": (C.c_int, []),
+    "b2_reload_env": (C.c_int, []),
     "b2_conv_fprop": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "b2_conv_dgrad": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "b2_conv_wgrad_workspace": (_i64, [C.POINTER(WgradArgs)]),

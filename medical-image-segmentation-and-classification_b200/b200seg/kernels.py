@@ -210,6 +210,11 @@ def _sync_deterministic():
         del _DET["bufs"][dev]
 
 
+def reload_switches():
+    """the library caches the B200SEG_* environment switches: re-read them after changing os.environ"""
+    _lib.check(_lib.load().b2_reload_env(), "b2_reload_env")
+
+
 def _stream():
     if _DET["want"] != (torch.cuda.current_device() in _DET["bufs"]):
         _sync_deterministic()

@@ -33,6 +33,10 @@ int  cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
+// B200SEG_* switches are read from the environment ONCE (mutex-guarded cache; b2_reload_env() re-reads them): a launch
+// costs no getenv scans, and concurrent forward / autograd-engine threads see one consistent configuration.
+int env_switch(const char* name, int dflt);
+
 // TMA descriptor encode (driver entry point fetched through the runtime; no libcuda link dependency).
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1; bf16 elements.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

@@ -32,6 +32,7 @@
 // Used for fprop (reference nn.Conv2d call sites, see include/b200seg.h) and for dgrad (flipped/transposed
 // weight packing).  The K dimension may span two source tensors (elided torch.cat).
 #include <stdlib.h>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -755,10 +756,7 @@ int encode_act_tmap(CUtensorMap* tm, const void* base, int c, int ld, int n, int
   return encode_act_tmap_ex(tm, base, c, n, h, w, ld, (long long)ld * w, (long long)ld * w * h, Wb, Hb, Nb, 1);
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
+static int env_int(const char* name, int dflt) { return env_switch(name, dflt); }
 
 static int pick_block_n(int cout, bool wide_rows) {
   const int forced = env_int("B200SEG_BLOCK_N", 0);
@@ -1032,20 +1030,27 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   } else {
     tmY = tmA0;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
+  {
+    // forward runs on the caller's thread, backward on the autograd engine's: set the attributes exactly once
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+      cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      attr_err = e;
+    });
+    B2_CHECK_CUDA(attr_err);
   }
   // persistent grid: one CTA per SM.  When the number of clusters is a multiple of n_tiles every CTA keeps one n-tile
   // for its whole life and its BN statistics stay in registers; otherwise they are flushed whenever the slab changes.
   const int C = p.cluster;
   int clusters = num_sms() / C;
   if (C > 1) {
+    static std::mutex mc_mu;
     static int max_clusters[5] = {0, 0, 0, 0, 0};
+    std::lock_guard<std::mutex> mc_lock(mc_mu);
     if (max_clusters[C] == 0) {
       cudaLaunchConfig_t qc = {};
       qc.gridDim = dim3((unsigned)(num_sms() / C * C));

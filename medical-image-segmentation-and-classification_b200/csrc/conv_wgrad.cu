@@ -21,6 +21,7 @@
 // Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
 #include <stdlib.h>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -375,21 +376,16 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   // 3x3: two 64-channel X blocks x 3 taps per CTA (N 384 as two MMAs that share the dY tile, 3 pipeline stages):
   // the kernel is bound by the L2 -> SM load rate, and this moves 64 KB per 6.3 MFLOP instead of 40 KB per 3.1
   // (B200SEG_WG_CPB=1 selects the older one-block layout, N 192 with 5 stages)
-  const char* cpb_env = getenv("B200SEG_WG_CPB");
-  const int cpb3 = (cpb_env != nullptr && atoi(cpb_env) == 1) ? 1 : 2;
-  {
-    const char* dbg = getenv("B200SEG_DEBUG_SKIP");
-    p.debug_skip = dbg ? atoi(dbg) : 0;
-  }
+  const int cpb3 = env_switch("B200SEG_WG_CPB", 2) == 1 ? 1 : 2;
+  p.debug_skip = env_switch("B200SEG_DEBUG_SKIP", 0);
   p.cpb = a->ksize == 3 ? cpb3 : (a->ksize == 2 ? 2 : 4);
   if (p.cpb > cbt) p.cpb = cbt;
   p.ncolb = p.ksize * p.cpb;
   pl->gy = p.ksize;
   {
-    const char* rp_env = getenv("B200SEG_WG_ROWPAIR");
     const int dm = a->dy_mul == 0 ? 1 : a->dy_mul;
     const bool rp_ok = a->cout == 64 && xstride == 1 && p.Hb == 1 && p.Nb == 1 &&
-                       !(rp_env != nullptr && atoi(rp_env) == 0);
+                       env_switch("B200SEG_WG_ROWPAIR", 1) != 0;
     (void)dm;
     p.rowpair = 0;
     p.rp_dir = p.pad_h >= 1 ? 1 : -1;
@@ -430,8 +426,7 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   pl->count = (long long)a->cout * p.taps * p.ctot;
   {
     // X-halo mode: 3x3, unit stride, chunk = 64 consecutive pixels of one image row
-    const char* xe = getenv("B200SEG_WG_XHALO");
-    const int want = xe ? atoi(xe) : 1;
+    const int want = env_switch("B200SEG_WG_XHALO", 1);
     // chunk = Hb rows of Wb pixels (64 x 1, 32 x 2, 16 x 4): the halo box has Hb rows of Wb + 2 pixels <= 72 rows
     p.xh = (want != 0 && a->ksize == 3 && xstride == 1 && !a->custom_pad && p.Nb == 1 && p.Wb >= 16 &&
             (p.Wb + 2) * p.Hb * 128 <= kXhBox) ? 1 : 0;
@@ -505,15 +500,21 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
   } else {
     tmX1 = tmX0;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    // Ask for the full 228 KB shared-memory carveout even when a launch needs less: the driver otherwise picks the
-    // smallest configuration that fits this kernel (196 KB for 194 KB used), and the memory-bound kernels meant to run
-    // next to it on the side-stream schedule (BatchNorm backward, gate) find no shared memory left on the SM.
-    B2_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
+  {
+    // (the weight gradients are launched from the autograd engine thread, possibly several at once: set exactly once)
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      // Ask for the full 228 KB shared-memory carveout even when a launch needs less: the driver otherwise picks the
+      // smallest configuration that fits this kernel (196 KB for 194 KB used), and the memory-bound kernels meant to
+      // run next to it on the side-stream schedule (BatchNorm backward, gate) find no shared memory left on the SM.
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+      attr_err = e;
+    });
+    B2_CHECK_CUDA(attr_err);
   }
   dim3 grid(pl.gy * pl.gz, pl.splits, 1);
   conv_wgrad_kernel<<<grid, kWgThreads, pl.smem_bytes, stream>>>(tmDY, tmX0, tmX1, pl.p);

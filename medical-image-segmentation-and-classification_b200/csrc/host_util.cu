@@ -1,6 +1,9 @@
 // b200seg — host utilities: thread-local error string, arch check, TMA descriptor encoding.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <map>
 #include <mutex>
+#include <string>
 
 #include "common.cuh"
 
@@ -30,6 +33,22 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// ---------------------------------------------------------------------------------------------
+// environment switches, read once
+// ---------------------------------------------------------------------------------------------
+static std::mutex g_env_mu;
+static std::map<std::string, int> g_env_cache;
+
+int env_switch(const char* name, int dflt) {
+  std::lock_guard<std::mutex> lk(g_env_mu);
+  auto it = g_env_cache.find(name);
+  if (it != g_env_cache.end()) return it->second == INT32_MIN ? dflt : it->second;
+  const char* v = getenv(name);
+  const int val = v ? atoi(v) : INT32_MIN;       // INT32_MIN = "not set": the caller's default applies
+  g_env_cache.emplace(name, val);
+  return v ? val : dflt;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -165,6 +184,12 @@ int b2_set_deterministic(void* workspace, int64_t bytes) {
 }
 
 int b2_get_deterministic(void) { return b2::det_enabled() ? 1 : 0; }
+
+int b2_reload_env(void) {
+  std::lock_guard<std::mutex> lk(b2::g_env_mu);
+  b2::g_env_cache.clear();
+  return B2_OK;
+}
 
 int b2_arch_check(void) {
   int dev = 0;

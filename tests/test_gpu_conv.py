@@ -145,12 +145,15 @@ def test_wgrad_rowpair_2x2_phase_matches_plain(cin):
     dz = nhwc(torch.randn(n, cout, 2 * h, 2 * w, device="cuda", generator=g))
     for a, b in ((0, 0), (0, 1), (1, 0), (1, 1)):
         os.environ["B200SEG_WG_ROWPAIR"] = "0"
+        K.reload_switches()              # the library caches its environment switches
         plain = K.conv_wgrad(dz, x, 2, dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b))
         os.environ["B200SEG_WG_ROWPAIR"] = "1"
+        K.reload_switches()
         try:
             pair = K.conv_wgrad(dz, x, 2, dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b))
         finally:
             del os.environ["B200SEG_WG_ROWPAIR"]
+            K.reload_switches()
         # fp32 reference: dW[co, r, s, ci] = sum_p dY[p, co] * X[p + (r - pad_h, s - pad_w), ci]
         dys = nchw(dz)[:, :, a::2, b::2]
         xp = F.pad(nchw(x), (1 - b, b, 1 - a, a))       # (left, right, top, bottom)
@@ -180,6 +183,7 @@ def test_fprop_dgrad_rowpair_mode_matches_plain(n, h, w, cin):
     res = {}
     for mode in ("0", "1"):
         os.environ["B200SEG_FPROP_ROWPAIR"] = mode
+        K.reload_switches()
         try:
             st = torch.zeros(2, cout, dtype=torch.float64, device="cuda")
             y = K.conv_igemm(x, wf, cout, 3, bias=b, stats=st, relu=True)
@@ -187,6 +191,7 @@ def test_fprop_dgrad_rowpair_mode_matches_plain(n, h, w, cin):
             res[mode] = (y, st, dx)
         finally:
             del os.environ["B200SEG_FPROP_ROWPAIR"]
+            K.reload_switches()
     ref = torch.relu(F.conv2d(nchw(x), wt.to(torch.bfloat16).float(), b, padding=1))
     assert rel(nchw(res["1"][0]), ref) < 4e-3
     refd = F.conv_transpose2d(nchw(dy2), wt2.to(torch.bfloat16).float(), padding=1)

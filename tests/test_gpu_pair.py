@@ -19,14 +19,18 @@ class _pair:
         self.mode = mode
 
     def __enter__(self):
+        from b200seg import kernels as K
         self.old = os.environ.get("B200SEG_PAIR")
         os.environ["B200SEG_PAIR"] = self.mode
+        K.reload_switches()              # the library caches its environment switches
 
     def __exit__(self, *a):
+        from b200seg import kernels as K
         if self.old is None:
             del os.environ["B200SEG_PAIR"]
         else:
             os.environ["B200SEG_PAIR"] = self.old
+        K.reload_switches()
 
 
 SHAPES = [
@@ -62,7 +66,8 @@ def test_pair_mode_bit_identical(n, h, w, cin, cout, k, mode):
         torch.cuda.synchronize()
         return y, stats, dx
 
-    y0, s0, dx0 = run()
+    with _pair("0"):                            # single-CTA baseline (pair mode is the default)
+        y0, s0, dx0 = run()
     with _pair(mode):
         for _ in range(3):                      # repeated: a protocol race rarely shows on the first launch
             y1, s1, dx1 = run()
@@ -96,7 +101,8 @@ def test_pair_mode_two_sources_stride_and_placement(mode):
         torch.cuda.synchronize()
         return ya, yb, yc, yd
 
-    ref = run()
+    with _pair("0"):
+        ref = run()
     with _pair(mode):
         got = run()
     for r, o in zip(ref, got):
@@ -122,7 +128,8 @@ def test_pair_mode_whole_model_step():
         torch.cuda.synchronize()
         return logits.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters()}
 
-    l0, g0 = run()
+    with _pair("0"):
+        l0, g0 = run()
     with _pair("2"):
         l1, g1 = run()
     assert torch.equal(l0, l1)
