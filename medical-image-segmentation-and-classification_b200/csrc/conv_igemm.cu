@@ -821,8 +821,16 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   p.cb1 = (a->c1 + 63) / 64;
   const int cbt = p.cb0 + p.cb1;
   p.cout = a->cout;
-  p.n_tiles = a->cout / p.block_n;
   p.m_tiles = p.tw * p.th * tn;
+  // Small M (batch 1 ... 4 per GPU at the deep levels): with fewer work items than half the SMs every item streams its
+  // whole K range of activations anyway, so narrower tiles cost nothing there and put 2-4x as many SMs to work on the
+  // weights (a 1024 -> 1024 @16^2 layer at batch 4: 16 -> 64 items).  The fused gate needs F_int in one tile.
+  if (gate == nullptr && env_int("B200SEG_BLOCK_N", 0) == 0 && env_int("B200SEG_SMALL_M", 1) != 0) {
+    const int slots = num_sms() / 2;               // CTA pairs
+    while (p.block_n > 64 && (long long)((p.m_tiles * (fold == 1 ? 4 : 1) + 1) / 2) * (a->cout / p.block_n) * 2 <= slots)
+      p.block_n /= 2;
+  }
+  p.n_tiles = a->cout / p.block_n;
   p.m_tiles_phase = p.m_tiles;
   if (fold == 1) p.m_tiles *= 4;                 // the four phases are an extra tile dimension
   p.y = static_cast<__nv_bfloat16*>(a->y);
