@@ -78,6 +78,8 @@ struct IgemmParams {
                       //       addend chain, one epilogue per output tile instead of four.
   int fold_c;         // channel count of the fine-grid tensor behind the 5-D view (fprop: Cout, dgrad: C of dz)
   int m_tiles_phase;  // fold == 1: m-tiles per phase
+  uint32_t mg_nt, mg_tw, mg_th, mg_mtp;   // magic multipliers (ceil(2^32 / d)) of n_tiles, tw, th, m_tiles_phase: the tile
+                      // decode runs once per tile in every warp role and integer division was 8 % of the epilogue's time
   int pair;           // CTA-pair mode (cluster == 2): ONE tcgen05.mma.cta_group::2 with M = 256 covers the two m-tiles of
                       // the pair; each CTA stages its own activation tile and HALF of the weight rows in its own shared
                       // memory (no multicast: each SM receives half the weight bytes), the rank-0 CTA issues the MMAs,
@@ -142,6 +144,25 @@ __device__ __forceinline__ uint32_t ctile_off(int block_n, int row, int ch) {
     return (uint32_t)(panel * (kTileM * 128) + row * 128 + ((((cc >> 3) ^ (row & 7))) << 4) + ((cc & 7) << 1));
   }
   return (uint32_t)(row * 64 + ((((ch >> 3) ^ ((row >> 1) & 3))) << 4) + ((ch & 7) << 1));
+}
+
+// t / d through the precomputed magic multiplier mg = ceil(2^32 / d); exact while t * d < 2^32 (checked on the host)
+__device__ __forceinline__ int fast_div(int t, int d, uint32_t mg) {
+  return d == 1 ? t : (int)__umulhi((uint32_t)t, mg);
+}
+
+// BatchNorm statistics: one staged 16 B chunk (8 channels of one row) joins the sum / sum of squares of the ROUNDED
+// values (fp32; folded into the fp64 accumulators every few tiles)
+__device__ __forceinline__ void stats_accum(const uint4 u, float* s, float* q) {
+  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = bf16lo(w4[j]), b = bf16hi(w4[j]);
+    s[2 * j] += a;
+    s[2 * j + 1] += b;
+    q[2 * j] = fmaf(a, a, q[2 * j]);
+    q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
+  }
 }
 
 // kPair: the CTA-pair variant is a separate instantiation — a kernel that contains cta_group::2 instructions can only
@@ -223,21 +244,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int b_taps = p.halo ? 3 : 1;           // weight taps per stage
     const int b_rows = p.block_n / C;            // weight rows this CTA fetches (and multicasts) per tap
     for (int item = cluster_id; item < total_items; item += num_clusters) {
-      const int n_tile = item % p.n_tiles;
+      const int m_group = fast_div(item, p.n_tiles, p.mg_nt);
+      const int n_tile = item - m_group * p.n_tiles;
       // pixel origin of the item's tile(s); a ragged last item recomputes the last tile (its result is dropped)
       int w0s[2], h0s[2], n0s[2];
       int tph = 0;                                 // fold == 1: the phase of the item's tile(s)
       for (int q = 0; q < a_slots; ++q) {
-        int t = (item / p.n_tiles) * per_item + (p.dm ? q : (int)crank);
+        int t = m_group * per_item + (p.dm ? q : (int)crank);
         if (t >= p.m_tiles) t = p.m_tiles - 1;
         if (p.fold == 1) {
-          tph = t / p.m_tiles_phase;
+          tph = fast_div(t, p.m_tiles_phase, p.mg_mtp);
           t -= tph * p.m_tiles_phase;
         }
-        const int tw_i = t % p.tw;
-        t /= p.tw;
-        const int th_i = t % p.th;
-        const int tn_i = t / p.th;
+        const int t1 = fast_div(t, p.tw, p.mg_tw);
+        const int tw_i = t - t1 * p.tw;
+        const int tn_i = fast_div(t1, p.th, p.mg_th);
+        const int th_i = t1 - tn_i * p.th;
         w0s[q] = tw_i * p.Wb;
         h0s[q] = th_i * (p.rp ? 2 : p.Hb);
         n0s[q] = tn_i * p.Nb;
@@ -431,10 +453,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     double acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    // fp32 partial sums of the last few tiles (<= kFoldTiles * 32 values each): the fp64 pipe is narrow, so the
+    // conversion + DADD per channel runs once per kFoldTiles tiles instead of once per tile
+    constexpr int kFoldTiles = 4;
+    float fs[8], fq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) fs[j] = fq[j] = 0.f;
+    int fpending = 0;
+    auto fold_stats = [&]() {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += (double)fs[j];
+        acc[8 + j] += (double)fq[j];
+        fs[j] = fq[j] = 0.f;
+      }
+      fpending = 0;
+    };
 
     // add the group's partial sums into stats[]: lanes owning the same chunk are combined by shuffles, the four
     // warps through the (idle) staging tile, so each channel costs one fp64 atomic per group and flush
     auto flush_stats = [&](int n_tile_) {
+      fold_stats();
       for (int off = nchunks; off < 32; off <<= 1) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
@@ -473,12 +512,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int ti = g;; ti += G) {
       const int item = cluster_id + (p.dm ? (ti >> 1) : ti) * num_clusters;
       if (item >= total_items) break;
-      const int n_tile = item % p.n_tiles;
+      const int m_group = fast_div(item, p.n_tiles, p.mg_nt);
+      const int n_tile = item - m_group * p.n_tiles;
       const int ch_base = n_tile * p.block_n;
-      int t = (item / p.n_tiles) * per_item + (p.dm ? (ti & 1) : (int)crank);
+      int t = m_group * per_item + (p.dm ? (ti & 1) : (int)crank);
       int eph = 0;                                 // fold == 1: phase of this tile
       if (p.fold == 1 && t < p.m_tiles) {
-        eph = t / p.m_tiles_phase;
+        eph = fast_div(t, p.m_tiles_phase, p.mg_mtp);
       }
       if (t >= p.m_tiles || (p.debug_skip & 4)) {
         // ragged last group: this CTA only kept the pipeline protocol going; hand the accumulator straight back
@@ -504,10 +544,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         cur_n_tile = n_tile;
       }
       if (p.fold == 1) t -= eph * p.m_tiles_phase;
-      const int tw_i = t % p.tw;
-      t /= p.tw;
-      const int th_i = t % p.th;
-      const int tn_i = t / p.th;
+      const int t1 = fast_div(t, p.tw, p.mg_tw);
+      const int tw_i = t - t1 * p.tw;
+      const int tn_i = fast_div(t1, p.th, p.mg_th);
+      const int th_i = t1 - tn_i * p.th;
       const int w0 = tw_i * p.Wb, h0 = th_i * (p.rp ? 2 : p.Hb), n0 = tn_i * p.Nb;
       // pixels of the tile that exist (tiles at the right / bottom / batch edge are clipped): row r of the tile is pixel
       // (n0 + r / (Wb Hb), h0 + (r / Wb) % Hb, w0 + r % Wb); all three box extents are powers of two
@@ -673,30 +713,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
       if (p.stats != nullptr) {
-        // column sums of the ROUNDED outputs (what BatchNorm sees under autocast), 8 channels per thread
-        float s[8], q[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+        // column sums of the ROUNDED outputs (what BatchNorm sees under autocast), 8 channels per thread: rows
+        // r_begin .. r_begin + nchunks - 1 of the staged tile, chunk `schunk`
         const int r_begin = sgrp * nchunks;
-        const int r_end = r_begin + nchunks;
-        for (int r = r_begin; r < r_end; ++r) {
-          if (!row_valid(r)) continue;
-          const uint4 u = *reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, schunk * 8));
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+        if (tile_full) {
+          // whole tile valid: batches of rows whose loads are all in flight before the first one is consumed
+          if (p.block_n >= 64) {      // nchunks = 8 / 16 / 32, r_begin % 8 == 0: row r_begin + i has swizzle term i & 7
+            const uint8_t* base = ctile + (uint32_t)(schunk >> 3) * (uint32_t)(kTileM * 128) + (uint32_t)r_begin * 128u;
+            const uint32_t sc7 = (uint32_t)(schunk & 7);
+            for (int i0 = 0; i0 < nchunks; i0 += 8) {
+              uint4 u[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = bf16lo(w4[j]), b = bf16hi(w4[j]);
-            s[2 * j] += a;
-            s[2 * j + 1] += b;
-            q[2 * j] = fmaf(a, a, q[2 * j]);
-            q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
+              for (int i = 0; i < 8; ++i)
+                u[i] = *reinterpret_cast<const uint4*>(base + (uint32_t)(i0 + i) * 128u + ((sc7 ^ (uint32_t)i) << 4));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) stats_accum(u[i], fs, fq);
+            }
+          } else {                    // 32-channel tiles: nchunks = 4, 64 B rows, chunk ^= (row >> 1) & 3
+            uint4 u[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t r = (uint32_t)(r_begin + i);
+              u[i] = *reinterpret_cast<const uint4*>(ctile + r * 64u + ((((uint32_t)schunk) ^ ((r >> 1) & 3u)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) stats_accum(u[i], fs, fq);
+          }
+        } else {
+          for (int r = r_begin; r < r_begin + nchunks; ++r) {
+            if (!row_valid(r)) continue;
+            stats_accum(*reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, schunk * 8)), fs, fq);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[j] += (double)s[j];
-          acc[8 + j] += (double)q[j];
-        }
+        if (++fpending == kFoldTiles) fold_stats();
       }
     }
     if (p.stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
@@ -1081,6 +1130,20 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   const int per_item = p.dm ? 2 : C;
   const long long total = (long long)((p.m_tiles + per_item - 1) / per_item) * p.n_tiles;
   B2_REQUIRE(total < (1ll << 31), B2_ERR_SHAPE, "too many tiles");
+  {
+    // magic multipliers of the tile decode (fast_div): exact while dividend * divisor < 2^32
+    auto magic = [](int d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+    long long dmax = p.n_tiles;
+    if (p.tw > dmax) dmax = p.tw;
+    if (p.th > dmax) dmax = p.th;
+    const long long tmax = total > p.m_tiles ? total : p.m_tiles;
+    B2_REQUIRE(tmax * dmax < (1ll << 32) && (long long)p.m_tiles * p.m_tiles_phase < (1ll << 32), B2_ERR_SHAPE,
+               "too many tiles for the tile decode");
+    p.mg_nt = magic(p.n_tiles);
+    p.mg_tw = magic(p.tw);
+    p.mg_th = magic(p.th);
+    p.mg_mtp = magic(p.m_tiles_phase);
+  }
   if (clusters > total) clusters = (int)total;
   if (clusters > p.n_tiles && (total / clusters) >= 16) clusters = (clusters / p.n_tiles) * p.n_tiles;
   p.m_stride = 0;
