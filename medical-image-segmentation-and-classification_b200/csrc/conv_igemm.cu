@@ -80,6 +80,11 @@ struct IgemmParams {
   int m_tiles_phase;  // fold == 1: m-tiles per phase
   uint32_t mg_nt, mg_tw, mg_th, mg_mtp;   // magic multipliers (ceil(2^32 / d)) of n_tiles, tw, th, m_tiles_phase: the tile
                       // decode runs once per tile in every warp role and integer division was 8 % of the epilogue's time
+  int wres;           // weight-resident mode: the CTA's whole weight slab (all taps x channel blocks of its single n-tile;
+                      // all four phases of a merged UpConv fprop) is loaded into shared memory ONCE and the ring only
+                      // carries activations.  The Cout = 64 layers at 256^2 were bound by the L2 -> SM fabric
+                      // (64->64: 51 KB of activations + 36 KB of weights per 128-pixel tile at ~10 TB/s chip-wide).
+  int wres_bytes;     // bytes of the resident slab (this CTA's half in pair mode)
   int pair;           // CTA-pair mode (cluster == 2): ONE tcgen05.mma.cta_group::2 with M = 256 covers the two m-tiles of
                       // the pair; each CTA stages its own activation tile and HALF of the weight rows in its own shared
                       // memory (no multicast: each SM receives half the weight bytes), the rank-0 CTA issues the MMAs,
@@ -176,15 +181,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int a_slots = p.dm ? 2 : 1;                                    // activation tiles per stage
   const int nbuf = p.dm ? 4 : 2;                                       // accumulators in TMEM
-  const int stage_bytes = a_slots * p.a_stage_bytes + p.b_stage_bytes;
+  const int stage_bytes = a_slots * p.a_stage_bytes + (p.wres ? 0 : p.b_stage_bytes);
   const int ctile_bytes = p.ctile_bytes;
   uint8_t* ctile0 = smem + p.stages * stage_bytes;                     // per group: 128 x block_n bf16, 1024 B aligned
-  uint8_t* tail = ctile0 + p.epi_groups * ctile_bytes;
+  uint8_t* wres_base = ctile0 + p.epi_groups * ctile_bytes;            // resident weights (wres mode), 1024 B aligned
+  uint8_t* tail = wres_base + p.wres_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full_bar = empty_bar + kMaxStages;                    // [4]
   uint64_t* tmem_empty_bar = tmem_full_bar + 4;                        // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
+  uint64_t* wres_bar = reinterpret_cast<uint64_t*>(tail + 264);        // resident weights have landed
   float* s_bias0 = reinterpret_cast<float*>(tail + 320);               // [group][256]
   float* s_psi0 = s_bias0 + kMaxEpiGroups * 256;                       // [group][256] (fused gate: psi weights)
 
@@ -207,6 +214,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // the leader's MMAs frees the slot in both CTAs
       mbar_init(&empty_bar[s], p.pair ? 1u : (uint32_t)C);
     }
+    mbar_init(wres_bar, 1);
     for (int b = 0; b < 4; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], p.pair ? 8u : 4u);   // one arrival per epilogue warp (of both CTAs of a pair)
@@ -240,9 +248,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     // pair mode: the leader's barrier collects the bytes of BOTH CTAs (own A tile + half of B each)
-    const uint32_t tx = (uint32_t)(a_slots * p.a_tx_bytes + p.b_stage_bytes) * (p.pair ? 2u : 1u);
+    const uint32_t tx = (uint32_t)(a_slots * p.a_tx_bytes + (p.wres ? 0 : p.b_stage_bytes)) * (p.pair ? 2u : 1u);
     const int b_taps = p.halo ? 3 : 1;           // weight taps per stage
     const int b_rows = p.block_n / C;            // weight rows this CTA fetches (and multicasts) per tap
+    if (p.wres) {
+      // weight-resident mode: every weight block the K loop of a tile walks — (phase,) tap group o, channel block cb,
+      // in that order, the same boxes the streamed stages use — is fetched once, onto one barrier (n_tiles == 1)
+      if (elect_one()) {
+        const uint32_t wtx = (uint32_t)p.wres_bytes * (p.pair ? 2u : 1u);
+        uint32_t lbar = 0u;
+        if constexpr (kPair) {
+          lbar = mapa_shared(smem_u32(wres_bar), 0);
+          if (crank == 0) mbar_arrive_expect_tx(wres_bar, wtx);
+        } else {
+          mbar_arrive_expect_tx(wres_bar, wtx);
+        }
+        (void)lbar;
+        const int outer_n = p.halo ? 3 : p.taps;
+        const int nph = p.fold == 1 ? 4 : 1;
+        int j = 0;
+        for (int ph = 0; ph < nph; ++ph) {
+          for (int o = 0; o < outer_n; ++o) {
+            const int wtap = p.fold == 1 ? ph * 4 + o : (p.halo ? o * 3 : o);
+            for (int cb = 0; cb < cbt; ++cb, ++j) {
+              uint8_t* sb = wres_base + j * p.b_stage_bytes;
+              if constexpr (kPair) tma_load_3d_pair(sb, &tmB, lbar, cb * kKBlock, (int)crank * b_rows, wtap);
+              else tma_load_3d(sb, &tmB, wres_bar, cb * kKBlock, 0, wtap);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
     for (int item = cluster_id; item < total_items; item += num_clusters) {
       const int m_group = fast_div(item, p.n_tiles, p.mg_nt);
       const int n_tile = item - m_group * p.n_tiles;
@@ -313,7 +350,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
               if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx);
               load_a(sa, w0, h0, n0, lbar);
-              tma_load_3d_pair(sb, &tmB, lbar, cb * kKBlock, n_tile * p.block_n + (int)crank * b_rows, tap0);
+              if (!p.wres)
+                tma_load_3d_pair(sb, &tmB, lbar, cb * kKBlock, n_tile * p.block_n + (int)crank * b_rows, tap0);
             } else {
             if (p.debug_skip & 1) {
               mbar_arrive(&full_bar[stage]);
@@ -321,7 +359,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             mbar_arrive_expect_tx(&full_bar[stage], tx);
             load_a(sa, w0, h0, n0, 0u);
             if (p.dm) load_a(sa + p.a_stage_bytes, w0s[1], h0s[1], n0s[1], 0u);   // second tile of the item
-            if (p.rp) {
+            if (p.wres) {
+              // weights are resident
+            } else if (p.rp) {
               for (int tp = 0; tp < 3; ++tp)       // [W(o-1, tp) ; W(o, tp)]: 2 taps, element stride 3, 64 rows each
                 tma_load_3d(sb + tp * (128 * 128), &tmB, &full_bar[stage], cb * kKBlock, 0, tap0 + tp);
             } else if (C == 1) {
@@ -354,7 +394,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int ti = 0;
     const int sub = p.halo ? 3 : 1;
     const int nb_shift = p.dm ? 2 : 1;           // log2(accumulators in TMEM)
+    const uint32_t wres_addr = smem_u32(wres_base);
+    if (p.wres) {
+      mbar_wait(wres_bar, 0);                    // the resident weights (of both CTAs of a pair) have landed
+      tc_fence_after();
+    }
     for (int item = cluster_id; item < total_items; item += num_clusters, ++ti) {
+      int wres_it0 = 0;                          // wres + merged UpConv fprop: first weight block of the tile's phase
+      if (p.wres && p.fold == 1) {
+        int t = fast_div(item, p.n_tiles, p.mg_nt) * per_item;
+        if (t >= p.m_tiles) t = p.m_tiles - 1;
+        wres_it0 = fast_div(t, p.m_tiles_phase, p.mg_mtp) * p.num_k_iters;
+      }
       // local tile counter lt = a_slots * ti + q  ->  accumulator lt % nbuf, barrier phase (lt / nbuf) & 1
       for (int q = 0; q < a_slots; ++q) {
         const uint32_t lt = (uint32_t)(a_slots * ti + q);
@@ -366,7 +417,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + a_slots * p.a_stage_bytes;
+          const uint32_t b_addr = p.wres ? wres_addr + (uint32_t)((wres_it0 + it) * p.b_stage_bytes)
+                                         : a_addr + a_slots * p.a_stage_bytes;
           if (!p.base_off_mode) {
             // Descriptors differ only in the 14-bit start-address field (bytes >> 4) of the low word, and smem
             // addresses are < 256 KB, so stepping a descriptor is one 32-bit add: +2 per 16-element K step (32 B),
@@ -453,9 +505,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     double acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-    // fp32 partial sums of the last few tiles (<= kFoldTiles * 32 values each): the fp64 pipe is narrow, so the
-    // conversion + DADD per channel runs once per kFoldTiles tiles instead of once per tile
-    constexpr int kFoldTiles = 4;
+    // fp32 partial sums of the last few tiles (32 values each, as many as one N = 256 tile contributes): the fp64 pipe
+    // is narrow, so the conversion + DADD per channel runs once per 32 rows instead of once per tile
+    const int fold_tiles = 32 / nchunks;         // 8, 4, 2, 1 tiles for N = 32, 64, 128, 256
     float fs[8], fq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) fs[j] = fq[j] = 0.f;
@@ -745,7 +797,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             stats_accum(*reinterpret_cast<const uint4*>(ctile + ctile_off(p.block_n, r, schunk * 8)), fs, fq);
           }
         }
-        if (++fpending == kFoldTiles) fold_stats();
+        if (++fpending >= fold_tiles) fold_stats();
       }
     }
     if (p.stats != nullptr && cur_n_tile >= 0) flush_stats(cur_n_tile);
@@ -971,7 +1023,7 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
       p.b_stage_bytes /= 2;          // each CTA of the pair stages half of the weight rows
     }
   }
-  const int stage_bytes = (p.dm ? 2 : 1) * p.a_stage_bytes + p.b_stage_bytes;
+  int stage_bytes = (p.dm ? 2 : 1) * p.a_stage_bytes + p.b_stage_bytes;
   // Two epilogue groups (two staging tiles) when the accumulator drain, not the MMA, paces a tile: the drain costs
   // about 1750 + 36 * BLOCK_N clocks per tile per group (measured), the MMAs K/16 * BLOCK_N/2.  A second group is
   // not worth giving up pipeline stages for when the main loop is the longer of the two anyway.
@@ -1002,14 +1054,29 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
     if (p.pair) c = 2;
     p.cluster = c;
   }
-  const int budget = 232448 - 1024 - tail_bytes - p.epi_groups * ctile_bytes;
+  // Weight-resident mode (IgemmParams::wres): one n-tile, the whole slab next to >= 4 activation-only stages, and
+  // enough tiles per CTA that fetching all weights before the first MMA costs nothing.  B200SEG_WRES=0 switches it off.
+  int budget = 232448 - 1024 - tail_bytes - p.epi_groups * ctile_bytes;
+  p.wres = 0;
+  p.wres_bytes = 0;
+  {
+    const long long wb = (long long)(fold == 1 ? 4 : 1) * p.num_k_iters * p.b_stage_bytes;
+    const int a_only = (p.dm ? 2 : 1) * p.a_stage_bytes;
+    if (env_int("B200SEG_WRES", 1) != 0 && p.n_tiles == 1 && !p.rp && (p.cluster == 1 || p.pair) && !p.base_off_mode &&
+        p.debug_skip == 0 && p.m_tiles >= 4 * num_sms() && wb % 1024 == 0 && (budget - wb) / a_only >= 4) {
+      p.wres = 1;
+      p.wres_bytes = (int)wb;
+      stage_bytes = a_only;
+      budget -= (int)wb;
+    }
+  }
   int stages = budget / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (env_int("B200SEG_MAX_STAGES", 0) >= 2 && stages > env_int("B200SEG_MAX_STAGES", 0))
     stages = env_int("B200SEG_MAX_STAGES", 0);
   B2_REQUIRE(stages >= 2, B2_ERR_SHAPE, "tile configuration does not fit shared memory");
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + p.epi_groups * ctile_bytes + tail_bytes + 1024;
+  const int smem_bytes = stages * stage_bytes + p.epi_groups * ctile_bytes + p.wres_bytes + tail_bytes + 1024;
 
   CUtensorMap tmA0, tmA1, tmB, tmY;
   const int boxw = p.halo ? p.Wb + 2 : p.Wb;
