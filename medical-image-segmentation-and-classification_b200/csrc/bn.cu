@@ -409,6 +409,13 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_reduce_light_kernel(
     const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums,
     DetBuf det) {
   __shared__ float red[kBlock * 4];
+  // gridDim.y channel slices of m.tpp * 4 channels: a block ends in 2 * (slice width) atomics instead of 2 C, which is
+  // what bounded the many-channel layers (1184 blocks x 1024 fp64 atomics at C = 512: 0.115 ms for 0.024 ms of data)
+  const int c_off = blockIdx.y * (m.tpp * 4);
+  dy += c_off;
+  z += c_off;
+  scale += c_off;
+  shift += c_off;
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
   const bool active = r < m.rows;
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_reduce_light_kernel(
   if (active && r == 0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = g * 4 + j;
+      const int c = c_off + g * 4 + j;
       const double a0 = (double)keep0[j];
       const double a1 = (double)invstd[c] * ((double)s1[j] - (double)mean[c] * a0);
       red_out(sums, det, c, a0);
@@ -651,12 +658,22 @@ extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int
   B2_REQUIRE(aligned16(dy, lddy) && aligned16(z, ldz), B2_ERR_ALIGN, "bn_bwd_reduce operands misaligned");
   ChanMap lm;
   const bool light = light_map(c, &lm);
-  const int grid = light ? chan_grid(npix, lm, 8) : chan_grid(npix, m, 4);
+  int slices = 1;
+  if (light && c % 64 == 0 && c > 64 && env_switch("B200SEG_BN_SLICE", 1) != 0) {
+    slices = c / 64;                 // 64-channel slices: 16 threads per pixel, 16 pixels per block iteration
+    lm.tpp = 16;
+    lm.rows = kBlock / 16;
+  }
+  int grid = light ? chan_grid(npix, lm, 8) : chan_grid(npix, m, 4);
+  if (slices > 1) {
+    grid = (grid + slices - 1) / slices;
+    if (grid < 1) grid = 1;
+  }
   DetBuf det;
   rc = det_begin(&det, grid, 2 * c, (cudaStream_t)stream);
   if (rc) return rc;
   if (light) {
-    bn_bwd_reduce_light_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+    bn_bwd_reduce_light_kernel<<<dim3(grid, slices), kBlock, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, relu,
         sums, det);
   } else {
