@@ -77,6 +77,10 @@ struct IgemmParams {
                       //       addend chain, one epilogue per output tile instead of four.
   int fold_c;         // channel count of the fine-grid tensor behind the 5-D view (fprop: Cout, dgrad: C of dz)
   int m_tiles_phase;  // fold == 1: m-tiles per phase
+  int fold_il;        // fold == 1: the phase is the INNER tile dimension — tile index t = 8 * pair + 2 * phase + member, so the
+                      // four phases of a pair of coarse tiles run back to back (in neighbouring clusters) and the coarse
+                      // input is fetched from DRAM once instead of once per phase (128 -> 64 @128^2: 1074 -> 270 MB read);
+                      // consecutive tiles (a CTA pair / a double-M item) keep sharing one phase = one set of weights
   uint32_t mg_nt, mg_tw, mg_th, mg_mtp;   // magic multipliers (ceil(2^32 / d)) of n_tiles, tw, th, m_tiles_phase: the tile
                       // decode runs once per tile in every warp role and integer division was 8 % of the epilogue's time
   int wres;           // weight-resident mode: the CTA's whole weight slab (all taps x channel blocks of its single n-tile;
@@ -240,8 +244,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         int t = m_group * per_item + (p.dm ? q : (int)crank);
         if (t >= p.m_tiles) t = p.m_tiles - 1;
         if (p.fold == 1) {
-          tph = fast_div(t, p.m_tiles_phase, p.mg_mtp);
-          t -= tph * p.m_tiles_phase;
+          if (p.fold_il) {
+            tph = (t >> 1) & 3;
+            t = ((t >> 3) << 1) | (t & 1);
+          } else {
+            tph = fast_div(t, p.m_tiles_phase, p.mg_mtp);
+            t -= tph * p.m_tiles_phase;
+          }
         }
         const int t1 = fast_div(t, p.tw, p.mg_tw);
         const int tw_i = t - t1 * p.tw;
@@ -354,7 +363,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (p.wres && p.fold == 1) {
         int t = fast_div(item, p.n_tiles, p.mg_nt) * per_item;
         if (t >= p.m_tiles) t = p.m_tiles - 1;
-        wres_it0 = fast_div(t, p.m_tiles_phase, p.mg_mtp) * p.num_k_iters;
+        wres_it0 = (p.fold_il ? ((t >> 1) & 3) : fast_div(t, p.m_tiles_phase, p.mg_mtp)) * p.num_k_iters;
       }
       // local tile counter lt = a_slots * ti + q  ->  accumulator lt % nbuf, barrier phase (lt / nbuf) & 1
       for (int q = 0; q < a_slots; ++q) {
@@ -520,7 +529,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       int t = m_group * per_item + (p.dm ? (ti & 1) : (int)crank);
       int eph = 0;                                 // fold == 1: phase of this tile
       if (p.fold == 1 && t < p.m_tiles) {
-        eph = fast_div(t, p.m_tiles_phase, p.mg_mtp);
+        eph = p.fold_il ? ((t >> 1) & 3) : fast_div(t, p.m_tiles_phase, p.mg_mtp);
       }
       if (t >= p.m_tiles || (p.debug_skip & 4)) {
         // ragged last group: this CTA only kept the pipeline protocol going; hand the accumulator straight back
@@ -545,7 +554,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         cur_n_tile = n_tile;
       }
-      if (p.fold == 1) t -= eph * p.m_tiles_phase;
+      if (p.fold == 1) t = p.fold_il ? (((t >> 3) << 1) | (t & 1)) : t - eph * p.m_tiles_phase;
       const int t1 = fast_div(t, p.tw, p.mg_tw);
       const int tw_i = t - t1 * p.tw;
       const int tn_i = fast_div(t1, p.th, p.mg_th);
@@ -890,6 +899,8 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   }
   p.n_tiles = a->cout / p.block_n;
   p.m_tiles_phase = p.m_tiles;
+  p.fold_il = (fold == 1 && p.m_tiles % 2 == 0 && env_int("B200SEG_FOLD_INTERLEAVE", 1) != 0 &&
+               env_int("B200SEG_CLUSTER", 0) <= 2) ? 1 : 0;
   if (fold == 1) p.m_tiles *= 4;                 // the four phases are an extra tile dimension
   p.y = static_cast<__nv_bfloat16*>(a->y);
   p.ldy = a->ldy;
