@@ -62,6 +62,9 @@ def parse():
     return ap.parse_args()
 
 
+TRAFFIC_FILE = "r02b_traffic.json"      # ncu DRAM counters of one step of the default workload (tools/profile_step.py)
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -73,14 +76,17 @@ def measured_peaks():
 def measured_traffic():
     """mean DRAM bytes per launch of the tensor-core kernels, from the committed ncu capture of one training step of
     the default workload (tools/profile_step.py + tools/summarize_traffic.py); {} if the capture is absent"""
-    p = ROOT / "profiles" / "r02_traffic.json"
+    p = ROOT / "profiles" / TRAFFIC_FILE
     if not p.exists():
         return {}
     d = json.loads(p.read_text())
     out = {}
-    for short, name in (("conv_igemm", "b2::conv_igemm_kernel"), ("conv_wgrad", "b2::conv_wgrad_kernel")):
-        if name in d and d[name]["launches"]:
-            out[short] = (d[name]["read_GB"] + d[name]["write_GB"]) * 1e9 / d[name]["launches"]
+    # fprop / dgrad launches are conv_igemm_kernel or, for the Cout = 64 3x3 layers on wide images, conv_c64_kernel
+    for short, names in (("conv_igemm", ("b2::conv_igemm_kernel", "b2::conv_c64_kernel")),
+                         ("conv_wgrad", ("b2::conv_wgrad_kernel",))):
+        n = sum(d[k]["launches"] for k in names if k in d)
+        if n:
+            out[short] = sum(d[k]["read_GB"] + d[k]["write_GB"] for k in names if k in d) * 1e9 / n
     return out
 
 
@@ -420,13 +426,13 @@ def run_b200(args):
         "gpu_launches": launches,
         "replicas_in_sync": replicas_in_sync,
         "clocks": clocks,
-        "roofline": {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM; fprop + dgrad launches)",
+        "roofline": {"kernel": "conv_igemm_kernel + conv_c64_kernel (tcgen05 implicit GEMM; every fprop + dgrad launch of the step)",
                      "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                      "achieved_algorithmic": ach_alg,
                      "note": "achieved = FLOPs the launches executed / their CUDA-event time; achieved_algorithmic "
                              "counts the folded UpConv launches at the reference's 3x3-on-the-fine-grid FLOPs (x2.25)",
                      "traffic": traffic.get("conv_igemm"), "traffic_unit": "bytes per launch (mean over the step's "
-                     "launches; ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_traffic.json)",
+                     "launches; ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/" + TRAFFIC_FILE + ")",
                      "algorithmic_bytes_per_launch": by_i / max(n, 1),
                      "peak_source": peak_src, "launches_per_step": n // 2,
                      "ms_per_step_in_kernel": tms / 2, "share_of_step": (tms / 2) / step_ms},
