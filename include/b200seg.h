@@ -135,6 +135,12 @@ typedef struct b2_wgrad_args {
   /* dY as the sub-lattice dy[n, h*dy_mul + dy_off_h, w*dy_mul + dy_off_w, :]; custom X tap offsets (see b2_conv_args) */
   int32_t dy_mul, dy_off_h, dy_off_w;
   int32_t custom_pad, pad_h, pad_w;
+  /* extension (0 = off): merged weight gradient of a folded UpConv (Upsample x2 -> conv3x3, AttentionUNet.py:15-27).
+   * ksize 2, dy_mul 2, no offsets: dy is the gradient on the FINE grid [n, 2h, 2w, cout], x the coarse input, and
+   * dw receives all four phase gradients [phase = 2a + b][cout][2x2][cin] (phase (a,b): dy[2h+a, 2w+b] against
+   * x[h + a + ty - 1, w + b + tx - 1]) from ONE launch instead of four dy_off launches.  cout must be 64 or a
+   * multiple of 128, cin a multiple of 64, the coarse image at least 16 pixels wide (B2_ERR_SHAPE otherwise). */
+  int32_t fold;
 } b2_wgrad_args;
 
 int64_t b2_conv_wgrad_workspace(const b2_wgrad_args* a);

@@ -43,7 +43,7 @@ class WgradArgs(C.Structure):
                 ("dw", _vp), ("accumulate", _i32),
                 ("workspace", _vp), ("workspace_bytes", _i64), ("x_stride", _i32),
                 ("dy_mul", _i32), ("dy_off_h", _i32), ("dy_off_w", _i32),
-                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32)]
+                ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32), ("fold", _i32)]
 
 
 class F32ConvArgs(C.Structure):

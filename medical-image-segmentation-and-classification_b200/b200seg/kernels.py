@@ -488,9 +488,11 @@ def conv_igemm(x0, wpk, cout, ksize, x1=None, bias=None, addend=None, stats=None
 
 
 def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, dy_mul=1, dy_off=(0, 0), pad=None,
-               alg_scale=1.0):
+               alg_scale=1.0, fold=False):
     """dW fp32 [Cout, k*k, C0+C1] = sum_p dY[p] (x) X[p+tap].  x_stride=2 (ksize 2): X lives on the 2x finer grid
-    (weight gradient of ConvTranspose2d(k=2,s=2) with dy := its input, x := its output gradient)."""
+    (weight gradient of ConvTranspose2d(k=2,s=2) with dy := its input, x := its output gradient).
+    fold=True (ksize 2, dy_mul 2): all four phase gradients of a folded UpConv, [4, Cout, 4, Cin], in one launch;
+    returns None when the library does not take the shape in that mode (the caller launches the phases)."""
     n, hd, wd_, cout, lddy = _nhwc(dy)
     assert hd % dy_mul == 0 and wd_ % dy_mul == 0
     h, w = hd // dy_mul, wd_ // dy_mul                          # dY is read as a sub-lattice when dy_mul > 1
@@ -499,7 +501,7 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, d
     c1, ld1 = 0, 0
     if x1 is not None:
         _, _, _, c1, ld1 = _nhwc(x1)
-    taps = ksize * ksize
+    taps = 16 if fold else ksize * ksize
     dw = out if out is not None else torch.empty((cout, taps, c0 + c1), dtype=torch.float32, device=dy.device)
     assert dw.is_contiguous() and dw.numel() == cout * taps * (c0 + c1)
     a = WgradArgs()
@@ -513,7 +515,10 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, d
     a.dy_mul, a.dy_off_h, a.dy_off_w = dy_mul, dy_off[0], dy_off[1]
     if pad is not None:
         a.custom_pad, a.pad_h, a.pad_w = 1, pad[0], pad[1]
+    a.fold = int(fold)
     need = _lib.load().b2_conv_wgrad_workspace(C.byref(a))
+    if need == -1 and fold:                 # B2_ERR_SHAPE
+        return None
     if need < 0:
         _lib.check(int(need), "b2_conv_wgrad_workspace")
     ws = torch.empty(int(need), dtype=torch.uint8, device=dy.device)
@@ -521,7 +526,7 @@ def conv_wgrad(dy, x0, ksize, x1=None, out=None, accumulate=False, x_stride=1, d
     t0 = _prof_begin()
     call("b2_conv_wgrad", C.byref(a), _stream())
     _prof_end("conv_wgrad", 2.0 * n * h * w * cout * (c0 + c1) * taps, t0, alg_scale,
-              2.0 * (n * h * w * cout + n * hx * wx * (c0 + c1)) + 4.0 * taps * cout * (c0 + c1))
+              2.0 * (n * h * w * cout * (4 if fold else 1) + n * hx * wx * (c0 + c1)) + 4.0 * taps * cout * (c0 + c1))
     return dw
 
 

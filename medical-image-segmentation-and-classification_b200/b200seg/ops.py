@@ -427,6 +427,7 @@ def conv_bn_act_module(x, conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, relu:
 # ----------------------------------------------------------------------------------------------------------
 _PHASES = ((0, 0), (0, 1), (1, 0), (1, 1))
 _UPFOLD_MERGED = os.environ.get("B200SEG_UPFOLD_MERGED", "1") != "0"     # 0: four launches per direction (A/B switch)
+_UPFOLD_WGRAD_MERGED = os.environ.get("B200SEG_UPFOLD_WGRAD_MERGED", "1") != "0"   # 0: four weight-gradient launches
 
 
 @custom_op("b200seg::upconv_bn_act", mutates_args=())
@@ -489,8 +490,12 @@ def upconv_bn_act_bwd(dy: Tensor, x: Tensor, weight: Tensor, z: Tensor, coef: Te
         dx = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     with K.wgrad_stream(dz, x, allow=K.grad_is_stolen(weight)):
         dweff = torch.empty((4, cout, 4, cin), dtype=torch.float32, device=dev)
-        for ph, (a, b) in enumerate(_PHASES):
-            K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
+        # all four phases in ONE launch (every X row fetched once per filter row, the two column phases share it)
+        merged = _UPFOLD_WGRAD_MERGED and (cout == 64 or cout % 128 == 0) and cin % 64 == 0 and \
+            K.conv_wgrad(dz, x, 2, out=dweff, dy_mul=2, fold=True, alg_scale=2.25) is not None
+        if not merged:
+            for ph, (a, b) in enumerate(_PHASES):
+                K.conv_wgrad(dz, x, 2, out=dweff[ph], dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b), alg_scale=2.25)
         dw = K.fold_upconv_wgrad(dweff, out=K.grad_slot(weight, (cout, 9, cin)))
     return dx, dw, db, dgamma, dbeta
 

@@ -60,6 +60,14 @@ struct WgradParams {
                      // the box (the 128B swizzle is a function of the absolute smem address).  Halves the bytes a
                      // CTA pulls through the L2 -> SM fabric.  nbox = boxes per stage (2), kXhBox bytes apart.
   int nbox;
+  int fold;          // merged folded-UpConv weight gradient (b2_wgrad_args::fold): dY is the FINE tensor, phase (a, b) its
+                     // (2h+a, 2w+b) sub-lattice; a CTA owns (a, filter row ty) = blockIdx % 4, loads the b = 0 and b = 1
+                     // sub-lattice tiles and ONE halo row of X (coarse row h + a + ty - 1), and tap (b, tx) is the MMA
+                     // whose B descriptor starts (b + tx) pixels into the halo box.  1: cout >= 128 — A = 128 channels
+                     // per b, accumulators [b][tx][block][64] (512 TMEM columns).  2: cout == 64 — the two b tiles are
+                     // the two halves of ONE M = 128 operand, three shift MMAs (rows 0..63 keep shifts 0, 1 = tx 0, 1;
+                     // rows 64..127 keep shifts 1, 2), accumulators [shift][block][64]
+  int a_bytes;       // smem bytes reserved per stage for the dY tiles (16 KB; 32 KB when fold == 1)
   int debug_skip;    // timing experiments only (B200SEG_DEBUG_SKIP): 1 = no TMA loads, 2 = no MMAs
   float* ws;         // [splits][cout][taps][ctot]
 };
@@ -69,7 +77,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                   const __grid_constant__ CUtensorMap tmX1, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = 2 * kBoxBytes + p.b_stage_bytes;
+  const int stage_bytes = p.a_bytes + p.b_stage_bytes;
   uint8_t* tail = smem + p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
   uint64_t* empty_bar = full_bar + 8;
@@ -105,7 +113,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX0);
   }
-  const uint32_t tmem_cols = p.ncolb * 64 > 256 ? 512u : 256u;
+  const uint32_t tmem_cols = (p.fold == 1 ? 4 * p.cpb : p.fold == 2 ? 3 * p.cpb : p.ncolb) * 64 > 256 ? 512u : 256u;
   if (warp == 1) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
@@ -127,7 +135,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     if (nchunks > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = p.xh ? (uint32_t)(p.a_boxes * kBoxBytes + xh_live * (p.Wb + 2) * p.Hb * 128)
+      const uint32_t tx = p.fold ? (uint32_t)(2 * p.a_boxes * kBoxBytes + xh_live * (p.Wb + 2) * p.Hb * 128)
+                          : p.xh ? (uint32_t)(p.a_boxes * kBoxBytes + xh_live * (p.Wb + 2) * p.Hb * 128)
                                : (uint32_t)((p.a_boxes + ncol_live) * kBoxBytes);
       int tw_i = chunk_begin % p.tw;
       int th_i = (chunk_begin / p.tw) % p.th;
@@ -137,9 +146,25 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + 2 * kBoxBytes;
+          uint8_t* sb = sa + p.a_bytes;
           if (p.debug_skip & 1) {
             mbar_arrive(&full_bar[stage]);
+          } else if (p.fold) {
+            mbar_arrive_expect_tx(&full_bar[stage], tx);
+            const int fa = rg >> 1, fty = rg & 1;
+            // dY: the (a, b = 0) and (a, b = 1) sub-lattices of the fine tensor (traversal stride 2 in w and h)
+            for (int b = 0; b < 2; ++b)
+              tma_load_5d(sa + b * p.a_boxes * kBoxBytes, &tmDY, &full_bar[stage], 0, 2 * w0 + b, 2 * h0 + fa, n0,
+                          co_tile * 2);
+            // X: one halo row per 64-channel block, coarse row h + a + ty - 1, pixels w0 - 1 .. w0 + Wb
+            for (int b = 0; b < xh_live; ++b) {
+              const int cib = cib_base + b;
+              if (cib < p.cb0)
+                tma_load_4d(sb + b * kXhBox, &tmX0, &full_bar[stage], cib * 64, w0 - 1, h0 + fa + fty - 1, n0);
+              else
+                tma_load_4d(sb + b * kXhBox, &tmX1, &full_bar[stage], (cib - p.cb0) * 64, w0 - 1, h0 + fa + fty - 1,
+                            n0);
+            }
           } else {
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           // dY: both 64-channel blocks of the 128-row M tile in one 5-D box (.., channel block)
@@ -209,14 +234,33 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + 2 * kBoxBytes;
+          const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
           // 16 pixels (K) = two 8-row groups, 1024 B apart (SBO); 64-channel MN blocks 8 KB apart (LBO).  A K step
           // of 16 pixels moves the start address by 2048 B = +128 in the (bytes >> 4) address field of the low word.
           uint32_t a_lo = desc_lo0 + (a_addr >> 4);
           uint32_t b_lo = desc_lo0 + (b_addr >> 4);
           const uint32_t b1_off = (uint32_t)(ncol0 * kBoxBytes) >> 4;
           const int nk = (p.debug_skip & 2) ? 0 : kChunkPix / 16;
-          if (p.xh) {
+          if (p.fold == 1) {
+            // taps (b, tx): A = the b sub-lattice tile, B = the halo boxes shifted by b + tx pixels
+            const uint32_t bx_lo = descx_lo0 + (b_addr >> 4);
+            const uint32_t ncx = (uint32_t)(xh_live * 64);
+#pragma unroll
+            for (int k = 0; k < kChunkPix / 16; ++k) {
+              if (k < nk) {
+                const uint32_t koff = (uint32_t)(((16 * k) / p.Wb) * (p.Wb + 2) + (16 * k) % p.Wb) * 8u;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                  const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)b * ((2u * kBoxBytes) >> 4) + 128u * k);
+#pragma unroll
+                  for (int tx = 0; tx < 2; ++tx)
+                    umma_bf16(tmem_base + (uint32_t)(b * 2 + tx) * ncx, da,
+                              descx_hi | (uint64_t)(bx_lo + 8u * (uint32_t)(b + tx) + koff), idescx,
+                              (it | k) != 0 ? 1u : 0u);
+                }
+              }
+            }
+          } else if (p.xh) {
             // three taps = three MMAs on the same halo boxes, B start shifted by one pixel (128 B = +8) per tap;
             // N = all boxes of the stage (kXhBox apart), accumulator columns [tap][box][64]
             const uint32_t bx_lo = descx_lo0 + (b_addr >> 4);
@@ -260,20 +304,30 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     // epilogue: row = output channel within the tile; columns = (column block, channel)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const int co = p.rowpair ? (row & 63) : co_tile * 128 + row;
+    const int co = (p.rowpair || p.fold == 2) ? (row & 63) : co_tile * 128 + row;
     const bool valid = co < p.cout;
     float* out = p.ws + ((size_t)split * p.cout + (valid ? co : 0)) * ((size_t)p.taps * p.ctot);
+    if (p.fold) out = p.ws + (size_t)split * 16 * p.cout * p.ctot;      // [phase][cout][2x2][ctot]
     if (nchunks > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const int ncol_epi = p.xh ? 3 * xh_live : ncol_live;
+    const int ncol_epi = p.fold == 1 ? 4 * xh_live : p.xh ? 3 * xh_live : ncol_live;
     for (int j = 0; j < ncol_epi; ++j) {
       int tap = rg * p.ksize + (j % p.ksize);
       int cib = cib_base + j / p.ksize;
       bool live = valid;
-      if (p.xh) {
+      if (p.fold) {
+        // accumulator columns are [q][box][64]; q = (b, tx) (fold 1) or the shift b + tx (fold 2: b = M half)
+        const int q = j / xh_live;
+        const int fb = p.fold == 1 ? q >> 1 : row >> 6;
+        const int ftx = p.fold == 1 ? q & 1 : q - fb;
+        live = valid && ftx >= 0 && ftx < 2;
+        cib = cib_base + j % xh_live;
+        const int ph = (rg >> 1) * 2 + fb;
+        tap = (ph * p.cout + (valid ? co : 0)) * 4 + (rg & 1) * 2 + (live ? ftx : 0);     // row index into [ph][co][tap]
+      } else if (p.xh) {
         // accumulator columns are [tap s][box b][64]: b = X block (plain) or X row group (row-pair mode)
         const int sx = j / xh_live, b = j % xh_live;
         if (p.rowpair) {
@@ -332,7 +386,16 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= count) return;
   float4 acc = accumulate ? *reinterpret_cast<const float4*>(dw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < splits; ++s) {
+  // eight partial tiles in flight per thread (the splits are `count` floats apart); summation order stays 0, 1, 2, ...
+  int s = 0;
+  for (; s + 8 <= splits; s += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(ws + (size_t)(s + u) * count + i));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+  }
+  for (; s < splits; ++s) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * count + i));
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
@@ -352,11 +415,17 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   B2_REQUIRE(a->ksize >= 1 && a->ksize <= 3, B2_ERR_SHAPE, "ksize %d unsupported", a->ksize);
   B2_REQUIRE(xstride == 1 || (xstride == 2 && a->ksize == 2), B2_ERR_SHAPE,
              "x_stride %d unsupported (2 only with ksize 2)", xstride);
-  B2_REQUIRE(a->ksize != 2 || xstride == 2 || a->custom_pad != 0, B2_ERR_SHAPE,
+  B2_REQUIRE(a->ksize != 2 || xstride == 2 || a->custom_pad != 0 || a->fold != 0, B2_ERR_SHAPE,
              "ksize 2 needs x_stride 2 or explicit tap offsets");
   B2_REQUIRE(a->cout % 8 == 0 && a->c0 % 8 == 0 && a->c1 % 8 == 0, B2_ERR_SHAPE, "channels must be multiples of 8");
   B2_REQUIRE(a->c1 == 0 || a->c0 % 64 == 0, B2_ERR_SHAPE, "c0=%d must be a multiple of 64 when c1>0", a->c0);
   B2_REQUIRE((a->c0 + a->c1) % 4 == 0, B2_ERR_SHAPE, "cin must be a multiple of 4");
+  if (a->fold) {
+    B2_REQUIRE(a->ksize == 2 && xstride == 1 && a->dy_mul == 2 && !a->custom_pad && a->dy_off_h == 0 &&
+                   a->dy_off_w == 0, B2_ERR_SHAPE, "fold: ksize 2, dy_mul 2, no offsets / custom taps");
+    B2_REQUIRE((a->cout == 64 || a->cout % 128 == 0) && a->c0 % 64 == 0 && a->c1 % 64 == 0, B2_ERR_SHAPE,
+               "fold: cout %d must be 64 or a multiple of 128, cin a multiple of 64", a->cout);
+  }
   WgradParams& p = pl->p;
   memset(&p, 0, sizeof(p));
   int rc = conv_tile_geometry(a->n, a->h, a->w, kChunkPix, &p.Wb, &p.Hb, &p.Nb, &p.tw, &p.th, &pl->tn);
@@ -402,6 +471,16 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
       pl->gy = 1;
     }
   }
+  if (a->fold) {
+    p.fold = a->cout == 64 ? 2 : 1;
+    p.taps = 16;
+    p.rowpair = 0;
+    p.cpb = cbt < 2 ? cbt : 2;
+    p.ncolb = (p.fold == 1 ? 4 : 3) * p.cpb;
+    p.a_boxes = p.fold == 1 ? 2 : 1;
+    pl->gy = 4;
+  }
+  p.a_bytes = p.fold == 1 ? 4 * kBoxBytes : 2 * kBoxBytes;
   p.gy = pl->gy;
   pl->gz = ((a->cout + 127) / 128) * ((cbt + p.cpb - 1) / p.cpb);
   const int base = pl->gy * pl->gz;
@@ -431,9 +510,14 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
     p.xh = (want != 0 && a->ksize == 3 && xstride == 1 && !a->custom_pad && p.Nb == 1 && p.Wb >= 16 &&
             (p.Wb + 2) * p.Hb * 128 <= kXhBox) ? 1 : 0;
     p.nbox = p.rowpair ? p.rowpair : p.cpb;
+    if (p.fold) {
+      p.xh = (p.Nb == 1 && p.Wb >= 16 && (p.Wb + 2) * p.Hb * 128 <= kXhBox) ? 1 : 0;
+      B2_REQUIRE(p.xh, B2_ERR_SHAPE, "fold: image %dx%d too small for the halo-row chunks (Wb %d Hb %d Nb %d)", a->h,
+                 a->w, p.Wb, p.Hb, p.Nb);
+    }
   }
   p.b_stage_bytes = p.xh ? p.nbox * kXhBox : p.ncolb * kBoxBytes;
-  const int stage_bytes = 2 * kBoxBytes + p.b_stage_bytes;
+  const int stage_bytes = p.a_bytes + p.b_stage_bytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
@@ -480,7 +564,14 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     uint64_t dims[5] = {c_in_block, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n, (uint64_t)((a->cout + 63) / 64)};
     uint64_t str[5] = {2, (uint64_t)dm * a->lddy * 2, (uint64_t)dm * fw * a->lddy * 2, fh * fw * a->lddy * 2, 128};
     uint32_t box[5] = {64, (uint32_t)pl.p.Wb, (uint32_t)pl.p.Hb, (uint32_t)pl.p.Nb, (uint32_t)pl.p.a_boxes};
-    if (pl.p.rowpair) {
+    if (pl.p.fold) {
+      // the fine tensor itself, traversed with stride 2 in w and h: coordinate (2w + b, 2h + a) selects the phase
+      uint64_t fdims[5] = {c_in_block, fw, fh, (uint64_t)a->n, (uint64_t)((a->cout + 63) / 64)};
+      uint64_t fstr[5] = {2, (uint64_t)a->lddy * 2, fw * a->lddy * 2, fh * fw * a->lddy * 2, 128};
+      uint32_t fbox[5] = {64, (uint32_t)pl.p.Wb * 2, (uint32_t)pl.p.Hb * 2, (uint32_t)pl.p.Nb, (uint32_t)pl.p.a_boxes};
+      uint32_t fes[5] = {1, 2, 2, 1, 1};
+      rc = encode_tmap_bf16(&tmDY, a->dy, 5, fdims, fstr, fbox, CU_TENSOR_MAP_SWIZZLE_128B, fes);
+    } else if (pl.p.rowpair) {
       uint32_t box4[4] = {64, (uint32_t)pl.p.Wb, 1, 1};
       rc = encode_tmap_bf16(&tmDY, dyb, 4, dims, str, box4, CU_TENSOR_MAP_SWIZZLE_128B);
     } else {

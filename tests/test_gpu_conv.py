@@ -163,6 +163,44 @@ def test_wgrad_rowpair_2x2_phase_matches_plain(cin):
         assert rel(pair, plain) < 1e-5
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [
+    (2, 64, 128, 128, 64),       # fold 2 (Cout = 64: the column phases are the two halves of the M operand)
+    (2, 64, 64, 256, 128),       # fold 1, one row per chunk
+    (3, 32, 32, 512, 256),       # two rows per chunk, two Cout tiles
+    (2, 16, 16, 1024, 512),      # four rows per chunk
+    (2, 16, 16, 64, 128),        # a single X channel block
+    (1, 20, 28, 128, 128),       # clipped chunks (general extents)
+    (1, 12, 20, 192, 64),        # ... with an odd number of X blocks, Cout = 64
+])
+def test_wgrad_folded_upconv_merged_matches_phases(n, h, w, cin, cout):
+    """b2_wgrad_args::fold — the four phase weight gradients of a folded UpConv (AttentionUNet.py:15-27) from ONE
+    launch must equal the four dy_off launches and the fp32 reference."""
+    from b200seg import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = nhwc(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    dz = nhwc(torch.randn(n, cout, 2 * h, 2 * w, device="cuda", generator=g))
+    merged = K.conv_wgrad(dz, x, 2, dy_mul=2, fold=True)
+    assert merged is not None and merged.shape == (cout, 16, cin)
+    merged = merged.view(4, cout, 4, cin)
+    for ph, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        plain = K.conv_wgrad(dz, x, 2, dy_mul=2, dy_off=(a, b), pad=(1 - a, 1 - b))
+        dys = nchw(dz)[:, :, a::2, b::2]
+        xp = F.pad(nchw(x), (1 - b, b, 1 - a, a))
+        ref = torch.nn.grad.conv2d_weight(xp, (cout, cin, 2, 2), dys)
+        got = merged[ph].reshape(cout, 2, 2, cin).permute(0, 3, 1, 2)
+        assert rel(got, ref) < 1e-3, (a, b, rel(got, ref))
+        assert rel(merged[ph], plain) < 1e-5, (a, b, rel(merged[ph], plain))
+
+
+def test_wgrad_folded_upconv_merged_rejects_narrow_images():
+    """coarse images narrower than 16 pixels are not taken in merged mode: the wrapper reports it (None) and the
+    caller launches the phases"""
+    from b200seg import kernels as K
+    x = torch.zeros(1, 8, 8, 64, device="cuda", dtype=torch.bfloat16)
+    dz = torch.zeros(1, 16, 16, 64, device="cuda", dtype=torch.bfloat16)
+    assert K.conv_wgrad(dz, x, 2, dy_mul=2, fold=True) is None
+
+
 @pytest.mark.parametrize("n,h,w,cin", [(2, 256, 256, 64), (2, 128, 128, 128), (1, 6, 128, 64)])
 def test_fprop_dgrad_rowpair_mode_matches_plain(n, h, w, cin):
     """Cout = 64 row-pair mode of the implicit-GEMM kernel (B200SEG_FPROP_ROWPAIR=1: two output rows per tile, stacked
