@@ -220,6 +220,11 @@ int b2_maxpool2x2_fwd(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t 
                       int32_t ldy, b2_stream_t stream);
 int b2_maxpool2x2_bwd(const void* dy, int32_t lddy, const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w,
                       int32_t c, void* dx, int32_t lddx, b2_stream_t stream);
+/* dx = maxpool gradient + addend: the skip tensor of a U-Net level has two consumers (the pool, AttentionUNet.py:88-94,
+ * and the decoder's gate / concat, :100-101); taking the decoder-side gradient as the addend replaces autograd's
+ * separate full-size accumulation (one rounding, as ATen's add of the two bf16 gradients). */
+int b2_maxpool2x2_bwd_add(const void* dy, int32_t lddy, const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w,
+                          int32_t c, const void* addend, int32_t ldadd, void* dx, int32_t lddx, b2_stream_t stream);
 int b2_upsample2x_fwd(const void* x, int32_t ldx, int32_t n, int32_t h, int32_t w, int32_t c, void* y,
                       int32_t ldy, b2_stream_t stream);
 int b2_upsample2x_bwd(const void* dy, int32_t lddy, int32_t n, int32_t h, int32_t w, int32_t c, void* dx,

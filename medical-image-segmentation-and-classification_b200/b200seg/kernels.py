@@ -158,6 +158,36 @@ def step_begin():
             st["buf"][:st["high"]].zero_()
     st["off"] = 0
     st["armed"] = True
+    _ZPOOL.pop(dev, None)
+
+
+# Zero-filled op OUTPUTS that may outlive the step (bias gradients that autograd adopts as .grad, statistics a caller
+# may keep): slices of a pool that is allocated FRESH once per step (one fill launch instead of ~50), never recycled —
+# a slice keeps the pool's storage alive for as long as anyone holds it.  Main-stream tensors only, and at most ONE slice
+# among the inputs and outputs of any custom op (torch.library rejects outputs that share a storage with each other
+# or with an input).
+_ZPOOL = {}
+_ZPOOL_BYTES = 256 << 10
+
+
+def zeros_out(shape, dtype, device):
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    st = _ARENA["bufs"].get(dev) if device.type == "cuda" else None
+    if st is None or not st["armed"]:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    if nbytes > _ZPOOL_BYTES // 4:
+        return torch.zeros(shape, dtype=dtype, device=device)
+    pool = _ZPOOL.get(dev)
+    off = 0 if pool is None else (pool["off"] + 255) & ~255
+    if pool is None or off + nbytes > _ZPOOL_BYTES:
+        pool = _ZPOOL[dev] = {"buf": torch.zeros(_ZPOOL_BYTES, dtype=torch.uint8, device=device), "off": 0}
+        off = 0
+    pool["off"] = off + nbytes
+    return pool["buf"][off:off + nbytes].view(dtype).view(shape)
 
 
 def zeros_scratch(shape, dtype, device):
@@ -737,7 +767,7 @@ def bn_bwd(dy, z, coef, gamma, relu=True, training=True, want_dbias=False):
     dz = new_act(n, h, w, c, z.device)
     dgamma = torch.empty((c,), dtype=torch.float32, device=z.device)
     dbeta = torch.empty((c,), dtype=torch.float32, device=z.device)
-    dbias = torch.zeros((c,), dtype=torch.float32, device=z.device) if want_dbias else None
+    dbias = zeros_out((c,), torch.float32, z.device) if want_dbias else None
     call("b2_bn_bwd_apply", _p(dy), lddy, _p(z), ldz, npix, c, _p(coef[2]), _p(coef[3]), _p(coef[0]), _p(coef[1]),
          _p(gamma), int(relu), int(training), _p(sums), _p(dz), c, _p(dgamma), _p(dbeta), _p(dbias), _stream())
     return (dz, dgamma, dbeta, dbias) if want_dbias else (dz, dgamma, dbeta)
@@ -753,11 +783,16 @@ def maxpool_fwd(x):
     return y
 
 
-def maxpool_bwd(dy, x):
+def maxpool_bwd(dy, x, addend=None):
     n, h, w, c, ld = _nhwc(x)
     lddy = _nhwc(dy)[4]
     dx = new_act(n, h, w, c, x.device)
-    call("b2_maxpool2x2_bwd", _p(dy), lddy, _p(x), ld, n, h, w, c, _p(dx), c, _stream())
+    if addend is not None:
+        assert addend.shape == x.shape
+        call("b2_maxpool2x2_bwd_add", _p(dy), lddy, _p(x), ld, n, h, w, c, _p(addend), _nhwc(addend)[4], _p(dx), c,
+             _stream())
+    else:
+        call("b2_maxpool2x2_bwd", _p(dy), lddy, _p(x), ld, n, h, w, c, _p(dx), c, _stream())
     return dx
 
 
@@ -807,7 +842,7 @@ def gate_psi_fwd(g1p, x1p, coef_g, coef_x, wpsi, bpsi):
     n, h, w, fint, ld = _nhwc(g1p)
     assert _nhwc(x1p)[4] == ld
     q = torch.empty((n, h, w), dtype=BF16, device=g1p.device)
-    qstats = torch.zeros((2,), dtype=torch.float64, device=g1p.device)    # an output of the gate op: not arena memory
+    qstats = zeros_out((2,), torch.float64, g1p.device)    # an output of the gate op: not arena memory
     call("b2_gate_psi_fwd", _p(g1p), _p(x1p), ld, n * h * w, fint, _p(coef_g[2]), _p(coef_g[3]), _p(coef_x[2]),
          _p(coef_x[3]), _p(wpsi), _p(bpsi), _p(q), _p(qstats), _stream())
     return q, qstats
@@ -854,15 +889,15 @@ def gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coe
     dev = g1p.device
     k = _gate_coef(coef_g, gamma_g, coef_x, gamma_x, coef1, gamma1, wpsi)
     sums = zeros_scratch((4, fint), torch.float64, dev)
-    dwpsi = torch.zeros((fint,), dtype=torch.float32, device=dev)
-    dbpsi = torch.zeros((1,), dtype=torch.float32, device=dev)
+    dwpsi = torch.zeros((fint,), dtype=torch.float32, device=dev)   # (one pool slice per custom op at most: the outputs
+    dbpsi = torch.zeros((1,), dtype=torch.float32, device=dev)      # of an op may not share a storage)
     call("b2_gate_psi_bwd_reduce", _p(dsig), _p(q), _p(g1p), _p(x1p), ld, npix, fint, C.byref(k), _p(sums1),
          int(training), _p(sums), _p(dwpsi), _p(dbpsi), _stream())
     dg1p = new_act(n, h, w, fint, dev)
     dx1p = new_act(n, h, w, fint, dev)
     dgb = torch.empty((4, fint), dtype=torch.float32, device=dev)
     dbn1 = torch.empty((2,), dtype=torch.float32, device=dev)
-    dbias = torch.zeros((2, fint), dtype=torch.float32, device=dev)     # bias grads of the W_g / W_x convs
+    dbias = zeros_out((2, fint), torch.float32, dev)     # bias grads of the W_g / W_x convs
     assert ld == fint
     call("b2_gate_psi_bwd_apply", _p(dsig), _p(q), _p(g1p), _p(x1p), ld, npix, fint, C.byref(k), _p(sums1),
          int(training), _p(sums), _p(dg1p), _p(dx1p), _p(dgb), _p(dbn1), _p(dbias), _stream())
@@ -875,7 +910,7 @@ def gate_psi_bwd(dsig, sums1, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coe
 def loss_fwd(z, t, w_bce=1.0, w_dice=0.0, smooth=1.0):
     assert z.dtype == torch.float32 and t.dtype == torch.float32 and z.is_contiguous() and t.is_contiguous()
     assert z.numel() == t.numel()
-    sums = torch.zeros((6,), dtype=torch.float64, device=z.device)   # an output of seg_loss the caller may keep: not arena memory
+    sums = zeros_out((6,), torch.float64, z.device)   # an output of seg_loss the caller may keep: not arena memory
     loss = torch.empty((), dtype=torch.float32, device=z.device)
     call("b2_loss_fwd", _p(z), _p(t), z.numel(), _p(sums), _stream())
     call("b2_loss_finalize", _p(sums), z.numel(), float(w_bce), float(w_dice), float(smooth), _p(loss), _stream())

@@ -43,12 +43,18 @@ class AttentionUNet(nn.Module):
 
     def features(self, x: torch.Tensor):
         """Everything up to the head, on internal NHWC bf16 activations."""
-        pool = ops.maxpool2x2
+        # (pooled, skip): the pass-through output is what the decoder consumes, so the skip's decoder-side gradient is
+        # added inside the pool-backward kernel (ops.maxpool2x2_pass)
+        pool = ops.maxpool2x2_pass
         x1 = self.conv1._internal(x)
-        x2 = self.conv2(pool(x1))
-        x3 = self.conv3(pool(x2))
-        x4 = self.conv4(pool(x3))
-        x5 = self.conv5(pool(x4))
+        p1, x1 = pool(x1)
+        x2 = self.conv2(p1)
+        p2, x2 = pool(x2)
+        x3 = self.conv3(p2)
+        p3, x3 = pool(x3)
+        x4 = self.conv4(p3)
+        p4, x4 = pool(x4)
+        x5 = self.conv5(p4)
 
         d5 = self.up5(x5)
         d5 = self.up_conv5((self.att5(g=d5, x=x4), d5))      # cat((x4, d5), dim=1): skip first (ref :101)

@@ -36,12 +36,18 @@ class R2U_Net(nn.Module):
         return skip
 
     def features(self, x: torch.Tensor):
-        pool = ops.maxpool2x2
+        # (pooled, skip): the pass-through output is what the decoder consumes, so the skip's decoder-side gradient is
+        # added inside the pool-backward kernel (ops.maxpool2x2_pass)
+        pool = ops.maxpool2x2_pass
         x1 = self.RRCNN1._internal(x if self.RRCNN1.conv_1x1.in_channels <= 4 else ops.to_nhwc(x))
-        x2 = self.RRCNN2(pool(x1))
-        x3 = self.RRCNN3(pool(x2))
-        x4 = self.RRCNN4(pool(x3))
-        x5 = self.RRCNN5(pool(x4))
+        p1, x1 = pool(x1)
+        x2 = self.RRCNN2(p1)
+        p2, x2 = pool(x2)
+        x3 = self.RRCNN3(p2)
+        p3, x3 = pool(x3)
+        x4 = self.RRCNN4(p3)
+        p4, x4 = pool(x4)
+        x5 = self.RRCNN5(p4)
 
         d5 = self.up5(x5)
         d5 = self.up_RRCNN5((self._skip(5, d5, x4), d5))     # cat((x4, d5), dim=1) — R2U_Net.py:94

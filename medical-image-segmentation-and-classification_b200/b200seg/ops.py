@@ -560,6 +560,37 @@ def _(x):
     return x.new_empty((n, h // 2, w // 2, c))
 
 
+class _MaxPoolPass(torch.autograd.Function):
+    """(pool(x), x): the skip tensor of a U-Net level feeds the pool AND the decoder (gate / concat).  Handing the
+    decoder the pass-through output makes this node x's only consumer, so the decoder-side gradient arrives here and
+    is added inside the pool-backward kernel (b2_maxpool2x2_bwd_add) instead of autograd's separate accumulation
+    pass over the full-size tensor (AttentionUNet.py:88-101; R2U_Net.py:78-95)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = _c(x)
+        ctx.save_for_backward(xc)
+        ctx.set_materialize_grads(False)
+        return K.maxpool_fwd(xc), x
+
+    @staticmethod
+    def backward(ctx, dy, dpass):
+        (x,) = ctx.saved_tensors
+        if dy is None:
+            return dpass
+        return K.maxpool_bwd(_c(dy), x, addend=_c(dpass) if dpass is not None else None)
+
+
+_POOL_PASS = os.environ.get("B200SEG_POOL_PASS", "1") != "0"      # 0: plain pool, autograd accumulates (A/B switch)
+
+
+def maxpool2x2_pass(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """-> (MaxPool2d(2, 2)(x), x as the tensor the decoder should consume)"""
+    if not _POOL_PASS or not (torch.is_grad_enabled() and x.requires_grad):
+        return maxpool2x2(x), x
+    return _MaxPoolPass.apply(x)
+
+
 @custom_op("b200seg::upsample2x", mutates_args=())
 def upsample2x(x: Tensor) -> Tensor:
     """nn.Upsample(scale_factor=2) (nearest): AttentionUNet.py:18, R2U_Net.py:25"""

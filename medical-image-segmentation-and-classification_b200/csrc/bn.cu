@@ -474,6 +474,14 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_apply_light_kernel(
     int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, DetBuf det) {
   __shared__ float red[kBlock * 4];
+  // gridDim.y channel slices of m.tpp * 4 channels (as in the reduce kernel): with C / 4 threads per pixel a thread of a
+  // 512- or 1024-channel layer met only a handful of pixels, and its prologue (six per-channel coefficient loads, two of
+  // them fp64, and the fp64 coefficient algebra) cost more than its share of the tensor: 32^2 x 512 ran at 2.2 TB/s,
+  // 16^2 x 1024 at 1.1 TB/s.  A 64-channel slice gives every thread 16x the pixels for the same prologue.
+  const int c_off = blockIdx.y * (m.tpp * 4);
+  dy += c_off;
+  z += c_off;
+  dz += c_off;
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
   const bool active = r < m.rows;
@@ -482,12 +490,12 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_apply_light_kernel(
   for (int j = 0; j < 4; ++j) bsum[j] = 0.f;
   if (active) {
     float sc[4], sh[4], ka[4], kb[4], kc[4];
-    load4f(scale + g * 4, sc);
-    load4f(shift + g * 4, sh);
+    load4f(scale + c_off + g * 4, sc);
+    load4f(shift + c_off + g * 4, sh);
     const double inv_m = 1.0 / (double)npix;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = g * 4 + j;
+      const int c = c_off + g * 4 + j;
       const float ga = gamma ? __ldg(gamma + c) : 1.f;
       const float is = __ldg(invstd + c), mu = __ldg(mean + c);
       const double a0 = sums[c], a1 = sums[C + c];
@@ -537,7 +545,7 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_apply_light_kernel(
     rows_reduce4(bsum, m.tpp, m.rows, g, r, active, red);
     if (active && r == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) red_out(dbias, det, g * 4 + j, bsum[j]);
+      for (int j = 0; j < 4; ++j) red_out(dbias, det, c_off + g * 4 + j, bsum[j]);
     }
   }
 }
@@ -697,7 +705,17 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
              "bn_bwd_apply operands misaligned");
   ChanMap lm;
   const bool light = light_map(c, &lm);
-  const int grid = light ? chan_grid(npix, lm, 8) : chan_grid(npix, m, 4);
+  int slices = 1;
+  if (light && c % 64 == 0 && c > 64 && env_switch("B200SEG_BN_SLICE", 1) != 0) {
+    slices = c / 64;                 // 64-channel slices: 16 threads per pixel, 16 pixels per block iteration
+    lm.tpp = 16;
+    lm.rows = kBlock / 16;
+  }
+  int grid = light ? chan_grid(npix, lm, 8) : chan_grid(npix, m, 4);
+  if (slices > 1) {
+    grid = (grid + slices - 1) / slices;
+    if (grid < 1) grid = 1;
+  }
   DetBuf det;
   det.partial = nullptr;
   det.n = c;
@@ -706,7 +724,7 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
     if (rc) return rc;
   }
   if (light) {
-    bn_bwd_apply_light_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+    bn_bwd_apply_light_kernel<<<dim3(grid, slices), kBlock, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, gamma,
         relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det);
   } else {

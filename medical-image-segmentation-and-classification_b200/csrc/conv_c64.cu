@@ -18,6 +18,13 @@
 //              is walked as strips of consecutive rows of one image column segment.  Rows outside a strip are neither
 //              accumulated nor stored (the boundary input rows run N = 64 / 128 pieces), so strips cost one extra input
 //              row at each inner end.
+//   fold     : the folded UpConv with Cout = 64 (Upsample x2 -> conv3x3 as four 2x2 phase convolutions of the COARSE
+//              input, AttentionUNet.py:15-27; ops.upconv_bn_act) streams the same way.  A CTA owns one column phase b
+//              (fine pixels 2w + b; half of the CTAs each): coarse input row r feeds the FOUR fine rows 2r-1 .. 2r+2
+//              — stacked weights [(a=1,ty=1) ; (a=0,ty=1) ; (a=1,ty=0) ; (a=0,ty=0)] per (tx, channel block), N = 256 —
+//              with the two horizontal taps tx as descriptor shifts of b + tx pixels, and the ring advances by two
+//              rows per input row.  Every input row is fetched once per column phase instead of once per (phase, tap):
+//              the generic kernel's merged launch pulled 5.4 GB through the L2 -> SM fabric for 0.27 GB of input.
 //   warps    : 0 = TMA producer, 1 = MMA issuer, 2-5 / 6-9 = two epilogue groups taking alternate output rows
 //              (tcgen05.ld -> +bias, ReLU -> bf16 -> swizzled staging tile -> TMA store, BatchNorm sum / sum of squares
 //              of the rounded values as in conv_igemm.cu).
@@ -48,6 +55,7 @@ struct C64Params {
   double* stats;
   double* stats_partial;    // deterministic mode: [grid * epi_groups][128]
   int relu;
+  int fold;                 // 1: folded UpConv (see the header); H, W, rows_total are those of the COARSE input
   int debug_skip;           // timing experiments only (B200SEG_C64_SKIP; results are wrong): 1 no TMA loads, 2 no MMAs,
                             // 4 no drain at all, 8 no statistics pass, 16 no TMA store
 };
@@ -78,7 +86,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const C64Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int wres_bytes = 9 * p.cbt * 8192;                             // 9 taps x cbt blocks x 64 rows x 128 B
+  const int wres_bytes = (p.fold ? 8 : 9) * p.cbt * 8192;              // taps x cbt blocks x 64 rows x 128 B
   uint8_t* wres = smem + p.stages * kC64AStage;                        // resident weights
   uint8_t* ctile0 = wres + wres_bytes;                                 // per group: 128 x 64 bf16 staging tile
   uint8_t* tail = ctile0 + p.epi_groups * (kTileM * 128);
@@ -92,8 +100,12 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long range_begin = p.rows_total * (long long)blockIdx.x / p.grid;
-  const long long range_end = p.rows_total * (long long)(blockIdx.x + 1) / p.grid;
+  // fold: CTAs [0, grid/2) take column phase 0, the rest phase 1; each half splits all (coarse) row tiles
+  const int fb = p.fold ? ((int)blockIdx.x >= p.grid / 2 ? 1 : 0) : 0;
+  const int rgrid = p.fold ? (fb ? p.grid - p.grid / 2 : p.grid / 2) : p.grid;
+  const int ridx = p.fold ? (fb ? (int)blockIdx.x - p.grid / 2 : (int)blockIdx.x) : (int)blockIdx.x;
+  const long long range_begin = p.rows_total * (long long)ridx / rgrid;
+  const long long range_end = p.rows_total * (long long)(ridx + 1) / rgrid;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -125,6 +137,15 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // ------------------------------ TMA producer ------------------------------
     if (elect_one()) {
       mbar_arrive_expect_tx(wres_bar, (uint32_t)wres_bytes);
+      if (p.fold) {
+        for (int s = 0; s < 2; ++s)            // s = tx
+          for (int cb = 0; cb < p.cbt; ++cb)
+            for (int j = 0; j < 4; ++j) {      // fine row 2r-1+j: row phase a = 1 - (j & 1), filter row ty = 1 - (j >> 1)
+              const int wa = 1 - (j & 1), wty = 1 - (j >> 1);
+              tma_load_3d(wres + ((s * p.cbt + cb) * 256 + j * 64) * 128, &tmB, wres_bar, cb * kKBlock, 0,
+                          (2 * wa + fb) * 4 + 2 * wty + s);
+            }
+      } else
       for (int s = 0; s < 3; ++s)
         for (int cb = 0; cb < p.cbt; ++cb)
           for (int j = 0; j < 3; ++j)          // stacked [kr = 2 ; kr = 1 ; kr = 0] for horizontal tap s
@@ -181,6 +202,85 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint32_t lr_base = 0;                         // local row counter of the strip's first output row
     long long cur = range_begin;
     Strip st;
+    while (p.fold && next_strip(p, cur, range_end, st)) {
+      // ---- folded UpConv: coarse input row r -> fine rows 2r-1 .. 2r+2 of the strip's fine range [2 ha, 2 hb) ----
+      const int r0 = st.ha > 0 ? st.ha - 1 : 0;
+      const int rl = st.hb < p.H ? st.hb : p.H - 1;
+      const int f0 = 2 * st.ha, f1 = 2 * st.hb - 1;                    // first / last fine row of the strip
+      const uint32_t fs_step = (uint32_t)p.cbt * 2048u;                // 256 rows x 128 B per (tx, channel block)
+      for (int r = r0; r <= rl; ++r) {
+        const int lo = 2 * r - 1 > f0 ? 2 * r - 1 : f0;
+        const int hi = 2 * r + 2 < f1 ? 2 * r + 2 : f1;
+        const int cnt = hi - lo + 1;                                   // 1 .. 4
+        const uint32_t lr_lo = lr_base + (uint32_t)(lo - f0);
+        const uint32_t sl = lr_lo & 7u;
+        const uint32_t off = (uint32_t)(lo - (2 * r - 1));             // position in the 256-row weight stack
+        // fresh rows (first touched by this input row): all at the strip's first input row, else 2r+1 and 2r+2
+        int nfresh = r == r0 ? cnt : hi - 2 * r;
+        if (nfresh < 0) nfresh = 0;
+        for (int j = cnt - nfresh; j < cnt; ++j) {
+          const uint32_t lr = lr_lo + (uint32_t)j;
+          mbar_wait(&tmem_empty_bar[lr & 7u], ((lr >> 3) & 1u) ^ 1u);
+        }
+        tc_fence_after();
+        const int c0 = (int)(kC64Slots - sl) < cnt ? (int)(kC64Slots - sl) : cnt;   // rows before the ring wraps
+        const uint32_t d0 = tmem_base + sl * 64u;
+        for (int cb = 0; cb < p.cbt; ++cb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            // the halo box starts at coarse pixel w0 - 1: tap tx of column phase b reads pixel w + b + tx - 1
+            const uint32_t a0 = a_ring_lo + (uint32_t)stage * (uint32_t)(kC64AStage >> 4) + 8u * (uint32_t)fb;
+            const uint32_t b0 = wres_lo + (uint32_t)cb * 2048u + off * 512u;
+            if (!no_mma) {
+              if (cb == 0) {             // K step 0: one N = 64 MMA per fine row, the fresh ones overwrite
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < cnt)
+                    umma_bf16(tmem_base + ((sl + (uint32_t)j) & 7u) * 64u, desc_hi | (uint64_t)a0,
+                              desc_hi | (uint64_t)(b0 + (uint32_t)j * 512u), idesc1, j >= cnt - nfresh ? 0u : 1u);
+              } else if (c0 == cnt) {
+                umma_bf16(d0, desc_hi | (uint64_t)a0, desc_hi | (uint64_t)b0, idesc_n0 + ((uint32_t)cnt << 20), 1u);
+              } else {
+                umma_bf16(d0, desc_hi | (uint64_t)a0, desc_hi | (uint64_t)b0, idesc_n0 + ((uint32_t)c0 << 20), 1u);
+                umma_bf16(tmem_base, desc_hi | (uint64_t)a0, desc_hi | (uint64_t)(b0 + (uint32_t)c0 * 512u),
+                          idesc_n0 + ((uint32_t)(cnt - c0) << 20), 1u);
+              }
+              // K steps 1 .. 7: tap tx = kk / 4, 16 channels k = kk % 4
+              if (c0 == cnt) {
+                const uint32_t id = idesc_n0 + ((uint32_t)cnt << 20);
+#pragma unroll
+                for (int kk = 1; kk < 8; ++kk)
+                  umma_bf16(d0, desc_hi | (uint64_t)(a0 + (uint32_t)(8 * (kk >> 2) + 2 * (kk & 3))),
+                            desc_hi | (uint64_t)(b0 + (uint32_t)(kk >> 2) * fs_step + (uint32_t)(2 * (kk & 3))), id, 1u);
+              } else {
+                const uint32_t id_a = idesc_n0 + ((uint32_t)c0 << 20), id_b = idesc_n0 + ((uint32_t)(cnt - c0) << 20);
+                const uint32_t b1 = b0 + (uint32_t)c0 * 512u;
+#pragma unroll
+                for (int kk = 1; kk < 8; ++kk) {
+                  const uint64_t da = desc_hi | (uint64_t)(a0 + (uint32_t)(8 * (kk >> 2) + 2 * (kk & 3)));
+                  const uint32_t bk = (uint32_t)(kk >> 2) * fs_step + (uint32_t)(2 * (kk & 3));
+                  umma_bf16(d0, da, desc_hi | (uint64_t)(b0 + bk), id_a, 1u);
+                  umma_bf16(tmem_base, da, desc_hi | (uint64_t)(b1 + bk), id_b, 1u);
+                }
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (cb == p.cbt - 1) {
+              // fine rows that received their last contribution: those up to 2r, everything at the last input row
+              for (int f = lo; f <= hi; ++f)
+                if (f <= 2 * r || r == rl) umma_commit(&tmem_full_bar[(lr_base + (uint32_t)(f - f0)) & 7u]);
+            }
+          }
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      lr_base += (uint32_t)(2 * (st.hb - st.ha));
+    }
     while (next_strip(p, cur, range_end, st)) {
       const int r0 = st.ha > 0 ? st.ha - 1 : 0;
       const int rl = st.hb < p.H ? st.hb : p.H - 1;
@@ -282,7 +382,9 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       long long cur = range_begin;
       Strip st;
       while (next_strip(p, cur, range_end, st)) {
-        for (int h = st.ha; h < st.hb; ++h, ++lr) {
+        // fold: the strip's output rows are the fine rows [2 ha, 2 hb) of this CTA's column phase
+        const int h_begin = p.fold ? 2 * st.ha : st.ha, h_end = p.fold ? 2 * st.hb : st.hb;
+        for (int h = h_begin; h < h_end; ++h, ++lr) {
           if (G == 2 && (lr & 1) != g) continue;
           const uint32_t slot = (uint32_t)lr & 7u;
           // the group's previous TMA store must have finished READING the staging tile before it is overwritten
@@ -329,7 +431,8 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           fence_proxy_async();
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (et == 0 && !(p.debug_skip & 16)) {
-            tma_store_4d(&tmY, ctile, 0, st.w0, h, st.n);
+            if (p.fold) tma_store_5d(&tmY, ctile, 0, fb, st.w0, h, st.n);     // (c, column phase, coarse w, fine h, n)
+            else tma_store_4d(&tmY, ctile, 0, st.w0, h, st.n);
             tma_store_commit();
           }
           if (p.stats != nullptr && !(p.debug_skip & 8)) {
@@ -400,8 +503,10 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
   const int stride = a->stride == 0 ? 1 : a->stride;
   const int out_mul = a->out_mul == 0 ? 1 : a->out_mul;
   const int in_mul = a->in_mul == 0 ? 1 : a->in_mul;
-  if (a->ksize != 3 || a->cout != 64 || stride != 1 || out_mul != 1 || in_mul != 1 || a->custom_pad != 0 ||
-      a->fold_mode != 0 || a->addend != nullptr || a->w % kTileM != 0 || a->c0 % 64 != 0 || a->c1 % 64 != 0)
+  const int fold = a->fold_mode == 1 ? 1 : 0;           // merged folded-UpConv fprop (ksize 2, y on the 2x grid)
+  if (fold && (a->ksize != 2 || a->c1 != 0 || a->ldy != a->cout || env_switch("B200SEG_C64_FOLD", 1) == 0)) return 0;
+  if ((!fold && (a->ksize != 3 || a->fold_mode != 0)) || a->cout != 64 || stride != 1 || out_mul != 1 || in_mul != 1 ||
+      a->custom_pad != 0 || a->addend != nullptr || a->w % kTileM != 0 || a->c0 % 64 != 0 || a->c1 % 64 != 0)
     return 0;
   const int cb0 = a->c0 / 64, cbt = cb0 + a->c1 / 64;
   if (cbt < 1 || cbt > 2) return 0;
@@ -420,10 +525,11 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.bias = a->bias;
   p.stats = a->stats;
   p.relu = a->relu;
+  p.fold = fold;
   p.debug_skip = env_switch("B200SEG_C64_SKIP", 0);
   p.mg_tw = p.tw <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)p.tw - 1) / (uint64_t)p.tw);
   const int tail_bytes = 320 + 64 * 4 + 192;
-  const int wres_bytes = 9 * cbt * 8192;
+  const int wres_bytes = (fold ? 8 : 9) * cbt * 8192;
   p.epi_groups = 2;
   int budget = 232448 - 1024 - tail_bytes - wres_bytes - 2 * kTileM * 128;
   if (budget / kC64AStage < 3) {       // two channel blocks: one staging tile, the main loop is twice as long anyway
@@ -449,14 +555,22 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
     tmA1 = tmA0;
   }
   {
-    uint64_t dims[3] = {(uint64_t)(a->c0 + a->c1), (uint64_t)a->cout, 9};
+    uint64_t dims[3] = {(uint64_t)(a->c0 + a->c1), (uint64_t)a->cout, (uint64_t)(fold ? 16 : 9)};
     uint64_t str[3] = {2, (uint64_t)a->ktot * 2, (uint64_t)a->w_tap_stride * 2};
     uint32_t box[3] = {64, 64, 1};
     rc = encode_tmap_bf16(&tmB, a->wpk, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  rc = encode_act_tmap_ex(&tmY, a->y, a->cout, a->n, a->h, a->w, a->ldy, (long long)a->ldy * a->w,
-                          (long long)a->ldy * a->w * a->h, kTileM, 1, 1, 1);
+  if (fold) {      // y [n, 2h, 2w, 64] as (c, column phase, coarse w, fine h, n): a store writes every other fine pixel
+    const uint64_t ld = (uint64_t)a->ldy;
+    uint64_t dims[5] = {64, 2, (uint64_t)a->w, (uint64_t)a->h * 2, (uint64_t)a->n};
+    uint64_t str[5] = {2, ld * 2, ld * 4, ld * 4 * a->w, ld * 8 * a->w * a->h};
+    uint32_t box[5] = {64, 1, (uint32_t)kTileM, 1, 1};
+    rc = encode_tmap_bf16(&tmY, a->y, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    rc = encode_act_tmap_ex(&tmY, a->y, a->cout, a->n, a->h, a->w, a->ldy, (long long)a->ldy * a->w,
+                            (long long)a->ldy * a->w * a->h, kTileM, 1, 1, 1);
+  }
   if (rc) return rc;
   {
     static std::once_flag attr_once;

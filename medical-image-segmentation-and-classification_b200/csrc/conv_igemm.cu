@@ -582,6 +582,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (kHasAdd) {
         const long long pix = ((long long)(n0 + nl) * p.H + (h0 + hl)) * p.W + (w0 + wl);
         arow = valid ? p.addend + pix * p.ldadd + ch_base : nullptr;
+        // The addend rows are plain global loads issued after the accumulator is ready, so every 32-column chunk of a
+        // tile used to pay a DRAM round trip inside the drain (the gate's 1x1 dgrad with the direct x gradient as
+        // addend ran at 3.7 TB/s where the same launch without addend reaches 5 TB/s).  Pull the rows of the NEXT tile
+        // this group will drain into L2 now; its loads then hit L2.
+        const int ti2 = ti + G;
+        const int item2 = cluster_id + (p.dm ? (ti2 >> 1) : ti2) * num_clusters;
+        if (item2 < total_items && !p.rp) {
+          const int m_group2 = fast_div(item2, p.n_tiles, p.mg_nt);
+          const int t2 = m_group2 * per_item + (p.dm ? (ti2 & 1) : (int)crank);
+          if (t2 < p.m_tiles) {
+            const int u1 = fast_div(t2, p.tw, p.mg_tw);
+            const int u_w = t2 - u1 * p.tw;
+            const int u_n = fast_div(u1, p.th, p.mg_th);
+            const int u_h = u1 - u_n * p.th;
+            const int w2 = u_w * p.Wb + wl, h2 = u_h * p.Hb + hl, n2 = u_n * p.Nb + nl;
+            if (w2 < p.W && h2 < p.H && n2 < p.N) {
+              const __nv_bfloat16* nrow = p.addend + (((long long)n2 * p.H + h2) * p.W + w2) * p.ldadd +
+                                          (item2 - m_group2 * p.n_tiles) * p.block_n;
+              for (int c = 0; c < p.block_n; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + c));
+            }
+          }
+        }
       }
       if (p.gate_x != nullptr) {
         // ---------------- fused attention-gate epilogue (eval mode) ----------------

@@ -216,6 +216,8 @@ __device__ __forceinline__ float gate_dq(float ds, float qv, float g1, float mu1
 // The two psi-backward kernels are templates on V = channels per thread: V = 8 (16-byte accesses) or V = 4 (8-byte
 // accesses, half the per-channel register state: <= 80 registers, three blocks per SM and room next to a persistent
 // weight-gradient CTA of the side stream).  V = 4 is used whenever F_int / 4 threads per pixel fit a block.
+// U = pixels in flight per thread: 4 (two blocks per SM) for F_int <= 128, where it measured 4-9 % faster than 2
+// (three blocks per SM); the kernels are as much instruction- as latency-bound (B200SEG_GATE_U forces either).
 // ---------------------------------------------------------------------------------------------------------
 template <int V> struct GVec;
 template <> struct GVec<8> { using T = uint4; };
@@ -236,18 +238,28 @@ template <int V> __device__ __forceinline__ void gv_loadf(const float* p, bool h
 }
 
 // backward phase 2: reductions for BN_g, BN_x and the psi conv
-template <int V>
-__global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kernel(
+template <int V, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) gate_psi_bwd_reduce_kernel(
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int L, GateBwdCoef c,
     const double* __restrict__ sums1, int training, double* __restrict__ sums, float* __restrict__ dwpsi,
-    float* __restrict__ dbpsi, DetBuf det) {
+    float* __restrict__ dbpsi, int slice, DetBuf det) {
   using VT = typename GVec<V>::T;
-  extern __shared__ float red[];   // [4][fint] + 1
-  for (int i = threadIdx.x; i < 4 * fint + 1; i += blockDim.x) red[i] = 0.f;
+  // gridDim.y channel slices of `slice` channels (0: one slice = all of F_int): a block then ends in 5 * slice global
+  // atomics instead of 5 * F_int, and gridDim.x (= blocks adding to one address) shrinks by the slice count — the
+  // same-address atomics of ~1200 blocks were a fixed 30-90 us per launch, whatever the tensor size.
+  const int c_off = slice ? blockIdx.y * slice : 0;
+  const int fw = slice ? (fint - c_off < slice ? fint - c_off : slice) : fint;      // channels of this slice
+  g1p += c_off;
+  x1p += c_off;
+  c.scale_g += c_off; c.shift_g += c_off; c.mean_g += c_off; c.invstd_g += c_off;
+  c.scale_x += c_off; c.shift_x += c_off; c.mean_x += c_off; c.invstd_x += c_off;
+  c.wpsi += c_off;
+  extern __shared__ float red[];   // [4][fw] + 1
+  for (int i = threadIdx.x; i < 4 * fw + 1; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
-  const bool has = lig * V < fint;
+  const bool has = lig * V < fw;
   // per-channel constants kept in registers: BN affine (mask recomputation), means (centred sums), psi weights.
   // The xhat sums are accumulated as sum da * (v - mean) and scaled by invstd once per block.
   float sg[V], hg[V], mg[V], sx[V], hx[V], mx[V], wp[V];
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kerne
   for (int j = 0; j < V; ++j) ab[j] = agg[j] = agx[j] = aw[j] = 0.f;
   if (has) {
     const long long stride = (long long)gridDim.x * gpb;
-    constexpr int U = 2;                      // pixels in flight per thread (all loads issued before the math)
+    // U pixels in flight per thread (all loads issued before the math)
     for (long long p0 = (long long)blockIdx.x * gpb + grp; p0 < npix; p0 += U * stride) {
       VT gv[U], xv[U];
       float ds[U], qv[U];
@@ -305,12 +317,12 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kerne
     if (det.partial == nullptr) {
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        atomicAdd(&red[0 * fint + lig * V + j], ab[j]);
-        atomicAdd(&red[1 * fint + lig * V + j], agg[j] * __ldg(c.invstd_g + lig * V + j));
-        atomicAdd(&red[2 * fint + lig * V + j], agx[j] * __ldg(c.invstd_x + lig * V + j));
-        atomicAdd(&red[3 * fint + lig * V + j], aw[j]);
+        atomicAdd(&red[0 * fw + lig * V + j], ab[j]);
+        atomicAdd(&red[1 * fw + lig * V + j], agg[j] * __ldg(c.invstd_g + lig * V + j));
+        atomicAdd(&red[2 * fw + lig * V + j], agx[j] * __ldg(c.invstd_x + lig * V + j));
+        atomicAdd(&red[3 * fw + lig * V + j], aw[j]);
       }
-      if (lig == 0) atomicAdd(&red[4 * fint], abp);
+      if (lig == 0) atomicAdd(&red[4 * fw], abp);
     }
   }
   if (det.partial != nullptr) {
@@ -319,29 +331,30 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kerne
       if (grp == gsel && has) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          red[0 * fint + lig * V + j] += ab[j];
-          red[1 * fint + lig * V + j] += agg[j] * __ldg(c.invstd_g + lig * V + j);
-          red[2 * fint + lig * V + j] += agx[j] * __ldg(c.invstd_x + lig * V + j);
-          red[3 * fint + lig * V + j] += aw[j];
+          red[0 * fw + lig * V + j] += ab[j];
+          red[1 * fw + lig * V + j] += agg[j] * __ldg(c.invstd_g + lig * V + j);
+          red[2 * fw + lig * V + j] += agx[j] * __ldg(c.invstd_x + lig * V + j);
+          red[3 * fw + lig * V + j] += aw[j];
         }
-        if (lig == 0) red[4 * fint] += abp;
+        if (lig == 0) red[4 * fw] += abp;
       }
       __syncthreads();
     }
   }
   __syncthreads();
   // partial-row layout in deterministic mode: [0, 4 fint) = sums, [4 fint, 5 fint) = dwpsi, [5 fint] = dbpsi
-  for (int i = threadIdx.x; i < fint; i += blockDim.x) {
-    red_out(sums, det, 0 * fint + i, (double)red[0 * fint + i]);   // dbeta_g
-    red_out(sums, det, 1 * fint + i, (double)red[1 * fint + i]);   // dgamma_g
-    red_out(sums, det, 2 * fint + i, (double)red[0 * fint + i]);   // dbeta_x (same upstream gradient)
-    red_out(sums, det, 3 * fint + i, (double)red[2 * fint + i]);   // dgamma_x
-    if (det.partial != nullptr) det.partial[(size_t)blockIdx.x * det.n + 4 * fint + i] = (double)red[3 * fint + i];
-    else atomicAdd(&dwpsi[i], red[3 * fint + i]);
+  for (int i = threadIdx.x; i < fw; i += blockDim.x) {
+    const int ci = c_off + i;
+    red_out(sums, det, 0 * fint + ci, (double)red[0 * fw + i]);   // dbeta_g
+    red_out(sums, det, 1 * fint + ci, (double)red[1 * fw + i]);   // dgamma_g
+    red_out(sums, det, 2 * fint + ci, (double)red[0 * fw + i]);   // dbeta_x (same upstream gradient)
+    red_out(sums, det, 3 * fint + ci, (double)red[2 * fw + i]);   // dgamma_x
+    if (det.partial != nullptr) det.partial[(size_t)blockIdx.x * det.n + 4 * fint + ci] = (double)red[3 * fw + i];
+    else atomicAdd(&dwpsi[ci], red[3 * fw + i]);
   }
-  if (threadIdx.x == 0) {
-    if (det.partial != nullptr) det.partial[(size_t)blockIdx.x * det.n + 5 * fint] = (double)red[4 * fint];
-    else atomicAdd(dbpsi, red[4 * fint]);
+  if (threadIdx.x == 0 && blockIdx.y == 0) {       // every slice sees all pixels: sum dq is taken by the first one
+    if (det.partial != nullptr) det.partial[(size_t)blockIdx.x * det.n + 5 * fint] = (double)red[4 * fw];
+    else atomicAdd(dbpsi, red[4 * fw]);
   }
 }
 
@@ -350,8 +363,8 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_reduce_kerne
 //                                           Cg = -gamma*invstd*dbeta/m - Bg*mean          (same for the x branch)
 // so only the mask coefficients and three constants per branch stay in registers.  Also accumulates the column sums
 // of the ROUNDED outputs = bias gradients of the W_g / W_x convolutions (dbias[0][c], dbias[1][c]).
-template <int V>
-__global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_apply_kernel(
+template <int V, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB) gate_psi_bwd_apply_kernel(
     const float* __restrict__ dsig, const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ g1p,
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int tpp, int rows, GateBwdCoef c,
     const double* __restrict__ sums1, int training, const double* __restrict__ sums,
@@ -359,21 +372,27 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_apply_kernel
     float* __restrict__ dbn1, float* __restrict__ dbias, DetBuf det) {
   using VT = typename GVec<V>::T;
   __shared__ float red[256 * V];
+  // gridDim.y channel slices of tpp * V channels (see the reduce kernel)
+  const int c_off = blockIdx.y * (tpp * V);
+  g1p += c_off;
+  x1p += c_off;
+  dg1p += c_off;
+  dx1p += c_off;
   const int gch = threadIdx.x % tpp, r = threadIdx.x / tpp;
-  const bool active = r < rows;
+  const bool active = r < rows && c_off + gch * V < fint;
   float bsg[V], bsx[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) bsg[j] = bsx[j] = 0.f;
   if (active) {
     float sg[V], hg[V], sx[V], hx[V], wg[V], bg[V], cg[V], wx[V], bx[V], cx[V];
-    gv_loadf<V>(c.scale_g + gch * V, true, sg);
-    gv_loadf<V>(c.shift_g + gch * V, true, hg);
-    gv_loadf<V>(c.scale_x + gch * V, true, sx);
-    gv_loadf<V>(c.shift_x + gch * V, true, hx);
+    gv_loadf<V>(c.scale_g + c_off + gch * V, true, sg);
+    gv_loadf<V>(c.shift_g + c_off + gch * V, true, hg);
+    gv_loadf<V>(c.scale_x + c_off + gch * V, true, sx);
+    gv_loadf<V>(c.shift_x + c_off + gch * V, true, hx);
     const double inv_m = 1.0 / (double)npix;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      const int ch = gch * V + j;
+      const int ch = c_off + gch * V + j;
       const float wp = bf16_round(__ldg(c.wpsi + ch));
       const float igv = __ldg(c.invstd_g + ch), mgv = __ldg(c.mean_g + ch);
       const float ixv = __ldg(c.invstd_x + ch), mxv = __ldg(c.mean_x + ch);
@@ -395,14 +414,14 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_apply_kernel
         dgamma_beta[3 * fint + ch] = (float)dbg;
       }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
       dbn1[0] = (float)sums1[1];   // dgamma1
       dbn1[1] = (float)sums1[0];   // dbeta1
     }
     const float g1 = __ldg(c.gamma1), mu1 = __ldg(c.mean1), is1 = __ldg(c.invstd1);
     const float k0 = (float)(sums1[0] * inv_m), k1 = (float)(sums1[1] * inv_m);
     const long long stride = (long long)gridDim.x * rows;
-    constexpr int U = 2;                      // pixels in flight per thread
+    // U pixels in flight per thread
     for (long long p0 = (long long)blockIdx.x * rows + r; p0 < npix; p0 += U * stride) {
       VT gv[U], xv[U];
       float ds[U], qv[U];
@@ -462,7 +481,7 @@ __global__ void __launch_bounds__(256, V == 8 ? 2 : 3) gate_psi_bwd_apply_kernel
         for (int j = 0; j < V; ++j) {
           float s = 0.f;
           for (int rr = 0; rr < rows; ++rr) s += red[(rr * tpp + gch) * V + j];
-          red_out(dbias, det, which * fint + gch * V + j, s);
+          red_out(dbias, det, which * fint + c_off + gch * V + j, s);
         }
       }
     }
@@ -563,21 +582,29 @@ extern "C" int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const vo
                                       float* dbpsi, b2_stream_t stream) {
   B2_REQUIRE(fint % 8 == 0 && fint <= 256, B2_ERR_SHAPE, "F_int=%d must be a multiple of 8, <= 256", fint);
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld), B2_ERR_ALIGN, "gate operands misaligned");
-  const size_t smem = (size_t)(4 * fint + 1) * sizeof(float);
   const bool light = gate_light(fint);
-  const int L = g_pow2ceil(fint / (light ? 4 : 8));
-  const int grid = g_grid(npix, 256 / L, light ? 8 : 4);
+  // 64-channel slices (gridDim.y) once F_int exceeds one: 16 threads per pixel, 16 pixels per block iteration
+  const int slice = (light && fint > 64 && env_switch("B200SEG_GATE_SLICE", 1) != 0) ? 64 : 0;
+  const int slices = slice ? (fint + slice - 1) / slice : 1;
+  const size_t smem = (size_t)(4 * (slice ? slice : fint) + 1) * sizeof(float);
+  const int L = g_pow2ceil((slice ? slice : fint) / (light ? 4 : 8));
+  int grid = g_grid(npix, 256 / L, light ? 8 : 4);
+  grid = (grid + slices - 1) / slices;
   DetBuf det;
   int rc = det_begin(&det, grid, 5 * fint + 1, (cudaStream_t)stream);
   if (rc) return rc;
-  if (light) {
-    gate_psi_bwd_reduce_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  if (light && env_switch("B200SEG_GATE_U", fint <= 128 ? 4 : 2) == 4) {
+    gate_psi_bwd_reduce_kernel<4, 4, 2><<<dim3(grid, slices), 256, smem, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, det);
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det);
+  } else if (light) {
+    gate_psi_bwd_reduce_kernel<4, 2, 3><<<dim3(grid, slices), 256, smem, (cudaStream_t)stream>>>(
+        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det);
   } else {
-    gate_psi_bwd_reduce_kernel<8><<<grid, 256, smem, (cudaStream_t)stream>>>(
+    gate_psi_bwd_reduce_kernel<8, 2, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, det);
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, 0, det);
   }
   B2_LAUNCH_CHECK();
   if (det.partial) {
@@ -599,8 +626,14 @@ extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const voi
   B2_REQUIRE(g_al(g1p, ld) && g_al(x1p, ld) && g_al(dg1p, ld) && g_al(dx1p, ld), B2_ERR_ALIGN,
              "gate operands misaligned");
   const bool light = gate_light(fint);
-  const int tpp = fint / (light ? 4 : 8), rows = 256 / tpp;
-  const int grid = g_grid(npix, rows, 16);
+  int tpp = fint / (light ? 4 : 8), slices = 1;
+  if (light && fint > 64 && env_switch("B200SEG_GATE_SLICE", 1) != 0) {
+    tpp = 16;                                     // 64-channel slices
+    slices = (fint + 63) / 64;
+  }
+  const int rows = 256 / tpp;
+  int grid = g_grid(npix, rows, 8);
+  grid = (grid + slices - 1) / slices;
   DetBuf det;
   det.partial = nullptr;
   det.n = 2 * fint;
@@ -608,13 +641,18 @@ extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const voi
     int rc = det_begin(&det, grid, 2 * fint, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  if (light) {
-    gate_psi_bwd_apply_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  if (light && env_switch("B200SEG_GATE_U", fint <= 128 ? 4 : 2) == 4) {
+    gate_psi_bwd_apply_kernel<4, 4, 2><<<dim3(grid, slices), 256, 0, (cudaStream_t)stream>>>(
+        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
+        rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
+        dbias, det);
+  } else if (light) {
+    gate_psi_bwd_apply_kernel<4, 2, 3><<<dim3(grid, slices), 256, 0, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
         rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
         dbias, det);
   } else {
-    gate_psi_bwd_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    gate_psi_bwd_apply_kernel<8, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
         rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
         dbias, det);

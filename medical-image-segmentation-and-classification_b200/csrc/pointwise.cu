@@ -116,7 +116,8 @@ __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int l
 // arg-max recomputed from the saved input; first maximum in window scan order wins (ATen's tie rule)
 __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                       const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int cg,
-                                      __nv_bfloat16* __restrict__ dx, int lddx) {
+                                      __nv_bfloat16* __restrict__ dx, int lddx,
+                                      const __nv_bfloat16* __restrict__ addend, int ldadd) {
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -146,6 +147,16 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k][j] = (k == best) ? d[j] : 0.f;
+    }
+    if (addend != nullptr) {     // dx = pool gradient + the gradient x received from its other consumer (one rounding)
+      float a[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        unpack8p(__ldg(reinterpret_cast<const uint4*>(addend + off[k] * ldadd + g * 8)), a[k]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[k][j] += a[k][j];
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dx + off[k] * lddx + g * 8) = pack8p(o[k]);
@@ -346,7 +357,22 @@ extern "C" int b2_maxpool2x2_bwd(const void* dy, int32_t lddy, const void* x, in
   B2_REQUIRE(al16(x, ldx) && al16(dy, lddy) && al16(dx, lddx), B2_ERR_ALIGN, "maxpool operands misaligned");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
   maxpool2x2_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx);
+      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx, nullptr,
+      0);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_maxpool2x2_bwd_add(const void* dy, int32_t lddy, const void* x, int32_t ldx, int32_t n, int32_t h,
+                                     int32_t w, int32_t c, const void* addend, int32_t ldadd, void* dx, int32_t lddx,
+                                     b2_stream_t stream) {
+  B2_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, B2_ERR_SHAPE, "maxpool needs c%%8==0 and even h,w");
+  B2_REQUIRE(al16(x, ldx) && al16(dy, lddy) && al16(dx, lddx) && addend != nullptr && al16(addend, ldadd),
+             B2_ERR_ALIGN, "maxpool operands misaligned / addend missing");
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  maxpool2x2_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx,
+      (const __nv_bfloat16*)addend, ldadd);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

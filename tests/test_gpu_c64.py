@@ -149,3 +149,61 @@ def test_c64_deterministic_mode_is_bitwise_reproducible():
         K.set_deterministic(False)
     for y, s in outs[1:]:
         assert torch.equal(y, outs[0][0]) and torch.equal(s, outs[0][1])
+
+
+# folded UpConv with Cout = 64 (the Up2 level): n, coarse h, coarse w, cin
+FOLD_CASES = [
+    (10, 128, 128, 128),      # the AttU_Net Up2 shape, smaller batch
+    (5, 251, 128, 64),        # odd height, one channel block
+    (3, 150, 256, 128),       # two column segments per row
+    (300, 4, 128, 64),        # four-row images: strips with the top and bottom edge
+    (37, 33, 128, 128),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin", FOLD_CASES)
+def test_c64_folded_upconv_fprop_matches_reference_and_generic_kernel(n, h, w, cin):
+    """The merged folded-UpConv fprop (Upsample x2 -> conv3x3, AttentionUNet.py:15-27) through the row-streaming kernel
+    (column phase per CTA, four fine rows per coarse input row, N = 256) against Upsample + conv2d in fp32 and against
+    the generic kernel's merged launch (B200SEG_C64_FOLD=0)."""
+    from b200seg import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(h + w + cin)
+    x = torch.randn(n, cin, h, w, device="cuda", generator=g)
+    wt = torch.randn(64, cin, 3, 3, device="cuda", generator=g) / (cin * 9) ** 0.5
+    b = torch.randn(64, device="cuda", generator=g)
+    xb = nhwc(x)
+    wf, _ = K.pack_weights_upfold(wt, want_dgrad=False)
+
+    def run():
+        stats = torch.zeros(2, 64, dtype=torch.float64, device="cuda")
+        z = torch.full((n, 2 * h, 2 * w, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+        K.conv_igemm(xb, wf.view(16, 64, cin), 64, 2, bias=b, stats=stats, out=z, fold=1)
+        torch.cuda.synchronize()
+        return z, stats
+
+    z, stats = run()
+    os.environ["B200SEG_C64_FOLD"] = "0"
+    K.reload_switches()
+    try:
+        zg, stats_g = run()
+    finally:
+        del os.environ["B200SEG_C64_FOLD"]
+        K.reload_switches()
+    assert torch.isfinite(z.float()).all()
+    # both kernels accumulate the same bf16 products in fp32: they differ by summation order only
+    assert rel(nchw(z), nchw(zg)) < 2e-3
+    # fp32 reference on the folded (fp32-summed, bf16-rounded) weights: phase (a, b) = 2x2 conv of the coarse input
+    ref = torch.empty(n, 64, 2 * h, 2 * w, device="cuda")
+    xf = nchw(xb)
+    for ph, (a, bb) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        wp = wf[ph].float().view(2, 2, 64, cin).permute(2, 3, 0, 1)          # [cout, cin, ty, tx]
+        xp = F.pad(xf, (1 - bb, bb, 1 - a, a))
+        ref[:, :, a::2, bb::2] = F.conv2d(xp, wp, b)
+    assert rel(nchw(z), ref) < 4e-3, rel(nchw(z), ref)
+    # the literal op on the unfolded weights (bf16 rounding of the summed taps differs): looser
+    lit = F.conv2d(F.interpolate(xf, scale_factor=2, mode="nearest"), wt.to(torch.bfloat16).float(), b, padding=1)
+    assert rel(nchw(z), lit) < 1e-2
+    # statistics of the rounded outputs
+    zf = z.double().reshape(-1, 64)
+    assert rel(stats[0], zf.sum(0)) < 1e-6 and rel(stats[1], (zf * zf).sum(0)) < 1e-6
+    assert rel(stats, stats_g) < 1e-4
