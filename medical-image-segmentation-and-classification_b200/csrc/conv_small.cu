@@ -152,27 +152,34 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[co][j] = (has && co < cout) ? bf16_round(w[co * cin + lig * 8 + j]) : 0.f;
   // block-uniform trip count so the full-mask shuffles below are always executed by every lane
-  for (long long base = (long long)blockIdx.x * gpb; base < npix; base += (long long)gridDim.x * gpb) {
-    const long long p = base + grp;
-    const bool live = p < npix;
-    float f[8];
-    if (has && live) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * ldx + lig * 8));
-      f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
-      f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
-    } else {
+  constexpr int U = 2;                          // pixels in flight per thread
+  const long long stride = (long long)gridDim.x * gpb;
+  for (long long base = (long long)blockIdx.x * gpb; base < npix; base += U * stride) {
+    uint4 u[U];
+    bool live[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    for (int k = 0; k < U; ++k) {
+      const long long p = base + k * stride + grp;
+      live[k] = p < npix;
+      u[k] = (has && live[k]) ? __ldg(reinterpret_cast<const uint4*>(x + p * ldx + lig * 8)) : make_uint4(0, 0, 0, 0);
     }
-    const long long b = p / hw, r = p % hw;
 #pragma unroll
-    for (int co = 0; co < CO; ++co) {
-      if (co < cout) {
-        float s = 0.f;
+    for (int k = 0; k < U; ++k) {
+      const long long p = base + k * stride + grp;
+      float f[8];
+      f[0] = bf16lo(u[k].x); f[1] = bf16hi(u[k].x); f[2] = bf16lo(u[k].y); f[3] = bf16hi(u[k].y);
+      f[4] = bf16lo(u[k].z); f[5] = bf16hi(u[k].z); f[6] = bf16lo(u[k].w); f[7] = bf16hi(u[k].w);
+      // (pixel counts are far below 2^31: 32-bit division)
+      const unsigned b = (unsigned)p / (unsigned)hw, r = (unsigned)p - b * (unsigned)hw;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s = fmaf(f[j], wr[co][j], s);
-        for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lig == 0 && live) y[(b * cout + co) * hw + r] = s + (bias ? bias[co] : 0.f);
+      for (int co = 0; co < CO; ++co) {
+        if (co < cout) {
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s = fmaf(f[j], wr[co][j], s);
+          for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (lig == 0 && live[k]) y[((long long)b * cout + co) * hw + r] = s + (bias ? bias[co] : 0.f);
+        }
       }
     }
   }
@@ -202,35 +209,48 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
       aw[co][j] = 0.f;
     }
   }
-  for (long long p = (long long)blockIdx.x * gpb + grp; p < npix; p += (long long)gridDim.x * gpb) {
-    const long long b = p / hw, r = p % hw;
-    float f[8], g[8];
-    if (has) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * ldx + lig * 8));
-      f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
-      f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
-    } else {
+  constexpr int U = CO <= 2 ? 4 : 2;            // pixels in flight per thread (loads issued before the math)
+  const long long pstride = (long long)gridDim.x * gpb;
+  for (long long p0 = (long long)blockIdx.x * gpb + grp; p0 < npix; p0 += U * pstride) {
+    uint4 xu[U];
+    float dv[U][CO];
+    bool live[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    for (int k = 0; k < U; ++k) {
+      const long long p = p0 + k * pstride;
+      live[k] = p < npix;
+      const long long pc = live[k] ? p : p0;
+      const long long b = (unsigned)pc / (unsigned)hw, r = (unsigned)pc - (unsigned)b * (unsigned)hw;   // npix < 2^31
+      xu[k] = has ? __ldg(reinterpret_cast<const uint4*>(x + pc * ldx + lig * 8)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int co = 0; co < CO; ++co) dv[k][co] = (co < cout && live[k]) ? __ldg(dy + (b * cout + co) * hw + r) : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    for (int k = 0; k < U; ++k) {
+      if (!live[k]) continue;
+      const long long p = p0 + k * pstride;
+      float f[8], g[8];
+      f[0] = bf16lo(xu[k].x); f[1] = bf16hi(xu[k].x); f[2] = bf16lo(xu[k].y); f[3] = bf16hi(xu[k].y);
+      f[4] = bf16lo(xu[k].z); f[5] = bf16hi(xu[k].z); f[6] = bf16lo(xu[k].w); f[7] = bf16hi(xu[k].w);
 #pragma unroll
-    for (int co = 0; co < CO; ++co) {
-      if (co < cout) {
-        const float d = __ldg(dy + (b * cout + co) * hw + r);
-        if (lig == 0) ab[co] += d;
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          g[j] = fmaf(d, wr[co][j], g[j]);
-          aw[co][j] = fmaf(d, f[j], aw[co][j]);
+      for (int co = 0; co < CO; ++co) {
+        if (co < cout) {
+          const float d = dv[k][co];
+          if (lig == 0) ab[co] += d;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            g[j] = fmaf(d, wr[co][j], g[j]);
+            aw[co][j] = fmaf(d, f[j], aw[co][j]);
+          }
         }
       }
-    }
-    if (has && dx != nullptr) {
-      *reinterpret_cast<uint4*>(dx + p * lddx + lig * 8) =
-          make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
-                     pack_bf16x2(g[6], g[7]));
+      if (has && dx != nullptr) {
+        *reinterpret_cast<uint4*>(dx + p * lddx + lig * 8) =
+            make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                       pack_bf16x2(g[6], g[7]));
+      }
     }
   }
   if (det.partial == nullptr) {
@@ -328,6 +348,7 @@ extern "C" int b2_head_fwd(const void* x, int32_t ldx, int64_t npix, int32_t hw,
                            const float* bias, int32_t cout, float* y, b2_stream_t stream) {
   B2_REQUIRE(cin % 8 == 0 && cin <= 256, B2_ERR_SHAPE, "head cin=%d must be a multiple of 8, <= 256", cin);
   B2_REQUIRE(cout >= 1 && cout <= 8, B2_ERR_SHAPE, "head cout=%d must be in 1..8", cout);
+  B2_REQUIRE(npix > 0 && npix < (1ll << 31) && hw > 0, B2_ERR_SHAPE, "head: pixel count out of range");
   B2_REQUIRE(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, B2_ERR_ALIGN, "x misaligned");
   const int L = pow2ceil(cin / 8);
   const int gpb = 256 / L;
@@ -347,13 +368,15 @@ extern "C" int b2_head_bwd(const float* dy, const void* x, int32_t ldx, int64_t 
                            b2_stream_t stream) {
   B2_REQUIRE(cin % 8 == 0 && cin <= 256, B2_ERR_SHAPE, "head cin=%d must be a multiple of 8, <= 256", cin);
   B2_REQUIRE(cout >= 1 && cout <= 8, B2_ERR_SHAPE, "head cout=%d must be in 1..8", cout);
+  B2_REQUIRE(npix > 0 && npix < (1ll << 31) && hw > 0, B2_ERR_SHAPE, "head: pixel count out of range");
   B2_REQUIRE(ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, B2_ERR_ALIGN, "x misaligned");
   B2_REQUIRE(dx == nullptr || (lddx % 8 == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0), B2_ERR_ALIGN,
              "dx misaligned");
   const int L = pow2ceil(cin / 8);
   const int gpb = 256 / L;
   long long grid = (npix + gpb - 1) / gpb;
-  const long long cap = (long long)num_sms() * 16;
+  // (every block ends in cout * (cin + 1) atomics on the same addresses: few, long-running blocks)
+  const long long cap = (long long)num_sms() * 6;
   if (grid > cap) grid = cap;
   const size_t smem = (size_t)(cout * cin + cout) * sizeof(float);
   DetBuf det;

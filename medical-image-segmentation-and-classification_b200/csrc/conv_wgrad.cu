@@ -402,6 +402,39 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   *reinterpret_cast<float4*>(dw + i) = acc;
 }
 
+// Small gradients (1x1 gate convolutions, Cout = 64 layers) with many splits: 32 float4 columns x 8 split lanes per block —
+// lane l adds splits l, l + 8, ..., the lanes are combined in lane order through shared memory (fixed order).  With one
+// thread per column these launches were a chain of ~150 dependent-latency loads on 2-36 blocks (30 us for 1 MB).
+__global__ void __launch_bounds__(256) wgrad_reduce_wide_kernel(const float* __restrict__ ws, float* __restrict__ dw,
+                                                                long long count, int splits, int accumulate) {
+  __shared__ float4 sh[8][32];
+  const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const long long i = ((long long)blockIdx.x * 32 + col) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < count) {
+    int s = sl;
+    for (; s + 24 < splits; s += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(ws + (size_t)(s + 8 * u) * count + i));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; s < splits; s += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (size_t)s * count + i));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  sh[sl][col] = acc;
+  __syncthreads();
+  if (sl == 0 && i < count) {
+    float4 t = accumulate ? *reinterpret_cast<const float4*>(dw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t.x += sh[k][col].x; t.y += sh[k][col].y; t.z += sh[k][col].z; t.w += sh[k][col].w; }
+    *reinterpret_cast<float4*>(dw + i) = t;
+  }
+}
+
 struct WgradPlan {
   WgradParams p;
   int splits, gy, gz, tn;
@@ -611,6 +644,10 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
   conv_wgrad_kernel<<<grid, kWgThreads, pl.smem_bytes, stream>>>(tmDY, tmX0, tmX1, pl.p);
   B2_LAUNCH_CHECK();
   const long long n4 = (pl.count + 3) / 4;
+  if (n4 <= 16384 && pl.splits >= 16)
+    wgrad_reduce_wide_kernel<<<(unsigned)((n4 + 31) / 32), 256, 0, stream>>>(pl.p.ws, a->dw, pl.count, pl.splits,
+                                                                            a->accumulate);
+  else
   wgrad_reduce_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(pl.p.ws, a->dw, pl.count, pl.splits,
                                                                        a->accumulate);
   B2_LAUNCH_CHECK();
