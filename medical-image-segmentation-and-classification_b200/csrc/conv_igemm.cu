@@ -1190,12 +1190,17 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   {
     // magic multipliers of the tile decode (fast_div): exact while dividend * divisor < 2^32
     auto magic = [](int d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
-    long long dmax = p.n_tiles;
-    if (p.tw > dmax) dmax = p.tw;
-    if (p.th > dmax) dmax = p.th;
-    const long long tmax = total > p.m_tiles ? total : p.m_tiles;
-    B2_REQUIRE(tmax * dmax < (1ll << 32) && (long long)p.m_tiles * p.m_tiles_phase < (1ll << 32), B2_ERR_SHAPE,
-               "too many tiles for the tile decode");
+    // one condition per division of the decode: items / n_tiles; tiles (of one phase) / tw; (tiles / tw) / th; and, for
+    // the merged UpConv fprop without interleaved phases only, tiles / m_tiles_phase
+    const long long lim = 1ll << 32;
+    const long long tiles1 = p.fold == 1 ? p.m_tiles_phase : p.m_tiles;
+    const bool ok_nt = p.n_tiles <= 1 || total * p.n_tiles < lim;
+    const bool ok_tw = p.tw <= 1 || tiles1 * p.tw < lim;
+    const bool ok_th = p.th <= 1 || (tiles1 / (p.tw > 0 ? p.tw : 1) + 1) * p.th < lim;
+    const bool ok_ph = !(p.fold == 1 && !p.fold_il) || (long long)p.m_tiles * p.m_tiles_phase < lim;
+    B2_REQUIRE(ok_nt && ok_tw && ok_th && ok_ph, B2_ERR_SHAPE,
+               "too many tiles for the tile decode (items %lld, n_tiles %d, m_tiles %d, tw %d, th %d)", total, p.n_tiles,
+               p.m_tiles, p.tw, p.th);
     p.mg_nt = magic(p.n_tiles);
     p.mg_tw = magic(p.tw);
     p.mg_th = magic(p.th);

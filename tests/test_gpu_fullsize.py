@@ -111,3 +111,43 @@ def test_full_batch_training_step_is_permutation_invariant():
     den = sum(float(b.double().pow(2).sum()) for b in g0)
     print(f"full-size step: loss {l0:.6f}, permuted-batch gradient difference {(num / den) ** 0.5:.2e}")
     assert (num / den) ** 0.5 < 1e-4
+
+
+def test_batch128_inference_matches_chunks():
+    """BASELINE.json configs[4] sweeps the inference batch to 512: a 128-image 256^2 batch has 65536 m-tiles per layer at
+    the top level — the tile decode's magic-multiplier divisions must stay exact there (a too-tight host check once
+    rejected these launches).  The logits of the big batch must equal those of the same images in chunks of 32."""
+    from b200seg.models.segmentation_models import R2U_Net
+    torch.manual_seed(0)
+    model = R2U_Net(t=1).cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(128, 3, 256, 256, device="cuda", generator=g)
+    with torch.no_grad():
+        big = model(x)
+        parts = torch.cat([model(x[i:i + 32]) for i in range(0, 128, 32)])
+    torch.cuda.synchronize()
+    assert torch.isfinite(big).all()
+    err = float((big.double() - parts.double()).norm() / parts.double().norm())
+    assert err < 1e-3, err
+
+
+def test_conv_igemm_accepts_128_image_batches():
+    """the generic tile kernel at the largest tile counts of the configs (N = 128 images): statistics = checksum of the
+    stored output"""
+    from b200seg import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, side, cin, cout = 128, 256, 64, 128
+    x = torch.randn(n, side, side, cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.05
+    wf, _ = K.pack_weights(w)
+    stats = torch.zeros(2, cout, dtype=torch.float64, device="cuda")
+    y = K.conv_igemm(x, wf, cout, 3, stats=stats)
+    torch.cuda.synchronize()
+    yf = y[::16].double().reshape(-1, cout)          # every 16th image against torch on the same bf16 operands
+    ref = torch.nn.functional.conv2d(x[::16].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, cout).double()
+    assert float((yf - ref).norm() / ref.norm()) < 4e-3
+    s = torch.zeros(cout, dtype=torch.float64, device="cuda")
+    for i in range(0, n, 16):
+        s += y[i:i + 16].double().reshape(-1, cout).sum(0)
+    assert float((stats[0] - s).norm() / s.norm()) < 1e-6
