@@ -112,14 +112,6 @@ struct IgemmParams {
   const float* gate_h1;
 };
 
-__device__ __forceinline__ void tma_load_5d_pair(void* smem, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1,
-                                                 int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
-      "%6, %7}], [%2];" ::"r"(smem_u32(smem)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 __device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t lbo, uint32_t sbo, uint32_t bo) {
   return umma_desc_sw128(smem_addr, lbo, sbo) | ((uint64_t)(bo & 7u) << 49);
 }

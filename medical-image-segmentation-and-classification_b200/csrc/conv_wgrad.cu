@@ -18,6 +18,11 @@
 // of the absolute shared-memory address, so the shifted view reads the right bytes.  The kernel is bound by the bytes
 // it pulls through the L2 -> SM fabric; this halves them (64 -> 33 KB per chunk): 128->128 @128^2 0.378 -> 0.226 ms
 // (1367 TFLOP/s), 64->64 @256^2 0.720 -> 0.308 ms.
+// CTA pairs (3x3 halo mode, Cout a multiple of 256, an even number of X blocks): the kernel is bound by shared-memory
+// bandwidth — an M = 128 x N = 128 MMA reads 4 KB of dY and 4 KB of X per 64 issue clocks, the whole operand port, while
+// TMA writes the next stage into the same memory.  tcgen05.mma.cta_group::2 runs M = 256 over two SMs: each CTA holds its
+// own Cout tile of dY and HALF of the X operand (one of the two halo boxes), so a CTA reads 4 + 2 KB per MMA and
+// receives 24 instead of 32.5 KB per stage.
 // Split-K over pixel chunks across CTAs; partial tiles go to a workspace and a second kernel reduces them in a fixed
 // order (deterministic), optionally accumulating into dW (shared weights of Recurrent_block, R2U_Net.py:15-20).
 #include <stdlib.h>
@@ -60,6 +65,7 @@ struct WgradParams {
                      // the box (the 128B swizzle is a function of the absolute smem address).  Halves the bytes a
                      // CTA pulls through the L2 -> SM fabric.  nbox = boxes per stage (2), kXhBox bytes apart.
   int nbox;
+  int pair;          // CTA pair (cta_group::2): blockIdx.x = rank + 2 * (rg + gy * (co pair + co pairs * channel group))
   int fold;          // merged folded-UpConv weight gradient (b2_wgrad_args::fold): dY is the FINE tensor, phase (a, b) its
                      // (2h+a, 2w+b) sub-lattice; a CTA owns (a, filter row ty) = blockIdx % 4, loads the b = 0 and b = 1
                      // sub-lattice tiles and ONE halo row of X (coarse row h + a + ty - 1), and tap (b, tx) is the MMA
@@ -72,6 +78,9 @@ struct WgradParams {
   float* ws;         // [splits][cout][taps][ctot]
 };
 
+// kPair is a separate instantiation: a kernel that contains cta_group::2 instructions can only be launched as 2-CTA
+// clusters, so the single-CTA kernel must not contain them.
+template <bool kPair>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
                   const __grid_constant__ CUtensorMap tmX1, const WgradParams p) {
@@ -90,11 +99,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   // CTAs that read the same pixels (same split; different filter row / channel group) have adjacent block indices,
   // so they run in the same wave and the dY / X chunks they share are fetched from DRAM once
   const int split = blockIdx.y;
-  const int rg = blockIdx.x % p.gy;                   // filter row (3x3) or 0
-  const int zz = blockIdx.x / p.gy;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;     // pair: rank 0 issues the MMAs
+  const int bx = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int rg = bx % p.gy;                           // filter row (3x3) or 0
+  const int zz = bx / p.gy;
   const int co_tiles = (p.cout + 127) / 128;
-  const int co_tile = zz % co_tiles;
-  const int cgrp = zz / co_tiles;                     // channel-block group
+  const int co_groups = kPair ? co_tiles / 2 : co_tiles;
+  const int co_tile = kPair ? 2 * (zz % co_groups) + (int)crank : zz % co_groups;
+  const int cgrp = zz / co_groups;                    // channel-block group
   const int cib_base = cgrp * p.cpb;
   const int cbt = p.cb0 + p.cb1;
 
@@ -115,11 +127,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   }
   const uint32_t tmem_cols = (p.fold == 1 ? 4 * p.cpb : p.fold == 2 ? 3 * p.cpb : p.ncolb) * 64 > 256 ? 512u : 256u;
   if (warp == 1) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if constexpr (kPair) {
+      tmem_alloc_pair(tmem_slot, tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();       // the peer's barriers are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -147,6 +165,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         if (elect_one()) {
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + p.a_bytes;
+          if constexpr (kPair) {
+            // both CTAs load into their own shared memory — their Cout tile of dY and ONE of the two X halo boxes —
+            // and the bytes are counted on the LEADER's barrier, which only the leader arms
+            const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0)
+              mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)(2 * kBoxBytes + (p.Wb + 2) * p.Hb * 128));
+            tma_load_5d_pair(sa, &tmDY, lbar, 0, w0, h0, n0, co_tile * 2);
+            const int cib = cib_base + (int)crank;
+            if (cib < p.cb0)
+              tma_load_4d_pair(sb, &tmX0, lbar, cib * 64, w0 - p.pad_w, h0 + rg - p.pad_h, n0);
+            else
+              tma_load_4d_pair(sb, &tmX1, lbar, (cib - p.cb0) * 64, w0 - p.pad_w, h0 + rg - p.pad_h, n0);
+          } else
           if (p.debug_skip & 1) {
             mbar_arrive(&full_bar[stage]);
           } else if (p.fold) {
@@ -212,7 +243,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && !(kPair && crank != 0)) {
     if (nchunks > 0) {
       // up to 6 column blocks (3x3: two 64-channel X blocks x three taps): N <= 256 per instruction, so the columns
       // are issued as two MMAs that share the dY tile (A) and write adjacent TMEM column ranges
@@ -241,6 +272,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           uint32_t b_lo = desc_lo0 + (b_addr >> 4);
           const uint32_t b1_off = (uint32_t)(ncol0 * kBoxBytes) >> 4;
           const int nk = (p.debug_skip & 2) ? 0 : kChunkPix / 16;
+          if constexpr (kPair) {
+            // M = 256 over the pair: three taps x four K steps, B = one halo box per CTA (N = 128 in all)
+            const uint32_t bx_lo = descx_lo0 + (b_addr >> 4);
+            const uint32_t idescp = umma_idesc_bf16(256, 128, 1, 1);
+#pragma unroll
+            for (int k = 0; k < kChunkPix / 16; ++k) {
+              const uint64_t da = desc_hi | (uint64_t)(a_lo + 128u * k);
+              const uint32_t koff = (uint32_t)(((16 * k) / p.Wb) * (p.Wb + 2) + (16 * k) % p.Wb) * 8u;
+#pragma unroll
+              for (int tp = 0; tp < 3; ++tp)
+                umma_bf16_pair(tmem_base + tp * 128u, da, descx_hi | (uint64_t)(bx_lo + 8u * tp + koff), idescp,
+                               (it | k) != 0 ? 1u : 0u);
+            }
+          } else
           if (p.fold == 1) {
             // taps (b, tx): A = the b sub-lattice tile, B = the halo boxes shifted by b + tx pixels
             const uint32_t bx_lo = descx_lo0 + (b_addr >> 4);
@@ -289,7 +334,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                           idesc1, (it | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (kPair) umma_commit_pair(&empty_bar[stage], 3);     // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -297,10 +343,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(tmem_full_bar);
+      if (elect_one()) {
+        if constexpr (kPair) umma_commit_pair(tmem_full_bar, 3);           // both CTAs drain their half of M = 256
+        else umma_commit(tmem_full_bar);
+      }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2) {
     // epilogue: row = output channel within the tile; columns = (column block, channel)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
@@ -377,7 +426,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if constexpr (kPair) cluster_sync_all();       // no CTA leaves while its peer may still signal its barriers
+  if (warp == 1) {
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 // dw[i] = (accumulate ? dw[i] : 0) + sum_s ws[s][i]   (fixed summation order)
@@ -549,7 +602,10 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
                  a->w, p.Wb, p.Hb, p.Nb);
     }
   }
-  p.b_stage_bytes = p.xh ? p.nbox * kXhBox : p.ncolb * kBoxBytes;
+  // CTA pairs: 3x3 halo mode, two Cout tiles per pair, each CTA holds one of the two X boxes
+  p.pair = (env_switch("B200SEG_WG_PAIR", 1) != 0 && p.xh && a->ksize == 3 && !p.rowpair && !p.fold && p.cpb == 2 &&
+            a->cout % 256 == 0 && cbt % 2 == 0 && p.debug_skip == 0) ? 1 : 0;
+  p.b_stage_bytes = p.pair ? kXhBox : (p.xh ? p.nbox * kXhBox : p.ncolb * kBoxBytes);
   const int stage_bytes = p.a_bytes + p.b_stage_bytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
@@ -629,19 +685,40 @@ extern "C" int b2_conv_wgrad(const b2_wgrad_args* a, b2_stream_t stream_) {
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(conv_wgrad_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
       // Ask for the full 228 KB shared-memory carveout even when a launch needs less: the driver otherwise picks the
       // smallest configuration that fits this kernel (196 KB for 194 KB used), and the memory-bound kernels meant to
       // run next to it on the side-stream schedule (BatchNorm backward, gate) find no shared memory left on the SM.
       if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(conv_wgrad_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
       attr_err = e;
     });
     B2_CHECK_CUDA(attr_err);
   }
   dim3 grid(pl.gy * pl.gz, pl.splits, 1);
-  conv_wgrad_kernel<<<grid, kWgThreads, pl.smem_bytes, stream>>>(tmDY, tmX0, tmX1, pl.p);
+  if (pl.p.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = (size_t)pl.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_wgrad_kernel<true>, tmDY, tmX0, tmX1, pl.p));
+  } else {
+    conv_wgrad_kernel<false><<<grid, kWgThreads, pl.smem_bytes, stream>>>(tmDY, tmX0, tmX1, pl.p);
+  }
   B2_LAUNCH_CHECK();
   const long long n4 = (pl.count + 3) / 4;
   if (n4 <= 16384 && pl.splits >= 16)

@@ -138,3 +138,41 @@ def test_pair_mode_whole_model_step():
             assert torch.equal(g0[k], g1[k]), k              # tensor-core weight gradients: deterministic on identical inputs
         else:
             assert torch.allclose(g0[k], g1[k], rtol=1e-4, atol=1e-7), k
+
+
+WG_SHAPES = [
+    # n, h, w, cin, cout: Cout a multiple of 256, an even number of 64-channel X blocks
+    (2, 64, 64, 128, 256),
+    (3, 32, 32, 256, 512),
+    (2, 16, 16, 512, 1024),
+    (64, 16, 16, 256, 256),       # many pixel chunks: several splits per pair
+    (1, 20, 28, 128, 256),        # clipped chunks
+    (2, 64, 64, 192, 256),        # an odd number of X blocks: the pair mode must step aside
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", WG_SHAPES)
+def test_wgrad_pair_mode_matches_single_cta(n, h, w, cin, cout):
+    """CTA-pair weight gradient (conv_wgrad_kernel<true>: tcgen05.mma.cta_group::2, M = 256 = two Cout tiles, each CTA
+    holding one of the two X halo boxes) against the single-CTA kernel (B200SEG_WG_PAIR=0) and the fp32 reference.
+    Both accumulate the pixel chunks of a split in the same order, so the results are bit-identical."""
+    import torch.nn.functional as F
+    from b200seg import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = nhwc(torch.randn(n, cin, h, w, device="cuda", generator=g))
+    dy = nhwc(torch.randn(n, cout, h, w, device="cuda", generator=g))
+    pair = K.conv_wgrad(dy, x, 3)
+    os.environ["B200SEG_WG_PAIR"] = "0"
+    K.reload_switches()
+    try:
+        single = K.conv_wgrad(dy, x, 3)
+    finally:
+        del os.environ["B200SEG_WG_PAIR"]
+        K.reload_switches()
+    torch.cuda.synchronize()
+    assert torch.equal(pair, single)
+    ref = torch.nn.grad.conv2d_weight(x.float().permute(0, 3, 1, 2), (cout, cin, 3, 3), dy.float().permute(0, 3, 1, 2),
+                                      padding=1)
+    got = pair.reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    err = float((got.double() - ref.double()).norm() / ref.double().norm())
+    assert err < 1e-3, err
