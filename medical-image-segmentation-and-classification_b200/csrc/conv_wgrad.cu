@@ -170,13 +170,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             // and the bytes are counted on the LEADER's barrier, which only the leader arms
             const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (crank == 0)
-              mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)(2 * kBoxBytes + (p.Wb + 2) * p.Hb * 128));
-            tma_load_5d_pair(sa, &tmDY, lbar, 0, w0, h0, n0, co_tile * 2);
+              mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)(p.a_bytes + (p.Wb + 2) * p.Hb * 128));
             const int cib = cib_base + (int)crank;
+            int xrow = h0 + rg - p.pad_h, xcol = w0 - p.pad_w;
+            if (p.fold) {          // merged folded UpConv (fold == 1): both column-phase tiles of dY, X row h + a + ty - 1
+              const int fa = rg >> 1, fty = rg & 1;
+              for (int b = 0; b < 2; ++b)
+                tma_load_5d_pair(sa + b * 2 * kBoxBytes, &tmDY, lbar, 0, 2 * w0 + b, 2 * h0 + fa, n0, co_tile * 2);
+              xrow = h0 + fa + fty - 1;
+              xcol = w0 - 1;
+            } else {
+              tma_load_5d_pair(sa, &tmDY, lbar, 0, w0, h0, n0, co_tile * 2);
+            }
             if (cib < p.cb0)
-              tma_load_4d_pair(sb, &tmX0, lbar, cib * 64, w0 - p.pad_w, h0 + rg - p.pad_h, n0);
+              tma_load_4d_pair(sb, &tmX0, lbar, cib * 64, xcol, xrow, n0);
             else
-              tma_load_4d_pair(sb, &tmX1, lbar, (cib - p.cb0) * 64, w0 - p.pad_w, h0 + rg - p.pad_h, n0);
+              tma_load_4d_pair(sb, &tmX1, lbar, (cib - p.cb0) * 64, xcol, xrow, n0);
           } else
           if (p.debug_skip & 1) {
             mbar_arrive(&full_bar[stage]);
@@ -278,12 +287,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
             const uint32_t idescp = umma_idesc_bf16(256, 128, 1, 1);
 #pragma unroll
             for (int k = 0; k < kChunkPix / 16; ++k) {
-              const uint64_t da = desc_hi | (uint64_t)(a_lo + 128u * k);
               const uint32_t koff = (uint32_t)(((16 * k) / p.Wb) * (p.Wb + 2) + (16 * k) % p.Wb) * 8u;
+              if (p.fold) {        // taps (b, tx): A = the b sub-lattice tile, B shifted by b + tx pixels
 #pragma unroll
-              for (int tp = 0; tp < 3; ++tp)
-                umma_bf16_pair(tmem_base + tp * 128u, da, descx_hi | (uint64_t)(bx_lo + 8u * tp + koff), idescp,
-                               (it | k) != 0 ? 1u : 0u);
+                for (int b = 0; b < 2; ++b) {
+                  const uint64_t da = desc_hi | (uint64_t)(a_lo + (uint32_t)b * ((2u * kBoxBytes) >> 4) + 128u * k);
+#pragma unroll
+                  for (int tx = 0; tx < 2; ++tx)
+                    umma_bf16_pair(tmem_base + (uint32_t)(b * 2 + tx) * 128u, da,
+                                   descx_hi | (uint64_t)(bx_lo + 8u * (uint32_t)(b + tx) + koff), idescp,
+                                   (it | k) != 0 ? 1u : 0u);
+                }
+              } else {
+                const uint64_t da = desc_hi | (uint64_t)(a_lo + 128u * k);
+#pragma unroll
+                for (int tp = 0; tp < 3; ++tp)
+                  umma_bf16_pair(tmem_base + tp * 128u, da, descx_hi | (uint64_t)(bx_lo + 8u * tp + koff), idescp,
+                                 (it | k) != 0 ? 1u : 0u);
+              }
             }
           } else
           if (p.fold == 1) {
@@ -603,8 +624,8 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
     }
   }
   // CTA pairs: 3x3 halo mode, two Cout tiles per pair, each CTA holds one of the two X boxes
-  p.pair = (env_switch("B200SEG_WG_PAIR", 1) != 0 && p.xh && a->ksize == 3 && !p.rowpair && !p.fold && p.cpb == 2 &&
-            a->cout % 256 == 0 && cbt % 2 == 0 && p.debug_skip == 0) ? 1 : 0;
+  p.pair = (env_switch("B200SEG_WG_PAIR", 1) != 0 && p.xh && (a->ksize == 3 || p.fold == 1) && !p.rowpair && p.fold != 2 &&
+            p.cpb == 2 && a->cout % 256 == 0 && cbt % 2 == 0 && p.debug_skip == 0) ? 1 : 0;
   p.b_stage_bytes = p.pair ? kXhBox : (p.xh ? p.nbox * kXhBox : p.ncolb * kBoxBytes);
   const int stage_bytes = p.a_bytes + p.b_stage_bytes;
   int stages = (200 * 1024) / stage_bytes;
