@@ -65,6 +65,12 @@ struct WgradParams {
                      // the box (the 128B swizzle is a function of the absolute smem address).  Halves the bytes a
                      // CTA pulls through the L2 -> SM fabric.  nbox = boxes per stage (2), kXhBox bytes apart.
   int nbox;
+  int tapn;          // X-halo mode, single CTA: the three taps of one halo box are ONE N = 192 MMA — N blocks one pixel
+                     // (128 B) apart, i.e. a descriptor with LBO = 128 B over the overlapping shifted views — instead of
+                     // three N = 128 MMAs over both boxes: the dY slice is read twice instead of three times per K step
+                     // (the kernel is bound by shared-memory operand bandwidth).  Accumulators [box][tap][64].
+                     // MEASURED SLOWER (B200SEG_WG_TAPN=1, off by default): 64->64 @256^2 0.339 -> 0.372 ms, 128->128
+                     // @128^2 0.259 -> 0.288 ms — the overlapping N blocks cost more than the saved dY reads.
   int pair;          // CTA pair (cta_group::2): blockIdx.x = rank + 2 * (rg + gy * (co pair + co pairs * channel group))
   int fold;          // merged folded-UpConv weight gradient (b2_wgrad_args::fold): dY is the FINE tensor, phase (a, b) its
                      // (2h+a, 2w+b) sub-lattice; a CTA owns (a, filter row ty) = blockIdx % 4, loads the b = 0 and b = 1
@@ -326,6 +332,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                 }
               }
             }
+          } else if (p.xh && p.tapn) {
+            const uint64_t desct = umma_desc_sw128(0, 128, 1024);      // N blocks = taps, one pixel (128 B) apart
+            const uint64_t desct_hi = desct & 0xFFFFFFFF00000000ull;
+            const uint32_t bt_lo = (uint32_t)desct + (b_addr >> 4);
+            const uint32_t idesct = umma_idesc_bf16(128, 192, 1, 1);
+#pragma unroll
+            for (int k = 0; k < kChunkPix / 16; ++k) {
+              if (k < nk) {
+                const uint64_t da = desc_hi | (uint64_t)(a_lo + 128u * k);
+                const uint32_t koff = (uint32_t)(((16 * k) / p.Wb) * (p.Wb + 2) + (16 * k) % p.Wb) * 8u;
+                for (int b = 0; b < xh_live; ++b)
+                  umma_bf16(tmem_base + (uint32_t)b * 192u, da,
+                            desct_hi | (uint64_t)(bt_lo + (uint32_t)b * (uint32_t)(kXhBox >> 4) + koff), idesct,
+                            (it | k) != 0 ? 1u : 0u);
+              }
+            }
           } else if (p.xh) {
             // three taps = three MMAs on the same halo boxes, B start shifted by one pixel (128 B = +8) per tap;
             // N = all boxes of the stage (kXhBox apart), accumulator columns [tap][box][64]
@@ -389,17 +411,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       int cib = cib_base + j / p.ksize;
       bool live = valid;
       if (p.fold) {
-        // accumulator columns are [q][box][64]; q = (b, tx) (fold 1) or the shift b + tx (fold 2: b = M half)
-        const int q = j / xh_live;
+        // accumulator columns are [q][box][64] ([box][q][64] with tapn); q = (b, tx) (fold 1) or the shift b + tx
+        // (fold 2: b = M half)
+        const int q = p.tapn ? j % 3 : j / xh_live;
         const int fb = p.fold == 1 ? q >> 1 : row >> 6;
         const int ftx = p.fold == 1 ? q & 1 : q - fb;
         live = valid && ftx >= 0 && ftx < 2;
-        cib = cib_base + j % xh_live;
+        cib = cib_base + (p.tapn ? j / 3 : j % xh_live);
         const int ph = (rg >> 1) * 2 + fb;
         tap = (ph * p.cout + (valid ? co : 0)) * 4 + (rg & 1) * 2 + (live ? ftx : 0);     // row index into [ph][co][tap]
       } else if (p.xh) {
         // accumulator columns are [tap s][box b][64]: b = X block (plain) or X row group (row-pair mode)
-        const int sx = j / xh_live, b = j % xh_live;
+        const int sx = p.tapn ? j % 3 : j / xh_live, b = p.tapn ? j / 3 : j % xh_live;
         if (p.rowpair) {
           const int fr = row < 64 ? b + 1 : (b == 0 ? 0 : -1);
           live = fr >= 0;
@@ -626,6 +649,7 @@ static int wgrad_plan(const b2_wgrad_args* a, WgradPlan* pl) {
   // CTA pairs: 3x3 halo mode, two Cout tiles per pair, each CTA holds one of the two X boxes
   p.pair = (env_switch("B200SEG_WG_PAIR", 1) != 0 && p.xh && (a->ksize == 3 || p.fold == 1) && !p.rowpair && p.fold != 2 &&
             p.cpb == 2 && a->cout % 256 == 0 && cbt % 2 == 0 && p.debug_skip == 0) ? 1 : 0;
+  p.tapn = (p.xh && !p.pair && p.fold != 1 && env_switch("B200SEG_WG_TAPN", 0) != 0) ? 1 : 0;
   p.b_stage_bytes = p.pair ? kXhBox : (p.xh ? p.nbox * kXhBox : p.ncolb * kBoxBytes);
   const int stage_bytes = p.a_bytes + p.b_stage_bytes;
   int stages = (200 * 1024) / stage_bytes;
