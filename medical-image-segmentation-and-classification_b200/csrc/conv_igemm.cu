@@ -1018,6 +1018,9 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
     if (p.dm) p.epi_groups = 2;        // the two tiles of an item finish together: one group each
     const int budget2 = 232448 - 1024 - tail_bytes - 2 * ctile_bytes;
     if (p.epi_groups == 2 && budget2 / stage_bytes < 2) p.epi_groups = 1;
+    // pair-mode N = 256 tiles: two 64 KB staging tiles leave three pipeline stages, which costs more than the second
+    // group's drain overlap buys (128->256 @64^2 fprop: 0.164 ms with two groups, 0.125 ms with one)
+    if (p.epi_groups == 2 && p.pair && p.block_n == 256 && forced_g == 0 && budget2 / stage_bytes < 4) p.epi_groups = 1;
   }
   // Clusters: per tile a CTA streams A_bytes + B_bytes / cluster from L2; at about 42 B/clk per SM (L2 -> SM fabric,
   // 6300 B/clk chip-wide) the weight re-fetch is what bounds every layer with BLOCK_N <= 128.
