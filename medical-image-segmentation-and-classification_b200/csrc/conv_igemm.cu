@@ -96,6 +96,9 @@ struct IgemmParams {
   int ldy;
   const float* bias;
   const __nv_bfloat16* addend;
+  int add_tma;        // the addend tile is TMA-loaded into the group's staging tile at the START of the tile's drain (same
+                      // box and swizzle as the output store) and added in place: per-thread row loads issued after the
+                      // accumulator was ready made every 32-column chunk pay a global-memory round trip inside the drain
   int ldadd;
   double* stats;
   double* stats_partial;   // deterministic mode: [gridDim.x * epi_groups][2 * cout] rows, one per (CTA, epilogue group)
@@ -122,7 +125,7 @@ template <bool kHasAdd, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
-                  const IgemmParams p) {
+                  const __grid_constant__ CUtensorMap tmAdd, const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int a_slots = p.dm ? 2 : 1;                                    // activation tiles per stage
@@ -138,6 +141,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* tmem_empty_bar = tmem_full_bar + 4;                        // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 4);
   uint64_t* wres_bar = reinterpret_cast<uint64_t*>(tail + 264);        // resident weights have landed
+  uint64_t* add_bar = reinterpret_cast<uint64_t*>(tail + 272);         // [kMaxEpiGroups]: a group's addend tile has landed
   float* s_bias0 = reinterpret_cast<float*>(tail + 320);               // [group][256]
   float* s_psi0 = s_bias0 + kMaxEpiGroups * 256;                       // [group][256] (fused gate: psi weights)
 
@@ -161,6 +165,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_init(&empty_bar[s], p.pair ? 1u : (uint32_t)C);
     }
     mbar_init(wres_bar, 1);
+    for (int b = 0; b < kMaxEpiGroups; ++b) mbar_init(&add_bar[b], 1);
     for (int b = 0; b < 4; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], p.pair ? 8u : 4u);   // one arrival per epilogue warp (of both CTAs of a pair)
@@ -510,6 +515,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     };
 
     int cur_n_tile = -1;
+    uint32_t add_phase = 0;                      // parity of this group's addend barrier
     const int nb_shift = p.dm ? 2 : 1;           // log2(accumulators in TMEM)
     // ti = local tile counter of this CTA (group g takes ti = g, g + G, ...); double-M: item = ti / 2, tile ti & 1
     for (int ti = g;; ti += G) {
@@ -563,6 +569,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // the group's previous TMA store must have finished READING the staging tile before it is overwritten
       if (p.tma_store && et == 0) tma_store_wait_read();
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (kHasAdd && p.add_tma) {
+        // the addend tile lands in the staging tile while this group waits for the accumulator
+        if (et == 0) {
+          mbar_arrive_expect_tx(&add_bar[g], (uint32_t)(kTileM * p.block_n * 2));
+          for (int pn = 0; pn < (p.block_n >> 6); ++pn)
+            tma_load_4d(ctile + pn * (kTileM * 128), &tmAdd, &add_bar[g], ch_base + pn * 64, w0, h0, n0);
+        }
+      }
 
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)ti >> nb_shift) & 1u);
       tc_fence_after();
@@ -580,7 +594,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // this group will drain into L2 now; its loads then hit L2.
         const int ti2 = ti + G;
         const int item2 = cluster_id + (p.dm ? (ti2 >> 1) : ti2) * num_clusters;
-        if (item2 < total_items && !p.rp) {
+        if (p.add_tma) {
+          mbar_wait(&add_bar[g], add_phase);
+          add_phase ^= 1u;
+        } else if (item2 < total_items && !p.rp) {
           const int m_group2 = fast_div(item2, p.n_tiles, p.mg_nt);
           const int t2 = m_group2 * per_item + (p.dm ? (ti2 & 1) : (int)crank);
           if (t2 < p.m_tiles) {
@@ -651,16 +668,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + q * 4);
           bs[q * 4 + 0] = b4.x; bs[q * 4 + 1] = b4.y; bs[q * 4 + 2] = b4.z; bs[q * 4 + 3] = b4.w;
         }
-        uint4 au[4];
-        if (kHasAdd) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            au[q] = arow != nullptr ? __ldg(reinterpret_cast<const uint4*>(arow + c) + q) : make_uint4(0, 0, 0, 0);
-        }
-        tmem_ld_wait();
         // staging address of this row's 16 B chunks: panel (64 channels) + row + swizzled chunk
         const uint32_t cbase = (uint32_t)(c >> 6) * (uint32_t)(kTileM * 128) + row_off;
         const uint32_t chunk0 = (uint32_t)((c & 63) >> 3);
+        uint4 au[4];
+        if (kHasAdd) {
+          if (p.add_tma) {           // the TMA-loaded addend tile has the layout of the output tile: read in place
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              au[q] = *reinterpret_cast<const uint4*>(ctile + cbase + (((chunk0 + q) ^ row_x) << 4));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              au[q] = arow != nullptr ? __ldg(reinterpret_cast<const uint4*>(arow + c) + q) : make_uint4(0, 0, 0, 0);
+          }
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t pk[4];
@@ -1139,6 +1162,15 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   } else {
     tmY = tmA0;
   }
+  CUtensorMap tmAdd = tmY;
+  p.add_tma = 0;
+  if (a->addend != nullptr && p.tma_store && p.block_n >= 64 && fold == 0 && gate == nullptr && !p.rp && out_mul == 1 &&
+      a->cout % 64 == 0 && env_int("B200SEG_ADD_TMA", 1) != 0) {
+    rc = encode_act_tmap_ex(&tmAdd, a->addend, a->cout, a->n, a->h, a->w, a->ldadd, (long long)a->ldadd * a->w,
+                            (long long)a->ldadd * a->w * a->h, p.Wb, p.Hb, p.Nb, 1);
+    if (rc) return rc;
+    p.add_tma = 1;
+  }
   {
     // forward runs on the caller's thread, backward on the autograd engine's: set the attributes exactly once
     static std::once_flag attr_once;
@@ -1226,13 +1258,13 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   p.stats_partial = det.partial;
   if (p.pair) {
     if (p.addend != nullptr)
-      B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, tmA0, tmA1, tmB, tmY, p));
+      B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, true>, tmA0, tmA1, tmB, tmY, tmAdd, p));
     else
-      B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, tmA0, tmA1, tmB, tmY, p));
+      B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, tmA0, tmA1, tmB, tmY, tmAdd, p));
   } else if (p.addend != nullptr) {
-    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, tmA0, tmA1, tmB, tmY, p));
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, tmA0, tmA1, tmB, tmY, tmAdd, p));
   } else {
-    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, tmA0, tmA1, tmB, tmY, p));
+    B2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, tmA0, tmA1, tmB, tmY, tmAdd, p));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, det_rows, 2 * p.cout, 2 * p.cout, p.stats, stream);
