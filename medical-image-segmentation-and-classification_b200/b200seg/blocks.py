@@ -134,6 +134,12 @@ class AttentionGate(nn.Module):
         out = attention_gate_module(self, g, x)
         return ops.to_nchw(out) if ext else out
 
+    def gate_pass(self, g, x):
+        """(forward(g, x), g) on internal activations — the second value is g as the tensor the decoder's concat should
+        consume, so that g's concat-side gradient is added inside the gate's backward (ops_gate._GatePass)."""
+        from .ops_gate import attention_gate_module
+        return attention_gate_module(self, g, x, with_pass=True)
+
 
 class Recurrent_block(nn.Module):
     """One shared conv3x3+BN+ReLU applied t+1 times with x + x1 re-injection — R2U_Net.py:4-20."""

@@ -57,13 +57,17 @@ class AttentionUNet(nn.Module):
         x5 = self.conv5(p4)
 
         d5 = self.up5(x5)
-        d5 = self.up_conv5((self.att5(g=d5, x=x4), d5))      # cat((x4, d5), dim=1): skip first (ref :101)
+        a5, d5 = self.att5.gate_pass(g=d5, x=x4)      # cat((x4, d5), dim=1): skip first (ref :101)
+        d5 = self.up_conv5((a5, d5))
         d4 = self.up4(d5)
-        d4 = self.up_conv4((self.att4(g=d4, x=x3), d4))
+        a4, d4 = self.att4.gate_pass(g=d4, x=x3)
+        d4 = self.up_conv4((a4, d4))
         d3 = self.up3(d4)
-        d3 = self.up_conv3((self.att3(g=d3, x=x2), d3))
+        a3, d3 = self.att3.gate_pass(g=d3, x=x2)
+        d3 = self.up_conv3((a3, d3))
         d2 = self.up2(d3)
-        d2 = self.up_conv2((self.att2(g=d2, x=x1), d2))
+        a2, d2 = self.att2.gate_pass(g=d2, x=x1)
+        d2 = self.up_conv2((a2, d2))
         return d2
 
     def forward(self, x: torch.Tensor):

@@ -56,13 +56,17 @@ class R2AttU_Net(nn.Module):
         x5 = self.RRCNN5(p4)
 
         d5 = self.up5(x5)
-        d5 = self.up_RRCNN5((self.att5(g=d5, x=x4), d5))     # R2AttU_Net.py:137-139
+        a5, d5 = self.att5.gate_pass(g=d5, x=x4)     # R2AttU_Net.py:137-139
+        d5 = self.up_RRCNN5((a5, d5))
         d4 = self.up4(d5)
-        d4 = self.up_RRCNN4((self.att4(g=d4, x=x3), d4))
+        a4, d4 = self.att4.gate_pass(g=d4, x=x3)
+        d4 = self.up_RRCNN4((a4, d4))
         d3 = self.up3(d4)
-        d3 = self.up_RRCNN3((self.att3(g=d3, x=x2), d3))
+        a3, d3 = self.att3.gate_pass(g=d3, x=x2)
+        d3 = self.up_RRCNN3((a3, d3))
         d2 = self.up2(d3)
-        d2 = self.up_RRCNN2((self.att2(g=d2, x=x1), d2))
+        a2, d2 = self.att2.gate_pass(g=d2, x=x1)
+        d2 = self.up_RRCNN2((a2, d2))
         return d2
 
     def forward(self, x):

@@ -10,7 +10,8 @@ updated by the caller from the returned (sum, sumsq) buffers.
 """
 from __future__ import annotations
 
-from typing import Tuple
+import os
+from typing import Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -75,7 +76,8 @@ def _(g, x, wg, *rest):
 @custom_op("b200seg::attention_gate_bwd", mutates_args=())
 def attention_gate_bwd(dout: Tensor, g: Tensor, x: Tensor, wg: Tensor, wx: Tensor, psi: Tensor, q: Tensor,
                        g1p: Tensor, x1p: Tensor, coef_g: Tensor, gamma_g: Tensor, coef_x: Tensor, gamma_x: Tensor,
-                       coef_1: Tensor, gamma_1: Tensor, wpsi: Tensor, training: bool, need_dg: bool, need_dx: bool
+                       coef_1: Tensor, gamma_1: Tensor, wpsi: Tensor, training: bool, need_dg: bool, need_dx: bool,
+                       dg_add: Optional[Tensor] = None
                        ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     fint = wg.shape[0]
     dev = dout.device
@@ -84,7 +86,8 @@ def attention_gate_bwd(dout: Tensor, g: Tensor, x: Tensor, wg: Tensor, wx: Tenso
                                                                 gamma_x, coef_1, gamma_1, wpsi, training=training)
     if need_dg:
         _, wgd = K.packed(wg, want_dgrad=True)
-        dg = K.conv_igemm(dg1p, wgd, g.shape[3], 1, dgrad=True)
+        # dg_add: the gradient g received from its other consumer (the concat), added in the GEMM epilogue
+        dg = K.conv_igemm(dg1p, wgd, g.shape[3], 1, dgrad=True, addend=_c(dg_add) if dg_add is not None else None)
     else:
         dg = torch.empty((0,), dtype=torch.bfloat16, device=dev)
     if need_dx:
@@ -133,24 +136,70 @@ def _backward(ctx, dout, *_unused):
 attention_gate.register_autograd(_backward, setup_context=_setup)
 
 
-def attention_gate_module(gate, g: Tensor, x: Tensor) -> Tensor:
-    """gate: an AttentionGate module (W_g, W_x, psi Sequentials with the reference's layout)"""
+class _GatePass(torch.autograd.Function):
+    """(gate(g, x), g): the UpConv output g feeds the gate AND the concat (AttentionUNet.py:99-101).  Handing the concat
+    the pass-through output makes this node g's only consumer, so the concat-side gradient arrives here and rides the
+    W_g dgrad's epilogue as its addend instead of autograd's separate accumulation pass over the full-size tensor."""
+
+    @staticmethod
+    def forward(ctx, g, x, *rest):
+        (wg, _bg, wx, _bx, gamma_g, _b, _rm, _rv, gamma_x, _b2, _rm2, _rv2, wpsi, _bpsi, gamma_1, _b1, _rm1, _rv1,
+         training, _eps) = rest
+        out, q, psi, g1p, x1p, coef_g, coef_x, coef_1, stats_g, stats_x, qstats = attention_gate(g, x, *rest)
+        ctx.save_for_backward(_c(g), _c(x), wg, wx, psi, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coef_1, gamma_1,
+                              wpsi)
+        ctx.training = training
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(stats_g, stats_x, qstats)
+        return out, g, stats_g, stats_x, qstats
+
+    @staticmethod
+    def backward(ctx, dout, dg_pass, *_unused):
+        g, x, wg, wx, psi, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coef_1, gamma_1, wpsi = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        if dout is None:                      # the gate's own output was not used: only the pass-through gradient flows
+            return (dg_pass,) + (None,) * 21
+        dg, dx, dwg, dwx, dgb, dbn1, dwpsi, dbpsi, dbias = attention_gate_bwd(
+            dout, g, x, wg, wx, psi, q, g1p, x1p, coef_g, gamma_g, coef_x, gamma_x, coef_1, gamma_1, wpsi, ctx.training,
+            bool(need[0]), bool(need[1]), dg_pass if need[0] else None)
+        fint = wg.shape[0]
+        if dwg.numel() == 0:
+            dwg = K.grad_slot(wg, (fint, 1, wg.shape[1]))
+        if dwx.numel() == 0:
+            dwx = K.grad_slot(wx, (fint, 1, wx.shape[1]))
+        return (dg if need[0] else None, dx if need[1] else None,
+                _dw_as_param_grad(dwg, wg), dbias[0], _dw_as_param_grad(dwx, wx), dbias[1],
+                dgb[0], dgb[1], None, None, dgb[2], dgb[3], None, None,
+                dwpsi.view_as(wpsi), dbpsi, dbn1[0:1], dbn1[1:2], None, None, None, None)
+
+
+_GATE_PASS = os.environ.get("B200SEG_GATE_PASS", "1") != "0"      # 0: autograd accumulates g's two gradients (A/B switch)
+
+
+def attention_gate_module(gate, g: Tensor, x: Tensor, with_pass: bool = False):
+    """gate: an AttentionGate module (W_g, W_x, psi Sequentials with the reference's layout).
+    with_pass=True returns (out, g_pass): g_pass is g as the tensor the concat should consume (see _GatePass)."""
     bn_g, bn_x, bn_1 = gate.W_g[1], gate.W_x[1], gate.psi[1]
-    import os
     if os.environ.get("B200SEG_FOLD_BN", "1") != "0" and os.environ.get("B200SEG_GATE_FUSED", "1") != "0":
         from . import ops_infer
         if ops_infer.inference_mode(bn_g) and ops_infer.gate_fusable(gate, g, x):
-            return ops_infer.attention_gate_fused(gate, g, x)          # eval + no_grad: the whole gate in ONE kernel
+            out = ops_infer.attention_gate_fused(gate, g, x)           # eval + no_grad: the whole gate in ONE kernel
+            return (out, g) if with_pass else out
     training = bn_g.training
-    res = attention_gate(g, x, gate.W_g[0].weight, gate.W_g[0].bias, gate.W_x[0].weight, gate.W_x[0].bias,
-                         bn_g.weight, bn_g.bias, bn_g.running_mean, bn_g.running_var,
-                         bn_x.weight, bn_x.bias, bn_x.running_mean, bn_x.running_var,
-                         gate.psi[0].weight, gate.psi[0].bias, bn_1.weight, bn_1.bias, bn_1.running_mean,
-                         bn_1.running_var, training, float(bn_1.eps))
-    out, stats_g, stats_x, qstats = res[0], res[8], res[9], res[10]
+    args = (g, x, gate.W_g[0].weight, gate.W_g[0].bias, gate.W_x[0].weight, gate.W_x[0].bias,
+            bn_g.weight, bn_g.bias, bn_g.running_mean, bn_g.running_var,
+            bn_x.weight, bn_x.bias, bn_x.running_mean, bn_x.running_var,
+            gate.psi[0].weight, gate.psi[0].bias, bn_1.weight, bn_1.bias, bn_1.running_mean,
+            bn_1.running_var, training, float(bn_1.eps))
+    g_pass = g
+    if with_pass and _GATE_PASS and torch.is_grad_enabled() and g.requires_grad:
+        out, g_pass, stats_g, stats_x, qstats = _GatePass.apply(*args)
+    else:
+        res = attention_gate(*args)
+        out, stats_g, stats_x, qstats = res[0], res[8], res[9], res[10]
     if training:
         n, h, w, _ = x.shape
         for bn, st in ((bn_g, stats_g), (bn_x, stats_x), (bn_1, qstats)):
             bn_update_running_(st.detach(), n * h * w, float(bn.momentum), bn.running_mean, bn.running_var,
                                bn.num_batches_tracked)
-    return out
+    return (out, g_pass) if with_pass else out
