@@ -93,25 +93,33 @@ __global__ void __launch_bounds__(kBlock) channel_sum_kernel(const __nv_bfloat16
                                                              long long npix, int C, ChanMap m,
                                                              float* __restrict__ db, DetBuf det) {
   __shared__ float red[kBlock * 8];
+  // gridDim.y channel slices of m.tpp * 8 channels: a block ends in one atomic per channel of its slice, and with ~1200
+  // blocks on the same C addresses those atomics were a fixed ~100 us per launch whatever the tensor size
+  const int c_off = blockIdx.y * (m.tpp * 8);
+  dy += c_off;
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
-  const bool active = r < m.rows;
+  const bool active = r < m.rows && c_off + g * 8 < C;
   float s[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = 0.f;
   if (active) {
-    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
-      float f[8];
-      unpack8(u, f);
+    const long long step = (long long)gridDim.x * m.rows;
+    for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += 2 * step) {      // two pixels in flight
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(dy + p * lddy + g * 8));
+      const uint4 u1 = p + step < npix ? __ldg(reinterpret_cast<const uint4*>(dy + (p + step) * lddy + g * 8))
+                                       : make_uint4(0u, 0u, 0u, 0u);
+      float f[8], h[8];
+      unpack8(u0, f);
+      unpack8(u1, h);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] += f[j];
+      for (int j = 0; j < 8; ++j) s[j] += f[j] + h[j];
     }
   }
   rows_reduce8(s, m.tpp, m.rows, g, r, active, red);
   if (active && r == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red_out(db, det, g * 8 + j, s[j]);
+    for (int j = 0; j < 8; ++j) red_out(db, det, c_off + g * 8 + j, s[j]);
   }
 }
 
@@ -607,11 +615,20 @@ extern "C" int b2_channel_sum(const void* dy, int32_t lddy, int64_t npix, int32_
   if (rc) return rc;
   B2_REQUIRE(aligned16(dy, lddy), B2_ERR_ALIGN, "dy misaligned");
   B2_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * c, (cudaStream_t)stream));
-  const int grid = chan_grid(npix, m, 8);
+  int slices = 1;
+  if (c > 64 && env_switch("B200SEG_BN_SLICE", 1) != 0) {      // 64-channel slices: 8 threads per pixel, 32 pixels per pass
+    slices = (c + 63) / 64;
+    m.tpp = 8;
+    m.rows = kBlock / 8;
+  }
+  int grid = chan_grid(npix, m, 4);
+  grid = (grid + slices - 1) / slices;
+  if (grid < 1) grid = 1;
   DetBuf det;
   rc = det_begin(&det, grid, c, (cudaStream_t)stream);
   if (rc) return rc;
-  channel_sum_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy, npix, c, m, db, det);
+  channel_sum_kernel<<<dim3(grid, slices), kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy, npix, c, m,
+                                                                              db, det);
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, c, db, (cudaStream_t)stream);
   return B2_OK;
