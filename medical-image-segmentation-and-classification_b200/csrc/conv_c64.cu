@@ -55,6 +55,8 @@ struct C64Params {
   double* stats;
   double* stats_partial;    // deterministic mode: [grid * epi_groups][128]
   int relu;
+  int add;                  // 1: an addend tile (tmAdd; same geometry as y) is TMA-loaded into the group's staging tile at
+                            // the start of each row's drain and added before ReLU / rounding (dgrad + incoming gradient)
   int fold;                 // 1: folded UpConv (see the header); H, W, rows_total are those of the COARSE input
   int debug_skip;           // timing experiments only (B200SEG_C64_SKIP; results are wrong): 1 no TMA loads, 2 no MMAs,
                             // 4 no drain at all, 8 no statistics pass, 16 no TMA store
@@ -83,7 +85,8 @@ __device__ __forceinline__ bool next_strip(const C64Params& p, long long& cur, l
 
 __global__ void __launch_bounds__(kC64Threads, 1)
 conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY, const C64Params p) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmY,
+                const __grid_constant__ CUtensorMap tmAdd, const C64Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int wres_bytes = (p.fold ? 8 : 9) * p.cbt * 8192;              // taps x cbt blocks x 64 rows x 128 B
@@ -95,8 +98,9 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint64_t* tmem_full_bar = empty_bar + kC64MaxStages;                 // [kC64Slots]
   uint64_t* tmem_empty_bar = tmem_full_bar + kC64Slots;                // [kC64Slots]
   uint64_t* wres_bar = tmem_empty_bar + kC64Slots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(tail + 320);                // [64]
+  uint64_t* add_bar = wres_bar + 1;                                    // [2]: a group's addend tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(add_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tail + 336);                // [64]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,6 +121,8 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       mbar_init(&tmem_empty_bar[b], 4);         // one arrival per warp of the draining epilogue group
     }
     mbar_init(wres_bar, 1);
+    mbar_init(&add_bar[0], 1);
+    mbar_init(&add_bar[1], 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB);
@@ -378,6 +384,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 8; ++j) fs[j] = fq[j] = 0.f;
       int fpending = 0;
+      uint32_t add_phase = 0;
       int lr = 0;
       long long cur = range_begin;
       Strip st;
@@ -390,6 +397,10 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           // the group's previous TMA store must have finished READING the staging tile before it is overwritten
           if (et == 0) tma_store_wait_read();
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+          if (p.add && et == 0) {
+            mbar_arrive_expect_tx(&add_bar[g], (uint32_t)(kTileM * 128));
+            tma_load_4d(ctile, &tmAdd, &add_bar[g], 0, st.w0, h, st.n);
+          }
           mbar_wait(&tmem_full_bar[slot], ((uint32_t)lr >> 3) & 1u);
           tc_fence_after();
           if (p.debug_skip & 4) {
@@ -408,6 +419,18 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (lane == 0) mbar_arrive(&tmem_empty_bar[slot]);        // accumulator drained
           const uint32_t row_off = (uint32_t)row * 128u;
           const uint32_t row_x = (uint32_t)(row & 7);
+          if (p.add) {
+            mbar_wait(&add_bar[g], add_phase);
+            add_phase ^= 1u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint4 au = *reinterpret_cast<const uint4*>(ctile + row_off + ((((uint32_t)q) ^ row_x) << 4));
+              v[q * 8 + 0] += bf16lo(au.x); v[q * 8 + 1] += bf16hi(au.x);
+              v[q * 8 + 2] += bf16lo(au.y); v[q * 8 + 3] += bf16hi(au.y);
+              v[q * 8 + 4] += bf16lo(au.z); v[q * 8 + 5] += bf16hi(au.z);
+              v[q * 8 + 6] += bf16lo(au.w); v[q * 8 + 7] += bf16hi(au.w);
+            }
+          }
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             uint32_t pk[4];
@@ -506,7 +529,10 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
   const int fold = a->fold_mode == 1 ? 1 : 0;           // merged folded-UpConv fprop (ksize 2, y on the 2x grid)
   if (fold && (a->ksize != 2 || a->c1 != 0 || a->ldy != a->cout || env_switch("B200SEG_C64_FOLD", 1) == 0)) return 0;
   if ((!fold && (a->ksize != 3 || a->fold_mode != 0)) || a->cout != 64 || stride != 1 || out_mul != 1 || in_mul != 1 ||
-      a->custom_pad != 0 || a->addend != nullptr || a->w % kTileM != 0 || a->c0 % 64 != 0 || a->c1 % 64 != 0)
+      a->custom_pad != 0 || a->w % kTileM != 0 || a->c0 % 64 != 0 || a->c1 % 64 != 0)
+    return 0;
+  if (a->addend != nullptr && (fold || a->add_after_act || a->ldadd % 8 != 0 ||
+                               (reinterpret_cast<uintptr_t>(a->addend) & 15) != 0))
     return 0;
   const int cb0 = a->c0 / 64, cbt = cb0 + a->c1 / 64;
   if (cbt < 1 || cbt > 2) return 0;
@@ -525,10 +551,11 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
   p.bias = a->bias;
   p.stats = a->stats;
   p.relu = a->relu;
+  p.add = a->addend != nullptr ? 1 : 0;
   p.fold = fold;
   p.debug_skip = env_switch("B200SEG_C64_SKIP", 0);
   p.mg_tw = p.tw <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)p.tw - 1) / (uint64_t)p.tw);
-  const int tail_bytes = 320 + 64 * 4 + 192;
+  const int tail_bytes = 320 + 16 + 64 * 4 + 192;
   const int wres_bytes = (fold ? 8 : 9) * cbt * 8192;
   p.epi_groups = 2;
   int budget = 232448 - 1024 - tail_bytes - wres_bytes - 2 * kTileM * 128;
@@ -572,6 +599,12 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
                             (long long)a->ldy * a->w * a->h, kTileM, 1, 1, 1);
   }
   if (rc) return rc;
+  CUtensorMap tmAdd = tmY;
+  if (p.add) {
+    rc = encode_act_tmap_ex(&tmAdd, a->addend, a->cout, a->n, a->h, a->w, a->ldadd, (long long)a->ldadd * a->w,
+                            (long long)a->ldadd * a->w * a->h, kTileM, 1, 1, 1);
+    if (rc) return rc;
+  }
   {
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -588,7 +621,7 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   p.stats_partial = det.partial;
-  conv_c64_kernel<<<p.grid, kC64Threads, smem_bytes, stream>>>(tmA0, tmA1, tmB, tmY, p);
+  conv_c64_kernel<<<p.grid, kC64Threads, smem_bytes, stream>>>(tmA0, tmA1, tmB, tmY, tmAdd, p);
   B2_LAUNCH_CHECK();
   if (det.partial) {
     rc = det_finish(det.partial, det_rows, 128, 128, p.stats, stream);

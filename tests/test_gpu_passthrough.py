@@ -86,3 +86,41 @@ def test_gate_pass_matches_autograd_accumulation(deterministic):
     assert num / den < 2e-3, num / den
     worst = max(_rel(g1[k], g0[k]) for k in g0 if g0[k].numel() > 1000)
     assert worst < 2e-2, worst
+
+
+@pytest.mark.parametrize("t", [1, 2, 3])
+def test_recurrent_pass_matches_autograd_accumulation(deterministic, t):
+    """Recurrent_block with its input travelling along the applications as a pass-through (ops._CbaPass: the identity
+    gradients join the first application's dgrad epilogue) against the plain composition whose t + 1 gradients autograd
+    accumulates: equal up to the rounding of the fused sum (eval-mode BatchNorm, so that one rounding is not amplified).
+    (The pass-through is off by default — measured neutral — and forced on here.)"""
+    from b200seg import ops
+    from b200seg.blocks import RRCNN_block
+    torch.manual_seed(t)
+    blk = RRCNN_block(64, 128, t=t).cuda().eval()
+    for p in blk.parameters():
+        p.requires_grad_(True)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(3, 64, 32, 32, device="cuda", generator=g)
+    dy = torch.randn(3, 128, 32, 32, device="cuda", generator=g)
+
+    def run():
+        blk.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        y = blk(xi)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        return y.detach().clone(), xi.grad.clone(), {k: p.grad.clone() for k, p in blk.named_parameters()}
+
+    default = ops._RECURRENT_PASS
+    try:
+        ops._RECURRENT_PASS = True
+        y1, dx1, g1 = run()
+        ops._RECURRENT_PASS = False
+        y0, dx0, g0 = run()
+    finally:
+        ops._RECURRENT_PASS = default
+    assert torch.equal(y1, y0)
+    assert _rel(dx1, dx0) < 5e-3, _rel(dx1, dx0)
+    for k in g0:
+        assert _rel(g1[k], g0[k]) < 1e-2, (k, _rel(g1[k], g0[k]))
