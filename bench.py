@@ -62,7 +62,7 @@ def parse():
     return ap.parse_args()
 
 
-TRAFFIC_FILE = "r02e_traffic.json"      # ncu DRAM counters of one step of the default workload (tools/profile_step.py)
+TRAFFIC_FILE = "r02f_traffic.json"      # ncu DRAM counters of one step of the default workload (tools/profile_step.py)
 
 
 def measured_peaks():
