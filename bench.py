@@ -98,11 +98,14 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Started BEFORE the warm-up: nvidia-smi takes a few hundred ms to come up, longer than a short timed region.
+        Rows are stamped on arrival; stop() keeps those that fall between mark_begin() and mark_end()."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -111,7 +114,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -121,8 +130,15 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else float("-inf")
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.05]
+        window = "timed region"
+        if not inside:       # a timed region shorter than one sampling period: the rows taken under load around it
+            inside = [r for ts, r in self.rows if ts >= t0 - 1.0]
+            window = "timed region +- 1 s (under load)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -133,7 +149,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -302,6 +318,9 @@ def run_b200(args):
     run_stream.wait_stream(torch.cuda.current_stream())
     torch.cuda.set_stream(run_stream)
     _tick("model built, warm-up begins")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                   # (comes up during the warm-up; only rows inside the timed region are used)
     for _ in range(n_warm):
         stepper(x_dev, t_dev)
     torch.cuda.synchronize()
@@ -322,12 +341,12 @@ def run_b200(args):
     def run_step():
         return stepper(x_run, t_run, inputs_are_static=graphed)
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = _lib.launch_count
+    sampler.mark_begin()
     ms = timed(run_step, args.steps)
+    sampler.mark_end()
     launches = (_lib.launch_count - l0) if not graphed else launches_per_step * args.steps
+    time.sleep(0.06)                      # let the sampler deliver the last row of the region
     clocks = sampler.stop() if rank == 0 else None
     _tick("timed region done")
 
