@@ -84,3 +84,43 @@ def test_aug_params_size_matches_header():
     from b200seg.data import PARAM_FLOATS
     assert _struct_fields("b2_aug_params") == PARAM_FLOATS          # 6 + 2 floats + 4 ints, 4 bytes each
     assert C.sizeof(C.c_float) == 4
+
+
+def test_bench_clock_sampler_keeps_the_rows_of_the_timed_region():
+    """bench.py's nvidia-smi sampler starts before the warm-up and stamps its rows; only those inside the timed region
+    count (median clock, throttle reasons), with the rows around it as the fallback for a region shorter than one period."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    def row(mhz, cap):
+        return ["0", str(mhz), "1965", "900.0", "Not Active", "Not Active", "Not Active", "Active" if cap else "Not Active"]
+
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.rows = [(0.5, row(1965, False)), (1.1, row(1700, True)), (1.2, row(1650, True)), (1.3, row(1600, True)),
+              (2.5, row(1965, False))]
+    s.t0, s.t1 = 1.0, 1.35
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1650 and out["sm_max_mhz"] == 1965
+    assert out["reasons"] == ["sw_power_cap"] and out["window"] == "timed region"
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.rows = [(0.2, row(1900, False)), (1.5, row(1800, True))]
+    s.t0, s.t1 = 1.0, 1.01                      # no row inside: the rows taken under load around it
+    out = s.stop()
+    assert out["samples"] == 2 and "under load" in out["window"]
+    assert bench.ClockSampler(0).stop()["sm_mhz"] is None          # nvidia-smi unavailable
