@@ -184,6 +184,34 @@ __global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* _
   float sc[8], sh[8];
   load8f(scale + g * 8, sc);
   load8f(shift + g * 8, sh);
+  if (addend == nullptr) {
+    // plain y = act(z * scale + shift): four pixels in flight per thread (with one, a thread had a single 16-byte load
+    // outstanding and the kernel ran at 82 % of the copy bandwidth)
+    constexpr int U = 4;
+    const long long step = (long long)gridDim.x * m.rows;
+    for (long long p0 = (long long)blockIdx.x * m.rows + r; p0 < npix; p0 += U * step) {
+      uint4 u[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long p = p0 + k * step;
+        u[k] = p < npix ? __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long p = p0 + k * step;
+        if (p >= npix) break;
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaf(f[j], sc[j], sh[j]);
+          if (relu) f[j] = fmaxf(f[j], 0.f);
+        }
+        *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = pack8(f);
+      }
+    }
+    return;
+  }
   for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
     float f[8];
