@@ -212,35 +212,52 @@ __global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* _
     }
     return;
   }
+  if (ysum != nullptr) {
+    // x + act(bn(z)) (Recurrent_block, R2U_Net.py:19): two pixels = four 16-byte loads in flight per thread
+    constexpr int U = 2;
+    const long long step = (long long)gridDim.x * m.rows;
+    for (long long p0 = (long long)blockIdx.x * m.rows + r; p0 < npix; p0 += U * step) {
+      uint4 u[U], a[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long p = p0 + k * step;
+        const bool ok = p < npix;
+        u[k] = ok ? __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        a[k] = ok ? __ldg(reinterpret_cast<const uint4*>(addend + p * ldadd + g * 8)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long p = p0 + k * step;
+        if (p >= npix) break;
+        float f[8], fa[8], fo[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[j] = fmaf(f[j], sc[j], sh[j]);
+          if (relu) f[j] = fmaxf(f[j], 0.f);
+        }
+        const uint4 o = pack8(f);
+        if (y != nullptr) *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = o;
+        unpack8(a[k], fa);
+        unpack8(o, fo);   // the sum is taken on the ROUNDED activation, as torch does (x + x1 on bf16 tensors)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fo[j] += fa[j];
+        *reinterpret_cast<uint4*>(ysum + p * ldysum + g * 8) = pack8(fo);
+      }
+    }
+    return;
+  }
+  // residual mode (torchvision Bottleneck: relu(bn3(z) + identity)): the addend joins BEFORE the activation
   for (long long p = (long long)blockIdx.x * m.rows + r; p < npix; p += (long long)gridDim.x * m.rows) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8));
-    float f[8];
-    unpack8(u, f);
-    if (addend != nullptr && ysum == nullptr) {
-      // residual mode (torchvision Bottleneck: relu(bn3(z) + identity)): add BEFORE the activation
-      float fa[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(addend + p * ldadd + g * 8)), fa);
+    float f[8], fa[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(z + p * ldz + g * 8)), f);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(addend + p * ldadd + g * 8)), fa);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = bf16_round(fmaf(f[j], sc[j], sh[j])) + fa[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+    for (int j = 0; j < 8; ++j) {
+      f[j] = bf16_round(fmaf(f[j], sc[j], sh[j])) + fa[j];
+      if (relu) f[j] = fmaxf(f[j], 0.f);
     }
-    if (relu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-    const uint4 o = pack8(f);
-    if (y != nullptr) *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = o;   // y may be skipped when only y+addend is needed
-    if (ysum != nullptr) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + p * ldadd + g * 8));
-      float fa[8], fo[8];
-      unpack8(a, fa);
-      unpack8(o, fo);   // the sum is taken on the ROUNDED activation, as torch does (x + x1 on bf16 tensors)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) fo[j] += fa[j];
-      *reinterpret_cast<uint4*>(ysum + p * ldysum + g * 8) = pack8(fo);
-    }
+    *reinterpret_cast<uint4*>(y + p * ldy + g * 8) = pack8(f);
   }
 }
 
