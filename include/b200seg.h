@@ -337,7 +337,8 @@ int b2_adamw_multi(const b2_tensor_ref* refs, const int32_t* block_tensor, const
  * b2_pack_weights / b2_pack_weights_upfold / the im2col stem matrix) of EVERY convolution weight, right after
  * b2_adamw_multi updated the fp32 masters (utils/helpers.py:333-335), so that no conv call of the next step packs
  * anything.  `refs` is a DEVICE array; item_start = exclusive prefix sum of the per-tensor work items
- * (kind 0: taps * ceil(cout/32) * ceil(cin/32); kind 1: 16 * ...; kind 2: ceil(cout/32) * ceil(cols/32));
+ * (kind 0 / 1: ceil(cout/32) * ceil(cin/32) — one item is a 32 x 32 tile of all taps, ksize <= 3; kind 2:
+ * ceil(cout/32) * ceil(cols/32));
  * total_items = their sum.
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct b2_pack_ref {

@@ -161,8 +161,8 @@ class FusedClipAdamW(torch.optim.Optimizer):
         rows, start = [], 0
         for pk in packs:
             tco, tci = (pk.cout + 31) // 32, (pk.cin + 31) // 32
-            items = tco * ((pk.cols + 31) // 32) if pk.code == 2 else \
-                (16 if pk.code == 1 else pk.ksize * pk.ksize) * tco * tci
+            assert pk.code == 2 or pk.ksize <= 3
+            items = tco * ((pk.cols + 31) // 32) if pk.code == 2 else tco * tci      # one item = a 32 x 32 tile, all taps
             lo = (pk.cout & 0xFFFFFFFF) | (pk.cin << 32)
             hi = (pk.ksize & 0xFFFFFFFF) | (pk.code << 32)
             rows.append([pk.ptr, pk.wf.data_ptr(), pk.wd.data_ptr() if pk.wd is not None else 0, lo, hi,

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < 8; ++j) wr[co][j] = (has && co < cout) ? bf16_round(w[co * cin + lig * 8 + j]) : 0.f;
   // block-uniform trip count so the full-mask shuffles below are always executed by every lane
-  constexpr int U = 2;                          // pixels in flight per thread
+  constexpr int U = CO <= 2 ? 4 : 2;            // pixels in flight per thread
   const long long stride = (long long)gridDim.x * gpb;
   for (long long base = (long long)blockIdx.x * gpb; base < npix; base += U * stride) {
     uint4 u[U];

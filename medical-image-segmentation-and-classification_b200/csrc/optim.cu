@@ -152,17 +152,25 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackRef* 
   __shared__ int starts[kPackMaxRefs];
   // The table of first work items sits in shared memory (one coalesced read): the binary search for an item's tensor
   // used to be ~7 dependent global loads per 4 KB tile, which is what the launch spent its time on (1 TB/s).
+  __shared__ int which;
   for (int i = threadIdx.x; i < nrefs; i += 256) starts[i] = refs[i].item_start;
   __syncthreads();
   for (int gi = blockIdx.x; gi < total_items; gi += gridDim.x) {
-    int lo = 0, hi = nrefs - 1;      // last ref with item_start <= gi
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (starts[mid] <= gi) lo = mid; else hi = mid - 1;
+    // ONE thread searches (the launch was issue-bound: 70 % of the issue slots, most of them 256 threads repeating
+    // the search and the item decode for four elements each)
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = nrefs - 1;    // last ref with item_start <= gi
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (starts[mid] <= gi) lo = mid; else hi = mid - 1;
+      }
+      which = lo;
     }
+    __syncthreads();
+    const int lo = which;
     const PackRef r = refs[lo];
     pack_item(r, gi - starts[lo], tile);
-    __syncthreads();                 // the tile is reused by the next item
+    __syncthreads();                 // the tile (and `which`) are reused by the next item
   }
 }
 
@@ -187,49 +195,67 @@ __device__ __forceinline__ void pack_item(const PackRef& r, int item, float (*ti
     }
     return;
   }
+  // One work item = one 32 (co) x 32 (ci) tile of ALL taps: a thread loads the k x k taps of its four elements in one
+  // batch (up to 36 loads in flight), then walks the slabs (tap, or phase * 4 + tap for kind 1) out of registers.  With
+  // one item per (tile, slab) the launch was issue-bound: ~650 instructions per thread and item, 450 of them the search,
+  // the PackRef copy and the index algebra, for four elements.
   const int tci = (r.cin + 31) / 32;
+  const int taps = r.ksize * r.ksize;             // <= 9 (checked on the host)
   const int ci_t = item % tci;
-  item /= tci;
-  const int co_t = item % tco;
-  const int slab = item / tco;                          // tap (kind 0) or phase * 4 + tap (kind 1)
+  const int co_t = item / tci;
   const int co0 = co_t * 32, ci0 = ci_t * 32;
-  const int taps = r.ksize * r.ksize;
-  // all four rows of a thread are LOADED before anything is stored: the stores may alias the loads as far as the
-  // compiler knows, and interleaved they made four dependent DRAM round trips per tile (the launch ran at 1 TB/s)
-  float vals[4];
+  float wv[4][9];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int co = co0 + ty + 8 * q, ci = ci0 + tx;
-    float v = 0.f;
-    if (co < r.cout && ci < r.cin) {
-      const float* __restrict__ base = r.w + co * r.s_co + ci * r.s_ci;
-      if (r.kind == 0) {
-        v = __ldg(base + (slab / r.ksize) * r.s_kh + (slab % r.ksize) * r.s_kw);
-      } else {
-        const int phase = slab >> 2, tap = slab & 3;
-        const int a = phase >> 1, b = phase & 1, u = tap >> 1, vv = tap & 1;
+    const bool in = co < r.cout && ci < r.cin;
+    const float* __restrict__ base = r.w + co * r.s_co + ci * r.s_ci;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      wv[q][t] = (in && t < taps) ? __ldg(base + (t / r.ksize) * r.s_kh + (t % r.ksize) * r.s_kw) : 0.f;
+  }
+  const int nslab = r.kind == 0 ? taps : 16;
+  for (int slab = 0; slab < nslab; ++slab) {
+    float vals[4];
+    if (r.kind == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = wv[q][0];
+#pragma unroll
+        for (int t = 1; t < 9; ++t) v = t == slab ? wv[q][t] : v;      // register select (no dynamic indexing)
+        vals[q] = v;
+      }
+    } else {
+      const int phase = slab >> 2, tap = slab & 3;
+      const int a = phase >> 1, b = phase & 1, u = tap >> 1, vv = tap & 1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v = 0.f;       // same summation order as pack_weights_upfold_kernel: rows outer, columns inner
+#pragma unroll
         for (int rw = 0; rw < 3; ++rw)
+#pragma unroll
           for (int c = 0; c < 3; ++c)
-            if (upfold_member_(a, u, rw) && upfold_member_(b, vv, c)) v += __ldg(base + rw * r.s_kh + c * r.s_kw);
+            if (upfold_member_(a, u, rw) && upfold_member_(b, vv, c)) v += wv[q][rw * 3 + c];
+        vals[q] = v;
       }
     }
-    vals[q] = v;
-  }
+    if (slab > 0) __syncthreads();               // the previous slab's transposed reads of the tile are done
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int rr = ty + 8 * q;
-    const int co = co0 + rr, ci = ci0 + tx;
-    if (co < r.cout && ci < r.cin && r.wf != nullptr)
-      r.wf[((long long)slab * r.cout + co) * r.cin + ci] = __float2bfloat16_rn(vals[q]);
-    tile[rr][tx] = vals[q];
-  }
-  if (r.wd == nullptr) return;
-  __syncthreads();
-  const int dslab = r.kind == 0 ? (taps - 1 - slab) : ((slab & ~3) + (3 - (slab & 3)));
-  for (int rr = ty; rr < 32; rr += 8) {
-    const int ci = ci0 + rr, co = co0 + tx;
-    if (co < r.cout && ci < r.cin)
-      r.wd[((long long)dslab * r.cin + ci) * r.cout + co] = __float2bfloat16_rn(tile[tx][rr]);
+    for (int q = 0; q < 4; ++q) {
+      const int rr = ty + 8 * q;
+      const int co = co0 + rr, ci = ci0 + tx;
+      if (co < r.cout && ci < r.cin && r.wf != nullptr)
+        r.wf[((long long)slab * r.cout + co) * r.cin + ci] = __float2bfloat16_rn(vals[q]);
+      tile[rr][tx] = vals[q];
+    }
+    if (r.wd == nullptr) continue;
+    __syncthreads();
+    const int dslab = r.kind == 0 ? (taps - 1 - slab) : ((slab & ~3) + (3 - (slab & 3)));
+    for (int rr = ty; rr < 32; rr += 8) {
+      const int ci = ci0 + rr, co = co0 + tx;
+      if (co < r.cout && ci < r.cin)
+        r.wd[((long long)dslab * r.cin + ci) * r.cout + co] = __float2bfloat16_rn(tile[tx][rr]);
+    }
   }
 }
 
