@@ -192,6 +192,21 @@ int b2_bn_finalize(const double* stats, int32_t c, int64_t count, const float* g
                    float eps, float momentum, float* running_mean, float* running_var,
                    int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
                    b2_stream_t stream);
+/* The running-statistics half of b2_bn_finalize (momentum update with the unbiased variance, num_batches_tracked += 1;
+ * nn.BatchNorm2d semantics, AttentionUNet.py:7) for MANY layers in one launch: a training step of AttU_Net has 34
+ * BatchNorm calls whose updates are off the data path, so the step queues them and flushes once.  `refs` is a HOST
+ * array of n entries (they travel to the device as kernel parameters, 64 per launch: nothing to keep alive, safe
+ * under CUDA-graph capture); the entries of one call must refer to DISTINCT layers; max_c = the largest channel count. */
+typedef struct b2_bn_run_ref {
+  const double* stats;             /* [2][c]: sum, sum of squares */
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  int64_t count;                   /* elements per channel */
+  int32_t c;
+  float momentum;
+} b2_bn_run_ref;
+int b2_bn_update_running_multi(const b2_bn_run_ref* refs, int32_t n, int32_t max_c, b2_stream_t stream);
 int b2_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                       const float* running_var, float eps, int32_t c, float* mean, float* invstd, float* scale,
                       float* shift, b2_stream_t stream);

@@ -46,6 +46,12 @@ class WgradArgs(C.Structure):
                 ("custom_pad", _i32), ("pad_h", _i32), ("pad_w", _i32), ("fold", _i32)]
 
 
+class BnRunRef(C.Structure):
+    """struct b2_bn_run_ref"""
+    _fields_ = [("stats", _vp), ("running_mean", _vp), ("running_var", _vp), ("num_batches_tracked", _vp),
+                ("count", _i64), ("c", _i32), ("momentum", C.c_float)]
+
+
 class F32ConvArgs(C.Structure):
     """struct b2_f32_conv_args"""
     _fields_ = [("x0", _vp), ("x1", _vp), ("c0", _i32), ("c1", _i32), ("ldx0", _i32), ("ldx1", _i32),
@@ -96,6 +102,7 @@ SIGNATURES = {
     "b2_head_bwd": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "b2_channel_stats": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp]),
     "b2_bn_finalize": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b2_bn_update_running_multi": (C.c_int, [_vp, _i32, _i32, _vp]),
     "b2_bn_eval_coeffs": (C.c_int, [_vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "b2_bn_apply": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "b2_bn_bwd_reduce": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -56,7 +56,8 @@ class GraphedTrainStep:
     def _step(self, x, t):
         self.optimizer.zero_grad(set_to_none=True)
         K.step_begin()
-        logits = self.model(x)
+        with K.deferred_running_updates():          # the BatchNorm running-statistics updates of the forward: one launch
+            logits = self.model(x)
         if logits.dim() == 3:
             logits = logits.unsqueeze(1)            # helpers.py:323-324
         loss, _sums = ops.seg_loss(logits, t, *self.loss_weights)

@@ -748,8 +748,57 @@ def bn_apply(z, coef, relu=True, addend=None, want_sum=False, sum_only=False):
     return (y, ysum) if want_sum else y
 
 
+# Deferred running-statistics updates: they are off the data path (nothing in the step reads running_mean / running_var)
+# but each was a launch of its own on the step's critical stream — 34 per AttU_Net step, 70 per R2AttU_Net(t=2) step.
+# Inside `deferred_running_updates()` (engine.GraphedTrainStep) they are queued and flushed as ONE launch per round;
+# round k holds the k-th update of every BatchNorm of the step, so the t + 1 sequential updates of a Recurrent_block's
+# shared BatchNorm (R2U_Net.py:15-20) keep their order.
+_RUN = {"defer": False, "queue": []}
+
+
+@contextlib.contextmanager
+def deferred_running_updates():
+    if os.environ.get("B200SEG_DEFER_RUNNING", "1") == "0":      # A/B switch: one launch per BatchNorm call
+        yield
+        return
+    prev = _RUN["defer"]
+    _RUN["defer"] = True
+    try:
+        yield
+        flush_running_updates()
+    finally:
+        _RUN["defer"] = prev
+        if not prev:
+            _RUN["queue"].clear()
+
+
+def flush_running_updates():
+    q, _RUN["queue"] = _RUN["queue"], []
+    if not q:
+        return
+    rounds, seen = [], {}
+    for e in q:                                     # e = (stats, count, momentum, rm, rv, nbt)
+        k = seen.get(e[3].data_ptr(), 0)
+        seen[e[3].data_ptr()] = k + 1
+        while len(rounds) <= k:
+            rounds.append([])
+        rounds[k].append(e)
+    for rnd in rounds:
+        refs = (_lib.BnRunRef * len(rnd))()
+        max_c = 0
+        for i, (stats, count, momentum, rm, rv, nbt) in enumerate(rnd):
+            c = stats.numel() // 2
+            max_c = max(max_c, c)
+            refs[i].stats, refs[i].running_mean, refs[i].running_var = stats.data_ptr(), rm.data_ptr(), rv.data_ptr()
+            refs[i].num_batches_tracked, refs[i].count, refs[i].c, refs[i].momentum = nbt.data_ptr(), count, c, momentum
+        call("b2_bn_update_running_multi", refs, len(rnd), max_c, _stream())
+
+
 def bn_update_running(stats, count, momentum, running_mean, running_var, nbt):
     """momentum update of the running statistics from epilogue-produced (sum, sumsq); no coefficient outputs"""
+    if _RUN["defer"]:
+        _RUN["queue"].append((stats, int(count), float(momentum), running_mean, running_var, nbt))
+        return
     c = stats.numel() // 2
     z = C.c_void_p(0)
     call("b2_bn_finalize", _p(stats), c, int(count), z, z, 0.0, float(momentum), _p(running_mean), _p(running_var),

@@ -8,6 +8,8 @@
 // chunks of consecutive pixels (fully coalesced for ld == C).
 #include <stdlib.h>
 
+#include <string.h>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -135,7 +137,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, long
   if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (c >= C) return;
   const double m = stats[c] / (double)count;
-  double var = stats[C + c] / (double)count - m * m;
+  double var = __fma_rn(-m, m, stats[C + c] / (double)count);
   if (var < 0.0) var = 0.0;
   const float fm = (float)m;
   const float is = (float)(1.0 / sqrt(var + (double)eps));
@@ -148,9 +150,37 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, long
   }
   if (running_mean != nullptr) {
     const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * fm;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    // (explicit rounding points: the multi-layer kernel below must give the same bits)
+    running_mean[c] = __fmaf_rn(momentum, fm, __fmul_rn(1.f - momentum, running_mean[c]));
+    running_var[c] = __fmaf_rn(momentum, (float)unbiased, __fmul_rn(1.f - momentum, running_var[c]));
   }
+}
+
+// running statistics of MANY BatchNorm layers in one launch (b2_bn_update_running_multi): block (layer, 256-channel slab)
+struct BnRunRef {      // mirrors b2_bn_run_ref
+  const double* stats;
+  float* running_mean;
+  float* running_var;
+  long long* num_batches_tracked;
+  long long count;
+  int c;
+  float momentum;
+};
+static constexpr int kRunBatch = 64;      // layers per launch: the references travel as a kernel PARAMETER (3 KB), so
+struct BnRunBatch {                       // there is no device table to build or keep alive — safe under graph capture
+  BnRunRef r[kRunBatch];
+};
+__global__ void __launch_bounds__(256) bn_update_running_multi_kernel(const __grid_constant__ BnRunBatch batch) {
+  const BnRunRef& r = batch.r[blockIdx.x];
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c == 0) *r.num_batches_tracked += 1;
+  if (c >= r.c) return;
+  const double m = r.stats[c] / (double)r.count;
+  double var = __fma_rn(-m, m, r.stats[r.c + c] / (double)r.count);
+  if (var < 0.0) var = 0.0;
+  const double unbiased = r.count > 1 ? var * (double)r.count / (double)(r.count - 1) : var;
+  r.running_mean[c] = __fmaf_rn(r.momentum, (float)m, __fmul_rn(1.f - r.momentum, r.running_mean[c]));
+  r.running_var[c] = __fmaf_rn(r.momentum, (float)unbiased, __fmul_rn(1.f - r.momentum, r.running_var[c]));
 }
 
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -688,6 +718,19 @@ extern "C" int b2_bn_finalize(const double* stats, int32_t c, int64_t count, con
       stats, c, count, gamma, beta, eps, momentum, running_mean, running_var,
       reinterpret_cast<long long*>(num_batches_tracked), mean, invstd, scale, shift);
   B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_bn_update_running_multi(const b2_bn_run_ref* refs, int32_t n, int32_t max_c, b2_stream_t stream) {
+  static_assert(sizeof(BnRunRef) == sizeof(b2_bn_run_ref), "BnRunRef must mirror b2_bn_run_ref");
+  B2_REQUIRE(refs != nullptr && n > 0 && max_c > 0, B2_ERR_SHAPE, "empty running-statistics launch");
+  for (int i0 = 0; i0 < n; i0 += kRunBatch) {
+    const int m = n - i0 < kRunBatch ? n - i0 : kRunBatch;
+    BnRunBatch batch;
+    memcpy(batch.r, reinterpret_cast<const BnRunRef*>(refs) + i0, sizeof(BnRunRef) * (size_t)m);
+    bn_update_running_multi_kernel<<<dim3(m, (max_c + 255) / 256), 256, 0, (cudaStream_t)stream>>>(batch);
+    B2_LAUNCH_CHECK();
+  }
   return B2_OK;
 }
 

@@ -74,10 +74,13 @@ def _struct_fields(name):
 
 
 @pytest.mark.parametrize("cname,pyname", [("b2_conv_args", "ConvArgs"), ("b2_wgrad_args", "WgradArgs"),
-                                          ("b2_gate_args", "GateArgs"), ("b2_f32_conv_args", "F32ConvArgs")])
+                                          ("b2_gate_args", "GateArgs"), ("b2_f32_conv_args", "F32ConvArgs"),
+                                          ("b2_bn_run_ref", "BnRunRef")])
 def test_ctypes_structs_have_the_headers_field_count(cname, pyname):
     from b200seg import _lib
     assert len(getattr(_lib, pyname)._fields_) == _struct_fields(cname)
+    if pyname == "BnRunRef":
+        assert C.sizeof(_lib.BnRunRef) == 48          # 64 of them travel as one kernel parameter
 
 
 def test_aug_params_size_matches_header():

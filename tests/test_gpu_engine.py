@@ -156,3 +156,33 @@ def test_pinned_prefetcher_delivers_batches_in_order():
             got_x.append(xb.clone())
             got_t.append(tb.clone())
         assert torch.equal(torch.cat(got_x).cpu(), data) and torch.equal(torch.cat(got_t).cpu(), tgt)
+
+
+def test_deferred_running_updates_match_immediate_ones():
+    """kernels.deferred_running_updates (one b2_bn_update_running_multi launch per round instead of one launch per
+    BatchNorm call): running_mean / running_var / num_batches_tracked after a train-mode forward must be BIT-identical to
+    the immediate updates — including a Recurrent_block's shared BatchNorm, whose t + 1 sequential updates go to t + 1
+    rounds (R2U_Net.py:15-20)."""
+    from b200seg import kernels as K
+    from b200seg.models.segmentation_models import R2AttU_Net
+    from b200seg.utils.synthetic import xray_batch
+    torch.manual_seed(0)
+    model = R2AttU_Net(t=2).cuda().train()
+    x, _ = xray_batch(2, 64, 64, seed=2, device=torch.device("cuda"))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    K.set_deterministic(True)
+    try:
+        with torch.no_grad():
+            model(x)
+        torch.cuda.synchronize()
+        ref = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+        model.load_state_dict(state)
+        with torch.no_grad(), K.deferred_running_updates():
+            model(x)
+        torch.cuda.synchronize()
+    finally:
+        K.set_deterministic(False)
+    got = model.state_dict()
+    assert any(int(v) == 3 for k, v in ref.items() if "num_batches" in k)        # the shared BatchNorms: t + 1 = 3
+    bad = [k for k in ref if not torch.equal(ref[k], got[k])]
+    assert not bad, bad[:5]
