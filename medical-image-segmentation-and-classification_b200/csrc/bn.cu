@@ -57,6 +57,7 @@ __device__ __forceinline__ void rows_reduce8(float* acc, int tpp, int rows, int 
 __global__ void __launch_bounds__(kBlock) channel_stats_kernel(const __nv_bfloat16* __restrict__ z, int ldz,
                                                                long long npix, int C, ChanMap m,
                                                                double* __restrict__ stats, int want_sq, DetBuf det) {
+  pdl_enter();
   __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(kBlock) channel_stats_kernel(const __nv_bfloat
 __global__ void __launch_bounds__(kBlock) channel_sum_kernel(const __nv_bfloat16* __restrict__ dy, int lddy,
                                                              long long npix, int C, ChanMap m,
                                                              float* __restrict__ db, DetBuf det) {
+  pdl_enter();
   __shared__ float red[kBlock * 8];
   // gridDim.y channel slices of m.tpp * 8 channels: a block ends in one atomic per channel of its slice, and with ~1200
   // blocks on the same C addresses those atomics were a fixed ~100 us per launch whatever the tensor size
@@ -133,6 +135,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, long
                                    float momentum, float* running_mean, float* running_var,
                                    long long* num_batches_tracked, float* mean, float* invstd, float* scale,
                                    float* shift) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (c >= C) return;
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(kBlock) bn_apply_kernel(const __nv_bfloat16* _
                                                           __nv_bfloat16* __restrict__ y, int ldy,
                                                           const __nv_bfloat16* __restrict__ addend, int ldadd,
                                                           __nv_bfloat16* __restrict__ ysum, int ldysum) {
+  pdl_enter();
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
   if (r >= m.rows) return;
@@ -301,6 +305,7 @@ __global__ void __launch_bounds__(kBlock, 3) bn_bwd_reduce_kernel(
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums,
     DetBuf det) {
+  pdl_enter();
   __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -377,6 +382,7 @@ __global__ void __launch_bounds__(kBlock, 2) bn_bwd_apply_kernel(
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
     int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, DetBuf det) {
+  pdl_enter();
   __shared__ float red[kBlock * 8];
   const int t = threadIdx.x;
   const int g = t % m.tpp, r = t / m.tpp;
@@ -491,6 +497,7 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_reduce_light_kernel(
     int C, ChanMap m, const float* __restrict__ scale, const float* __restrict__ shift,
     const float* __restrict__ mean, const float* __restrict__ invstd, int relu, double* __restrict__ sums,
     DetBuf det) {
+  pdl_enter();
   __shared__ float red[kBlock * 4];
   // gridDim.y channel slices of m.tpp * 4 channels: a block ends in 2 * (slice width) atomics instead of 2 C, which is
   // what bounded the many-channel layers (1184 blocks x 1024 fp64 atomics at C = 512: 0.115 ms for 0.024 ms of data)
@@ -556,6 +563,7 @@ __global__ void __launch_bounds__(kBlock, 4) bn_bwd_apply_light_kernel(
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma, int relu,
     int training, const double* __restrict__ sums, __nv_bfloat16* __restrict__ dz, int lddz,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias, DetBuf det) {
+  pdl_enter();
   __shared__ float red[kBlock * 4];
   // gridDim.y channel slices of m.tpp * 4 channels (as in the reduce kernel): with C / 4 threads per pixel a thread of a
   // 512- or 1024-channel layer met only a handful of pixels, and its prologue (six per-channel coefficient loads, two of
@@ -676,8 +684,9 @@ extern "C" int b2_channel_stats(const void* z, int32_t ldz, int64_t npix, int32_
   DetBuf det;
   rc = det_begin(&det, grid, 2 * c, (cudaStream_t)stream);
   if (rc) return rc;
-  channel_stats_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z, ldz, npix, c, m, stats, 1,
-                                                                  det);
+  B2_CHECK_CUDA(launch_chain(channel_stats_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
+      (const __nv_bfloat16*)z, ldz, npix, c, m, stats, 1,
+                                                                  det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2 * c, stats, (cudaStream_t)stream);
   return B2_OK;
@@ -702,8 +711,9 @@ extern "C" int b2_channel_sum(const void* dy, int32_t lddy, int64_t npix, int32_
   DetBuf det;
   rc = det_begin(&det, grid, c, (cudaStream_t)stream);
   if (rc) return rc;
-  channel_sum_kernel<<<dim3(grid, slices), kBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, lddy, npix, c, m,
-                                                                              db, det);
+  B2_CHECK_CUDA(launch_chain(channel_sum_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
+      (const __nv_bfloat16*)dy, lddy, npix, c, m,
+                                                                              db, det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, c, db, (cudaStream_t)stream);
   return B2_OK;
@@ -714,9 +724,9 @@ extern "C" int b2_bn_finalize(const double* stats, int32_t c, int64_t count, con
                               float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
                               float* scale, float* shift, b2_stream_t stream) {
   B2_REQUIRE(c > 0 && count > 0, B2_ERR_SHAPE, "bad bn_finalize extent");
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  B2_CHECK_CUDA(launch_chain(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)stream, 1,
       stats, c, count, gamma, beta, eps, momentum, running_mean, running_var,
-      reinterpret_cast<long long*>(num_batches_tracked), mean, invstd, scale, shift);
+      reinterpret_cast<long long*>(num_batches_tracked), mean, invstd, scale, shift));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -755,9 +765,9 @@ extern "C" int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, 
   B2_REQUIRE(ysum == nullptr || (addend != nullptr && aligned16(ysum, ldysum)), B2_ERR_ALIGN,
              "bn_apply ysum misaligned or addend missing");
   B2_REQUIRE(addend == nullptr || aligned16(addend, ldadd), B2_ERR_ALIGN, "bn_apply addend misaligned");
-  bn_apply_kernel<<<chan_grid(npix, m, 16), kBlock, 0, (cudaStream_t)stream>>>(
+  B2_CHECK_CUDA(launch_chain(bn_apply_kernel, dim3(chan_grid(npix, m, 16)), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
       (const __nv_bfloat16*)z, ldz, npix, m, scale, shift, relu, (__nv_bfloat16*)y, ldy,
-      (const __nv_bfloat16*)addend, ldadd, (__nv_bfloat16*)ysum, ldysum);
+      (const __nv_bfloat16*)addend, ldadd, (__nv_bfloat16*)ysum, ldysum));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -786,13 +796,13 @@ extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int
   rc = det_begin(&det, grid, 2 * c, (cudaStream_t)stream);
   if (rc) return rc;
   if (light) {
-    bn_bwd_reduce_light_kernel<<<dim3(grid, slices), kBlock, 0, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(bn_bwd_reduce_light_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, relu,
-        sums, det);
+        sums, det));
   } else {
-    bn_bwd_reduce_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(bn_bwd_reduce_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, relu,
-        sums, det);
+        sums, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2 * c, sums, (cudaStream_t)stream);
@@ -829,13 +839,13 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
     if (rc) return rc;
   }
   if (light) {
-    bn_bwd_apply_light_kernel<<<dim3(grid, slices), kBlock, 0, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(bn_bwd_apply_light_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, gamma,
-        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det);
+        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det));
   } else {
-    bn_bwd_apply_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(bn_bwd_apply_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
         (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
-        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det);
+        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, c, dbias, (cudaStream_t)stream);

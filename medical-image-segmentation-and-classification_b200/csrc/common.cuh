@@ -37,6 +37,54 @@ int num_sms();
 // costs no getenv scans, and concurrent forward / autograd-engine threads see one consistent configuration.
 int env_switch(const char* name, int dflt);
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (B200SEG_PDL, default 0).  A kernel launched through launch_chain() with the switch on
+// carries cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident while the previous kernel of
+// the stream is still draining, so its launch latency and prologue (barrier init, TMEM allocation, descriptor
+// prefetch) overlap that kernel's tail — inside a captured graph the edge becomes a programmatic dependency.  EVERY
+// kernel launched this way executes pdl_wait() on all threads before its first global-memory access (reads AND writes:
+// the previous kernel may still be reading what this one overwrites), which also keeps completion transitive along the
+// chain.  pdl_trigger() lets the NEXT kernel start becoming resident; without it that happens when the CTA exits.
+// Both instructions are no-ops in a launch without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+inline int pdl_mode() { return env_switch("B200SEG_PDL", 0); }
+
+// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute when B200SEG_PDL != 0 (the kernel must
+// call pdl_wait() / pdl_enter() first thing).  `cluster` > 1 adds the cluster dimension.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_mode() != 0) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // TMA descriptor encode (driver entry point fetched through the runtime; no libcuda link dependency).
 // dims/strides innermost-first; strides in BYTES for dims 1..rank-1; bf16 elements.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

@@ -129,6 +129,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     tma_prefetch_desc(&tmY);
     if (p.cbt > p.cb0) tma_prefetch_desc(&tmA1);
   }
+  pdl_enter();            // (B200SEG_PDL) barrier init / descriptor prefetch above overlap the previous kernel's tail
   if (threadIdx.x >= 64 && threadIdx.x < 128) s_bias[threadIdx.x - 64] = p.bias ? p.bias[threadIdx.x - 64] : 0.f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
@@ -621,7 +622,8 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   p.stats_partial = det.partial;
-  conv_c64_kernel<<<p.grid, kC64Threads, smem_bytes, stream>>>(tmA0, tmA1, tmB, tmY, tmAdd, p);
+  B2_CHECK_CUDA(launch_chain(conv_c64_kernel, dim3(p.grid), dim3(kC64Threads), (size_t)(smem_bytes), stream, 1,
+      tmA0, tmA1, tmB, tmY, tmAdd, p));
   B2_LAUNCH_CHECK();
   if (det.partial) {
     rc = det_finish(det.partial, det_rows, 128, 128, p.stats, stream);

@@ -191,6 +191,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __syncthreads();
   if (C > 1) cluster_sync_all();       // peers' barriers are initialised before any multicast can reach them
   tc_fence_after();
+  // (B200SEG_PDL) everything above — barrier init, descriptor prefetch, TMEM allocation — may overlap the previous
+  // kernel's tail; nothing below may run before that kernel has completed
+  pdl_enter();
   const uint32_t tmem_base = *tmem_slot;
   const int cbt = p.cb0 + p.cb1;
 
@@ -1241,13 +1244,18 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_mode() != 0) {       // programmatic dependent launch (common.cuh): the kernel waits after its prologue
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   DetBuf det;
   det.partial = nullptr;
   const long long det_rows = (long long)clusters * C * p.epi_groups;

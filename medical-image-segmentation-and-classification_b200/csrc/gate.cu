@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) gate_psi_fwd_kernel(
     int L, const float* __restrict__ scale_g, const float* __restrict__ shift_g, const float* __restrict__ scale_x,
     const float* __restrict__ shift_x, const float* __restrict__ wpsi, const float* __restrict__ bpsi,
     __nv_bfloat16* __restrict__ q, double* __restrict__ qstats, DetBuf det) {
+  pdl_enter();
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
   const bool has = lig * 8 < fint;
   float sg[8], hg[8], sx[8], hx[8], wp[8];
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(256) gate_apply_fwd_kernel(const __nv_bfloat16
                                                              const float* __restrict__ shift1,
                                                              __nv_bfloat16* __restrict__ psi,
                                                              __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_enter();
   const int g = threadIdx.x % tpp, r = threadIdx.x / tpp;
   if (r >= rows) return;
   const float s1 = __ldg(scale1), h1 = __ldg(shift1);
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(256) gate_apply_bwd_kernel(
     const __nv_bfloat16* __restrict__ psi, const __nv_bfloat16* __restrict__ q, long long npix, int cg, int L,
     const float* __restrict__ mean1, const float* __restrict__ invstd1, __nv_bfloat16* __restrict__ dx, int lddx,
     float* __restrict__ dsig, double* __restrict__ sums1, DetBuf det) {
+  pdl_enter();
   const int lig = threadIdx.x % L, grp = threadIdx.x / L, gpb = blockDim.x / L;
   const float mu1 = __ldg(mean1), is1 = __ldg(invstd1);
   float l0 = 0.f, l1 = 0.f;
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(256, MINB) gate_psi_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ x1p, int ld, long long npix, int fint, int L, GateBwdCoef c,
     const double* __restrict__ sums1, int training, double* __restrict__ sums, float* __restrict__ dwpsi,
     float* __restrict__ dbpsi, int slice, DetBuf det) {
+  pdl_enter();
   using VT = typename GVec<V>::T;
   // gridDim.y channel slices of `slice` channels (0: one slice = all of F_int): a block then ends in 5 * slice global
   // atomics instead of 5 * F_int, and gridDim.x (= blocks adding to one address) shrinks by the slice count — the
@@ -370,6 +374,7 @@ __global__ void __launch_bounds__(256, MINB) gate_psi_bwd_apply_kernel(
     const double* __restrict__ sums1, int training, const double* __restrict__ sums,
     __nv_bfloat16* __restrict__ dg1p, __nv_bfloat16* __restrict__ dx1p, float* __restrict__ dgamma_beta,
     float* __restrict__ dbn1, float* __restrict__ dbias, DetBuf det) {
+  pdl_enter();
   using VT = typename GVec<V>::T;
   __shared__ float red[256 * V];
   // gridDim.y channel slices of tpp * V channels (see the reduce kernel)
@@ -525,9 +530,9 @@ extern "C" int b2_gate_psi_fwd(const void* g1p, const void* x1p, int32_t ld, int
   DetBuf det;
   int rc = det_begin(&det, grid, 2, (cudaStream_t)stream);
   if (rc) return rc;
-  gate_psi_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  B2_CHECK_CUDA(launch_chain(gate_psi_fwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
       (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L, scale_g, shift_g, scale_x, shift_x,
-      wpsi, bpsi, (__nv_bfloat16*)q, qstats, det);
+      wpsi, bpsi, (__nv_bfloat16*)q, qstats, det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2, qstats, (cudaStream_t)stream);
   return B2_OK;
@@ -539,9 +544,9 @@ extern "C" int b2_gate_apply_fwd(const void* x, int32_t ldx, const void* q, int6
   B2_REQUIRE(c % 8 == 0 && c <= 2048, B2_ERR_SHAPE, "gate C=%d must be a multiple of 8, <= 2048", c);
   B2_REQUIRE(g_al(x, ldx) && g_al(out, ldo), B2_ERR_ALIGN, "gate operands misaligned");
   const int tpp = c / 8, rows = 256 / tpp;
-  gate_apply_fwd_kernel<<<g_grid(npix, rows, 16), 256, 0, (cudaStream_t)stream>>>(
+  B2_CHECK_CUDA(launch_chain(gate_apply_fwd_kernel, dim3(g_grid(npix, rows, 16)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
       (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)q, npix, tpp, rows, scale1, shift1, (__nv_bfloat16*)psi,
-      (__nv_bfloat16*)out, ldo);
+      (__nv_bfloat16*)out, ldo));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -557,9 +562,9 @@ extern "C" int b2_gate_apply_bwd(const void* dout, int32_t lddout, const void* x
   DetBuf det;
   int rc = det_begin(&det, grid, 2, (cudaStream_t)stream);
   if (rc) return rc;
-  gate_apply_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  B2_CHECK_CUDA(launch_chain(gate_apply_bwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
       (const __nv_bfloat16*)dout, lddout, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)psi,
-      (const __nv_bfloat16*)q, npix, c / 8, L, mean1, invstd1, (__nv_bfloat16*)dx, lddx, dsig, sums1, det);
+      (const __nv_bfloat16*)q, npix, c / 8, L, mean1, invstd1, (__nv_bfloat16*)dx, lddx, dsig, sums1, det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2, sums1, (cudaStream_t)stream);
   return B2_OK;
@@ -594,17 +599,17 @@ extern "C" int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const vo
   int rc = det_begin(&det, grid, 5 * fint + 1, (cudaStream_t)stream);
   if (rc) return rc;
   if (light && env_switch("B200SEG_GATE_U", fint <= 128 ? 4 : 2) == 4) {
-    gate_psi_bwd_reduce_kernel<4, 4, 2><<<dim3(grid, slices), 256, smem, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<4, 4, 2>, dim3(grid, slices), dim3(256), (size_t)(smem), (cudaStream_t)stream, 1,
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det);
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det));
   } else if (light) {
-    gate_psi_bwd_reduce_kernel<4, 2, 3><<<dim3(grid, slices), 256, smem, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<4, 2, 3>, dim3(grid, slices), dim3(256), (size_t)(smem), (cudaStream_t)stream, 1,
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det);
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det));
   } else {
-    gate_psi_bwd_reduce_kernel<8, 2, 2><<<grid, 256, smem, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<8, 2, 2>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, 1,
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, 0, det);
+        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, 0, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) {
@@ -642,20 +647,20 @@ extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const voi
     if (rc) return rc;
   }
   if (light && env_switch("B200SEG_GATE_U", fint <= 128 ? 4 : 2) == 4) {
-    gate_psi_bwd_apply_kernel<4, 4, 2><<<dim3(grid, slices), 256, 0, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<4, 4, 2>, dim3(grid, slices), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
         rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias, det);
+        dbias, det));
   } else if (light) {
-    gate_psi_bwd_apply_kernel<4, 2, 3><<<dim3(grid, slices), 256, 0, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<4, 2, 3>, dim3(grid, slices), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
         rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias, det);
+        dbias, det));
   } else {
-    gate_psi_bwd_apply_kernel<8, 2, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<8, 2, 2>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
         dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
         rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias, det);
+        dbias, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2 * fint, dbias, (cudaStream_t)stream);

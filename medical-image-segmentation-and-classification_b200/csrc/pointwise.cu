@@ -88,6 +88,7 @@ __global__ void fold_upconv_wgrad_kernel(const float* __restrict__ dweff, int co
 
 __global__ void maxpool2x2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int cg,
                                       __nv_bfloat16* __restrict__ y, int ldy) {
+  pdl_enter();
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -118,6 +119,7 @@ __global__ void maxpool2x2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
                                       const __nv_bfloat16* __restrict__ x, int ldx, int n, int h, int w, int cg,
                                       __nv_bfloat16* __restrict__ dx, int lddx,
                                       const __nv_bfloat16* __restrict__ addend, int ldadd) {
+  pdl_enter();
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -212,6 +214,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
 
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b,
                            int ldb, long long npix, int cg, __nv_bfloat16* __restrict__ out, int ldo) {
+  pdl_enter();
   const long long total = npix * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -345,8 +348,8 @@ extern "C" int b2_maxpool2x2_fwd(const void* x, int32_t ldx, int32_t n, int32_t 
   B2_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, B2_ERR_SHAPE, "maxpool needs c%%8==0 and even h,w");
   B2_REQUIRE(al16(x, ldx) && al16(y, ldy), B2_ERR_ALIGN, "maxpool operands misaligned");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool2x2_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)y, ldy);
+  B2_CHECK_CUDA(launch_chain(maxpool2x2_fwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
+      (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)y, ldy));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -356,9 +359,9 @@ extern "C" int b2_maxpool2x2_bwd(const void* dy, int32_t lddy, const void* x, in
   B2_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, B2_ERR_SHAPE, "maxpool needs c%%8==0 and even h,w");
   B2_REQUIRE(al16(x, ldx) && al16(dy, lddy) && al16(dx, lddx), B2_ERR_ALIGN, "maxpool operands misaligned");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool2x2_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  B2_CHECK_CUDA(launch_chain(maxpool2x2_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx, nullptr,
-      0);
+      0));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -370,9 +373,9 @@ extern "C" int b2_maxpool2x2_bwd_add(const void* dy, int32_t lddy, const void* x
   B2_REQUIRE(al16(x, ldx) && al16(dy, lddy) && al16(dx, lddx) && addend != nullptr && al16(addend, ldadd),
              B2_ERR_ALIGN, "maxpool operands misaligned / addend missing");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool2x2_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  B2_CHECK_CUDA(launch_chain(maxpool2x2_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
       (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx,
-      (const __nv_bfloat16*)addend, ldadd);
+      (const __nv_bfloat16*)addend, ldadd));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -404,8 +407,8 @@ extern "C" int b2_add(const void* a, int32_t lda, const void* b, int32_t ldb, in
                       int32_t ldo, b2_stream_t stream) {
   B2_REQUIRE(c % 8 == 0, B2_ERR_SHAPE, "add needs c%%8==0");
   B2_REQUIRE(al16(a, lda) && al16(b, ldb) && al16(out, ldo), B2_ERR_ALIGN, "add operands misaligned");
-  add_kernel<<<ew_grid(npix * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, npix, c / 8, (__nv_bfloat16*)out, ldo);
+  B2_CHECK_CUDA(launch_chain(add_kernel, dim3(ew_grid(npix * (c / 8), 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
+      (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, npix, c / 8, (__nv_bfloat16*)out, ldo));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
