@@ -38,13 +38,15 @@ int num_sms();
 int env_switch(const char* name, int dflt);
 
 // ---------------------------------------------------------------------------------------------
-// Programmatic dependent launch (B200SEG_PDL, default 0).  A kernel launched through launch_chain() with the switch on
-// carries cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident while the previous kernel of
-// the stream is still draining, so its launch latency and prologue (barrier init, TMEM allocation, descriptor
-// prefetch) overlap that kernel's tail — inside a captured graph the edge becomes a programmatic dependency.  EVERY
-// kernel launched this way executes pdl_wait() on all threads before its first global-memory access (reads AND writes:
-// the previous kernel may still be reading what this one overwrites), which also keeps completion transitive along the
-// chain.  pdl_trigger() lets the NEXT kernel start becoming resident; without it that happens when the CTA exits.
+// Programmatic dependent launch (B200SEG_PDL, default 2 = the size rule below).  A kernel launched through
+// launch_chain() with the rule satisfied carries cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may
+// become resident while the previous kernel of the stream is still draining, so its launch latency and prologue
+// (barrier init, TMEM allocation, descriptor prefetch) overlap that kernel's tail — inside a captured graph the edge
+// becomes a programmatic dependency.  EVERY kernel launched this way executes pdl_wait() on all threads before its
+// first global-memory access (reads AND writes: the previous kernel may still be reading what this one overwrites);
+// pdl_trigger() comes after the wait, so when a dependent's CTAs start, everything older than their direct
+// predecessor has completed, and completion stays transitive along the chain.  Without the trigger the next kernel
+// becomes resident when the CTAs exit.
 // Both instructions are no-ops in a launch without the attribute.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -54,13 +56,21 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_trigger();
 }
 
-inline int pdl_mode() { return env_switch("B200SEG_PDL", 0); }
+// B200SEG_PDL: 0 off; 1 every chain launch; 2 (default) only launches whose tensor is at most B200SEG_PDL_MB (default 16) MiB —
+// the launch-bound regime (batch-1 inference, a few images per GPU); a long memory-bound kernel whose CTAs sit
+// resident behind the previous kernel only takes SM slots from the weight-gradient stream.
+inline bool pdl_allowed(long long work_bytes) {
+  const int mode = env_switch("B200SEG_PDL", 2);
+  if (mode == 0) return false;
+  if (mode == 1) return true;
+  return work_bytes <= (long long)env_switch("B200SEG_PDL_MB", 16) * (1ll << 20);
+}
 
-// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute when B200SEG_PDL != 0 (the kernel must
-// call pdl_wait() / pdl_enter() first thing).  `cluster` > 1 adds the cluster dimension.
+// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute when pdl_allowed(work_bytes) (the
+// kernel must call pdl_wait() / pdl_enter() first thing).  `cluster` > 1 adds the cluster dimension.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                                int cluster, Args&&... args) {
+                                int cluster, long long work_bytes, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -75,7 +85,7 @@ inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block,
     at[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (pdl_mode() != 0) {
+  if (pdl_allowed(work_bytes)) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

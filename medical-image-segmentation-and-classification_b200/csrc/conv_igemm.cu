@@ -1251,7 +1251,8 @@ static int conv_igemm_launch(const b2_conv_args* a, cudaStream_t stream, const G
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (pdl_mode() != 0) {       // programmatic dependent launch (common.cuh): the kernel waits after its prologue
+  // programmatic dependent launch (common.cuh): the kernel waits after its prologue; size rule on the output tensor
+  if (pdl_allowed((long long)p.m_tiles * 128 * p.cout * 2)) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
