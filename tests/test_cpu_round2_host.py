@@ -127,3 +127,28 @@ def test_bench_clock_sampler_keeps_the_rows_of_the_timed_region():
     out = s.stop()
     assert out["samples"] == 2 and "under load" in out["window"]
     assert bench.ClockSampler(0).stop()["sm_mhz"] is None          # nvidia-smi unavailable
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): rank 0 prints ONE JSON line with the base
+    keys plus impl / cpu_baseline / e2e (zero copy bytes); every other rank exits 0 without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-batch", "1",
+           "--side", "64"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["metric"] == "AttU_Net 256x256 train images/sec" and d["steps"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "workload" in d["config"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr[-500:])
