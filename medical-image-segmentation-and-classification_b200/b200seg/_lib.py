@@ -189,9 +189,22 @@ LAUNCHES_PER_CALL = {"b2_conv_wgrad": 2, "b2_channel_sum": 1, "b2_pack_weights_f
 launch_count = 0
 
 
+# B200SEG_NVTX=1: an NVTX range named after the entry point around every library call (tracing) — gives
+# `ncu --nvtx --nvtx-include "b2_conv_fprop/"` and timeline tools a per-op handle; read once at import
+_NVTX = os.environ.get("B200SEG_NVTX", "0") not in ("", "0")
+
+
 def call(name: str, *args):
     """Call an int-returning entry point and raise on a non-zero code."""
     global launch_count
-    rc = getattr(load(), name)(*args)
+    if _NVTX:
+        from torch.cuda import nvtx
+        nvtx.range_push(name)
+        try:
+            rc = getattr(load(), name)(*args)
+        finally:
+            nvtx.range_pop()
+    else:
+        rc = getattr(load(), name)(*args)
     check(rc, name)
     launch_count += LAUNCHES_PER_CALL.get(name, 1)

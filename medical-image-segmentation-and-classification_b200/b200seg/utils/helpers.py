@@ -9,10 +9,13 @@ Differences from the reference, all forced by the B200 path and listed in DESIGN
   * only `seg=True` is supported (the classification branch, helpers.py:257-283, is outside the hot path);
   * the training step (zero_grad .. optimizer.step, helpers.py:317-337) is captured once per batch shape in a CUDA graph
     and replayed (engine.GraphedTrainStep; B200SEG_TRAIN_GRAPH=0 launches eagerly), and CPU batches are staged through
-    pinned memory and copied on a copy stream while the previous step computes (engine.PinnedPrefetcher).
+    pinned memory and copied on a copy stream while the previous step computes (engine.PinnedPrefetcher);
+  * B200SEG_TRAIN_LOG=<file> appends one JSON line per epoch (losses, IoU, images/s of the training loop, graph
+    replays) next to the reference's per-epoch print (metrics / logging).
 """
 from __future__ import annotations
 
+import json
 import os
 import time
 
@@ -84,6 +87,7 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
             model.train()
             running = torch.zeros((), dtype=torch.float64, device=device)     # no per-step .item() (helpers.py:337)
             seen = 0
+            t_epoch = time.time()
             batches = PinnedPrefetcher(train_dl, device) if on_gpu else train_dl
             for x, y in batches:
                 if not x.is_cuda:
@@ -93,6 +97,8 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
                 loss = stepper(x.float(), y.float())
                 running += loss.detach().double() * x.size(0)
                 seen += x.size(0)
+            running_sum = float(running)              # the epoch's one host sync of the training loop
+            train_s = time.time() - t_epoch
 
             model.eval()
             val_loss = torch.zeros((), dtype=torch.float64, device=device)
@@ -125,8 +131,16 @@ def train(model, train_dl, val_dl, device, epochs, lr, name, save_dir, seg=False
                 n_train = _dataset_len(train_dl, seen)
             val_loss = float(val_loss) / max(n_val, 1)
             val_iou_f = float(val_iou) / max(n_batches, 1)
-            log(f"[{name}] Ep{epoch}: TrainLoss {float(running) / max(n_train, 1):.3f} | ValLoss {val_loss:.3f} | "
+            log(f"[{name}] Ep{epoch}: TrainLoss {running_sum / max(n_train, 1):.3f} | ValLoss {val_loss:.3f} | "
                 f"IoU {val_iou_f:.3f}")
+            log_path = os.environ.get("B200SEG_TRAIN_LOG")
+            if log_path and (reducer is None or reducer.rank == 0):
+                rec = {"name": name, "epoch": epoch, "train_loss": running_sum / max(n_train, 1), "val_loss": val_loss,
+                       "iou": val_iou_f, "images": seen, "train_s": train_s, "images_per_s": seen / max(train_s, 1e-9),
+                       "lr": optimizer.param_groups[0]["lr"], "graph_replays": stepper.replays,
+                       "eager_steps": stepper.eager_steps, "world_size": 1 if reducer is None else reducer.world}
+                with open(log_path, "a") as f:
+                    f.write(json.dumps(rec) + "\n")
             improved = val_loss < best_score
             scheduler.step()
             if improved:

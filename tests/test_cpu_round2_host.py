@@ -152,3 +152,30 @@ def test_bench_reference_arm_contract():
     assert d["gpu_launches"] == 0 and "workload" in d["config"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr[-500:])
+
+
+def test_nvtx_ranges_behind_env_flag():
+    """B200SEG_NVTX=1 wraps every library call in an NVTX range named after the entry point (a no-op without a
+    profiler) and leaves return-code checking and launch counting untouched."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = ("from b200seg import _lib\n"
+            "assert _lib._NVTX\n"
+            "n = _lib.launch_count\n"
+            "_lib.call('b2_reload_env')\n"
+            "assert _lib.launch_count == n + 1\n"
+            "import torch\n"
+            "if not torch.cuda.is_available():\n"
+            "    try:\n"
+            "        _lib.call('b2_arch_check')\n"
+            "        raise SystemExit('no error raised')\n"
+            "    except _lib.B2Error:\n"
+            "        pass\n"
+            "print('NVTX_OK')\n")
+    env = dict(os.environ, B200SEG_NVTX="1",
+               PYTHONPATH=str(root / "medical-image-segmentation-and-classification_b200") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "NVTX_OK" in r.stdout, (r.stdout, r.stderr[-1000:])

@@ -11,8 +11,10 @@ from torch.utils.data import DataLoader, TensorDataset
 pytestmark = pytest.mark.gpu
 
 
-def test_train_mirror_runs_and_saves_reference_layout(tmp_path):
+def test_train_mirror_runs_and_saves_reference_layout(tmp_path, monkeypatch):
+    import json
     from b200seg.utils.helpers import get_seg_model, train
+    monkeypatch.setenv("B200SEG_TRAIN_LOG", str(tmp_path / "train.jsonl"))
     from oracle.synthetic import xray_batch
     torch.manual_seed(0)
     x, t = xray_batch(8, 128, 128, seed=21)
@@ -31,6 +33,9 @@ def test_train_mirror_runs_and_saves_reference_layout(tmp_path):
     gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "AttentionUNet.npz"))
     assert list(ck.keys()) == [str(k) for k in gold["keys"]]
     get_seg_model("attentionunet").load_state_dict(ck, strict=True)
+    recs = [json.loads(ln) for ln in open(tmp_path / "train.jsonl")]       # B200SEG_TRAIN_LOG: one line per epoch
+    assert [r["epoch"] for r in recs] == [1, 2, 3] and all(r["images"] == 6 and r["images_per_s"] > 0 for r in recs)
+    assert abs(recs[0]["train_loss"] - losses[0]) < 1e-3 and recs[-1]["graph_replays"] + recs[-1]["eager_steps"] == 9
 
 
 @pytest.mark.parametrize("batch,side", [(1, 256), (3, 256), (1, 512)])
