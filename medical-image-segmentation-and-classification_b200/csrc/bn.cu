@@ -684,9 +684,8 @@ extern "C" int b2_channel_stats(const void* z, int32_t ldz, int64_t npix, int32_
   DetBuf det;
   rc = det_begin(&det, grid, 2 * c, (cudaStream_t)stream);
   if (rc) return rc;
-  B2_CHECK_CUDA(launch_chain(channel_stats_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-      (const __nv_bfloat16*)z, ldz, npix, c, m, stats, 1,
-                                                                  det));
+  B2_CHECK_CUDA(launch_chain(channel_stats_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
+      (long long)npix * c * 2, (const __nv_bfloat16*)z, ldz, npix, c, m, stats, 1, det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2 * c, stats, (cudaStream_t)stream);
   return B2_OK;
@@ -711,9 +710,8 @@ extern "C" int b2_channel_sum(const void* dy, int32_t lddy, int64_t npix, int32_
   DetBuf det;
   rc = det_begin(&det, grid, c, (cudaStream_t)stream);
   if (rc) return rc;
-  B2_CHECK_CUDA(launch_chain(channel_sum_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-      (const __nv_bfloat16*)dy, lddy, npix, c, m,
-                                                                              db, det));
+  B2_CHECK_CUDA(launch_chain(channel_sum_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0), (cudaStream_t)stream,
+      1, (long long)npix * c * 2, (const __nv_bfloat16*)dy, lddy, npix, c, m, db, det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, c, db, (cudaStream_t)stream);
   return B2_OK;
@@ -724,8 +722,8 @@ extern "C" int b2_bn_finalize(const double* stats, int32_t c, int64_t count, con
                               float* running_var, int64_t* num_batches_tracked, float* mean, float* invstd,
                               float* scale, float* shift, b2_stream_t stream) {
   B2_REQUIRE(c > 0 && count > 0, B2_ERR_SHAPE, "bad bn_finalize extent");
-  B2_CHECK_CUDA(launch_chain(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)stream, 1, 0,
-      stats, c, count, gamma, beta, eps, momentum, running_mean, running_var,
+  B2_CHECK_CUDA(launch_chain(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), (size_t)(0), (cudaStream_t)stream,
+      1, 0, stats, c, count, gamma, beta, eps, momentum, running_mean, running_var,
       reinterpret_cast<long long*>(num_batches_tracked), mean, invstd, scale, shift));
   B2_LAUNCH_CHECK();
   return B2_OK;
@@ -765,9 +763,9 @@ extern "C" int b2_bn_apply(const void* z, int32_t ldz, int64_t npix, int32_t c, 
   B2_REQUIRE(ysum == nullptr || (addend != nullptr && aligned16(ysum, ldysum)), B2_ERR_ALIGN,
              "bn_apply ysum misaligned or addend missing");
   B2_REQUIRE(addend == nullptr || aligned16(addend, ldadd), B2_ERR_ALIGN, "bn_apply addend misaligned");
-  B2_CHECK_CUDA(launch_chain(bn_apply_kernel, dim3(chan_grid(npix, m, 16)), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-      (const __nv_bfloat16*)z, ldz, npix, m, scale, shift, relu, (__nv_bfloat16*)y, ldy,
-      (const __nv_bfloat16*)addend, ldadd, (__nv_bfloat16*)ysum, ldysum));
+  B2_CHECK_CUDA(launch_chain(bn_apply_kernel, dim3(chan_grid(npix, m, 16)), dim3(kBlock), (size_t)(0),
+      (cudaStream_t)stream, 1, (long long)npix * c * 2, (const __nv_bfloat16*)z, ldz, npix, m, scale, shift, relu,
+      (__nv_bfloat16*)y, ldy, (const __nv_bfloat16*)addend, ldadd, (__nv_bfloat16*)ysum, ldysum));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -796,13 +794,13 @@ extern "C" int b2_bn_bwd_reduce(const void* dy, int32_t lddy, const void* z, int
   rc = det_begin(&det, grid, 2 * c, (cudaStream_t)stream);
   if (rc) return rc;
   if (light) {
-    B2_CHECK_CUDA(launch_chain(bn_bwd_reduce_light_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, relu,
-        sums, det));
+    B2_CHECK_CUDA(launch_chain(bn_bwd_reduce_light_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0),
+        (cudaStream_t)stream, 1, (long long)npix * c * 2, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
+        ldz, npix, c, lm, scale, shift, mean, invstd, relu, sums, det));
   } else {
-    B2_CHECK_CUDA(launch_chain(bn_bwd_reduce_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, relu,
-        sums, det));
+    B2_CHECK_CUDA(launch_chain(bn_bwd_reduce_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
+        (long long)npix * c * 2, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale,
+        shift, mean, invstd, relu, sums, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2 * c, sums, (cudaStream_t)stream);
@@ -839,13 +837,14 @@ extern "C" int b2_bn_bwd_apply(const void* dy, int32_t lddy, const void* z, int3
     if (rc) return rc;
   }
   if (light) {
-    B2_CHECK_CUDA(launch_chain(bn_bwd_apply_light_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, lm, scale, shift, mean, invstd, gamma,
-        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det));
+    B2_CHECK_CUDA(launch_chain(bn_bwd_apply_light_kernel, dim3(grid, slices), dim3(kBlock), (size_t)(0),
+        (cudaStream_t)stream, 1, (long long)npix * c * 2, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
+        ldz, npix, c, lm, scale, shift, mean, invstd, gamma, relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma,
+        dbeta, dbias, det));
   } else {
-    B2_CHECK_CUDA(launch_chain(bn_bwd_apply_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-        (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale, shift, mean, invstd, gamma,
-        relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det));
+    B2_CHECK_CUDA(launch_chain(bn_bwd_apply_kernel, dim3(grid), dim3(kBlock), (size_t)(0), (cudaStream_t)stream, 1,
+        (long long)npix * c * 2, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z, ldz, npix, c, m, scale,
+        shift, mean, invstd, gamma, relu, training, sums, (__nv_bfloat16*)dz, lddz, dgamma, dbeta, dbias, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, c, dbias, (cudaStream_t)stream);

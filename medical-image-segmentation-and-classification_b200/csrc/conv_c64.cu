@@ -623,8 +623,7 @@ int conv_c64_try_launch(const b2_conv_args* a, cudaStream_t stream) {
   }
   p.stats_partial = det.partial;
   B2_CHECK_CUDA(launch_chain(conv_c64_kernel, dim3(p.grid), dim3(kC64Threads), (size_t)(smem_bytes), stream, 1,
-      (long long)p.N * p.H * p.W * 128 * (p.fold ? 4 : 1),
-      tmA0, tmA1, tmB, tmY, tmAdd, p));
+      (long long)p.N * p.H * p.W * 128 * (p.fold ? 4 : 1), tmA0, tmA1, tmB, tmY, tmAdd, p));
   B2_LAUNCH_CHECK();
   if (det.partial) {
     rc = det_finish(det.partial, det_rows, 128, 128, p.stats, stream);

@@ -530,9 +530,9 @@ extern "C" int b2_gate_psi_fwd(const void* g1p, const void* x1p, int32_t ld, int
   DetBuf det;
   int rc = det_begin(&det, grid, 2, (cudaStream_t)stream);
   if (rc) return rc;
-  B2_CHECK_CUDA(launch_chain(gate_psi_fwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * fint * 2,
-      (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L, scale_g, shift_g, scale_x, shift_x,
-      wpsi, bpsi, (__nv_bfloat16*)q, qstats, det));
+  B2_CHECK_CUDA(launch_chain(gate_psi_fwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
+      (long long)npix * fint * 2, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L, scale_g,
+      shift_g, scale_x, shift_x, wpsi, bpsi, (__nv_bfloat16*)q, qstats, det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2, qstats, (cudaStream_t)stream);
   return B2_OK;
@@ -544,9 +544,9 @@ extern "C" int b2_gate_apply_fwd(const void* x, int32_t ldx, const void* q, int6
   B2_REQUIRE(c % 8 == 0 && c <= 2048, B2_ERR_SHAPE, "gate C=%d must be a multiple of 8, <= 2048", c);
   B2_REQUIRE(g_al(x, ldx) && g_al(out, ldo), B2_ERR_ALIGN, "gate operands misaligned");
   const int tpp = c / 8, rows = 256 / tpp;
-  B2_CHECK_CUDA(launch_chain(gate_apply_fwd_kernel, dim3(g_grid(npix, rows, 16)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-      (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)q, npix, tpp, rows, scale1, shift1, (__nv_bfloat16*)psi,
-      (__nv_bfloat16*)out, ldo));
+  B2_CHECK_CUDA(launch_chain(gate_apply_fwd_kernel, dim3(g_grid(npix, rows, 16)), dim3(256), (size_t)(0),
+      (cudaStream_t)stream, 1, (long long)npix * c * 2, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)q, npix,
+      tpp, rows, scale1, shift1, (__nv_bfloat16*)psi, (__nv_bfloat16*)out, ldo));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -562,9 +562,10 @@ extern "C" int b2_gate_apply_bwd(const void* dout, int32_t lddout, const void* x
   DetBuf det;
   int rc = det_begin(&det, grid, 2, (cudaStream_t)stream);
   if (rc) return rc;
-  B2_CHECK_CUDA(launch_chain(gate_apply_bwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-      (const __nv_bfloat16*)dout, lddout, (const __nv_bfloat16*)x, ldx, (const __nv_bfloat16*)psi,
-      (const __nv_bfloat16*)q, npix, c / 8, L, mean1, invstd1, (__nv_bfloat16*)dx, lddx, dsig, sums1, det));
+  B2_CHECK_CUDA(launch_chain(gate_apply_bwd_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1,
+      (long long)npix * c * 2, (const __nv_bfloat16*)dout, lddout, (const __nv_bfloat16*)x, ldx,
+      (const __nv_bfloat16*)psi, (const __nv_bfloat16*)q, npix, c / 8, L, mean1, invstd1, (__nv_bfloat16*)dx, lddx,
+      dsig, sums1, det));
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2, sums1, (cudaStream_t)stream);
   return B2_OK;
@@ -599,17 +600,19 @@ extern "C" int b2_gate_psi_bwd_reduce(const float* dsig, const void* q, const vo
   int rc = det_begin(&det, grid, 5 * fint + 1, (cudaStream_t)stream);
   if (rc) return rc;
   if (light && env_switch("B200SEG_GATE_U", fint <= 128 ? 4 : 2) == 4) {
-    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<4, 4, 2>, dim3(grid, slices), dim3(256), (size_t)(smem), (cudaStream_t)stream, 1, (long long)npix * fint * 2,
-        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det));
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<4, 4, 2>, dim3(grid, slices), dim3(256), (size_t)(smem),
+        (cudaStream_t)stream, 1, (long long)npix * fint * 2, dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p,
+        (const __nv_bfloat16*)x1p, ld, npix, fint, L, make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice,
+        det));
   } else if (light) {
-    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<4, 2, 3>, dim3(grid, slices), dim3(256), (size_t)(smem), (cudaStream_t)stream, 1, (long long)npix * fint * 2,
-        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice, det));
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<4, 2, 3>, dim3(grid, slices), dim3(256), (size_t)(smem),
+        (cudaStream_t)stream, 1, (long long)npix * fint * 2, dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p,
+        (const __nv_bfloat16*)x1p, ld, npix, fint, L, make_coef(coef), sums1, training, sums, dwpsi, dbpsi, slice,
+        det));
   } else {
-    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<8, 2, 2>, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, 1, (long long)npix * fint * 2,
-        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, L,
-        make_coef(coef), sums1, training, sums, dwpsi, dbpsi, 0, det));
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_reduce_kernel<8, 2, 2>, dim3(grid), dim3(256), (size_t)(smem),
+        (cudaStream_t)stream, 1, (long long)npix * fint * 2, dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p,
+        (const __nv_bfloat16*)x1p, ld, npix, fint, L, make_coef(coef), sums1, training, sums, dwpsi, dbpsi, 0, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) {
@@ -647,20 +650,20 @@ extern "C" int b2_gate_psi_bwd_apply(const float* dsig, const void* q, const voi
     if (rc) return rc;
   }
   if (light && env_switch("B200SEG_GATE_U", fint <= 128 ? 4 : 2) == 4) {
-    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<4, 4, 2>, dim3(grid, slices), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * fint * 2,
-        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
-        rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias, det));
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<4, 4, 2>, dim3(grid, slices), dim3(256), (size_t)(0),
+        (cudaStream_t)stream, 1, (long long)npix * fint * 2, dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p,
+        (const __nv_bfloat16*)x1p, ld, npix, fint, tpp, rows, make_coef(coef), sums1, training, sums,
+        (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1, dbias, det));
   } else if (light) {
-    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<4, 2, 3>, dim3(grid, slices), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * fint * 2,
-        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
-        rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias, det));
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<4, 2, 3>, dim3(grid, slices), dim3(256), (size_t)(0),
+        (cudaStream_t)stream, 1, (long long)npix * fint * 2, dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p,
+        (const __nv_bfloat16*)x1p, ld, npix, fint, tpp, rows, make_coef(coef), sums1, training, sums,
+        (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1, dbias, det));
   } else {
-    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<8, 2, 2>, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * fint * 2,
-        dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p, (const __nv_bfloat16*)x1p, ld, npix, fint, tpp,
-        rows, make_coef(coef), sums1, training, sums, (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1,
-        dbias, det));
+    B2_CHECK_CUDA(launch_chain(gate_psi_bwd_apply_kernel<8, 2, 2>, dim3(grid), dim3(256), (size_t)(0),
+        (cudaStream_t)stream, 1, (long long)npix * fint * 2, dsig, (const __nv_bfloat16*)q, (const __nv_bfloat16*)g1p,
+        (const __nv_bfloat16*)x1p, ld, npix, fint, tpp, rows, make_coef(coef), sums1, training, sums,
+        (__nv_bfloat16*)dg1p, (__nv_bfloat16*)dx1p, dgamma_beta, dbn1, dbias, det));
   }
   B2_LAUNCH_CHECK();
   if (det.partial) return det_finish(det.partial, grid, det.n, 2 * fint, dbias, (cudaStream_t)stream);

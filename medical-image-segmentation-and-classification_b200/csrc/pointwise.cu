@@ -348,8 +348,8 @@ extern "C" int b2_maxpool2x2_fwd(const void* x, int32_t ldx, int32_t n, int32_t 
   B2_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, B2_ERR_SHAPE, "maxpool needs c%%8==0 and even h,w");
   B2_REQUIRE(al16(x, ldx) && al16(y, ldy), B2_ERR_ALIGN, "maxpool operands misaligned");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  B2_CHECK_CUDA(launch_chain(maxpool2x2_fwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, total * 64,
-      (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)y, ldy));
+  B2_CHECK_CUDA(launch_chain(maxpool2x2_fwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0),
+      (cudaStream_t)stream, 1, total * 64, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)y, ldy));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -359,9 +359,9 @@ extern "C" int b2_maxpool2x2_bwd(const void* dy, int32_t lddy, const void* x, in
   B2_REQUIRE(c % 8 == 0 && h % 2 == 0 && w % 2 == 0, B2_ERR_SHAPE, "maxpool needs c%%8==0 and even h,w");
   B2_REQUIRE(al16(x, ldx) && al16(dy, lddy) && al16(dx, lddx), B2_ERR_ALIGN, "maxpool operands misaligned");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  B2_CHECK_CUDA(launch_chain(maxpool2x2_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, total * 64,
-      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx, nullptr,
-      0));
+  B2_CHECK_CUDA(launch_chain(maxpool2x2_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0),
+      (cudaStream_t)stream, 1, total * 64, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w,
+      c / 8, (__nv_bfloat16*)dx, lddx, nullptr, 0));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -373,9 +373,9 @@ extern "C" int b2_maxpool2x2_bwd_add(const void* dy, int32_t lddy, const void* x
   B2_REQUIRE(al16(x, ldx) && al16(dy, lddy) && al16(dx, lddx) && addend != nullptr && al16(addend, ldadd),
              B2_ERR_ALIGN, "maxpool operands misaligned / addend missing");
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  B2_CHECK_CUDA(launch_chain(maxpool2x2_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, total * 64,
-      (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w, c / 8, (__nv_bfloat16*)dx, lddx,
-      (const __nv_bfloat16*)addend, ldadd));
+  B2_CHECK_CUDA(launch_chain(maxpool2x2_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0),
+      (cudaStream_t)stream, 1, total * 64, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)x, ldx, n, h, w,
+      c / 8, (__nv_bfloat16*)dx, lddx, (const __nv_bfloat16*)addend, ldadd));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -407,8 +407,9 @@ extern "C" int b2_add(const void* a, int32_t lda, const void* b, int32_t ldb, in
                       int32_t ldo, b2_stream_t stream) {
   B2_REQUIRE(c % 8 == 0, B2_ERR_SHAPE, "add needs c%%8==0");
   B2_REQUIRE(al16(a, lda) && al16(b, ldb) && al16(out, ldo), B2_ERR_ALIGN, "add operands misaligned");
-  B2_CHECK_CUDA(launch_chain(add_kernel, dim3(ew_grid(npix * (c / 8), 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 1, (long long)npix * c * 2,
-      (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb, npix, c / 8, (__nv_bfloat16*)out, ldo));
+  B2_CHECK_CUDA(launch_chain(add_kernel, dim3(ew_grid(npix * (c / 8), 256)), dim3(256), (size_t)(0),
+      (cudaStream_t)stream, 1, (long long)npix * c * 2, (const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb,
+      npix, c / 8, (__nv_bfloat16*)out, ldo));
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
